@@ -1,0 +1,468 @@
+// SPDX-License-Identifier: Apache-2.0
+// tcgen05 + TMA GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   out[M,N] = sum_s A_s[M,K_s] . B_s[N,K_s]^T + bias[N] + rowbias[row/rows_per_group, N] + residual[M,N]
+//
+// One CTA computes one 128 x BN output tile.  Warp roles (192 threads):
+//   warp 0   : TMA producer  (one elected lane; A and B tiles of 64 K-elements per stage, SWIZZLE_128B)
+//   warp 1   : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma, fp32 accumulator in TMEM)
+//   warps 2-5: epilogue (tcgen05.ld the accumulator, fused bias / per-image bias / residual, bf16 store)
+// smem stages are sized so that two CTAs fit on one SM: one CTA's epilogue overlaps the other's main loop.
+//
+// The LoRA delta of hcpdiff (reference: hcpdiff/models/lora_layers_patch.py:44-57) enters as an extra
+// K-segment: A_1 = (x . W_down^T) [M, 64-padded], B_1 = alpha * W_up [N, 64-padded]; only ceil(r/16)
+// k-steps of that block are issued.
+//
+// The 3x3 convolution uses the same pipeline: the A tile of tap (kh,kw) and channel block c is a 4D (or 5D
+// for stride 2) TMA box over the NHWC activation at a shifted coordinate; coordinates outside the image are
+// zero-filled by the TMA unit, which IS the padding.  B is the weight matrix [Cout, 9*Cin].
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/hcp_b200.h"
+
+namespace hcp {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int kGemmThreads = 192;
+constexpr int kMaxTaps = 9;
+
+struct TapEntry {
+    int32_t c0_off;   // added to the innermost (channel) coordinate of A (stride-2: phase_w * Cin)
+    int32_t dw;       // added to the W coordinate
+    int32_t dh;       // added to the H coordinate
+    int32_t c2;       // 5D only: the H-phase coordinate
+    int32_t wk_off;   // K offset of this tap inside the weight matrix
+};
+
+struct alignas(64) GemmKParams {
+    CUtensorMap tmA[HCP_GEMM_MAX_SEG];
+    CUtensorMap tmB[HCP_GEMM_MAX_SEG];
+    int32_t nkb[HCP_GEMM_MAX_SEG];     // 64-wide k-blocks per segment (conv: per tap)
+    int32_t klast[HCP_GEMM_MAX_SEG];   // 16-wide k-steps issued in the last k-block of the segment (1..4)
+    int32_t nseg;
+    int32_t M, N;
+    int32_t tiles_n;
+    // convolution geometry (conv == 0: plain GEMM)
+    int32_t conv;                      // 0 none, 4 = 4D A map, 5 = 5D A map
+    int32_t ntaps;
+    TapEntry taps[kMaxTaps];
+    int32_t bw, bh, bn;                // box (w, h, images) of one M tile, bw*bh*bn == 128
+    int32_t tiles_w, tiles_h;          // tiles per image
+    int32_t oW, oH;                    // output feature-map extent (rows of `out` are (img, y, x))
+    int32_t sh, sw, oh0, ow0;          // output pixel of tile pixel (h,w) is (h*sh+oh0, w*sw+ow0)
+    // epilogue
+    const float* bias;
+    const float* rowbias;
+    int32_t rows_per_group;
+    const __nv_bfloat16* residual;
+    int64_t ldr;
+    __nv_bfloat16* out;
+    int64_t ldo;
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int STAGES = (BN <= 64) ? 4 : 3;
+    static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+    static constexpr int TMEM_COLS = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+    static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x % p.tiles_n;
+    const int m_tile = blockIdx.x / p.tiles_n;
+    const int n0 = n_tile * BN;
+
+    // tile origin
+    int m0 = m_tile * BLOCK_M;
+    int img0 = 0, h0 = 0, w0 = 0;
+    if (p.conv) {
+        if (p.bn == 1) {
+            const int per_img = p.tiles_w * p.tiles_h;
+            img0 = m_tile / per_img;
+            const int r = m_tile % per_img;
+            h0 = (r / p.tiles_w) * p.bh;
+            w0 = (r % p.tiles_w) * p.bw;
+        } else {
+            img0 = m_tile * p.bn;
+        }
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+        for (int s = 0; s < p.nseg; ++s) {
+            tma_prefetch_desc(&p.tmA[s]);
+            tma_prefetch_desc(&p.tmB[s]);
+        }
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                const int ntap = (p.conv && s == 0) ? p.ntaps : 1;
+                for (int t = 0; t < ntap; ++t) {
+                    for (int kb = 0; kb < p.nkb[s]; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+                        void* dA = sA + stage * A_STAGE_BYTES;
+                        void* dB = sB + stage * Cfg::B_STAGE_BYTES;
+                        if (p.conv && s == 0) {
+                            const TapEntry& te = p.taps[t];
+                            if (p.conv == 4)
+                                tma_load_4d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, w0 + te.dw,
+                                            h0 + te.dh, img0);
+                            else
+                                tma_load_5d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, w0 + te.dw,
+                                            te.c2, h0 + te.dh, img0);
+                            tma_load_2d(dB, &p.tmB[0], &full_bar[stage], te.wk_off + kb * BLOCK_K, n0);
+                        } else {
+                            tma_load_2d(dA, &p.tmA[s], &full_bar[stage], kb * BLOCK_K, m0);
+                            tma_load_2d(dB, &p.tmB[s], &full_bar[stage], kb * BLOCK_K, n0);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer ========================================
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t accum = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                const int ntap = (p.conv && s == 0) ? p.ntaps : 1;
+                for (int t = 0; t < ntap; ++t) {
+                    for (int kb = 0; kb < p.nkb[s]; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * A_STAGE_BYTES), 16, 1024);
+                        const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * Cfg::B_STAGE_BYTES), 16, 1024);
+                        const int ksteps = (kb == p.nkb[s] - 1) ? p.klast[s] : (BLOCK_K / 16);
+                        for (int k = 0; k < ksteps; ++k) {
+                            // +32 bytes (= 2 in descriptor units) per 16-element k-step inside the swizzle atom
+                            umma_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                            accum = 1;
+                        }
+                        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // ===================================== epilogue ==========================================
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int r = quarter * 32 + lane;            // row inside the tile
+        int64_t grow;                                 // row of `out`
+        bool row_ok;
+        int group;
+        if (p.conv) {
+            const int per = p.bw * p.bh;
+            const int im = img0 + r / per;
+            const int rr = r % per;
+            const int hh = h0 + rr / p.bw;
+            const int ww = w0 + rr % p.bw;
+            const int64_t opix = (int64_t)(hh * p.sh + p.oh0) * p.oW + (ww * p.sw + p.ow0);
+            grow = (int64_t)im * p.oH * p.oW + opix;
+            row_ok = grow < (int64_t)p.M;
+            group = im;
+        } else {
+            grow = m0 + r;
+            row_ok = grow < (int64_t)p.M;
+            group = p.rows_per_group > 0 ? (int)(grow / p.rows_per_group) : 0;
+        }
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(trow + c * 32, v);
+            tmem_wait_ld();
+            if (row_ok) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int col = n0 + c * 32 + g * 8;
+                    if (col < p.N) {
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+                        if (p.bias) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+                            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                        }
+                        if (p.rowbias) {
+                            const float* rb = p.rowbias + (int64_t)group * p.N + col;
+                            const float4 b0 = *reinterpret_cast<const float4*>(rb);
+                            const float4 b1 = *reinterpret_cast<const float4*>(rb + 4);
+                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                        }
+                        if (p.residual) {
+                            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + grow * p.ldr + col);
+                            float2 t;
+                            t = unpack_bf16x2(rv.x); f[0] += t.x; f[1] += t.y;
+                            t = unpack_bf16x2(rv.y); f[2] += t.x; f[3] += t.y;
+                            t = unpack_bf16x2(rv.z); f[4] += t.x; f[5] += t.y;
+                            t = unpack_bf16x2(rv.w); f[6] += t.x; f[7] += t.y;
+                        }
+                        uint4 o;
+                        o.x = pack_bf16x2(f[0], f[1]);
+                        o.y = pack_bf16x2(f[2], f[3]);
+                        o.z = pack_bf16x2(f[4], f[5]);
+                        o.w = pack_bf16x2(f[6], f[7]);
+                        *reinterpret_cast<uint4*>(p.out + grow * p.ldo + col) = o;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+static int launch_gemm(const GemmKParams& kp, int m_tiles, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
+        configured = true;
+    }
+    dim3 grid(kp.tiles_n * m_tiles);
+    gemm_tc_kernel<BN><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "gemm launch");
+    return HCP_OK;
+}
+
+static int pick_bn(int64_t N) {
+    if (N <= 32) return 32;
+    if (N <= 64) return 64;
+    if (N % 160 == 0) return 160;
+    if (N % 128 == 0) return 128;
+    if (N % 64 == 0 && N < 256) return 64;
+    return 128;
+}
+
+static int dispatch_gemm(int bn, const GemmKParams& kp, int m_tiles, cudaStream_t stream) {
+    switch (bn) {
+        case 32: return launch_gemm<32>(kp, m_tiles, stream);
+        case 64: return launch_gemm<64>(kp, m_tiles, stream);
+        case 128: return launch_gemm<128>(kp, m_tiles, stream);
+        case 160: return launch_gemm<160>(kp, m_tiles, stream);
+        default: return set_error(HCP_ERR_INVALID, "unsupported BLOCK_N");
+    }
+}
+
+}  // namespace hcp
+
+using namespace hcp;
+
+extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
+    if (!a || a->nseg < 1 || a->nseg > HCP_GEMM_MAX_SEG) return set_error(HCP_ERR_INVALID, "gemm: nseg");
+    if (a->M <= 0 || a->N <= 0 || (a->N % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: M/N (N must be a multiple of 8)");
+    if (!a->out || (a->ldo % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: out/ldo");
+    if (a->residual && (a->ldr % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: ldr");
+    GemmKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    const int bn = pick_bn(a->N);
+    for (int s = 0; s < a->nseg; ++s) {
+        if (a->k[s] <= 0 || (a->k[s] % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: k must be a positive multiple of 8");
+        if ((a->lda[s] % 8) != 0 || (a->ldb[s] % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: lda/ldb");
+        const int64_t nrb = a->n_rows_b[s] > 0 ? a->n_rows_b[s] : a->N;
+        int rc = make_tmap_2d(&kp.tmA[s], a->a[s], (uint64_t)a->k[s], (uint64_t)a->M, (uint64_t)a->lda[s], BLOCK_K, BLOCK_M);
+        if (rc) return rc;
+        rc = make_tmap_2d(&kp.tmB[s], a->b[s], (uint64_t)a->k[s], (uint64_t)nrb, (uint64_t)a->ldb[s], BLOCK_K, bn);
+        if (rc) return rc;
+        kp.nkb[s] = (int)((a->k[s] + BLOCK_K - 1) / BLOCK_K);
+        const int64_t rem = a->k[s] - (int64_t)(kp.nkb[s] - 1) * BLOCK_K;
+        kp.klast[s] = (int)((rem + 15) / 16);
+    }
+    kp.nseg = a->nseg;
+    kp.M = (int)a->M;
+    kp.N = (int)a->N;
+    kp.tiles_n = (int)((a->N + bn - 1) / bn);
+    kp.conv = 0;
+    kp.bias = a->bias;
+    kp.rowbias = a->rowbias;
+    kp.rows_per_group = (int)a->rows_per_group;
+    kp.residual = (const __nv_bfloat16*)a->residual;
+    kp.ldr = a->ldr;
+    kp.out = (__nv_bfloat16*)a->out;
+    kp.ldo = a->ldo;
+    const int m_tiles = (int)((a->M + BLOCK_M - 1) / BLOCK_M);
+    return dispatch_gemm(bn, kp, m_tiles, (cudaStream_t)stream_);
+}
+
+extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_) {
+    if (!a || !a->x || !a->w || !a->out) return set_error(HCP_ERR_INVALID, "conv3x3: null pointer");
+    if (a->Cin % 64 != 0 || a->Cout % 8 != 0) return set_error(HCP_ERR_INVALID, "conv3x3: Cin %% 64, Cout %% 8 required");
+    if (a->stride != 1 && a->stride != 2) return set_error(HCP_ERR_INVALID, "conv3x3: stride");
+    if (a->mode != 0 && !(a->mode == 1)) return set_error(HCP_ERR_INVALID, "conv3x3: mode");
+    GemmKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    const int bn = pick_bn(a->Cout);
+    const int64_t Cin = a->Cin;
+
+    // geometry of the "tile grid" (the grid the 128-pixel M tiles walk over) and of the output map
+    int64_t tH, tW;   // extent of the tile grid per image
+    int64_t oH, oW;   // output feature map
+    if (a->mode == 0) {
+        if (a->stride == 2 && ((a->Hin | a->Win) & 1)) return set_error(HCP_ERR_INVALID, "conv3x3: odd extent with stride 2");
+        oH = a->Hin / a->stride; oW = a->Win / a->stride;
+        tH = oH; tW = oW;
+    } else {
+        oH = a->Hin * 2; oW = a->Win * 2;
+        tH = a->Hin; tW = a->Win;   // one launch per output phase, tiles walk the dY grid
+    }
+    // box: bw*bh*bn == 128
+    int bw, bh, bnimg;
+    if (tW >= 128) { bw = 128; bh = 1; bnimg = 1; if (tW % 128) return set_error(HCP_ERR_INVALID, "conv3x3: W"); }
+    else {
+        bw = (int)tW;
+        if (128 % bw) return set_error(HCP_ERR_INVALID, "conv3x3: W must divide 128");
+        bh = 128 / bw;
+        if (bh <= tH) { if (tH % bh) return set_error(HCP_ERR_INVALID, "conv3x3: H tiling"); bnimg = 1; }
+        else { bh = (int)tH; if (128 % (bw * bh)) return set_error(HCP_ERR_INVALID, "conv3x3: H*W must divide 128"); bnimg = 128 / (bw * bh); }
+    }
+    kp.bw = bw; kp.bh = bh; kp.bn = bnimg;
+    kp.tiles_w = (int)(tW / bw);
+    kp.tiles_h = (int)(tH / bh);
+    kp.oW = (int)oW; kp.oH = (int)oH;
+    kp.nseg = 1;
+    kp.nkb[0] = (int)(Cin / BLOCK_K);
+    kp.klast[0] = 4;
+    kp.N = (int)a->Cout;
+    kp.M = (int)(a->B * oH * oW);
+    kp.tiles_n = (int)((a->Cout + bn - 1) / bn);
+    kp.bias = a->bias;
+    kp.rowbias = a->rowbias;
+    kp.rows_per_group = 0;
+    kp.residual = (const __nv_bfloat16*)a->residual;
+    kp.ldr = a->Cout;
+    kp.out = (__nv_bfloat16*)a->out;
+    kp.ldo = a->Cout;
+    int rc = make_tmap_2d(&kp.tmB[0], a->w, (uint64_t)(9 * Cin), (uint64_t)a->Cout, (uint64_t)(9 * Cin), BLOCK_K, bn);
+    if (rc) return rc;
+    const int m_tiles = (bnimg == 1) ? (int)(a->B * kp.tiles_w * kp.tiles_h) : (int)((a->B + bnimg - 1) / bnimg);
+    cudaStream_t stream = (cudaStream_t)stream_;
+
+    if (a->mode == 0 && a->stride == 1) {
+        kp.conv = 4;
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)a->Win, (uint64_t)a->Hin, (uint64_t)a->B};
+        uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)a->Win * Cin * 2, (uint64_t)a->Hin * a->Win * Cin * 2};
+        uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnimg};
+        rc = make_tmap_nd(&kp.tmA[0], a->x, 4, dims, strides, box);
+        if (rc) return rc;
+        kp.ntaps = 9;
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+                TapEntry& t = kp.taps[kh * 3 + kw];
+                t.c0_off = 0; t.dw = kw - 1; t.dh = kh - 1; t.c2 = 0;
+                t.wk_off = (int)((kh * 3 + kw) * Cin);
+            }
+        kp.sh = kp.sw = 1; kp.oh0 = kp.ow0 = 0;
+        return dispatch_gemm(bn, kp, m_tiles, stream);
+    }
+    if (a->mode == 0 && a->stride == 2) {
+        // view x as [B][Hin/2][2][Win/2][2*Cin]: input row ih = 2*oh + kh - 1 -> (phase, index)
+        kp.conv = 5;
+        uint64_t dims[5] = {(uint64_t)(2 * Cin), (uint64_t)(a->Win / 2), 2, (uint64_t)(a->Hin / 2), (uint64_t)a->B};
+        uint64_t strides[4] = {(uint64_t)(2 * Cin) * 2, (uint64_t)a->Win * Cin * 2, (uint64_t)(2 * a->Win * Cin) * 2,
+                               (uint64_t)a->Hin * a->Win * Cin * 2};
+        uint32_t box[5] = {BLOCK_K, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bnimg};
+        rc = make_tmap_nd(&kp.tmA[0], a->x, 5, dims, strides, box);
+        if (rc) return rc;
+        kp.ntaps = 9;
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+                TapEntry& t = kp.taps[kh * 3 + kw];
+                const int pw = (kw == 1) ? 0 : 1, ph = (kh == 1) ? 0 : 1;
+                t.c0_off = (int)(pw * Cin);
+                t.dw = (kw == 0) ? -1 : 0;
+                t.c2 = ph;
+                t.dh = (kh == 0) ? -1 : 0;
+                t.wk_off = (int)((kh * 3 + kw) * Cin);
+            }
+        kp.sh = kp.sw = 1; kp.oh0 = kp.ow0 = 0;
+        return dispatch_gemm(bn, kp, m_tiles, stream);
+    }
+    // mode 1: dgrad of the stride-2 conv.  x = dY [B, Hin, Win, Cin] (Cin = Cout of the fwd conv),
+    // out = dX [B, 2Hin, 2Win, Cout].  Output pixel (2i+ph, 2j+pw) gathers dY[i+dh, j+dw] over the taps whose
+    // parity matches:  ph=0: kh=1 (dh=0);  ph=1: kh=0 (dh=+1), kh=2 (dh=0).   w[co][kh][kw][ci] here is the
+    // dgrad weight = W_fwd[ci][kh][kw][co] (NOT flipped; the tap choice below does the bookkeeping).
+    kp.conv = 4;
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)a->Win, (uint64_t)a->Hin, (uint64_t)a->B};
+        uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)a->Win * Cin * 2, (uint64_t)a->Hin * a->Win * Cin * 2};
+        uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnimg};
+        rc = make_tmap_nd(&kp.tmA[0], a->x, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    kp.sh = kp.sw = 2;
+    for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+            int nt = 0;
+            for (int kh = 0; kh < 3; ++kh) {
+                if (((ph + 1 - kh) & 1) != 0) continue;
+                for (int kw = 0; kw < 3; ++kw) {
+                    if (((pw + 1 - kw) & 1) != 0) continue;
+                    TapEntry& t = kp.taps[nt++];
+                    t.c0_off = 0; t.c2 = 0;
+                    t.dh = (ph + 1 - kh) / 2;
+                    t.dw = (pw + 1 - kw) / 2;
+                    t.wk_off = (int)((kh * 3 + kw) * Cin);
+                }
+            }
+            kp.ntaps = nt;
+            kp.oh0 = ph; kp.ow0 = pw;
+            rc = dispatch_gemm(bn, kp, m_tiles, stream);
+            if (rc) return rc;
+        }
+    return HCP_OK;
+}

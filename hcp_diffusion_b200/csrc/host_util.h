@@ -1,0 +1,29 @@
+// SPDX-License-Identifier: Apache-2.0
+// Host-side helpers shared by the translation units of libhcpb200: thread-local error string,
+// and CUtensorMap construction through the driver entry point (no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace hcp {
+
+int set_error(int code, const char* msg);
+int set_cuda_error(cudaError_t e, const char* where);
+
+// bf16, SWIZZLE_128B, zero fill for out-of-bounds elements.  `dims`/`box` innermost first;
+// `strides_bytes` has rank-1 entries (the innermost stride is the element size).
+int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box);
+
+// [rows, inner] row-major matrix with row pitch `ld` elements; box = box_inner x box_rows.
+inline int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
+                        uint32_t box_inner, uint32_t box_rows) {
+    uint64_t dims[2] = {inner, rows};
+    uint64_t strides[1] = {ld * 2};
+    uint32_t box[2] = {box_inner, box_rows};
+    return make_tmap_nd(out, base, 2, dims, strides, box);
+}
+
+}  // namespace hcp

@@ -1,0 +1,157 @@
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference tree (/root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):  python tests/golden/make_golden.py
+
+Outputs (small, committed):
+  unet_struct_sd15.json   leaf modules of cfgs/unet_struct.txt -> parameter names/shapes/eps/stride (structure pin)
+  ref_lora_linear.pt      vectors produced by the REAL reference classes hcpdiff.models.lora_layers_patch.LoraLayer /
+                          lora_base_patch.LoraPatchContainer / plugin.PluginGroup: inputs, outputs, gradients and the
+                          checkpoint key names (the operator the CUDA kernels sit behind)
+"""
+import importlib
+import json
+import os
+import re
+import sys
+import types
+
+import torch
+from torch import nn
+
+REF = os.environ.get("HCP_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference_lora():
+    """Import hcpdiff.models.{plugin,lora_base_patch,lora_layers_patch} without diffusers/accelerate/hydra:
+    pre-register empty packages and stub the two helper modules they need."""
+    sys.dont_write_bytecode = True
+    for name, path in (("hcpdiff", "hcpdiff"), ("hcpdiff.utils", "hcpdiff/utils"), ("hcpdiff.models", "hcpdiff/models")):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join(REF, path)]
+            sys.modules[name] = m
+    u = types.ModuleType("hcpdiff.utils.utils")
+    u.low_rank_approximate = lambda w, rank: (_ for _ in ()).throw(NotImplementedError())
+    u.make_mask = lambda *a, **k: None
+    u.isinstance_list = lambda obj, cls_list: any(isinstance(obj, c) for c in cls_list)
+    sys.modules["hcpdiff.utils.utils"] = u
+    nu = types.ModuleType("hcpdiff.utils.net_utils")
+
+    def split_module_name(layer_name):
+        name_split = layer_name.rsplit(".", 1)
+        if len(name_split) == 1:
+            return "", name_split[0]
+        return name_split[0], name_split[1]
+
+    nu.split_module_name = split_module_name
+    sys.modules["hcpdiff.utils.net_utils"] = nu
+    lay = types.ModuleType("hcpdiff.models.layers")
+    lay.GroupLinear = type("GroupLinear", (nn.Module,), {})
+    sys.modules["hcpdiff.models.layers"] = lay
+    plugin = importlib.import_module("hcpdiff.models.plugin")
+    base = importlib.import_module("hcpdiff.models.lora_base_patch")
+    layers = importlib.import_module("hcpdiff.models.lora_layers_patch")
+    return plugin, base, layers
+
+
+def parse_struct(path):
+    """cfgs/unet_struct.txt -> {module_path: {'type':..., ...}} for leaf modules with parameters."""
+    stack = []   # (indent, name)
+    leaves = {}
+    line_re = re.compile(r"^(\s*)\((\w+)\): (\w+)\((.*)$")
+    for raw in open(path):
+        m = line_re.match(raw.rstrip("\n"))
+        if not m:
+            continue
+        indent, name, typ, rest = len(m.group(1)), m.group(2), m.group(3), m.group(4)
+        while stack and stack[-1][0] >= indent:
+            stack.pop()
+        full = ".".join([s[1] for s in stack] + [name])
+        stack.append((indent, name))
+        rest = rest[:-1] if rest.endswith(")") else rest
+        if typ == "Linear":
+            a = dict(re.findall(r"(\w+)=([\w\.]+)", rest))
+            leaves[full] = {"type": "Linear", "in": int(a["in_features"]), "out": int(a["out_features"]),
+                            "bias": a["bias"] == "True"}
+        elif typ == "Conv2d":
+            mm = re.match(r"(\d+), (\d+), kernel_size=\((\d+), (\d+)\), stride=\((\d+), (\d+)\)(?:, padding=\((\d+), (\d+)\))?", rest)
+            leaves[full] = {"type": "Conv2d", "in": int(mm.group(1)), "out": int(mm.group(2)), "k": int(mm.group(3)),
+                            "stride": int(mm.group(5)), "padding": int(mm.group(7) or 0)}
+        elif typ == "GroupNorm":
+            mm = re.match(r"(\d+), (\d+), eps=([\de\-\.]+)", rest)
+            leaves[full] = {"type": "GroupNorm", "groups": int(mm.group(1)), "ch": int(mm.group(2)), "eps": float(mm.group(3))}
+        elif typ == "LayerNorm":
+            mm = re.match(r"\((\d+),\), eps=([\de\-\.]+)", rest)
+            leaves[full] = {"type": "LayerNorm", "ch": int(mm.group(1)), "eps": float(mm.group(2))}
+    return leaves
+
+
+def make_struct():
+    leaves = parse_struct(os.path.join(REF, "cfgs/unet_struct.txt"))
+    with open(os.path.join(HERE, "unet_struct_sd15.json"), "w") as f:
+        json.dump(leaves, f, indent=0, sort_keys=True)
+    print("unet_struct_sd15.json:", len(leaves), "leaf modules")
+
+
+class _Attn(nn.Module):
+    def __init__(self, c, ctx):
+        super().__init__()
+        self.to_q = nn.Linear(c, c, bias=False)
+        self.to_k = nn.Linear(ctx, c, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(c, c, bias=True), nn.Dropout(0.0)])
+
+
+class _Blk(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.attn1 = _Attn(48, 48)
+        self.attn2 = _Attn(48, 24)
+
+
+def make_lora():
+    plugin, base, layers = import_reference_lora()
+    torch.manual_seed(0)
+    model = _Blk().float()
+    fx = {}
+    named = dict(model.named_modules())
+    # what reference make_hcpdiff does for one `lora_unet` item (cfg_net_tools.py:108-121): wrap_model on each match
+    blocks = {}
+    for lname in ("attn1", "attn2"):
+        d = layers.LoraLayer.wrap_model(0, named[lname], parent_block=None, host_name=None, rank=4, dropout=0.0, alpha=1.0,
+                                        exclude_key=None)
+        blocks.update({f"{lname}.{k}": v for k, v in d.items()})
+    # second stacked block on attn1.to_q (two `lora_unet` items hitting one layer)
+    d = layers.LoraLayer.wrap_model(1, named["attn1"].to_q, parent_block=named["attn1"], host_name="to_q", rank=2,
+                                    dropout=0.0, alpha=0.5)
+    second = d[""]
+    g = torch.Generator().manual_seed(5)
+    for blk in list(blocks.values()) + [second]:
+        blk.init_weights()
+        with torch.no_grad():
+            blk.layer.W_up.copy_(torch.randn(blk.layer.W_up.shape, generator=g) * 0.1)
+    group = plugin.PluginGroup(blocks)
+    fx["state_keys_model"] = sorted(model.state_dict().keys())
+    fx["ckpt_keys"] = sorted(group.state_dict().keys())
+    fx["ckpt"] = {k: v.clone() for k, v in group.state_dict().items()}
+    fx["second_block"] = {k: v.clone() for k, v in second.state_dict().items()}
+    fx["host"] = {k: v.clone() for k, v in model.state_dict().items() if "._host." in k}
+    x = torch.randn(3, 7, 48, generator=g)
+    ctx = torch.randn(3, 5, 24, generator=g)
+    x.requires_grad_(True)
+    outs = {"attn1.to_q": model.attn1.to_q(x), "attn1.to_k": model.attn1.to_k(x), "attn1.to_out.0": model.attn1.to_out[0](x),
+            "attn2.to_k": model.attn2.to_k(ctx), "attn2.to_q": model.attn2.to_q(x)}
+    loss = sum((o ** 2).sum() for o in outs.values())
+    loss.backward()
+    fx["x"], fx["ctx"] = x.detach().clone(), ctx.clone()
+    fx["outs"] = {k: v.detach().clone() for k, v in outs.items()}
+    fx["grad_x"] = x.grad.clone()
+    fx["grads"] = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None and "lora_block" in n}
+    torch.save(fx, os.path.join(HERE, "ref_lora_linear.pt"))
+    print("ref_lora_linear.pt: ckpt keys", fx["ckpt_keys"][:4], "...", len(fx["ckpt_keys"]))
+    print("  model keys sample:", [k for k in fx["state_keys_model"] if "to_q" in k][:6])
+
+
+if __name__ == "__main__":
+    make_struct()
+    make_lora()
