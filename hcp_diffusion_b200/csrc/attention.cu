@@ -1,0 +1,672 @@
+// SPDX-License-Identifier: Apache-2.0
+// Fused scaled-dot-product attention for sm_100a (tcgen05 + TMA), forward and backward.
+//
+// Replaces: diffusers Attention (AttnProcessor2_0 -> F.scaled_dot_product_attention, or xFormers when
+// `enable_xformers`, reference hcpdiff/train_ac.py:258-263) inside BasicTransformerBlock.attn1/attn2
+// (module structure: reference cfgs/unet_struct.txt:17-43) and its autograd backward.
+//
+// Layout: Q/K/V/O are token-major bf16 matrices [B, L, ld] in which head h occupies columns [h*d, (h+1)*d) -- the
+// layout the (fused) projection GEMMs write and the out-projection GEMM reads, so no head permute ever exists in
+// HBM.  A 4D TMA map (d, H, L, B) with box (64, 1, 128, 1) lands a [128 x 64] K-major SWIZZLE_128B tile of one head
+// in shared memory; columns >= d and rows >= L are zero-filled by the TMA unit.
+//
+// Forward, one CTA per (128 query rows, head, image), 4 softmax warps + 1 control warp:
+//   S = Q K^T            tcgen05.mma SS, fp32 S in TMEM columns [0,128)
+//   online softmax       thread == row (tcgen05.ld 32x32b); exp2 with folded scale; running max is only refreshed
+//                        (and O rescaled in TMEM) when it grows by > 2^8, so the rescale is rare
+//   P (bf16)             written back to TMEM over the S columns (tcgen05.st) and fed as the A operand from TMEM
+//   O += P V             tcgen05.mma TS; V tile is used straight from its row-major TMA box as an MN-major operand
+// Backward, one CTA per (128 kv rows, head, image) looping over query tiles:
+//   S = Q K^T, dP = dO V^T (TMEM) -> P, dS (bf16, smem) -> dV += P^T dO, dK += dS^T Q (TMEM accumulators,
+//   MN-major A operands), dQ_i = dS K (TMEM) reduced into an fp32 buffer with vector red.global.
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/hcp_b200.h"
+
+namespace hcp {
+
+constexpr int kAttnThreads = 160;          // warps 0-3: softmax/epilogue rows, warp 4: TMA + MMA control
+constexpr int TILE_BYTES = 128 * 128;      // one [128 rows x 64 cols] bf16 box
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ uint32_t lane_base(int warp) { return static_cast<uint32_t>(warp * 32) << 16; }
+
+// =============================================================================================
+// forward
+// =============================================================================================
+struct alignas(64) AttnFwdParams {
+    CUtensorMap tmQ, tmK, tmV;
+    int B, H, Lq, Lkv, d;
+    int nbox;            // ceil(d / 64)
+    int dn;              // d rounded up to a multiple of 16
+    int tmem_cols;
+    int kv_stages;       // 2, or 1 when the tiles are too large (d > 128)
+    float scale_log2;    // softmax scale * log2(e)
+    const float* kv_bias;   // [B, Lkv] additive bias (natural-log units) or nullptr
+    __nv_bfloat16* O;
+    int64_t ldo;
+    float* lse;          // [B, H, Lq], natural log
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tile_bytes = p.nbox * TILE_BYTES;
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + tile_bytes;           // kv_stages
+    uint8_t* sV = sK + p.kv_stages * tile_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.kv_stages * tile_bytes);
+    uint64_t* q_full = bars + 0;
+    uint64_t* kv_full = bars + 1;    // [2]
+    uint64_t* s_full = bars + 3;
+    uint64_t* p_ready = bars + 4;
+    uint64_t* pv_done = bars + 5;    // [2]
+    uint64_t* o_full = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int nkv = (p.Lkv + 127) / 128;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        mbar_init(&kv_full[0], 1);
+        mbar_init(&kv_full[1], 1);
+        mbar_init(s_full, 1);
+        mbar_init(p_ready, 128);
+        mbar_init(&pv_done[0], 1);
+        mbar_init(&pv_done[1], 1);
+        mbar_init(o_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) {
+        tmem_alloc(tmem_slot, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem;            // S fp32 [128 cols]; P bf16 packed aliases columns [0,64)
+    const uint32_t tO = tmem + 128;
+
+    if (warp == 4) {
+        if (elect_one()) {
+            auto load_kv = [&](int j) {
+                const int st = (p.kv_stages == 2) ? (j & 1) : 0;
+                mbar_arrive_expect_tx(&kv_full[st], 2 * tile_bytes);
+                for (int bx = 0; bx < p.nbox; ++bx) {
+                    tma_load_4d(sK + st * tile_bytes + bx * TILE_BYTES, &p.tmK, &kv_full[st], bx * 64, h, j * 128, b);
+                    tma_load_4d(sV + st * tile_bytes + bx * TILE_BYTES, &p.tmV, &kv_full[st], bx * 64, h, j * 128, b);
+                }
+            };
+            mbar_arrive_expect_tx(q_full, tile_bytes);
+            for (int bx = 0; bx < p.nbox; ++bx)
+                tma_load_4d(sQ + bx * TILE_BYTES, &p.tmQ, q_full, bx * 64, h, qt * 128, b);
+            load_kv(0);
+            if (p.kv_stages == 2 && nkv > 1) load_kv(1);
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < nkv; ++j) {
+                const int st = (p.kv_stages == 2) ? (j & 1) : 0;
+                const uint32_t ph = (p.kv_stages == 2) ? ((j >> 1) & 1) : (j & 1);
+                const int ncols = min(128, p.Lkv - j * 128);
+                const int n16 = (ncols + 15) & ~15;
+                mbar_wait(&kv_full[st], ph);
+                tc_fence_after();
+                // ---- S = Q K^T
+                const uint32_t idesc_s = make_idesc_bf16(128, n16, 0, 0);
+                const uint32_t kbase = smem_u32(sK + st * tile_bytes);
+                const uint32_t qbase = smem_u32(sQ);
+                for (int ks = 0; ks < p.dn / 16; ++ks) {
+                    const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
+                    umma_ss(tS, make_smem_desc(qbase + off, 16, 1024), make_smem_desc(kbase + off, 16, 1024), idesc_s,
+                            ks > 0);
+                }
+                umma_commit(s_full);
+                // while the softmax warps work on tile j: refill the stage tile j-1 used
+                if (p.kv_stages == 2 && j >= 1 && j + 1 < nkv) {
+                    mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                    load_kv(j + 1);
+                }
+                mbar_wait(p_ready, j & 1);
+                tc_fence_after();
+                // ---- O += P V   (A = P from TMEM, B = V tile as MN-major operand)
+                const uint32_t idesc_pv = make_idesc_bf16(128, p.dn, 0, 1);
+                const uint32_t vbase = smem_u32(sV + st * tile_bytes);
+                for (int ks = 0; ks < n16 / 16; ++ks) {
+                    umma_ts(tO, tS + ks * 8, make_smem_desc(vbase + ks * 2048, TILE_BYTES, 1024), idesc_pv,
+                            (j > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&pv_done[st]);
+                if (p.kv_stages == 1 && j + 1 < nkv) {
+                    mbar_wait(&pv_done[0], j & 1);
+                    load_kv(j + 1);
+                }
+            }
+            umma_commit(o_full);
+        }
+    } else {
+        // ------------------------------ softmax: thread == query row ------------------------------
+        const int row = warp * 32 + lane;
+        const int qrow = qt * 128 + row;
+        const uint32_t lb = lane_base(warp);
+        float m = -INFINITY, l = 0.f;
+        const float* bias = p.kv_bias ? p.kv_bias + (int64_t)b * p.Lkv : nullptr;
+        for (int j = 0; j < nkv; ++j) {
+            const int kv0 = j * 128;
+            const int ncols = min(128, p.Lkv - kv0);
+            const int nch = (((ncols + 15) & ~15) + 31) >> 5;
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            // pass 1: row max (log2 domain)
+            float mx = -INFINITY;
+            for (int c = 0; c < nch; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tS + lb + c * 32, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int col = c * 32 + e;
+                    float s = __uint_as_float(v[e]) * p.scale_log2;
+                    if (bias && col < ncols) s += bias[kv0 + col] * kLog2e;
+                    s = (col < ncols) ? s : -INFINITY;
+                    mx = fmaxf(mx, s);
+                }
+            }
+            if (j == 0) {
+                m = (mx == -INFINITY) ? 0.f : mx;
+            } else {
+                const float m_new = fmaxf(m, mx);
+                if (__any_sync(0xffffffffu, m_new - m > 8.f)) {
+                    const float alpha = fast_exp2(m - m_new);
+                    l *= alpha;
+                    for (int c = 0; c < p.dn / 16; ++c) {
+                        uint32_t o[16];
+                        tmem_ld16(tO + lb + c * 16, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                        tmem_st16(tO + lb + c * 16, o);
+                    }
+                    tmem_wait_st();
+                    m = m_new;
+                }
+            }
+            // pass 2: P = exp2(s - m), packed bf16 back into TMEM (aliases the S columns already consumed)
+            for (int c = 0; c < nch; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tS + lb + c * 32, v);
+                tmem_wait_ld();
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    float pe[2];
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int col = c * 32 + e + t;
+                        float s = __uint_as_float(v[e + t]) * p.scale_log2;
+                        if (bias && col < ncols) s += bias[kv0 + col] * kLog2e;
+                        const float pv = fast_exp2(s - m);
+                        pe[t] = (col < ncols) ? pv : 0.f;
+                    }
+                    // accumulate the row sum from the bf16-rounded values the MMA will actually see
+                    const uint32_t u = pack_bf16x2(pe[0], pe[1]);
+                    const float2 r = unpack_bf16x2(u);
+                    l += r.x + r.y;
+                    pk[e >> 1] = u;
+                }
+                tmem_st16(tS + lb + c * 16, pk);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(p_ready);
+        }
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        const float inv = 1.f / l;
+        __nv_bfloat16* orow = p.O + ((int64_t)b * p.Lq + qrow) * p.ldo + (int64_t)h * p.d;
+        for (int c = 0; c < p.dn / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tO + lb + c * 16, o);
+            tmem_wait_ld();
+            if (qrow < p.Lq) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int col = c * 16 + g * 8;
+                    if (col < p.d) {
+                        uint4 w;
+                        w.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+                        w.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+                        w.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+                        w.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+                        *reinterpret_cast<uint4*>(orow + col) = w;
+                    }
+                }
+            }
+        }
+        if (qrow < p.Lq && p.lse) p.lse[((int64_t)b * p.H + h) * p.Lq + qrow] = (m + log2f(l)) * kLn2;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, p.tmem_cols);
+}
+
+// =============================================================================================
+// backward
+// =============================================================================================
+struct alignas(64) AttnBwdParams {
+    CUtensorMap tmQ, tmK, tmV, tmdO;
+    int B, H, Lq, Lkv, d;
+    int nbox, dn;
+    int col0, ncols_out;     // output column slice of this launch (col0 multiple of 64)
+    int q_stages;            // 1 or 2
+    int share_pds;           // P and dS share one smem buffer
+    float scale, scale_log2;
+    const float* kv_bias;
+    const float* lse;        // [B,H,Lq]
+    const float* delta;      // [B,H,Lq]  rowsum(dO * O)
+    float* dq_acc;           // [B,H,Lq,dq_ld] fp32
+    int dq_ld;
+    __nv_bfloat16 *dK, *dV;
+    int64_t lddk, lddv;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tile_bytes = p.nbox * TILE_BYTES;
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + tile_bytes;
+    uint8_t* sQ = sV + tile_bytes;                       // q_stages
+    uint8_t* sdO = sQ + p.q_stages * tile_bytes;         // q_stages
+    uint8_t* sP = sdO + p.q_stages * tile_bytes;         // [128 q rows x 128 kv] bf16 = 2 boxes
+    uint8_t* sdS = p.share_pds ? sP : sP + 2 * TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>((p.share_pds ? sP : sdS) + 2 * TILE_BYTES);
+    uint64_t* kv_full = bars + 0;
+    uint64_t* q_full = bars + 1;     // [2]
+    uint64_t* sdp_full = bars + 3;   // S and dP ready in TMEM
+    uint64_t* p_ready = bars + 4;    // P in smem           (128 arrivals)
+    uint64_t* ds_ready = bars + 5;   // dS in smem          (128 arrivals)
+    uint64_t* dv_done = bars + 6;    // dV MMA retired (P buffer reusable)
+    uint64_t* dq_full = bars + 7;    // dK, dQ MMAs retired
+    uint64_t* dq_read = bars + 8;    // dQ drained from TMEM (128 arrivals)
+    uint64_t* acc_full = bars + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int nq = (p.Lq + 127) / 128;
+    const int kv0 = jt * 128;
+    const int ncols = min(128, p.Lkv - kv0);
+
+    if (threadIdx.x == 0) {
+        mbar_init(kv_full, 1);
+        mbar_init(&q_full[0], 1);
+        mbar_init(&q_full[1], 1);
+        mbar_init(sdp_full, 1);
+        mbar_init(p_ready, 128);
+        mbar_init(ds_ready, 128);
+        mbar_init(dv_done, 1);
+        mbar_init(dq_full, 1);
+        mbar_init(dq_read, 128);
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem, tdV = tmem + 256, tdK = tmem + 384;
+
+    if (warp == 4) {
+        if (elect_one()) {
+            auto load_q = [&](int i) {
+                const int st = (p.q_stages == 2) ? (i & 1) : 0;
+                mbar_arrive_expect_tx(&q_full[st], 2 * tile_bytes);
+                for (int bx = 0; bx < p.nbox; ++bx) {
+                    tma_load_4d(sQ + st * tile_bytes + bx * TILE_BYTES, &p.tmQ, &q_full[st], bx * 64, h, i * 128, b);
+                    tma_load_4d(sdO + st * tile_bytes + bx * TILE_BYTES, &p.tmdO, &q_full[st], bx * 64, h, i * 128, b);
+                }
+            };
+            mbar_arrive_expect_tx(kv_full, 2 * tile_bytes);
+            for (int bx = 0; bx < p.nbox; ++bx) {
+                tma_load_4d(sK + bx * TILE_BYTES, &p.tmK, kv_full, bx * 64, h, kv0, b);
+                tma_load_4d(sV + bx * TILE_BYTES, &p.tmV, kv_full, bx * 64, h, kv0, b);
+            }
+            load_q(0);
+            mbar_wait(kv_full, 0);
+            const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+            const uint32_t idesc_acc = make_idesc_bf16(128, p.ncols_out, 1, 1);   // dV, dK: A and B MN-major
+            const uint32_t idesc_dq = make_idesc_bf16(128, p.ncols_out, 0, 1);    // dQ: A K-major, B MN-major
+            const uint32_t box0 = (p.col0 / 64) * TILE_BYTES;                     // first box of the output slice
+            for (int i = 0; i < nq; ++i) {
+                const int st = (p.q_stages == 2) ? (i & 1) : 0;
+                const uint32_t ph = (p.q_stages == 2) ? ((i >> 1) & 1) : (i & 1);
+                if (p.q_stages == 2 && i + 1 < nq) load_q(i + 1);   // stage (i+1)&1 was released by dq_full of i-1
+                mbar_wait(&q_full[st], ph);
+                tc_fence_after();
+                const uint32_t qb = smem_u32(sQ + st * tile_bytes), dob = smem_u32(sdO + st * tile_bytes);
+                const uint32_t kb = smem_u32(sK), vb = smem_u32(sV);
+                // S = Q K^T, dP = dO V^T  (contraction over d)
+                for (int ks = 0; ks < p.dn / 16; ++ks) {
+                    const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
+                    umma_ss(tS, make_smem_desc(qb + off, 16, 1024), make_smem_desc(kb + off, 16, 1024), idesc_s, ks > 0);
+                }
+                for (int ks = 0; ks < p.dn / 16; ++ks) {
+                    const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
+                    umma_ss(tdP, make_smem_desc(dob + off, 16, 1024), make_smem_desc(vb + off, 16, 1024), idesc_s, ks > 0);
+                }
+                umma_commit(sdp_full);
+                // dV += P^T dO   (M = kv, K = q rows: both operands MN-major, k-step = 16 q rows = 2048 B)
+                mbar_wait(p_ready, i & 1);
+                tc_fence_after();
+                const uint32_t pb = smem_u32(sP), dsb = smem_u32(sdS);
+                for (int ks = 0; ks < 8; ++ks) {
+                    umma_ss(tdV, make_smem_desc(pb + ks * 2048, TILE_BYTES, 1024),
+                            make_smem_desc(dob + box0 + ks * 2048, TILE_BYTES, 1024), idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(dv_done);
+                // dK += dS^T Q ;  dQ_i = dS K
+                mbar_wait(ds_ready, i & 1);
+                tc_fence_after();
+                for (int ks = 0; ks < 8; ++ks) {
+                    umma_ss(tdK, make_smem_desc(dsb + ks * 2048, TILE_BYTES, 1024),
+                            make_smem_desc(qb + box0 + ks * 2048, TILE_BYTES, 1024), idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
+                }
+                for (int ks = 0; ks < 8; ++ks) {   // contraction over kv: dS K-major (two 64-wide boxes), K_j MN-major
+                    const uint32_t aoff = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
+                    umma_ss(tdQ, make_smem_desc(dsb + aoff, 16, 1024),
+                            make_smem_desc(kb + box0 + ks * 2048, TILE_BYTES, 1024), idesc_dq, ks > 0);
+                }
+                umma_commit(dq_full);
+                if (p.q_stages == 1 && i + 1 < nq) {
+                    mbar_wait(dq_full, i & 1);      // Q/dO tile consumed
+                    load_q(i + 1);
+                }
+                mbar_wait(dq_read, i & 1);          // S/dP/dQ columns free again
+                tc_fence_after();
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // ------------------------------ thread == query row (S, dP) / kv row (dK, dV) --------------
+        const int row = warp * 32 + lane;
+        const uint32_t lb = lane_base(warp);
+        const float* bias = p.kv_bias ? p.kv_bias + (int64_t)b * p.Lkv : nullptr;
+        for (int i = 0; i < nq; ++i) {
+            const int qrow = i * 128 + row;
+            const bool qok = qrow < p.Lq;
+            const int64_t stat_idx = ((int64_t)b * p.H + h) * p.Lq + qrow;
+            const float lse2 = qok ? p.lse[stat_idx] * kLog2e : 0.f;
+            const float dlt = qok ? p.delta[stat_idx] : 0.f;
+            mbar_wait(sdp_full, i & 1);
+            tc_fence_after();
+            // ---- P = exp2(S*c - lse), dS = P * (dP - delta) * scale -> smem (K-major [q][kv], SWIZZLE_128B,
+            //      two 64-wide boxes each).  One pass unless P and dS must share a buffer (d > 128).
+            for (int pass = 0; pass < (p.share_pds ? 2 : 1); ++pass) {
+                const bool do_p = (pass == 0);
+                const bool do_ds = !p.share_pds || pass == 1;
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32], w[32];
+                    tmem_ld32(tS + lb + c * 32, v);
+                    if (do_ds) tmem_ld32(tdP + lb + c * 32, w);
+                    tmem_wait_ld();
+                    uint32_t pk[16], dk[16];
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        float pe[2], de[2];
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            const int col = c * 32 + e + t;
+                            float s = __uint_as_float(v[e + t]) * p.scale_log2;
+                            if (bias && col < ncols) s += bias[kv0 + col] * kLog2e;
+                            const float pv = (qok && col < ncols) ? fast_exp2(s - lse2) : 0.f;
+                            pe[t] = pv;
+                            de[t] = do_ds ? pv * (__uint_as_float(w[e + t]) - dlt) * p.scale : 0.f;
+                        }
+                        pk[e >> 1] = pack_bf16x2(pe[0], pe[1]);
+                        dk[e >> 1] = pack_bf16x2(de[0], de[1]);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t off = (c >> 1) * TILE_BYTES + sw128_offset(row, (c & 1) * 4 + g);
+                        if (do_p) *reinterpret_cast<uint4*>(sP + off) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+                        if (do_ds) *reinterpret_cast<uint4*>(sdS + off) = make_uint4(dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
+                    }
+                }
+                if (do_p) {
+                    fence_proxy_async_smem();
+                    mbar_arrive(p_ready);
+                    if (p.share_pds) mbar_wait(dv_done, i & 1);   // P consumed before dS overwrites the buffer
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(ds_ready);
+            // ---- drain dQ_i into the fp32 accumulator
+            mbar_wait(dq_full, i & 1);
+            tc_fence_after();
+            float* dqrow = p.dq_acc + stat_idx * p.dq_ld + p.col0;
+            for (int c = 0; c < p.ncols_out / 16; ++c) {
+                uint32_t o[16];
+                tmem_ld16(tdQ + lb + c * 16, o);
+                tmem_wait_ld();
+                if (qok) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = p.col0 + c * 16 + g * 4;
+                        if (col < p.d)
+                            red_add_v4(dqrow + c * 16 + g * 4, __uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]),
+                                       __uint_as_float(o[g * 4 + 2]), __uint_as_float(o[g * 4 + 3]));
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(dq_read);
+        }
+        // ---- dK, dV of this kv tile: thread == kv row
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int kvrow = kv0 + row;
+        for (int which = 0; which < 2; ++which) {
+            const uint32_t t = which ? tdK : tdV;
+            __nv_bfloat16* out = which ? p.dK : p.dV;
+            const int64_t ld = which ? p.lddk : p.lddv;
+            __nv_bfloat16* orow = out + ((int64_t)b * p.Lkv + kvrow) * ld + (int64_t)h * p.d + p.col0;
+            for (int c = 0; c < p.ncols_out / 16; ++c) {
+                uint32_t o[16];
+                tmem_ld16(t + lb + c * 16, o);
+                tmem_wait_ld();
+                if (kvrow < p.Lkv) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int col = p.col0 + c * 16 + g * 8;
+                        if (col < p.d) {
+                            uint4 w;
+                            w.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
+                            w.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+                            w.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+                            w.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+                            *reinterpret_cast<uint4*>(orow + c * 16 + g * 8) = w;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
+// delta[b,h,q] = sum_e dO*O ; also zero-fills the fp32 dQ accumulator.  One warp per (b,q,h).
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, int64_t ldo, const __nv_bfloat16* __restrict__ dO,
+                                     int64_t lddo, int B, int H, int Lq, int d, float* __restrict__ delta,
+                                     float* __restrict__ dq_acc, int dq_ld) {
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t total = (int64_t)B * Lq * H;
+    if (w >= total) return;
+    const int h = (int)(w % H);
+    const int64_t bq = w / H;
+    const int q = (int)(bq % Lq);
+    const int b = (int)(bq / Lq);
+    const __nv_bfloat16* o = O + bq * ldo + (int64_t)h * d;
+    const __nv_bfloat16* g = dO + bq * lddo + (int64_t)h * d;
+    float acc = 0.f;
+    for (int e = lane * 2; e < d; e += 64) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + e));
+        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g + e));
+        acc += a.x * c.x + a.y * c.y;
+    }
+    acc = warp_sum(acc);
+    const int64_t idx = ((int64_t)b * H + h) * Lq + q;
+    if (lane == 0) delta[idx] = acc;
+    float* z = dq_acc + idx * dq_ld;
+    for (int e = lane; e < dq_ld; e += 32) z[e] = 0.f;
+}
+
+// dQ bf16 [B, Lq, lddq] <- fp32 accumulator [B,H,Lq,dq_ld]
+__global__ void attn_bwd_post_kernel(const float* __restrict__ dq_acc, int dq_ld, int B, int H, int Lq, int d,
+                                     __nv_bfloat16* __restrict__ dQ, int64_t lddq) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per 4 elements
+    const int d4 = d / 4;
+    const int64_t total = (int64_t)B * Lq * H * d4;
+    if (i >= total) return;
+    const int e = (int)(i % d4) * 4;
+    const int64_t r = i / d4;
+    const int h = (int)(r % H);
+    const int64_t bq = r / H;
+    const int q = (int)(bq % Lq);
+    const int b = (int)(bq / Lq);
+    const float4 v = *reinterpret_cast<const float4*>(dq_acc + (((int64_t)b * H + h) * Lq + q) * dq_ld + e);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dQ + bq * lddq + (int64_t)h * d + e) = o;
+}
+
+static int make_head_map(CUtensorMap* m, const void* base, int64_t ld, int64_t B, int64_t H, int64_t L, int64_t d) {
+    uint64_t dims[4] = {(uint64_t)d, (uint64_t)H, (uint64_t)L, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)ld * 2, (uint64_t)L * ld * 2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    return make_tmap_nd(m, base, 4, dims, strides, box);
+}
+
+static int check_common(int64_t B, int64_t H, int64_t Lq, int64_t Lkv, int64_t d) {
+    if (B <= 0 || H <= 0 || Lq <= 0 || Lkv <= 0) return set_error(HCP_ERR_INVALID, "attention: empty problem");
+    if (d % 8 != 0 || d < 8 || d > 192) return set_error(HCP_ERR_INVALID, "attention: head dim must be a multiple of 8 in [8,192]");
+    return HCP_OK;
+}
+
+}  // namespace hcp
+
+using namespace hcp;
+
+extern "C" int hcp_attn_fwd_bf16(const hcp_attn_args* a, hcp_stream_t stream_) {
+    if (!a || !a->q || !a->k || !a->v || !a->o) return set_error(HCP_ERR_INVALID, "attn_fwd: null pointer");
+    int rc = check_common(a->B, a->H, a->Lq, a->Lkv, a->d);
+    if (rc) return rc;
+    AttnFwdParams p;
+    memset(&p, 0, sizeof(p));
+    if ((rc = make_head_map(&p.tmQ, a->q, a->ldq, a->B, a->H, a->Lq, a->d))) return rc;
+    if ((rc = make_head_map(&p.tmK, a->k, a->ldk, a->B, a->H, a->Lkv, a->d))) return rc;
+    if ((rc = make_head_map(&p.tmV, a->v, a->ldv, a->B, a->H, a->Lkv, a->d))) return rc;
+    p.B = (int)a->B; p.H = (int)a->H; p.Lq = (int)a->Lq; p.Lkv = (int)a->Lkv; p.d = (int)a->d;
+    p.nbox = (int)((a->d + 63) / 64);
+    p.dn = (int)((a->d + 15) / 16 * 16);
+    p.tmem_cols = (128 + p.dn <= 256) ? 256 : 512;
+    p.scale_log2 = a->scale * kLog2e;
+    p.kv_bias = a->kv_bias;
+    p.O = (__nv_bfloat16*)a->o; p.ldo = a->ldo;
+    p.lse = a->lse;
+    p.kv_stages = (p.nbox <= 2) ? 2 : 1;
+    const int smem = (1 + 2 * p.kv_stages) * p.nbox * TILE_BYTES + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn_fwd)");
+        configured = true;
+    }
+    dim3 grid((unsigned)((a->Lq + 127) / 128), (unsigned)a->H, (unsigned)a->B);
+    attn_fwd_kernel<<<grid, kAttnThreads, smem, (cudaStream_t)stream_>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "attn_fwd launch");
+    return HCP_OK;
+}
+
+extern "C" size_t hcp_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq, int64_t d) {
+    const int64_t dq_ld = (d + 3) / 4 * 4;
+    return (size_t)(B * H * Lq * (dq_ld + 1)) * sizeof(float);
+}
+
+extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream_) {
+    if (!a || !a->q || !a->k || !a->v || !a->o || !a->dout || !a->lse || !a->dq || !a->dk || !a->dv || !a->workspace)
+        return set_error(HCP_ERR_INVALID, "attn_bwd: null pointer");
+    int rc = check_common(a->B, a->H, a->Lq, a->Lkv, a->d);
+    if (rc) return rc;
+    if (a->workspace_bytes < hcp_attn_bwd_workspace_bytes(a->B, a->H, a->Lq, a->d))
+        return set_error(HCP_ERR_INVALID, "attn_bwd: workspace too small");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int dq_ld = (int)((a->d + 3) / 4 * 4);
+    float* delta = a->workspace;
+    float* dq_acc = a->workspace + a->B * a->H * a->Lq;
+    {
+        const int64_t warps = a->B * a->Lq * a->H;
+        const int threads = 256;
+        const int64_t blocks = (warps * 32 + threads - 1) / threads;
+        attn_bwd_prep_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const __nv_bfloat16*)a->o, a->ldo,
+                                                                       (const __nv_bfloat16*)a->dout, a->lddo, (int)a->B,
+                                                                       (int)a->H, (int)a->Lq, (int)a->d, delta, dq_acc, dq_ld);
+    }
+    AttnBwdParams p;
+    memset(&p, 0, sizeof(p));
+    if ((rc = make_head_map(&p.tmQ, a->q, a->ldq, a->B, a->H, a->Lq, a->d))) return rc;
+    if ((rc = make_head_map(&p.tmK, a->k, a->ldk, a->B, a->H, a->Lkv, a->d))) return rc;
+    if ((rc = make_head_map(&p.tmV, a->v, a->ldv, a->B, a->H, a->Lkv, a->d))) return rc;
+    if ((rc = make_head_map(&p.tmdO, a->dout, a->lddo, a->B, a->H, a->Lq, a->d))) return rc;
+    p.B = (int)a->B; p.H = (int)a->H; p.Lq = (int)a->Lq; p.Lkv = (int)a->Lkv; p.d = (int)a->d;
+    p.nbox = (int)((a->d + 63) / 64);
+    p.dn = (int)((a->d + 15) / 16 * 16);
+    p.scale = a->scale;
+    p.scale_log2 = a->scale * kLog2e;
+    p.kv_bias = a->kv_bias;
+    p.lse = a->lse;
+    p.delta = delta;
+    p.dq_acc = dq_acc;
+    p.dq_ld = dq_ld;
+    p.dK = (__nv_bfloat16*)a->dk; p.lddk = a->lddk;
+    p.dV = (__nv_bfloat16*)a->dv; p.lddv = a->lddv;
+    p.q_stages = (p.nbox == 1) ? 2 : 1;
+    p.share_pds = (p.nbox >= 3) ? 1 : 0;
+    const int smem = (2 + 2 * p.q_stages) * p.nbox * TILE_BYTES + (p.share_pds ? 2 : 4) * TILE_BYTES + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn_bwd)");
+        configured = true;
+    }
+    if (smem > 227 * 1024) return set_error(HCP_ERR_INVALID, "attn_bwd: shared memory budget exceeded");
+    dim3 grid((unsigned)((a->Lkv + 127) / 128), (unsigned)a->H, (unsigned)a->B);
+    // output column slices: at most 128 columns per launch, each starting on a 64-column box boundary
+    for (int col0 = 0; col0 < p.dn; col0 += 128) {
+        p.col0 = col0;
+        p.ncols_out = (p.dn - col0 < 128) ? (p.dn - col0) : 128;
+        attn_bwd_kernel<<<grid, kAttnThreads, smem, stream>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd launch");
+    }
+    {
+        const int64_t n = a->B * a->Lq * a->H * (a->d / 4);
+        attn_bwd_post_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dq_acc, dq_ld, (int)a->B, (int)a->H, (int)a->Lq,
+                                                                             (int)a->d, (__nv_bfloat16*)a->dq, a->lddq);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd post launch");
+    return HCP_OK;
+}

@@ -1,0 +1,464 @@
+// SPDX-License-Identifier: Apache-2.0
+// Small kernels at the edges of the UNet hot path (sm_100a): the 4-channel convolutions conv_in / conv_out
+// (NCHW fp32 at the module boundary <-> bf16 NHWC inside), the timestep-embedding MLP and all ResnetBlock2D
+// time_emb_proj layers as one skinny linear, LoRA parameter packing and LoRA gradient reduction, and the loss /
+// optimizer kernels either side of the UNet call.
+//
+// Replaces (reference): diffusers conv_in / conv_out / Timesteps / TimestepEmbedding / time_emb_proj
+// (cfgs/unet_struct.txt:2-8,95,931); LoraBlock.get_weight's alpha*W_up@W_down materialisation
+// (hcpdiff/models/lora_base_patch.py:61-62) -> packed low-rank operands; autograd of W_down/W_up;
+// Trainer.get_loss (hcpdiff/train_ac.py:506-515) and the AdamW step on the LoRA parameters (train_ac.py:485-494).
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/hcp_b200.h"
+
+namespace hcp {
+
+// ---------------------------------------------------------------------------------------------
+// conv_in: x NCHW fp32 [B,Cin(<=8),H,W] -> y NHWC bf16 [B,H,W,Cout];  w fp32 [Cout,Cin,3,3]
+// one thread per (pixel, output channel): the 9*Cin input taps are shared by the warp through L1
+// ---------------------------------------------------------------------------------------------
+__global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int B,
+                               int Cin, int H, int W, int Cout, __nv_bfloat16* __restrict__ y) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)B * H * W * Cout;
+    if (i >= total) return;
+    const int co = (int)(i % Cout);
+    const int64_t pix = i / Cout;
+    const int xw = (int)(pix % W), yh = (int)((pix / W) % H), b = (int)(pix / ((int64_t)H * W));
+    float acc = bias ? bias[co] : 0.f;
+    for (int ci = 0; ci < Cin; ++ci)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int ih = yh + kh - 1;
+            if (ih < 0 || ih >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int iw = xw + kw - 1;
+                if (iw < 0 || iw >= W) continue;
+                acc += x[(((int64_t)b * Cin + ci) * H + ih) * W + iw] * w[((co * Cin + ci) * 3 + kh) * 3 + kw];
+            }
+        }
+    y[i] = __float2bfloat16(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv_out: x NHWC bf16 [B,H,W,Cin] -> y NCHW fp32 [B,Cout(<=8),H,W];  w fp32 [Cout,Cin,3,3]
+// one warp per output pixel: lanes split the channels, shuffle-reduce the Cout partial sums
+// ---------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                int B, int H, int W, int Cin, float* __restrict__ y) {
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= (int64_t)B * H * W) return;
+    const int xw = (int)(warp % W), yh = (int)((warp / W) % H), b = (int)(warp / ((int64_t)H * W));
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    for (int kh = 0; kh < 3; ++kh) {
+        const int ih = yh + kh - 1;
+        if (ih < 0 || ih >= H) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+            const int iw = xw + kw - 1;
+            if (iw < 0 || iw >= W) continue;
+            const __nv_bfloat16* xp = x + (((int64_t)b * H + ih) * W + iw) * Cin;
+            for (int ci = lane * 2; ci < Cin; ci += 64) {
+                const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xp + ci));
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) {
+                    const float* wp = w + ((c * Cin + ci) * 3 + kh) * 3 + kw;
+                    acc[c] += v.x * wp[0] + v.y * wp[9];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+        const float s = warp_sum(acc[c]);
+        if (lane == 0) y[(((int64_t)b * COUT + c) * H + yh) * W + xw] = s + (bias ? bias[c] : 0.f);
+    }
+}
+
+// dgrad of conv_out: dy NCHW fp32 [B,Cout,H,W] -> dx NHWC bf16 [B,H,W,Cin]; one thread per (pixel, ci)
+template <int COUT>
+__global__ void conv_out_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, int B, int H, int W, int Cin,
+                                      __nv_bfloat16* __restrict__ dx) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)B * H * W * Cin;
+    if (i >= total) return;
+    const int ci = (int)(i % Cin);
+    const int64_t pix = i / Cin;
+    const int xw = (int)(pix % W), yh = (int)((pix / W) % H), b = (int)(pix / ((int64_t)H * W));
+    float acc = 0.f;
+    // dx[ih,iw,ci] = sum_{co,kh,kw} dy[co, ih-kh+1, iw-kw+1] * w[co,ci,kh,kw]
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int oh = yh - kh + 1;
+        if (oh < 0 || oh >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int ow = xw - kw + 1;
+            if (ow < 0 || ow >= W) continue;
+#pragma unroll
+            for (int c = 0; c < COUT; ++c)
+                acc += dy[(((int64_t)b * COUT + c) * H + oh) * W + ow] * w[((c * Cin + ci) * 3 + kh) * 3 + kw];
+        }
+    }
+    dx[i] = __float2bfloat16(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// skinny linear for M <= 16 rows: y[m,n] = sum_k f(x[m,k]) * W[n,k] + bias[n]   (one warp per output column n)
+// in_mode: 0 identity, 1 SiLU, 2 x is the timestep [M] and the K inputs are its sinusoidal embedding
+//          ([cos | sin], flip_sin_to_cos=True, downscale_freq_shift=0 -- diffusers Timesteps for SD1.x)
+// ---------------------------------------------------------------------------------------------
+constexpr int SK_MAX_M = 16;
+__global__ void skinny_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ Wt, const float* __restrict__ bias,
+                                     int M, int K, int N, int in_mode, int out_silu, float* __restrict__ y) {
+    extern __shared__ float sx[];   // [M][K] transformed inputs
+    for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
+        const int m = i / K, k = i % K;
+        float v;
+        if (in_mode == 2) {
+            const int half = K / 2;
+            const int j = (k < half) ? k : k - half;
+            const float freq = expf(-9.210340371976184f * (float)j / (float)half);   // ln(10000)
+            const float a = x[m] * freq;
+            v = (k < half) ? cosf(a) : sinf(a);
+        } else {
+            v = x[(int64_t)m * K + k];
+            if (in_mode == 1) v = v / (1.f + __expf(-v));
+        }
+        sx[i] = v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (n >= N) return;
+    float acc[SK_MAX_M];
+#pragma unroll
+    for (int m = 0; m < SK_MAX_M; ++m) acc[m] = 0.f;
+    const __nv_bfloat16* wr = Wt + (int64_t)n * K;
+    for (int k = lane * 2; k < K; k += 64) {
+        const float2 wv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(wr + k));
+#pragma unroll
+        for (int m = 0; m < SK_MAX_M; ++m)
+            if (m < M) acc[m] += sx[m * K + k] * wv.x + sx[m * K + k + 1] * wv.y;
+    }
+#pragma unroll
+    for (int m = 0; m < SK_MAX_M; ++m) {
+        if (m < M) {
+            float s = warp_sum(acc[m]);
+            if (lane == 0) {
+                s += bias ? bias[n] : 0.f;
+                if (out_silu) s = s / (1.f + __expf(-s));
+                y[(int64_t)m * N + n] = s;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast (weights once, encoder_hidden_states per step)
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ y) {
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(x + i);
+        uint2 o;
+        o.x = pack_bf16x2(v.x, v.y);
+        o.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(y + i) = o;
+    } else {
+        for (int64_t j = i; j < n; ++j) y[j] = __float2bfloat16(x[j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LoRA operand packing.  For every LoRA block (one launch for ALL blocks of the model, driven by a job table):
+//   A   [r_tot, in]  rows [c0, c0+r)            = bf16(W_down)               (B operand of T = x . A^T)
+//   AT  [in, 64]     cols [c0, c0+r)            = bf16(W_down^T)             (B operand of dX += U . A)
+//   Bl  [out_tot,64] rows [o0,o0+out), cols [c0,c0+r) = bf16(alpha * W_up)   (B operand of y += T . Bl^T)
+//   BlT [r_tot,out_tot] rows [c0,c0+r), cols [o0,o0+out) = bf16(alpha*W_up^T)(B operand of U = dY . Bl)
+// Buffers are zero-initialised once by the caller; blocks of one fused group tile them block-diagonally.
+// ---------------------------------------------------------------------------------------------
+__global__ void lora_pack_kernel(const hcp_lora_job* __restrict__ jobs, int njobs) {
+    const int j = blockIdx.y;
+    if (j >= njobs) return;
+    const hcp_lora_job jb = jobs[j];
+    const float alpha = jb.alpha;
+    const int r = jb.rank, in = jb.in_dim, out = jb.out_dim;
+    const int64_t n_down = (int64_t)r * in, n_up = (int64_t)out * r;
+    __nv_bfloat16* A = (__nv_bfloat16*)jb.A;
+    __nv_bfloat16* AT = (__nv_bfloat16*)jb.AT;
+    __nv_bfloat16* Bl = (__nv_bfloat16*)jb.Bl;
+    __nv_bfloat16* BlT = (__nv_bfloat16*)jb.BlT;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_down + n_up; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n_down) {
+            const int rr = (int)(i / in), k = (int)(i % in);
+            const __nv_bfloat16 v = __float2bfloat16(jb.w_down[i]);
+            A[(int64_t)(jb.c0 + rr) * in + k] = v;
+            AT[(int64_t)k * 64 + jb.c0 + rr] = v;
+        } else {
+            const int64_t t = i - n_down;
+            const int o = (int)(t / r), rr = (int)(t % r);
+            const __nv_bfloat16 v = __float2bfloat16(alpha * jb.w_up[t]);
+            Bl[(int64_t)(jb.o0 + o) * 64 + jb.c0 + rr] = v;
+            BlT[(int64_t)(jb.c0 + rr) * jb.out_tot + jb.o0 + o] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LoRA gradients.  out[j, n] += scale * sum_m S[m, c0 + j] * X[m, n]   for j < r, n < N
+//   dW_down[j, k]  : S = U (= dY . Bl) [M,64],  X = x  [M,in]    -> dst[j*N + n]        (transpose_out = 0)
+//   dW_up[o, j]    : S = T (= x . A^T) [M,64],  X = dY [M,out]   -> dst[n*r + j] * alpha (transpose_out = 1)
+// CTA: 256 rows x 64 columns of X; thread (col, row-quarter) accumulates r partial sums, quarters are combined in
+// shared memory, one fp32 atomicAdd per output element and CTA.
+// ---------------------------------------------------------------------------------------------
+constexpr int LG_ROWS = 256;
+constexpr int LG_MAX_R = 32;
+__global__ void __launch_bounds__(256) lora_grad_kernel(const __nv_bfloat16* __restrict__ S, const __nv_bfloat16* __restrict__ X,
+                                                        int64_t ldx, int M, int N, int n_off, int c0, int r, float scale,
+                                                        int transpose_out, float* __restrict__ dst) {
+    __shared__ float sbuf[LG_ROWS * (LG_MAX_R + 1)];            // S tile, later reused for the cross-quarter reduction
+    float (*sS)[LG_MAX_R + 1] = reinterpret_cast<float (*)[LG_MAX_R + 1]>(sbuf);
+    float (*sred)[64][LG_MAX_R + 1] = reinterpret_cast<float (*)[64][LG_MAX_R + 1]>(sbuf);
+    const int m0 = blockIdx.y * LG_ROWS;
+    const int n0 = blockIdx.x * 64;
+    for (int i = threadIdx.x; i < LG_ROWS * r; i += 256) {
+        const int rr = i / r, j = i % r;
+        sS[rr][j] = (m0 + rr < M) ? __bfloat162float(S[(int64_t)(m0 + rr) * 64 + c0 + j]) : 0.f;
+    }
+    __syncthreads();
+    const int col = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int n = n0 + col;
+    float acc[LG_MAX_R];
+#pragma unroll
+    for (int j = 0; j < LG_MAX_R; ++j) acc[j] = 0.f;
+    if (n < N) {
+        for (int rr = q * 64; rr < q * 64 + 64; ++rr) {
+            if (m0 + rr >= M) break;
+            const float xv = __bfloat162float(X[(int64_t)(m0 + rr) * ldx + n_off + n]);
+#pragma unroll
+            for (int j = 0; j < LG_MAX_R; ++j)
+                if (j < r) acc[j] += sS[rr][j] * xv;
+        }
+    }
+    __syncthreads();   // everyone is done reading sS
+#pragma unroll
+    for (int j = 0; j < LG_MAX_R; ++j)
+        if (j < r) sred[q][col][j] = acc[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * r; i += 256) {
+        const int cc = i % 64, j = i / 64;
+        if (n0 + cc < N) {
+            const float v = (sred[0][cc][j] + sred[1][cc][j] + sred[2][cc][j] + sred[3][cc][j]) * scale;
+            if (transpose_out) atomicAdd(dst + (int64_t)(n0 + cc) * r + j, v);
+            else atomicAdd(dst + (int64_t)j * N + n0 + cc, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss = mean((pred - target)^2) (fp32, reference train_ac.py:506-515 with loss.type == 'eps'), dpred = 2(pred-target)/n
+// ---------------------------------------------------------------------------------------------
+__global__ void mse_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n, float grad_scale,
+                                float* __restrict__ loss_sum, float* __restrict__ dpred) {
+    __shared__ float s_part[8];
+    float acc = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float d = pred[i] - target[i];
+        acc += d * d;
+        if (dpred) dpred[i] = 2.f * d * grad_scale / (float)n;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < (blockDim.x >> 5)) ? s_part[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(loss_sum, v / (float)n);
+    }
+}
+
+// x_t = sqrt(acp[t]) * x0 + sqrt(1 - acp[t]) * noise   (DDPMScheduler.add_noise, reference train_ac.py:437-447)
+__global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const int64_t* __restrict__ t,
+                                 const float* __restrict__ acp, int64_t per_image, int64_t n, float* __restrict__ xt) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = acp[t[i / per_image]];
+    xt[i] = sqrtf(a) * x0[i] + sqrtf(1.f - a) * noise[i];
+}
+
+// sum of squares of a flat fp32 buffer (for clip_grad_norm_, reference train_ac.py:485-490)
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+    __shared__ float s_part[8];
+    float acc = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += g[i] * g[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < (blockDim.x >> 5)) ? s_part[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(out, v);
+    }
+}
+
+// AdamW over one flat fp32 parameter buffer; grad is first scaled by gscale and clipped to max_norm using the
+// device-side sum of squares (no host sync).  step_count lives on the device so the kernel is CUDA-graph replayable.
+__global__ void adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                  int64_t n, const float* __restrict__ lr_ptr, float beta1, float beta2, float eps, float wd,
+                                  float gscale, const float* __restrict__ sumsq, float max_norm, const int* __restrict__ step_ptr) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float clip = 1.f;
+    if (sumsq && max_norm > 0.f) {
+        const float norm = sqrtf(*sumsq) * gscale;
+        clip = fminf(1.f, max_norm / (norm + 1e-6f));
+    }
+    const float lr = *lr_ptr;
+    const int step = *step_ptr;
+    const float grad = g[i] * gscale * clip;
+    const float mi = beta1 * m[i] + (1.f - beta1) * grad;
+    const float vi = beta2 * v[i] + (1.f - beta2) * grad * grad;
+    m[i] = mi;
+    v[i] = vi;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2 = 1.f - powf(beta2, (float)step);
+    float w = p[i];
+    w -= lr * wd * w;
+    w -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    p[i] = w;
+}
+__global__ void incr_step_kernel(int* step) { *step += 1; }
+
+}  // namespace hcp
+
+using namespace hcp;
+
+#define LAUNCH_CHECK(what)                                              \
+    do {                                                                \
+        cudaError_t e_ = cudaGetLastError();                            \
+        if (e_ != cudaSuccess) return set_cuda_error(e_, what);         \
+    } while (0)
+
+extern "C" int hcp_conv_in_f32(const float* x, const float* w, const float* bias, int64_t B, int64_t Cin, int64_t H, int64_t W,
+                               int64_t Cout, void* y, hcp_stream_t st) {
+    if (!x || !w || !y) return set_error(HCP_ERR_INVALID, "conv_in: null pointer");
+    const int64_t n = B * H * W * Cout;
+    conv_in_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>(x, w, bias, (int)B, (int)Cin, (int)H, (int)W, (int)Cout,
+                                                                            (__nv_bfloat16*)y);
+    LAUNCH_CHECK("conv_in launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_conv_out_f32(const void* x, const float* w, const float* bias, int64_t B, int64_t H, int64_t W, int64_t Cin,
+                                int64_t Cout, float* y, hcp_stream_t st) {
+    if (!x || !w || !y) return set_error(HCP_ERR_INVALID, "conv_out: null pointer");
+    if (Cout != 4 || (Cin & 1)) return set_error(HCP_ERR_INVALID, "conv_out: only Cout == 4, even Cin");
+    const int64_t n = B * H * W * 32;
+    conv_out_kernel<4><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, w, bias, (int)B, (int)H, (int)W,
+                                                                                (int)Cin, y);
+    LAUNCH_CHECK("conv_out launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_conv_out_dgrad_f32(const float* dy, const float* w, int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                                      void* dx, hcp_stream_t st) {
+    if (!dy || !w || !dx) return set_error(HCP_ERR_INVALID, "conv_out_dgrad: null pointer");
+    if (Cout != 4) return set_error(HCP_ERR_INVALID, "conv_out_dgrad: only Cout == 4");
+    const int64_t n = B * H * W * Cin;
+    conv_out_dgrad_kernel<4><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>(dy, w, (int)B, (int)H, (int)W, (int)Cin,
+                                                                                      (__nv_bfloat16*)dx);
+    LAUNCH_CHECK("conv_out_dgrad launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_skinny_linear(const float* x, const void* w_bf16, const float* bias, int64_t M, int64_t K, int64_t N, int in_mode,
+                                 int out_silu, float* y, hcp_stream_t st) {
+    if (!x || !w_bf16 || !y) return set_error(HCP_ERR_INVALID, "skinny_linear: null pointer");
+    if (M < 1 || M > SK_MAX_M || (K & 1)) return set_error(HCP_ERR_INVALID, "skinny_linear: 1 <= M <= 16, even K");
+    const size_t smem = (size_t)M * K * sizeof(float);
+    if (smem > 96 * 1024) return set_error(HCP_ERR_INVALID, "skinny_linear: M*K too large");
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(skinny_linear)");
+        configured = true;
+    }
+    const int warps = 8;
+    skinny_linear_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, smem, (cudaStream_t)st>>>(
+        x, (const __nv_bfloat16*)w_bf16, bias, (int)M, (int)K, (int)N, in_mode, out_silu, y);
+    LAUNCH_CHECK("skinny_linear launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_cast_f32_to_bf16(const float* x, int64_t n, void* y, hcp_stream_t st) {
+    if (!x || !y) return set_error(HCP_ERR_INVALID, "cast: null pointer");
+    if (n == 0) return HCP_OK;
+    const int64_t threads = (n + 3) / 4;
+    cast_f32_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)st>>>(x, n, (__nv_bfloat16*)y);
+    LAUNCH_CHECK("cast launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp_stream_t st) {
+    if (!jobs_device || njobs <= 0) return set_error(HCP_ERR_INVALID, "lora_pack: jobs");
+    dim3 grid(16, (unsigned)njobs);
+    lora_pack_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(jobs_device, (int)njobs);
+    LAUNCH_CHECK("lora_pack launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t M, int64_t N, int64_t n_off, int64_t c0, int64_t r,
+                             float scale, int transpose_out, float* dst, hcp_stream_t st) {
+    if (!S || !X || !dst) return set_error(HCP_ERR_INVALID, "lora_grad: null pointer");
+    if (r < 1 || r > LG_MAX_R || c0 + r > 64) return set_error(HCP_ERR_INVALID, "lora_grad: rank must be in [1,32] and fit the 64-wide T/U buffer");
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + LG_ROWS - 1) / LG_ROWS));
+    lora_grad_kernel<<<grid, 256, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)S, (const __nv_bfloat16*)X, ldx, (int)M, (int)N, (int)n_off,
+                                                        (int)c0, (int)r, scale, transpose_out, dst);
+    LAUNCH_CHECK("lora_grad launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_mse_loss(const float* pred, const float* target, int64_t n, float grad_scale, float* loss_sum, float* dpred,
+                            hcp_stream_t st) {
+    if (!pred || !target || !loss_sum) return set_error(HCP_ERR_INVALID, "mse_loss: null pointer");
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    mse_loss_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(pred, target, n, grad_scale, loss_sum, dpred);
+    LAUNCH_CHECK("mse_loss launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_add_noise(const float* x0, const float* noise, const int64_t* t, const float* alphas_cumprod, int64_t B,
+                             int64_t per_image, float* xt, hcp_stream_t st) {
+    if (!x0 || !noise || !t || !alphas_cumprod || !xt) return set_error(HCP_ERR_INVALID, "add_noise: null pointer");
+    const int64_t n = B * per_image;
+    add_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>(x0, noise, t, alphas_cumprod, per_image, n, xt);
+    LAUNCH_CHECK("add_noise launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_sumsq(const float* g, int64_t n, float* out, hcp_stream_t st) {
+    if (!g || !out) return set_error(HCP_ERR_INVALID, "sumsq: null pointer");
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(g, n, out);
+    LAUNCH_CHECK("sumsq launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_device, float beta1, float beta2,
+                              float eps, float weight_decay, float grad_scale, const float* sumsq_device, float max_norm,
+                              int* step_device, hcp_stream_t st) {
+    if (!p || !g || !m || !v || !lr_device || !step_device) return set_error(HCP_ERR_INVALID, "adamw: null pointer");
+    incr_step_kernel<<<1, 1, 0, (cudaStream_t)st>>>(step_device);
+    adamw_flat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>(p, g, m, v, n, lr_device, beta1, beta2, eps, weight_decay,
+                                                                               grad_scale, sumsq_device, max_norm, step_device);
+    LAUNCH_CHECK("adamw launch");
+    return HCP_OK;
+}

@@ -1,0 +1,535 @@
+// SPDX-License-Identifier: Apache-2.0
+// HBM-bound kernels of the UNet hot path (sm_100a): GroupNorm(+SiLU) and LayerNorm forward/backward with
+// warp-shuffle reductions, GEGLU, nearest-2x upsample.  All activations are bf16 NHWC / token-major, statistics
+// and accumulation fp32, 16-byte vector accesses.
+//
+// Replaces (reference module structure cfgs/unet_struct.txt): ResnetBlock2D.norm1/norm2 + nonlinearity (:93-99),
+// Transformer2DModel.norm (:13), conv_norm_out (:929), BasicTransformerBlock.norm1/2/3 (:44-46), GEGLU (:27-30),
+// Upsample2D's F.interpolate(scale_factor=2, mode='nearest') (:392) -- and their autograd backward.
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/hcp_b200.h"
+
+namespace hcp {
+
+__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+__device__ __forceinline__ float silu_grad(float z) {
+    const float s = 1.f / (1.f + __expf(-z));
+    return s * (1.f + z * (1.f - s));
+}
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// =============================================================================================
+// GroupNorm.  x is the channel-concatenation of x1 [B,HW,C1] and (optionally) x2 [B,HW,C2].
+// Pass A: per-(image, pixel-chunk) partial sums per group.  Pass B: finalise the statistics of the image
+// (every CTA re-reduces the few partials), then normalise / back-propagate its own pixel chunk.
+// =============================================================================================
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_G = 32;
+
+struct GNParams {
+    const __nv_bfloat16* x1; const __nv_bfloat16* x2;
+    int C1, C2, C, G, cg;
+    int B, HW, rows_per_cta, nchunks;
+    const float* gamma; const float* beta;
+    float eps; int silu;
+    float* partial;            // [B, nchunks, G, 2]
+    float* stats;              // [B, G, 2] (mean, rstd)
+    __nv_bfloat16* y;          // fwd out [B,HW,C]
+    // backward
+    const __nv_bfloat16* dy;   // [B,HW,C]
+    const __nv_bfloat16* add1; const __nv_bfloat16* add2;   // optional grads to add to dx1 / dx2
+    __nv_bfloat16* dx1; __nv_bfloat16* dx2;
+};
+
+__device__ __forceinline__ float2 gn_load2(const GNParams& p, int64_t pix, int c) {
+    // channel pair (c, c+1) of concatenated pixel `pix` (C1, C2 even)
+    const __nv_bfloat16* src = (c < p.C1) ? p.x1 + pix * p.C1 + c : p.x2 + pix * p.C2 + (c - p.C1);
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src));
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(GN_THREADS) gn_partial_kernel(const GNParams p) {
+    __shared__ float s_acc[GN_MAX_G * 2];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    for (int i = threadIdx.x; i < p.G * 2; i += GN_THREADS) s_acc[i] = 0.f;
+    __syncthreads();
+    const int r0 = chunk * p.rows_per_cta;
+    const int r1 = min(p.HW, r0 + p.rows_per_cta);
+    const int npair = p.C / 2;
+    const float* st = BWD ? p.stats + (int64_t)b * p.G * 2 : nullptr;
+    // a thread keeps a fixed channel pair while it walks the rows => its group is loop invariant per pair slot
+    for (int cp = threadIdx.x; cp < npair; cp += GN_THREADS) {
+        const int c = cp * 2;
+        const int g = c / p.cg;           // cg is even for every UNet layer, so a pair never straddles two groups
+        float a0 = 0.f, a1 = 0.f;
+        float gm0 = 0.f, gm1 = 0.f, bt0 = 0.f, bt1 = 0.f, mean = 0.f, rstd = 0.f;
+        if (BWD) {
+            gm0 = p.gamma[c]; gm1 = p.gamma[c + 1]; bt0 = p.beta[c]; bt1 = p.beta[c + 1];
+            mean = st[g * 2]; rstd = st[g * 2 + 1];
+        }
+        for (int r = r0; r < r1; ++r) {
+            const int64_t pix = (int64_t)b * p.HW + r;
+            const float2 v = gn_load2(p, pix, c);
+            if (!BWD) {
+                a0 += v.x + v.y;
+                a1 += v.x * v.x + v.y * v.y;
+            } else {
+                const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.dy + pix * p.C + c));
+                const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd;
+                float g0 = d.x * gm0, g1 = d.y * gm1;
+                if (p.silu) {
+                    g0 *= silu_grad(xh0 * gm0 + bt0);
+                    g1 *= silu_grad(xh1 * gm1 + bt1);
+                }
+                a0 += g0 + g1;
+                a1 += g0 * xh0 + g1 * xh1;
+            }
+        }
+        atomicAdd(&s_acc[g * 2], a0);
+        atomicAdd(&s_acc[g * 2 + 1], a1);
+    }
+    __syncthreads();
+    float* out = p.partial + ((int64_t)b * p.nchunks + chunk) * p.G * 2;
+    for (int i = threadIdx.x; i < p.G * 2; i += GN_THREADS) out[i] = s_acc[i];
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GNParams p) {
+    __shared__ float s_a[GN_MAX_G], s_b[GN_MAX_G];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const float n = (float)p.HW * (float)p.cg;
+    // finalise: warp w reduces group w, w+8, ... over the chunk partials with a shuffle reduction
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int g = warp; g < p.G; g += GN_THREADS / 32) {
+            float a0 = 0.f, a1 = 0.f;
+            for (int ch = lane; ch < p.nchunks; ch += 32) {
+                const float* src = p.partial + (((int64_t)b * p.nchunks + ch) * p.G + g) * 2;
+                a0 += src[0];
+                a1 += src[1];
+            }
+            a0 = warp_sum(a0);
+            a1 = warp_sum(a1);
+            if (lane == 0) {
+                if (!BWD) {
+                    const float mean = a0 / n;
+                    const float var = fmaxf(a1 / n - mean * mean, 0.f);
+                    const float rstd = rsqrtf(var + p.eps);
+                    s_a[g] = mean;
+                    s_b[g] = rstd;
+                    if (chunk == 0) {
+                        p.stats[((int64_t)b * p.G + g) * 2] = mean;
+                        p.stats[((int64_t)b * p.G + g) * 2 + 1] = rstd;
+                    }
+                } else {
+                    s_a[g] = a0 / n;   // mean(g)
+                    s_b[g] = a1 / n;   // mean(g * xhat)
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int r0 = chunk * p.rows_per_cta;
+    const int r1 = min(p.HW, r0 + p.rows_per_cta);
+    const int npair = p.C / 2;
+    const float* st = BWD ? p.stats + (int64_t)b * p.G * 2 : nullptr;
+    for (int cp = threadIdx.x; cp < npair; cp += GN_THREADS) {
+        const int c = cp * 2;
+        const int g = c / p.cg;
+        const float gm0 = p.gamma[c], gm1 = p.gamma[c + 1], bt0 = p.beta[c], bt1 = p.beta[c + 1];
+        if (!BWD) {
+            const float mean = s_a[g], rstd = s_b[g];
+            for (int r = r0; r < r1; ++r) {
+                const int64_t pix = (int64_t)b * p.HW + r;
+                const float2 v = gn_load2(p, pix, c);
+                float z0 = (v.x - mean) * rstd * gm0 + bt0;
+                float z1 = (v.y - mean) * rstd * gm1 + bt1;
+                if (p.silu) { z0 = silu_f(z0); z1 = silu_f(z1); }
+                *reinterpret_cast<__nv_bfloat162*>(p.y + pix * p.C + c) = __floats2bfloat162_rn(z0, z1);
+            }
+        } else {
+            const float mean = st[g * 2], rstd = st[g * 2 + 1];
+            const float m1 = s_a[g], m2 = s_b[g];
+            for (int r = r0; r < r1; ++r) {
+                const int64_t pix = (int64_t)b * p.HW + r;
+                const float2 v = gn_load2(p, pix, c);
+                const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.dy + pix * p.C + c));
+                const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd;
+                float g0 = d.x * gm0, g1 = d.y * gm1;
+                if (p.silu) {
+                    g0 *= silu_grad(xh0 * gm0 + bt0);
+                    g1 *= silu_grad(xh1 * gm1 + bt1);
+                }
+                float o0 = rstd * (g0 - m1 - xh0 * m2);
+                float o1 = rstd * (g1 - m1 - xh1 * m2);
+                __nv_bfloat16* dst;
+                const __nv_bfloat16* add;
+                if (c < p.C1) {
+                    dst = p.dx1 + pix * p.C1 + c;
+                    add = p.add1 ? p.add1 + pix * p.C1 + c : nullptr;
+                } else {
+                    dst = p.dx2 + pix * p.C2 + (c - p.C1);
+                    add = p.add2 ? p.add2 + pix * p.C2 + (c - p.C1) : nullptr;
+                }
+                if (add) {
+                    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(add));
+                    o0 += a.x; o1 += a.y;
+                }
+                *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o0, o1);
+            }
+        }
+    }
+}
+
+static int gn_geometry(const hcp_groupnorm_args* a, GNParams& p) {
+    if (!a || !a->x1 || !a->gamma || !a->beta || !a->workspace || !a->stats) return set_error(HCP_ERR_INVALID, "groupnorm: null pointer");
+    const int64_t C = a->C1 + a->C2;
+    if (a->G <= 0 || a->G > GN_MAX_G || C % a->G != 0) return set_error(HCP_ERR_INVALID, "groupnorm: groups");
+    const int64_t cg = C / a->G;
+    if ((cg & 1) || (a->C1 & 1) || (a->C2 & 1)) return set_error(HCP_ERR_INVALID, "groupnorm: channels per group must be even");
+    if (a->C2 > 0 && !a->x2) return set_error(HCP_ERR_INVALID, "groupnorm: x2");
+    memset(&p, 0, sizeof(p));
+    p.x1 = (const __nv_bfloat16*)a->x1; p.x2 = (const __nv_bfloat16*)a->x2;
+    p.C1 = (int)a->C1; p.C2 = (int)a->C2; p.C = (int)C; p.G = (int)a->G; p.cg = (int)cg;
+    p.B = (int)a->B; p.HW = (int)a->HW;
+    // ~4 CTAs per SM over the whole launch, at least 4 rows per CTA
+    int rows = (int)((a->B * a->HW + 591) / 592);
+    if (rows < 4) rows = 4;
+    if (rows > a->HW) rows = (int)a->HW;
+    p.rows_per_cta = rows;
+    p.nchunks = (int)((a->HW + rows - 1) / rows);
+    p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
+    p.partial = a->workspace; p.stats = a->stats;
+    if (a->workspace_bytes < (size_t)a->B * p.nchunks * p.G * 2 * sizeof(float)) return set_error(HCP_ERR_INVALID, "groupnorm: workspace too small");
+    return HCP_OK;
+}
+
+// =============================================================================================
+// LayerNorm: one warp per row, the row lives in registers (C <= 2048)
+// =============================================================================================
+constexpr int LN_MAX_C = 2048;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+    float2 t;
+    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* o) {
+    uint4 w;
+    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+    return w;
+}
+
+// NVPL = ceil((C/8) / 32): 16-byte vectors per lane (compile time so the row stays in registers)
+template <bool BWD, int NVPL>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                        const __nv_bfloat16* __restrict__ add, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, int64_t M, int C,
+                                                        float* __restrict__ stats, __nv_bfloat16* __restrict__ out) {
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const int nv = C / 8;
+    const __nv_bfloat16* xr = x + row * C;
+    float v[NVPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NVPL; ++k) {
+        const int i = lane + 32 * k;
+        if (i < nv) {
+            unpack8(*reinterpret_cast<const uint4*>(xr + i * 8), v[k]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s += v[k][e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[k][e] = 0.f;
+        }
+    }
+    if (!BWD) {
+        const float mean = warp_sum(s) / C;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < NVPL; ++k)
+            if (lane + 32 * k < nv) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { const float d = v[k][e] - mean; q += d * d; }
+            }
+        const float rstd = rsqrtf(warp_sum(q) / C + eps);
+        if (lane == 0 && stats) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+#pragma unroll
+        for (int k = 0; k < NVPL; ++k) {
+            const int i = lane + 32 * k;
+            if (i < nv) {
+                const int c = i * 8;
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = (v[k][e] - mean) * rstd * gamma[c + e] + beta[c + e];
+                *reinterpret_cast<uint4*>(out + row * C + c) = pack8(o);
+            }
+        }
+    } else {
+        const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+        float g[NVPL][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NVPL; ++k) {
+            const int i = lane + 32 * k;
+            if (i < nv) {
+                const int c = i * 8;
+                float d[8];
+                unpack8(*reinterpret_cast<const uint4*>(dy + row * C + c), d);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float xh = (v[k][e] - mean) * rstd;
+                    v[k][e] = xh;
+                    g[k][e] = d[e] * gamma[c + e];
+                    s1 += g[k][e];
+                    s2 += g[k][e] * xh;
+                }
+            }
+        }
+        s1 = warp_sum(s1) / C;
+        s2 = warp_sum(s2) / C;
+#pragma unroll
+        for (int k = 0; k < NVPL; ++k) {
+            const int i = lane + 32 * k;
+            if (i < nv) {
+                const int c = i * 8;
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = rstd * (g[k][e] - s1 - v[k][e] * s2);
+                if (add) {
+                    float a[8];
+                    unpack8(*reinterpret_cast<const uint4*>(add + row * C + c), a);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] += a[e];
+                }
+                *reinterpret_cast<uint4*>(out + row * C + c) = pack8(o);
+            }
+        }
+    }
+}
+
+template <bool BWD>
+static void launch_layernorm(const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* add, const float* gamma,
+                             const float* beta, float eps, int64_t M, int C, float* stats, __nv_bfloat16* out, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((M * 32 + 255) / 256);
+    const int nvpl = (C / 8 + 31) / 32;
+#define LN_CASE(N) case N: layernorm_kernel<BWD, N><<<blocks, 256, 0, st>>>(x, dy, add, gamma, beta, eps, M, C, stats, out); break;
+    switch (nvpl) {
+        LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+    }
+#undef LN_CASE
+}
+
+// =============================================================================================
+// GEGLU: u = [a | g] (each F wide);  h = a * gelu(g)
+// =============================================================================================
+__global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ u, int64_t M, int F, __nv_bfloat16* __restrict__ h) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per 8 outputs
+    const int nv = F / 8;
+    if (i >= M * nv) return;
+    const int64_t m = i / nv;
+    const int c = (int)(i % nv) * 8;
+    const uint4 ua = *reinterpret_cast<const uint4*>(u + m * 2 * F + c);
+    const uint4 ug = *reinterpret_cast<const uint4*>(u + m * 2 * F + F + c);
+    const uint32_t aa[4] = {ua.x, ua.y, ua.z, ua.w}, gg[4] = {ug.x, ug.y, ug.z, ug.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 a = unpack_bf16x2(aa[e]), g = unpack_bf16x2(gg[e]);
+        o[e] = pack_bf16x2(a.x * gelu_f(g.x), a.y * gelu_f(g.y));
+    }
+    *reinterpret_cast<uint4*>(h + m * F + c) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ dh, int64_t M, int F,
+                                 __nv_bfloat16* __restrict__ du) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int nv = F / 8;
+    if (i >= M * nv) return;
+    const int64_t m = i / nv;
+    const int c = (int)(i % nv) * 8;
+    const uint4 ua = *reinterpret_cast<const uint4*>(u + m * 2 * F + c);
+    const uint4 ug = *reinterpret_cast<const uint4*>(u + m * 2 * F + F + c);
+    const uint4 ud = *reinterpret_cast<const uint4*>(dh + m * F + c);
+    const uint32_t aa[4] = {ua.x, ua.y, ua.z, ua.w}, gg[4] = {ug.x, ug.y, ug.z, ug.w}, dd[4] = {ud.x, ud.y, ud.z, ud.w};
+    uint32_t oa[4], og[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 a = unpack_bf16x2(aa[e]), g = unpack_bf16x2(gg[e]), d = unpack_bf16x2(dd[e]);
+        oa[e] = pack_bf16x2(d.x * gelu_f(g.x), d.y * gelu_f(g.y));
+        og[e] = pack_bf16x2(d.x * a.x * gelu_grad(g.x), d.y * a.y * gelu_grad(g.y));
+    }
+    *reinterpret_cast<uint4*>(du + m * 2 * F + c) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+    *reinterpret_cast<uint4*>(du + m * 2 * F + F + c) = make_uint4(og[0], og[1], og[2], og[3]);
+}
+
+// =============================================================================================
+// nearest 2x upsample (NHWC) and its backward (sum of the 2x2 block)
+// =============================================================================================
+__global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, __nv_bfloat16* __restrict__ y) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per 8 output channels
+    const int nv = C / 8;
+    const int64_t total = (int64_t)B * 4 * H * W * nv;
+    if (i >= total) return;
+    const int c = (int)(i % nv) * 8;
+    const int64_t pix = i / nv;
+    const int wo = (int)(pix % (2 * W)), ho = (int)((pix / (2 * W)) % (2 * H)), b = (int)(pix / ((int64_t)4 * H * W));
+    const uint4 v = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + ho / 2) * W + wo / 2) * C + c);
+    *reinterpret_cast<uint4*>(y + pix * C + c) = v;
+}
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int B, int H, int W, int C, __nv_bfloat16* __restrict__ dx) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per 8 input channels
+    const int nv = C / 8;
+    const int64_t total = (int64_t)B * H * W * nv;
+    if (i >= total) return;
+    const int c = (int)(i % nv) * 8;
+    const int64_t pix = i / nv;
+    const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((int64_t)H * W));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+        for (int dw = 0; dw < 2; ++dw) {
+            const uint4 v = *reinterpret_cast<const uint4*>(dy + (((int64_t)b * 2 * H + 2 * h + dh) * 2 * W + 2 * w + dw) * C + c);
+            float2 t;
+            t = unpack_bf16x2(v.x); acc[0] += t.x; acc[1] += t.y;
+            t = unpack_bf16x2(v.y); acc[2] += t.x; acc[3] += t.y;
+            t = unpack_bf16x2(v.z); acc[4] += t.x; acc[5] += t.y;
+            t = unpack_bf16x2(v.w); acc[6] += t.x; acc[7] += t.y;
+        }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]); o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(dx + pix * C + c) = o;
+}
+
+// out = a + b (bf16), used where autograd fan-in cannot be folded into a producer kernel
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, int64_t n8,
+                                __nv_bfloat16* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const uint4 x = reinterpret_cast<const uint4*>(a)[i], y = reinterpret_cast<const uint4*>(b)[i];
+    const uint32_t xa[4] = {x.x, x.y, x.z, x.w}, ya[4] = {y.x, y.y, y.z, y.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 p = unpack_bf16x2(xa[e]), q = unpack_bf16x2(ya[e]);
+        o[e] = pack_bf16x2(p.x + q.x, p.y + q.y);
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+}  // namespace hcp
+
+using namespace hcp;
+
+#define LAUNCH_CHECK(what)                                              \
+    do {                                                                \
+        cudaError_t e_ = cudaGetLastError();                            \
+        if (e_ != cudaSuccess) return set_cuda_error(e_, what);         \
+    } while (0)
+
+extern "C" size_t hcp_groupnorm_workspace_bytes(int64_t B, int64_t HW, int64_t G) {
+    // upper bound on nchunks: rows_per_cta >= 4 and >= B*HW/592
+    int64_t rows = (B * HW + 591) / 592;
+    if (rows < 4) rows = 4;
+    if (rows > HW) rows = HW;
+    const int64_t nchunks = (HW + rows - 1) / rows;
+    return (size_t)(B * nchunks * G * 2) * sizeof(float);
+}
+
+extern "C" int hcp_groupnorm_fwd_bf16(const hcp_groupnorm_args* a, hcp_stream_t stream_) {
+    GNParams p;
+    int rc = gn_geometry(a, p);
+    if (rc) return rc;
+    if (!a->y) return set_error(HCP_ERR_INVALID, "groupnorm_fwd: y");
+    p.y = (__nv_bfloat16*)a->y;
+    dim3 grid(p.nchunks, p.B);
+    gn_partial_kernel<false><<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>(p);
+    gn_apply_kernel<false><<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>(p);
+    LAUNCH_CHECK("groupnorm_fwd launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_groupnorm_bwd_bf16(const hcp_groupnorm_args* a, hcp_stream_t stream_) {
+    GNParams p;
+    int rc = gn_geometry(a, p);
+    if (rc) return rc;
+    if (!a->dy || !a->dx1 || (a->C2 > 0 && !a->dx2)) return set_error(HCP_ERR_INVALID, "groupnorm_bwd: dy/dx");
+    p.dy = (const __nv_bfloat16*)a->dy;
+    p.add1 = (const __nv_bfloat16*)a->add1; p.add2 = (const __nv_bfloat16*)a->add2;
+    p.dx1 = (__nv_bfloat16*)a->dx1; p.dx2 = (__nv_bfloat16*)a->dx2;
+    dim3 grid(p.nchunks, p.B);
+    gn_partial_kernel<true><<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>(p);
+    gn_apply_kernel<true><<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>(p);
+    LAUNCH_CHECK("groupnorm_bwd launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, float eps, int64_t M, int64_t C,
+                                      float* stats, void* y, hcp_stream_t stream_) {
+    if (!x || !gamma || !beta || !y) return set_error(HCP_ERR_INVALID, "layernorm_fwd: null pointer");
+    if (C % 8 != 0 || C > LN_MAX_C || C <= 0) return set_error(HCP_ERR_INVALID, "layernorm: C must be a multiple of 8, <= 2048");
+    launch_layernorm<false>((const __nv_bfloat16*)x, nullptr, nullptr, gamma, beta, eps, M, (int)C, stats, (__nv_bfloat16*)y,
+                            (cudaStream_t)stream_);
+    LAUNCH_CHECK("layernorm_fwd launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_layernorm_bwd_bf16(const void* x, const void* dy, const void* add, const float* gamma, const float* stats,
+                                      int64_t M, int64_t C, void* dx, hcp_stream_t stream_) {
+    if (!x || !dy || !gamma || !stats || !dx) return set_error(HCP_ERR_INVALID, "layernorm_bwd: null pointer");
+    if (C % 8 != 0 || C > LN_MAX_C || C <= 0) return set_error(HCP_ERR_INVALID, "layernorm: C must be a multiple of 8, <= 2048");
+    launch_layernorm<true>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)add, gamma, nullptr, 0.f, M, (int)C,
+                           const_cast<float*>(stats), (__nv_bfloat16*)dx, (cudaStream_t)stream_);
+    LAUNCH_CHECK("layernorm_bwd launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_geglu_fwd_bf16(const void* u, int64_t M, int64_t F, void* h, hcp_stream_t stream_) {
+    if (!u || !h || F % 8 != 0) return set_error(HCP_ERR_INVALID, "geglu_fwd");
+    const int64_t n = M * (F / 8);
+    geglu_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)u, M, (int)F, (__nv_bfloat16*)h);
+    LAUNCH_CHECK("geglu_fwd launch");
+    return HCP_OK;
+}
+extern "C" int hcp_geglu_bwd_bf16(const void* u, const void* dh, int64_t M, int64_t F, void* du, hcp_stream_t stream_) {
+    if (!u || !dh || !du || F % 8 != 0) return set_error(HCP_ERR_INVALID, "geglu_bwd");
+    const int64_t n = M * (F / 8);
+    geglu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)u, (const __nv_bfloat16*)dh, M,
+                                                                                   (int)F, (__nv_bfloat16*)du);
+    LAUNCH_CHECK("geglu_bwd launch");
+    return HCP_OK;
+}
+extern "C" int hcp_upsample2x_fwd_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t C, void* y, hcp_stream_t stream_) {
+    if (!x || !y || C % 8 != 0) return set_error(HCP_ERR_INVALID, "upsample2x_fwd");
+    const int64_t n = B * 4 * H * W * (C / 8);
+    upsample2x_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, (int)B, (int)H, (int)W,
+                                                                                        (int)C, (__nv_bfloat16*)y);
+    LAUNCH_CHECK("upsample2x_fwd launch");
+    return HCP_OK;
+}
+extern "C" int hcp_upsample2x_bwd_bf16(const void* dy, int64_t B, int64_t H, int64_t W, int64_t C, void* dx, hcp_stream_t stream_) {
+    if (!dy || !dx || C % 8 != 0) return set_error(HCP_ERR_INVALID, "upsample2x_bwd");
+    const int64_t n = B * H * W * (C / 8);
+    upsample2x_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)dy, (int)B, (int)H, (int)W,
+                                                                                        (int)C, (__nv_bfloat16*)dx);
+    LAUNCH_CHECK("upsample2x_bwd launch");
+    return HCP_OK;
+}
+extern "C" int hcp_add_bf16(const void* a, const void* b, int64_t n, void* out, hcp_stream_t stream_) {
+    if (!a || !b || !out || n % 8 != 0) return set_error(HCP_ERR_INVALID, "add_bf16");
+    const int64_t n8 = n / 8;
+    add_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n8,
+                                                                                   (__nv_bfloat16*)out);
+    LAUNCH_CHECK("add_bf16 launch");
+    return HCP_OK;
+}

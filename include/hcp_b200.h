@@ -96,6 +96,149 @@ typedef struct hcp_conv3x3_args {
 
 int hcp_conv3x3_bf16(const hcp_conv3x3_args* args, hcp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused attention (tcgen05 flash-style forward, and backward).
+ *
+ * Replaces: diffusers Attention -> F.scaled_dot_product_attention / xformers.memory_efficient_attention
+ *           (selected at reference hcpdiff/train_ac.py:258-263) for BasicTransformerBlock.attn1 / attn2
+ *           (reference cfgs/unet_struct.txt:17-43), and its autograd backward.
+ * q/k/v/o/dout/dq/dk/dv: bf16 [B, L, ld] token-major, head h in columns [h*d, (h+1)*d); d % 8 == 0, d <= 192.
+ * kv_bias: optional fp32 [B, Lkv] additive logit bias = (1 - encoder_attention_mask) * -10000
+ *          (the diffusers convention restated at reference hcpdiff/models/controlnet.py:99-103).
+ * lse: fp32 [B, H, Lq] natural-log sum-exp of the scaled logits (saved for backward; may be NULL in fwd).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hcp_attn_args {
+    const void* q; int64_t ldq;
+    const void* k; int64_t ldk;
+    const void* v; int64_t ldv;
+    int64_t B, H, Lq, Lkv, d;
+    float scale;
+    const float* kv_bias;
+    void* o; int64_t ldo;
+    float* lse;
+} hcp_attn_args;
+
+int hcp_attn_fwd_bf16(const hcp_attn_args* args, hcp_stream_t stream);
+
+typedef struct hcp_attn_bwd_args {
+    const void* q; int64_t ldq;
+    const void* k; int64_t ldk;
+    const void* v; int64_t ldv;
+    const void* o; int64_t ldo;
+    const void* dout; int64_t lddo;
+    int64_t B, H, Lq, Lkv, d;
+    float scale;
+    const float* kv_bias;
+    const float* lse;
+    void* dq; int64_t lddq;
+    void* dk; int64_t lddk;
+    void* dv; int64_t lddv;
+    float* workspace;            /* >= hcp_attn_bwd_workspace_bytes(B,H,Lq,d) bytes, caller-owned scratch */
+    size_t workspace_bytes;
+} hcp_attn_bwd_args;
+
+size_t hcp_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq, int64_t d);
+int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* args, hcp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm (+SiLU) over NHWC bf16, optionally over the channel concatenation [x1 | x2] (up-block skip
+ * connections: the concat is never materialised un-normalised), forward and backward.
+ *
+ * Replaces: ResnetBlock2D.norm1/norm2 + SiLU (reference cfgs/unet_struct.txt:93-99), Transformer2DModel.norm
+ *           (:13, eps 1e-6, no SiLU), conv_norm_out + SiLU (:929) and torch.cat([h, skip], dim=1) in the up blocks.
+ * fwd: y[B,HW,C1+C2] = act(GN(cat(x1,x2))); stats[B,G,2] = (mean, rstd) saved for backward.
+ * bwd: dx1 = dGN/dx1 (+ add1), dx2 = dGN/dx2 (+ add2); gamma/beta gradients are not produced (frozen base).
+ * workspace: >= hcp_groupnorm_workspace_bytes(B, HW, G) bytes of caller-owned scratch.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hcp_groupnorm_args {
+    const void* x1; const void* x2;     /* bf16 [B,HW,C1], [B,HW,C2] (x2 may be NULL with C2 == 0) */
+    int64_t B, HW, C1, C2, G;
+    const float* gamma; const float* beta;   /* fp32 [C1+C2] */
+    float eps;
+    int32_t silu;
+    float* stats;                       /* fp32 [B,G,2]: written by fwd, read by bwd */
+    float* workspace; size_t workspace_bytes;
+    void* y;                            /* fwd: bf16 [B,HW,C1+C2] */
+    const void* dy;                     /* bwd: bf16 [B,HW,C1+C2] */
+    const void* add1; const void* add2; /* bwd: optional bf16 gradients accumulated into dx1 / dx2 */
+    void* dx1; void* dx2;               /* bwd outputs */
+} hcp_groupnorm_args;
+
+size_t hcp_groupnorm_workspace_bytes(int64_t B, int64_t HW, int64_t G);
+int hcp_groupnorm_fwd_bf16(const hcp_groupnorm_args* args, hcp_stream_t stream);
+int hcp_groupnorm_bwd_bf16(const hcp_groupnorm_args* args, hcp_stream_t stream);
+
+/* LayerNorm over the last dim of a bf16 [M,C] matrix (BasicTransformerBlock.norm1/2/3, cfgs/unet_struct.txt:44-46).
+ * stats fp32 [M,2] (mean, rstd).  bwd: dx = dLN/dx (+ add). */
+int hcp_layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, float eps, int64_t M, int64_t C, float* stats,
+                           void* y, hcp_stream_t stream);
+int hcp_layernorm_bwd_bf16(const void* x, const void* dy, const void* add, const float* gamma, const float* stats, int64_t M,
+                           int64_t C, void* dx, hcp_stream_t stream);
+
+/* GEGLU (cfgs/unet_struct.txt:27-30): u bf16 [M,2F] = [a | g];  h = a * gelu_erf(g);  du = [dh*gelu(g) | dh*a*gelu'(g)] */
+int hcp_geglu_fwd_bf16(const void* u, int64_t M, int64_t F, void* h, hcp_stream_t stream);
+int hcp_geglu_bwd_bf16(const void* u, const void* dh, int64_t M, int64_t F, void* du, hcp_stream_t stream);
+
+/* nearest x2 upsample of NHWC bf16 [B,H,W,C] (Upsample2D, cfgs/unet_struct.txt:392) and its backward */
+int hcp_upsample2x_fwd_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t C, void* y, hcp_stream_t stream);
+int hcp_upsample2x_bwd_bf16(const void* dy, int64_t B, int64_t H, int64_t W, int64_t C, void* dx, hcp_stream_t stream);
+int hcp_add_bf16(const void* a, const void* b, int64_t n, void* out, hcp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Module-boundary kernels: the UNet call takes NCHW fp32 latents and returns NCHW fp32 noise_pred
+ * (reference hcpdiff/models/wrapper.py:29); inside everything is bf16 NHWC.
+ * ---------------------------------------------------------------------------------------------- */
+int hcp_conv_in_f32(const float* x_nchw, const float* w, const float* bias, int64_t B, int64_t Cin, int64_t H, int64_t W,
+                    int64_t Cout, void* y_nhwc_bf16, hcp_stream_t stream);
+int hcp_conv_out_f32(const void* x_nhwc_bf16, const float* w, const float* bias, int64_t B, int64_t H, int64_t W, int64_t Cin,
+                     int64_t Cout, float* y_nchw, hcp_stream_t stream);
+int hcp_conv_out_dgrad_f32(const float* dy_nchw, const float* w, int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                           void* dx_nhwc_bf16, hcp_stream_t stream);
+/* y[M,N] fp32 = f(x)[M,K] . W[N,K]^T + bias, M <= 16.  in_mode 0: f = id, 1: f = SiLU, 2: x is timesteps [M] and f is the
+ * sinusoidal embedding (diffusers Timesteps: [cos | sin], freq = exp(-ln(1e4) * j / (K/2))).  W is bf16. */
+int hcp_skinny_linear(const float* x, const void* w_bf16, const float* bias, int64_t M, int64_t K, int64_t N, int in_mode,
+                      int out_silu, float* y, hcp_stream_t stream);
+int hcp_cast_f32_to_bf16(const float* x, int64_t n, void* y, hcp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LoRA operand packing / gradient reduction.
+ * Replaces LoraBlock.get_weight (alpha * mm(W_up, W_down), reference lora_base_patch.py:61-62,
+ * lora_layers_patch.py:44-45) and autograd of W_down / W_up.  One job per LoRA block; blocks that share a fused
+ * GEMM (to_q/to_k/to_v on the same input; several stacked blocks on one layer) tile the packed operands
+ * block-diagonally via (c0, o0).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hcp_lora_job {
+    const float* w_down;     /* fp32 [rank, in_dim]  (LoraLayer.LinearLayer.W_down) */
+    const float* w_up;       /* fp32 [out_dim, rank] (W_up) */
+    float alpha;             /* LoraBlock.alpha buffer = alpha / rank */
+    int32_t rank, in_dim, out_dim;
+    int32_t c0;              /* first rank column of this block inside the group's 64-wide T / U buffers */
+    int32_t o0;              /* first output row of this block inside the group's fused output */
+    int32_t out_tot;         /* fused output width of the group */
+    void* A;                 /* bf16 [r_tot, in_dim] */
+    void* AT;                /* bf16 [in_dim, 64] */
+    void* Bl;                /* bf16 [out_tot, 64] */
+    void* BlT;               /* bf16 [r_tot, out_tot] */
+} hcp_lora_job;
+
+int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp_stream_t stream);
+/* dst += scale * S[:, c0:c0+r]^T . X[:, n_off:n_off+N]   (S bf16 [M,64], X bf16 [M,ldx]);
+ * transpose_out = 0: dst fp32 [r,N];  1: dst fp32 [N,r]. */
+int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t M, int64_t N, int64_t n_off, int64_t c0, int64_t r,
+                  float scale, int transpose_out, float* dst, hcp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The step either side of the UNet call (reference hcpdiff/train_ac.py:437-447, 485-494, 506-515).
+ * ---------------------------------------------------------------------------------------------- */
+int hcp_add_noise(const float* x0, const float* noise, const int64_t* t, const float* alphas_cumprod, int64_t B,
+                  int64_t per_image, float* xt, hcp_stream_t stream);
+int hcp_mse_loss(const float* pred, const float* target, int64_t n, float grad_scale, float* loss_sum /* += mean */,
+                 float* dpred /* may be NULL */, hcp_stream_t stream);
+int hcp_sumsq(const float* g, int64_t n, float* out /* += */, hcp_stream_t stream);
+int hcp_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_device, float beta1, float beta2,
+                   float eps, float weight_decay, float grad_scale, const float* sumsq_device, float max_norm,
+                   int* step_device, hcp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
