@@ -56,6 +56,7 @@ struct alignas(64) GemmKParams {
     const float* bias;
     const float* rowbias;
     int32_t rows_per_group;
+    int64_t rowbias_ld;
     const __nv_bfloat16* residual;
     int64_t ldr;
     __nv_bfloat16* out;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                             f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                         }
                         if (p.rowbias) {
-                            const float* rb = p.rowbias + (int64_t)group * p.N + col;
+                            const float* rb = p.rowbias + (int64_t)group * p.rowbias_ld + col;
                             const float4 b0 = *reinterpret_cast<const float4*>(rb);
                             const float4 b1 = *reinterpret_cast<const float4*>(rb + 4);
                             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
@@ -331,6 +332,7 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     kp.bias = a->bias;
     kp.rowbias = a->rowbias;
     kp.rows_per_group = (int)a->rows_per_group;
+    kp.rowbias_ld = a->rowbias_ld > 0 ? a->rowbias_ld : a->N;
     kp.residual = (const __nv_bfloat16*)a->residual;
     kp.ldr = a->ldr;
     kp.out = (__nv_bfloat16*)a->out;
@@ -383,6 +385,7 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
     kp.bias = a->bias;
     kp.rowbias = a->rowbias;
     kp.rows_per_group = 0;
+    kp.rowbias_ld = a->rowbias_ld > 0 ? a->rowbias_ld : a->Cout;
     kp.residual = (const __nv_bfloat16*)a->residual;
     kp.ldr = a->Cout;
     kp.out = (__nv_bfloat16*)a->out;

@@ -1,0 +1,154 @@
+"""Execution-side glue between the nn.Module tree (the plugin surface) and the packed kernel operands.
+
+A `LinearGroup` owns the bf16 operands of one GEMM made of one or several sibling linear layers reading the same input
+(to_q/to_k/to_v of a self-attention; to_k/to_v of a cross-attention; a single layer), each of which may be a plain
+nn.Linear / 1x1 nn.Conv2d or a `LoraPatchContainer` carrying any number of stacked `LoraBlock`s.  Packs are rebuilt when the
+module identities, the stacked plugins or the (in-place) version of a base weight change.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+from .models.lora import LoraBlock, LoraPatchContainer
+from .ops import BF16, ConvPack, LinearPack, LoraBlockRef
+
+
+def host_and_blocks(child: nn.Module) -> Tuple[nn.Module, List[LoraBlock]]:
+    """(base layer, [LoraBlock, ...]) of a linear-like child; anything else fails loudly (no silent eager fallback)."""
+    if isinstance(child, LoraPatchContainer):
+        blocks = [child[name] for name in child.plugin_names]
+        for b in blocks:
+            if not isinstance(b, LoraBlock):
+                raise NotImplementedError(f"plugin {type(b).__name__} on a hot-path layer is not supported")
+            if b.dropout.p > 0 and b.training:
+                raise NotImplementedError("LoRA dropout > 0 is not supported on the B200 hot path (set dropout: 0)")
+        return child._host, blocks
+    if isinstance(child, (nn.Linear, nn.Conv2d)):
+        return child, []
+    raise NotImplementedError(f"layer type {type(child).__name__} on the UNet hot path is not supported by hcp_diffusion_b200")
+
+
+def _weight_2d(host: nn.Module) -> torch.Tensor:
+    w = host.weight
+    if isinstance(host, nn.Conv2d):
+        if host.kernel_size != (1, 1):
+            raise NotImplementedError("only 1x1 convolutions can be run as a linear group")
+        return w.reshape(w.shape[0], w.shape[1])
+    return w
+
+
+class LinearGroup:
+    def __init__(self, children: Sequence[nn.Module]):
+        self.children = list(children)
+        self.pack: Optional[LinearPack] = None
+        self._sig = None
+        self._k_splits = None
+
+    def _signature(self, k_splits):
+        sig = [tuple(k_splits) if k_splits else None]
+        for ch in self.children:
+            host, blocks = host_and_blocks(ch)
+            sig.append((id(ch), id(host), host.weight._version, host.weight.data_ptr(), tuple(id(b) for b in blocks)))
+        return tuple(sig)
+
+    def prepare(self, k_splits: Optional[Sequence[int]] = None) -> LinearPack:
+        k_splits = k_splits or self._k_splits
+        sig = self._signature(k_splits)
+        if self.pack is not None and sig == self._sig:
+            return self.pack
+        hosts = [host_and_blocks(ch) for ch in self.children]
+        for host, _ in hosts:
+            if host.weight.requires_grad:
+                raise NotImplementedError("training base weights (full fine-tune) needs the wgrad kernels, which are not built yet; "
+                                          "freeze the base model and train LoRA blocks")
+            if not host.weight.is_cuda:
+                raise _lib.HcpError("hcp_diffusion_b200 runs on CUDA only: move the model to a B200 device (there is no CPU path)")
+        w = torch.cat([_weight_2d(h) for h, _ in hosts], dim=0)
+        biases = [h.bias for h, _ in hosts]
+        bias = None
+        if any(b is not None for b in biases):
+            bias = torch.cat([b if b is not None else torch.zeros(h.weight.shape[0], device=w.device) for (h, _), b in zip(hosts, biases)])
+        pack = LinearPack(w, bias, k_splits)
+        refs, c0, o0 = [], 0, 0
+        for host, blocks in hosts:
+            for b in blocks:
+                ref = LoraBlockRef(b.layer.W_down, b.layer.W_up, float(b.alpha), c0, o0)
+                refs.append(ref)
+                c0 += ref.rank
+            o0 += host.weight.shape[0]
+        if refs:
+            pack.attach_lora(refs)
+        self.pack, self._sig, self._k_splits = pack, sig, k_splits
+        return pack
+
+    def __call__(self, xs: Sequence[torch.Tensor], residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        pack = self.prepare([x.shape[-1] for x in xs] if len(xs) > 1 else None)
+        return ops.fused_linear(pack, xs, residual)
+
+    def run_standalone(self, x: torch.Tensor) -> torch.Tensor:
+        """Used by LoraPatchContainer.forward: any float dtype in, same dtype out."""
+        if not x.is_cuda:
+            raise _lib.HcpError("hcp_diffusion_b200 has no CPU path: LoRA layers run on a B200 only")
+        pack = self.prepare()
+        if pack.lora:
+            pack_lora([self])
+        y = ops.fused_linear(pack, [x.to(BF16)], None)
+        return y.to(x.dtype)
+
+
+class _JobTable:
+    def __init__(self):
+        self.key = None
+        self.dev = None
+        self.n = 0
+
+
+_job_table = _JobTable()
+
+
+def pack_lora(groups: Sequence[LinearGroup], table: Optional[_JobTable] = None) -> None:
+    """One kernel launch that refreshes the packed low-rank operands of every LoRA-carrying group from the fp32 parameters."""
+    table = table or _JobTable()
+    jobs = []
+    for g in groups:
+        if g.pack is not None and g.pack.lora:
+            jobs += g.pack.jobs()
+    if not jobs:
+        return
+    key = tuple((j.w_down, j.w_up, j.A, j.alpha) for j in jobs)
+    if table.key != key:
+        arr = (_lib.LoraJob * len(jobs))(*jobs)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        table.dev = host.cuda()
+        table.key, table.n = key, len(jobs)
+    _lib.call("hcp_lora_pack", table.dev.data_ptr(), table.n, _lib.stream_ptr())
+
+
+class ConvGroup:
+    """Packed operands of one 3x3 convolution layer (frozen base weights; LoRA on 3x3 convolutions is not on this path)."""
+
+    def __init__(self, conv: nn.Module):
+        self.conv = conv
+        self.pack: Optional[ConvPack] = None
+        self._sig = None
+
+    def prepare(self) -> ConvPack:
+        conv = self.conv
+        if not isinstance(conv, nn.Conv2d):
+            raise NotImplementedError(f"{type(conv).__name__} on a 3x3 convolution of the hot path is not supported (LoRA/locon on Conv2d pending)")
+        sig = (id(conv), conv.weight._version, conv.weight.data_ptr())
+        if self.pack is None or sig != self._sig:
+            if conv.weight.requires_grad:
+                raise NotImplementedError("training base convolution weights needs the wgrad kernels, which are not built yet")
+            if not conv.weight.is_cuda:
+                raise _lib.HcpError("hcp_diffusion_b200 runs on CUDA only (there is no CPU path)")
+            if conv.kernel_size != (3, 3) or conv.padding != (1, 1) or conv.stride[0] not in (1, 2):
+                raise NotImplementedError("only 3x3 / pad 1 / stride 1|2 convolutions are supported")
+            self.pack = ConvPack(conv.weight, conv.bias, conv.stride[0])
+            self._sig = sig
+        return self.pack

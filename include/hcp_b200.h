@@ -62,6 +62,7 @@ typedef struct hcp_gemm_args {
     const float* bias;                     /* fp32 [N] or NULL */
     const float* rowbias;                  /* fp32 [ceil(M/rows_per_group), N] or NULL (time-embedding bias per image) */
     int64_t rows_per_group;
+    int64_t rowbias_ld;                    /* row pitch of rowbias in floats (0 -> N) */
     const void* residual;                  /* bf16 [M,N] pitch ldr, or NULL: added in the epilogue */
     int64_t ldr;
     void* out;                             /* bf16 [M,N] pitch ldo */
@@ -90,6 +91,7 @@ typedef struct hcp_conv3x3_args {
     int32_t mode;        /* 0 = forward conv, 1 = dgrad of the stride-2 conv */
     const float* bias;   /* fp32 [Cout] or NULL */
     const float* rowbias;/* fp32 [B, Cout] or NULL (time embedding projection, broadcast over H,W) */
+    int64_t rowbias_ld;  /* row pitch of rowbias in floats (0 -> Cout) */
     const void* residual;/* bf16 [B,Hout,Wout,Cout] or NULL */
     void* out;           /* bf16 [B,Hout,Wout,Cout] */
 } hcp_conv3x3_args;

@@ -1,0 +1,144 @@
+"""CPU tests of the host-side drop-in surface (no kernels are launched): module names/shapes of the product UNet against the
+reference dump, LoRA injection through `make_hcpdiff` with the reference's yaml patterns, state-dict / checkpoint key
+schemes against golden data generated from the real reference classes, checkpoint round trip, flat parameter buffers."""
+import json
+import os
+import re
+
+import pytest
+import torch
+from torch import nn
+
+from hcp_diffusion_b200.ckpt_manager import CkptManagerPKL, CkptManagerSafe, auto_manager
+from hcp_diffusion_b200.engine import FlatParams
+from hcp_diffusion_b200.models import LoraBlock, LoraLayer, LoraPatchContainer, PluginGroup, UNet2DConditionModel
+from hcp_diffusion_b200.utils.cfg_net_tools import HCPModelLoader, get_match_layers, make_hcpdiff
+from oracle import unet_ref as U
+
+TINY_KW = dict(sample_size=16, block_out_channels=(64, 128, 128, 128), attention_head_dim=2, cross_attention_dim=64)
+
+
+def test_unet_names_and_shapes_match_reference_dump(golden_dir):
+    with torch.device("meta"):
+        unet = UNet2DConditionModel()
+    got = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+    want = {k: tuple(v) for k, v in U.param_shapes(U.SD15).items()}
+    assert got == want
+    leaves = json.load(open(os.path.join(golden_dir, "unet_struct_sd15.json")))
+    mods = dict(unet.named_modules())
+    for name, m in leaves.items():
+        assert name in mods, name
+        assert type(mods[name]).__name__ == m["type"], name
+        if m["type"] == "Conv2d":
+            assert mods[name].stride[0] == m["stride"] and mods[name].padding[0] == m["padding"]
+        if m["type"] in ("GroupNorm", "LayerNorm"):
+            assert mods[name].eps == m["eps"]
+    assert unet.config.in_channels == 4 and unet.config.sample_size == 64 and unet.dtype == torch.float32
+
+
+def test_get_match_layers_semantics():
+    unet = UNet2DConditionModel(**TINY_KW)
+    named = dict(unet.named_modules())
+    attn = get_match_layers([r"re:.*\.attn.?$"], named)
+    assert len(attn) == 32 and all(re.search(r"\.attn[12]$", n) for n in attn)
+    assert get_match_layers(["conv_in", "conv_in", r"re:^conv_"], named) == ["conv_in", "conv_norm_out", "conv_act", "conv_out"]
+    metas = get_match_layers([r"pre_hook:re:.*\.ff$"], named, return_metas=True)
+    assert len(metas) == 16 and all(m["pre_hook"] for m in metas)
+    assert get_match_layers([""], named) == [""]        # the DreamBooth `layers: ['']` idiom = whole model
+
+
+def test_make_hcpdiff_injects_reference_key_scheme(golden_dir):
+    unet = UNet2DConditionModel(**TINY_KW)
+    unet.requires_grad_(False)
+    cfg = [{"lr": 1e-4, "rank": 4, "alpha": 1.0, "layers": [r"re:.*\.attn.?$"]},
+           {"lr": 2e-4, "rank": 2, "alpha": 0.5, "layers": ["down_blocks.0.attentions.0.transformer_blocks.0.attn1"]}]
+    groups, lora = make_hcpdiff(unet, None, cfg)
+    # like the reference, a later item overwrites the group entry of a layer it stacks onto (cfg_net_tools.py:117-119)
+    assert len(lora.plugin_dict) == 128 and [g["lr"] for g in groups] == [1e-4, 2e-4]
+    layer = "down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q"
+    sd = unet.state_dict()
+    # the same keys the real reference produces (tests/golden/ref_lora_linear.pt, 'attn1.to_q.*')
+    fx = torch.load(os.path.join(golden_dir, "ref_lora_linear.pt"))
+    ref_keys = {k[len("attn1.to_q."):] for k in fx["state_keys_model"] if k.startswith("attn1.to_q.")}
+    got_keys = {k[len(layer) + 1:] for k in sd if k.startswith(layer + ".")}
+    assert got_keys == ref_keys
+    ck = lora.state_dict()
+    ref_ck = {k.split(".___.")[1] for k in fx["ckpt_keys"] if k.startswith("attn1.to_q.")}
+    assert {k.split(".___.")[1] for k in ck if k.startswith(layer + ".___.")} == ref_ck
+    blk = lora[layer]
+    assert isinstance(blk, LoraLayer) and isinstance(getattr(unet.down_blocks[0].attentions[0].transformer_blocks[0].attn1, "to_q"), LoraPatchContainer)
+    assert blk.layer.W_down.shape == (2, 64) and blk.layer.W_up.shape == (64, 2) and float(blk.alpha) == 0.25
+    assert torch.count_nonzero(blk.layer.W_up) == 0                      # reference init: W_up zeros
+    trainable = [n for n, p in unet.named_parameters() if p.requires_grad]
+    assert trainable and all("lora_block_" in n for n in trainable)
+    # removing the plugins restores the plain module tree
+    lora.remove()
+    assert isinstance(unet.down_blocks[0].attentions[0].transformer_blocks[0].attn1.to_q, (nn.Linear, LoraPatchContainer))
+
+
+def test_lora_sd15_parameter_count():
+    with torch.device("meta"):
+        unet = UNet2DConditionModel()
+    named = dict(unet.named_modules())
+    layers = get_match_layers([r"re:.*\.attn.?$"], named)
+    n = 0
+    for l in layers:
+        for m in named[l].modules():
+            if isinstance(m, nn.Linear):
+                n += 8 * (m.in_features + m.out_features)
+    assert n == 1_594_368                                                 # 6.38 MB fp32
+
+
+def test_checkpoint_roundtrip_and_loader(tmp_path):
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel(**TINY_KW)
+    unet.requires_grad_(False)
+    _, lora = make_hcpdiff(unet, None, [{"rank": 4, "layers": [r"re:.*\.attn1$"]}])
+    for blk in lora.plugin_dict.values():
+        nn.init.normal_(blk.layer.W_up, std=0.1)
+    for mgr, ext in ((CkptManagerSafe(), "safetensors"), (CkptManagerPKL(), "ckpt")):
+        mgr.set_save_dir(str(tmp_path))
+        path = mgr.save_model_with_lora(None, lora, "unet", 7)
+        assert path.endswith(f"unet-7.{ext}") and type(auto_manager(path)) is type(mgr)
+        sd = mgr.load_ckpt(path)
+        assert set(sd) == {"lora"} and set(sd["lora"]) == set(lora.state_dict())
+        for k, v in lora.state_dict().items():
+            torch.testing.assert_close(sd["lora"][k], v.detach().cpu())
+    if True:
+        from safetensors import safe_open
+        with safe_open(os.path.join(tmp_path, "unet-7.safetensors"), framework="pt") as f:
+            assert all(k.startswith("lora:") and ".___." in k for k in f.keys())   # reference unfold_dict key scheme
+    # load into a fresh model
+    unet2 = UNet2DConditionModel(**TINY_KW)
+    groups = HCPModelLoader(unet2).load_lora([{"path": os.path.join(tmp_path, "unet-7.safetensors"), "alpha": 1.0}])
+    got = groups[0].state_dict()
+    for k, v in lora.state_dict().items():
+        torch.testing.assert_close(got[k], v.detach(), msg=k)
+
+
+def test_flat_params_keep_names_and_alias_storage():
+    unet = UNet2DConditionModel(**TINY_KW)
+    unet.requires_grad_(False)
+    groups, lora = make_hcpdiff(unet, None, [{"rank": 4, "layers": [r"re:.*\.attn.?$"]}])
+    params = [p for g in groups for p in g["params"]]
+    before = {k: v.clone() for k, v in lora.state_dict().items()}
+    flat = FlatParams(params)
+    assert flat.numel >= sum(p.numel() for p in params) and flat.numel % 4 == 0
+    for k, v in lora.state_dict().items():
+        torch.testing.assert_close(v, before[k])
+    p0 = params[0]
+    flat.data[flat.offsets[0]] = 123.0
+    assert float(p0.view(-1)[0]) == 123.0 and p0.grad.data_ptr() == flat.grad[flat.offsets[0]:].data_ptr()
+    flat.grad.fill_(1.0)
+    flat.zero_grad()
+    assert float(p0.grad.abs().sum()) == 0.0
+
+
+def test_cpu_call_fails_loudly():
+    unet = UNet2DConditionModel(**TINY_KW)
+    with pytest.raises(Exception, match="CUDA|CPU"):
+        unet(torch.zeros(1, 4, 16, 16), torch.tensor([1]), torch.zeros(1, 7, 64))
+    _, lora = make_hcpdiff(unet, None, [{"rank": 4, "layers": ["mid_block.attentions.0.transformer_blocks.0.attn1.to_q"]}])
+    cont = unet.mid_block.attentions[0].transformer_blocks[0].attn1.to_q
+    with pytest.raises(Exception, match="CUDA|CPU"):
+        cont(torch.zeros(2, 128))
