@@ -313,7 +313,7 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     memset(&kp, 0, sizeof(kp));
     const int bn = pick_bn(a->N);
     for (int s = 0; s < a->nseg; ++s) {
-        if (a->k[s] <= 0 || (a->k[s] % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: k must be a positive multiple of 8");
+        if (a->k[s] <= 0) return set_error(HCP_ERR_INVALID, "gemm: k must be positive");
         if ((a->lda[s] % 8) != 0 || (a->ldb[s] % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: lda/ldb");
         const int64_t nrb = a->n_rows_b[s] > 0 ? a->n_rows_b[s] : a->N;
         int rc = make_tmap_2d(&kp.tmA[s], a->a[s], (uint64_t)a->k[s], (uint64_t)a->M, (uint64_t)a->lda[s], BLOCK_K, BLOCK_M);

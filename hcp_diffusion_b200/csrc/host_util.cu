@@ -35,6 +35,17 @@ static PFN_encodeTiled get_encode() {
 
 int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                  const uint32_t* box) {
+    // cuTensorMapEncodeTiled is a driver call and needs a context current on THIS thread; autograd worker threads may
+    // not have touched the runtime yet (observed: CUDA_ERROR_INVALID_CONTEXT from a backward thread).  cudaSetDevice on
+    // the thread's current device binds its primary context (and, unlike cudaFree(0), is legal during stream capture).
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaSetDevice(dev);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaSetDevice (context bind)");
+        ctx_bound = true;
+    }
     PFN_encodeTiled enc = get_encode();
     if (!enc) return set_error(HCP_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(HCP_ERR_INVALID, "tensor map: base not 16-byte aligned");

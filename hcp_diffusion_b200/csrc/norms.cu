@@ -53,17 +53,18 @@ __device__ __forceinline__ float2 gn_load2(const GNParams& p, int64_t pix, int c
     return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src));
 }
 
+constexpr int GN_MAX_PAIRS = 2048;   // C <= 4096
+
 template <bool BWD>
 __global__ void __launch_bounds__(GN_THREADS) gn_partial_kernel(const GNParams p) {
-    __shared__ float s_acc[GN_MAX_G * 2];
+    // per-channel-pair partial sums, then ONE thread per group adds them in a fixed order: the result is deterministic
+    // (no floating-point atomics), which the batch-invariance property test relies on.
+    __shared__ float s_pair[GN_MAX_PAIRS][2];
     const int b = blockIdx.y, chunk = blockIdx.x;
-    for (int i = threadIdx.x; i < p.G * 2; i += GN_THREADS) s_acc[i] = 0.f;
-    __syncthreads();
     const int r0 = chunk * p.rows_per_cta;
     const int r1 = min(p.HW, r0 + p.rows_per_cta);
     const int npair = p.C / 2;
     const float* st = BWD ? p.stats + (int64_t)b * p.G * 2 : nullptr;
-    // a thread keeps a fixed channel pair while it walks the rows => its group is loop invariant per pair slot
     for (int cp = threadIdx.x; cp < npair; cp += GN_THREADS) {
         const int c = cp * 2;
         const int g = c / p.cg;           // cg is even for every UNet layer, so a pair never straddles two groups
@@ -91,12 +92,18 @@ __global__ void __launch_bounds__(GN_THREADS) gn_partial_kernel(const GNParams p
                 a1 += g0 * xh0 + g1 * xh1;
             }
         }
-        atomicAdd(&s_acc[g * 2], a0);
-        atomicAdd(&s_acc[g * 2 + 1], a1);
+        s_pair[cp][0] = a0;
+        s_pair[cp][1] = a1;
     }
     __syncthreads();
     float* out = p.partial + ((int64_t)b * p.nchunks + chunk) * p.G * 2;
-    for (int i = threadIdx.x; i < p.G * 2; i += GN_THREADS) out[i] = s_acc[i];
+    const int ppg = p.cg / 2;             // pairs per group
+    for (int i = threadIdx.x; i < p.G * 2; i += GN_THREADS) {
+        const int g = i >> 1, which = i & 1;
+        float acc = 0.f;
+        for (int k = 0; k < ppg; ++k) acc += s_pair[g * ppg + k][which];
+        out[i] = acc;
+    }
 }
 
 template <bool BWD>
@@ -193,6 +200,7 @@ static int gn_geometry(const hcp_groupnorm_args* a, GNParams& p) {
     if (a->G <= 0 || a->G > GN_MAX_G || C % a->G != 0) return set_error(HCP_ERR_INVALID, "groupnorm: groups");
     const int64_t cg = C / a->G;
     if ((cg & 1) || (a->C1 & 1) || (a->C2 & 1)) return set_error(HCP_ERR_INVALID, "groupnorm: channels per group must be even");
+    if (C / 2 > GN_MAX_PAIRS) return set_error(HCP_ERR_INVALID, "groupnorm: more than 4096 channels");
     if (a->C2 > 0 && !a->x2) return set_error(HCP_ERR_INVALID, "groupnorm: x2");
     memset(&p, 0, sizeof(p));
     p.x1 = (const __nv_bfloat16*)a->x1; p.x2 = (const __nv_bfloat16*)a->x2;
