@@ -19,13 +19,15 @@
 // Backward, one CTA per (128 kv rows, head, image) looping over query tiles:
 //   S = Q K^T, dP = dO V^T (TMEM) -> P, dS (bf16, smem) -> dV += P^T dO, dK += dS^T Q (TMEM accumulators,
 //   MN-major A operands), dQ_i = dS K (TMEM) reduced into an fp32 buffer with vector red.global.
+#include <stdlib.h>
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/hcp_b200.h"
 
 namespace hcp {
 
-constexpr int kAttnThreads = 160;          // warps 0-3: softmax/epilogue rows, warp 4: TMA + MMA control
+constexpr int kAttnThreads = 160;          // fwd: warps 0-3: softmax/epilogue rows, warp 4: TMA + MMA control
+constexpr int kAttnBwdThreads = 288;       // bwd: warps 0-7: two per TMEM lane quarter (each owns 64 kv columns), warp 8: control
 constexpr int TILE_BYTES = 128 * 128;      // one [128 rows x 64 cols] bf16 box
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -253,6 +255,241 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_fwd_kernel(const __grid_
 }
 
 // =============================================================================================
+// forward, version 2: two 128-row query tiles per CTA (they share every K/V tile that TMA brings in), 16 softmax warps
+// (per query tile: 4 TMEM lane quarters x 2 column halves) and one control warp that ping-pongs the tensor pipe between the
+// two tiles: while the softmax warps of tile A exponentiate tile j, the pipe runs S_B(j), PV_B(j-1)...  Each softmax thread
+// reads its 64 logits from TMEM ONCE, the row maximum of the two column halves is combined through shared memory.
+// =============================================================================================
+constexpr int kFwd2Threads = 17 * 32;
+
+struct alignas(64) AttnFwd2Params {
+    CUtensorMap tmQ, tmK, tmV;
+    int B, H, Lq, Lkv, d;
+    int nbox, dn;
+    int nq;              // query tiles per CTA: 2 (d <= 128) or 1
+    int kv_stages;
+    float scale_log2;
+    const float* kv_bias;
+    __nv_bfloat16* O;
+    int64_t ldo;
+    float* lse;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tile_bytes = p.nbox * TILE_BYTES;
+    uint8_t* sQ = smem;                                  // [nq]
+    uint8_t* sK = sQ + p.nq * tile_bytes;                // [kv_stages]
+    uint8_t* sV = sK + p.kv_stages * tile_bytes;         // [kv_stages]
+    float* sx = reinterpret_cast<float*>(sV + p.kv_stages * tile_bytes);   // [2 parity][2 tile][2 half][128] row-max exchange
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sx + 2 * 2 * 2 * 128);
+    uint64_t* q_full = bars + 0;
+    uint64_t* kv_full = bars + 1;     // [3]
+    uint64_t* kv_done = bars + 4;     // [3]
+    uint64_t* s_full = bars + 7;      // [2]
+    uint64_t* p_ready = bars + 9;     // [2]
+    uint64_t* o_full = bars + 11;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * p.nq * 128;
+    const int nkv = (p.Lkv + 127) / 128;
+    const int S = p.kv_stages;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_done[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 256); }
+        mbar_init(o_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 16) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 16) {
+        if (elect_one()) {
+            auto load_kv = [&](int j) {
+                const int st = j % S;
+                mbar_arrive_expect_tx(&kv_full[st], 2 * tile_bytes);
+                for (int bx = 0; bx < p.nbox; ++bx) {
+                    tma_load_4d(sK + st * tile_bytes + bx * TILE_BYTES, &p.tmK, &kv_full[st], bx * 64, h, j * 128, b);
+                    tma_load_4d(sV + st * tile_bytes + bx * TILE_BYTES, &p.tmV, &kv_full[st], bx * 64, h, j * 128, b);
+                }
+            };
+            auto issue_s = [&](int t, int j) {        // S_t = Q_t K_j^T
+                const int st = j % S;
+                const int ncols = min(128, p.Lkv - j * 128);
+                const uint32_t idesc = make_idesc_bf16(128, (ncols + 15) & ~15, 0, 0);
+                const uint32_t qb = smem_u32(sQ + t * tile_bytes), kb = smem_u32(sK + st * tile_bytes);
+                for (int ks = 0; ks < p.dn / 16; ++ks) {
+                    const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
+                    umma_ss(tmem + t * 128, make_smem_desc(qb + off, 16, 1024), make_smem_desc(kb + off, 16, 1024), idesc, ks > 0);
+                }
+                umma_commit(&s_full[t]);
+            };
+            auto issue_pv = [&](int t, int j) {       // O_t += P_t V_j  (P from TMEM, V MN-major)
+                const int st = j % S;
+                const int ncols = min(128, p.Lkv - j * 128);
+                const uint32_t idesc = make_idesc_bf16(128, p.dn, 0, 1);
+                const uint32_t vb = smem_u32(sV + st * tile_bytes);
+                for (int ks = 0; ks < ((ncols + 15) >> 4); ++ks)
+                    umma_ts(tmem + 256 + t * 128, tmem + t * 128 + ks * 8, make_smem_desc(vb + ks * 2048, TILE_BYTES, 1024), idesc,
+                            (j > 0 || ks > 0) ? 1u : 0u);
+            };
+            mbar_arrive_expect_tx(q_full, p.nq * tile_bytes);
+            for (int t = 0; t < p.nq; ++t)
+                for (int bx = 0; bx < p.nbox; ++bx)
+                    tma_load_4d(sQ + t * tile_bytes + bx * TILE_BYTES, &p.tmQ, q_full, bx * 64, h, q0 + t * 128, b);
+            for (int j = 0; j < min(S, nkv); ++j) load_kv(j);
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            for (int t = 0; t < p.nq; ++t) issue_s(t, 0);
+            for (int j = 0; j < nkv; ++j) {
+                const int st = j % S;
+                for (int t = 0; t < p.nq; ++t) {
+                    mbar_wait(&p_ready[t], j & 1);
+                    tc_fence_after();
+                    issue_pv(t, j);
+                    if (t == p.nq - 1) umma_commit(&kv_done[st]);      // K_j / V_j no longer needed once these retire
+                    if (j + 1 < nkv) {
+                        if (t == 0) {
+                            mbar_wait(&kv_full[(j + 1) % S], ((j + 1) / S) & 1);
+                            tc_fence_after();
+                        }
+                        issue_s(t, j + 1);
+                    }
+                }
+                if (j + S < nkv) {                                      // refill the stage tile j used
+                    mbar_wait(&kv_done[st], (j / S) & 1);
+                    load_kv(j + S);
+                }
+            }
+            umma_commit(o_full);
+        }
+    } else if ((warp >> 3) < p.nq) {
+        // ------------------------------ softmax: thread == (query row, 64-column half) ------------------------------
+        const int t = warp >> 3, quarter = warp & 3, half = (warp >> 2) & 1;
+        const int row = quarter * 32 + lane;
+        const int qrow = q0 + t * 128 + row;
+        const uint32_t lb = lane_base(quarter);
+        const uint32_t tS = tmem + t * 128, tO = tmem + 256 + t * 128;
+        const float* bias = p.kv_bias ? p.kv_bias + (int64_t)b * p.Lkv : nullptr;
+        float m = -INFINITY, l = 0.f;
+        for (int j = 0; j < nkv; ++j) {
+            const int kv0 = j * 128;
+            const int ncols = min(128, p.Lkv - kv0);
+            const int c0 = half * 64;
+            const bool special = (ncols < 128) || (bias != nullptr);
+            mbar_wait(&s_full[t], j & 1);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            tmem_ld32(tS + lb + c0, v0);
+            tmem_ld32(tS + lb + c0 + 32, v1);
+            tmem_wait_ld();
+            float sv[64];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                sv[e] = __uint_as_float(v0[e]) * p.scale_log2;
+                sv[32 + e] = __uint_as_float(v1[e]) * p.scale_log2;
+            }
+            if (special) {
+#pragma unroll
+                for (int e = 0; e < 64; ++e) {
+                    const int col = c0 + e;
+                    float s = sv[e];
+                    if (bias && col < ncols) s += bias[kv0 + col] * kLog2e;
+                    sv[e] = (col < ncols) ? s : -INFINITY;
+                }
+            }
+            float mx = sv[0];
+#pragma unroll
+            for (int e = 1; e < 64; ++e) mx = fmaxf(mx, sv[e]);
+            float* xch = sx + (((j & 1) * 2 + t) * 2) * 128;
+            xch[half * 128 + row] = mx;
+            named_bar_sync(1 + t, 256);
+            mx = fmaxf(mx, xch[(half ^ 1) * 128 + row]);
+            if (j == 0) {
+                m = (mx == -INFINITY) ? 0.f : mx;
+            } else {
+                const float m_new = fmaxf(m, mx);
+                if (__any_sync(0xffffffffu, m_new - m > 8.f)) {
+                    const float alpha = fast_exp2(m - m_new);
+                    l *= alpha;
+                    if (half == 0) {
+                        for (int c = 0; c < p.dn / 16; ++c) {
+                            uint32_t o[16];
+                            tmem_ld16(tO + lb + c * 16, o);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                            tmem_st16(tO + lb + c * 16, o);
+                        }
+                    }
+                    m = m_new;
+                }
+            }
+            uint32_t pk[32];
+#pragma unroll
+            for (int e = 0; e < 64; e += 2) {
+                const float p0 = fast_exp2(sv[e] - m), p1 = fast_exp2(sv[e + 1] - m);
+                l += p0 + p1;
+                pk[e >> 1] = pack_bf16x2(p0, p1);
+            }
+            tmem_st32(tS + lb + half * 32, pk);      // P (bf16) over the S columns every warp of this tile has already consumed
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&p_ready[t]);
+        }
+        // combine the two halves' row sums, then each half writes its share of the output columns
+        float* xch = sx + ((0 * 2 + t) * 2) * 128;
+        named_bar_sync(1 + t, 256);
+        xch[half * 128 + row] = l;
+        named_bar_sync(1 + t, 256);
+        l += xch[(half ^ 1) * 128 + row];
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        const float inv = 1.f / l;
+        __nv_bfloat16* orow = p.O + ((int64_t)b * p.Lq + qrow) * p.ldo + (int64_t)h * p.d;
+        for (int c = half; c < p.dn / 16; c += 2) {
+            uint32_t o[16];
+            tmem_ld16(tO + lb + c * 16, o);
+            tmem_wait_ld();
+            if (qrow < p.Lq) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int col = c * 16 + g * 8;
+                    if (col < p.d) {
+                        uint4 w;
+                        w.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+                        w.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+                        w.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+                        w.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+                        *reinterpret_cast<uint4*>(orow + col) = w;
+                    }
+                }
+            }
+        }
+        if (half == 0 && qrow < p.Lq && p.lse) p.lse[((int64_t)b * p.H + h) * p.Lq + qrow] = (m + log2f(l)) * kLn2;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
 // backward
 // =============================================================================================
 struct alignas(64) AttnBwdParams {
@@ -272,7 +509,7 @@ struct alignas(64) AttnBwdParams {
     int64_t lddk, lddv;
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+__global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int tile_bytes = p.nbox * TILE_BYTES;
@@ -305,15 +542,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(const __grid_
         mbar_init(&q_full[0], 1);
         mbar_init(&q_full[1], 1);
         mbar_init(sdp_full, 1);
-        mbar_init(p_ready, 128);
-        mbar_init(ds_ready, 128);
+        mbar_init(p_ready, 256);
+        mbar_init(ds_ready, 256);
         mbar_init(dv_done, 1);
         mbar_init(dq_full, 1);
-        mbar_init(dq_read, 128);
+        mbar_init(dq_read, 256);
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
-    if (warp == 4) {
+    if (warp == 8) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
@@ -323,7 +560,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(const __grid_
     const uint32_t tmem = *tmem_slot;
     const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem, tdV = tmem + 256, tdK = tmem + 384;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (elect_one()) {
             auto load_q = [&](int i) {
                 const int st = (p.q_stages == 2) ? (i & 1) : 0;
@@ -395,8 +632,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(const __grid_
         }
     } else {
         // ------------------------------ thread == query row (S, dP) / kv row (dK, dV) --------------
-        const int row = warp * 32 + lane;
-        const uint32_t lb = lane_base(warp);
+        const int quarter = warp & 3, half = warp >> 2;      // lanes [32*quarter, +32), kv columns [64*half, +64)
+        const int row = quarter * 32 + lane;
+        const uint32_t lb = lane_base(quarter);
         const float* bias = p.kv_bias ? p.kv_bias + (int64_t)b * p.Lkv : nullptr;
         for (int i = 0; i < nq; ++i) {
             const int qrow = i * 128 + row;
@@ -411,7 +649,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(const __grid_
             for (int pass = 0; pass < (p.share_pds ? 2 : 1); ++pass) {
                 const bool do_p = (pass == 0);
                 const bool do_ds = !p.share_pds || pass == 1;
-                for (int c = 0; c < 4; ++c) {
+                for (int c = half * 2; c < half * 2 + 2; ++c) {
                     uint32_t v[32], w[32];
                     tmem_ld32(tS + lb + c * 32, v);
                     if (do_ds) tmem_ld32(tdP + lb + c * 32, w);
@@ -452,7 +690,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(const __grid_
             mbar_wait(dq_full, i & 1);
             tc_fence_after();
             float* dqrow = p.dq_acc + stat_idx * p.dq_ld + p.col0;
-            for (int c = 0; c < p.ncols_out / 16; ++c) {
+            for (int c = half; c < p.ncols_out / 16; c += 2) {
                 uint32_t o[16];
                 tmem_ld16(tdQ + lb + c * 16, o);
                 tmem_wait_ld();
@@ -478,7 +716,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(const __grid_
             __nv_bfloat16* out = which ? p.dK : p.dV;
             const int64_t ld = which ? p.lddk : p.lddv;
             __nv_bfloat16* orow = out + ((int64_t)b * p.Lkv + kvrow) * ld + (int64_t)h * p.d + p.col0;
-            for (int c = 0; c < p.ncols_out / 16; ++c) {
+            for (int c = half; c < p.ncols_out / 16; c += 2) {
                 uint32_t o[16];
                 tmem_ld16(t + lb + c * 16, o);
                 tmem_wait_ld();
@@ -501,7 +739,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, 512);
+    if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
 // delta[b,h,q] = sum_e dO*O ; also zero-fills the fp32 dQ accumulator.  One warp per (b,q,h).
@@ -572,6 +810,36 @@ extern "C" int hcp_attn_fwd_bf16(const hcp_attn_args* a, hcp_stream_t stream_) {
     if (!a || !a->q || !a->k || !a->v || !a->o) return set_error(HCP_ERR_INVALID, "attn_fwd: null pointer");
     int rc = check_common(a->B, a->H, a->Lq, a->Lkv, a->d);
     if (rc) return rc;
+    static const bool use_v1 = getenv("HCP_ATTN_FWD_V1") != nullptr;
+    if (!use_v1) {
+        AttnFwd2Params p;
+        memset(&p, 0, sizeof(p));
+        if ((rc = make_head_map(&p.tmQ, a->q, a->ldq, a->B, a->H, a->Lq, a->d))) return rc;
+        if ((rc = make_head_map(&p.tmK, a->k, a->ldk, a->B, a->H, a->Lkv, a->d))) return rc;
+        if ((rc = make_head_map(&p.tmV, a->v, a->ldv, a->B, a->H, a->Lkv, a->d))) return rc;
+        p.B = (int)a->B; p.H = (int)a->H; p.Lq = (int)a->Lq; p.Lkv = (int)a->Lkv; p.d = (int)a->d;
+        p.nbox = (int)((a->d + 63) / 64);
+        p.dn = (int)((a->d + 15) / 16 * 16);
+        p.nq = (p.dn <= 128 && a->Lq > 128) ? 2 : 1;
+        p.kv_stages = (p.nbox == 1) ? 3 : (p.nbox == 2 ? 2 : 1);
+        p.scale_log2 = a->scale * kLog2e;
+        p.kv_bias = a->kv_bias;
+        p.O = (__nv_bfloat16*)a->o; p.ldo = a->ldo;
+        p.lse = a->lse;
+        const int smem = (p.nq + 2 * p.kv_stages) * p.nbox * TILE_BYTES + 4096 + 256 + 1024;
+        static bool configured2 = false;
+        if (!configured2) {
+            cudaError_t e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn_fwd2)");
+            configured2 = true;
+        }
+        if (smem > 227 * 1024) return set_error(HCP_ERR_INVALID, "attn_fwd: shared memory budget exceeded");
+        dim3 grid((unsigned)((a->Lq + 128 * p.nq - 1) / (128 * p.nq)), (unsigned)a->H, (unsigned)a->B);
+        attn_fwd2_kernel<<<grid, kFwd2Threads, smem, (cudaStream_t)stream_>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return set_cuda_error(e, "attn_fwd2 launch");
+        return HCP_OK;
+    }
     AttnFwdParams p;
     memset(&p, 0, sizeof(p));
     if ((rc = make_head_map(&p.tmQ, a->q, a->ldq, a->B, a->H, a->Lq, a->d))) return rc;
@@ -657,7 +925,7 @@ extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream
     for (int col0 = 0; col0 < p.dn; col0 += 128) {
         p.col0 = col0;
         p.ncols_out = (p.dn - col0 < 128) ? (p.dn - col0) : 128;
-        attn_bwd_kernel<<<grid, kAttnThreads, smem, stream>>>(p);
+        attn_bwd_kernel<<<grid, kAttnBwdThreads, smem, stream>>>(p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd launch");
     }
