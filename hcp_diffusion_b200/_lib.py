@@ -53,6 +53,7 @@ class GemmArgs(C.Structure):
         ("residual", C.c_void_p), ("ldr", C.c_int64),
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("flags", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -62,6 +63,7 @@ class ConvArgs(C.Structure):
         ("B", C.c_int64), ("Hin", C.c_int64), ("Win", C.c_int64), ("Cin", C.c_int64), ("Cout", C.c_int64),
         ("stride", C.c_int32), ("mode", C.c_int32),
         ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_ld", C.c_int64), ("residual", C.c_void_p), ("out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -104,12 +106,19 @@ class LoraJob(C.Structure):
     ]
 
 
+class LoraGradBlock(C.Structure):
+    _fields_ = [
+        ("n_lo", C.c_int64), ("n_hi", C.c_int64), ("c0", C.c_int32), ("rank", C.c_int32), ("scale", C.c_float),
+        ("transpose_out", C.c_int32), ("dst", C.c_void_p), ("dst_ld", C.c_int64),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 
 # every exported symbol of include/hcp_b200.h (checked by tests/test_abi.py)
 EXPORTS = [
-    "hcp_version", "hcp_last_error_string", "hcp_device_check", "hcp_gemm_bf16", "hcp_conv3x3_bf16",
+    "hcp_version", "hcp_last_error_string", "hcp_device_check", "hcp_gemm_bf16", "hcp_splitk_workspace_bytes", "hcp_conv3x3_bf16",
     "hcp_attn_fwd_bf16", "hcp_attn_bwd_workspace_bytes", "hcp_attn_bwd_bf16",
     "hcp_groupnorm_workspace_bytes", "hcp_groupnorm_fwd_bf16", "hcp_groupnorm_bwd_bf16",
     "hcp_layernorm_fwd_bf16", "hcp_layernorm_bwd_bf16", "hcp_geglu_fwd_bf16", "hcp_geglu_bwd_bf16",
@@ -133,6 +142,8 @@ def lib() -> C.CDLL:
             l.hcp_last_error_string.restype = C.c_char_p
             l.hcp_attn_bwd_workspace_bytes.restype = C.c_size_t
             l.hcp_attn_bwd_workspace_bytes.argtypes = [C.c_int64] * 4
+            l.hcp_splitk_workspace_bytes.restype = C.c_size_t
+            l.hcp_splitk_workspace_bytes.argtypes = [C.c_int64] * 3
             l.hcp_groupnorm_workspace_bytes.restype = C.c_size_t
             l.hcp_groupnorm_workspace_bytes.argtypes = [C.c_int64] * 3
             vp, i64, f32, i32 = C.c_void_p, C.c_int64, C.c_float, C.c_int
@@ -155,7 +166,7 @@ def lib() -> C.CDLL:
             l.hcp_skinny_linear.argtypes = [vp, vp, vp, i64, i64, i64, i32, i32, vp, vp]
             l.hcp_cast_f32_to_bf16.argtypes = [vp, i64, vp, vp]
             l.hcp_lora_pack.argtypes = [vp, i64, vp]
-            l.hcp_lora_grad.argtypes = [vp, vp, i64, i64, i64, i64, i64, i64, f32, i32, vp, vp]
+            l.hcp_lora_grad.argtypes = [vp, vp, i64, i64, i64, i64, C.POINTER(LoraGradBlock), C.c_int32, vp]
             l.hcp_add_noise.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp]
             l.hcp_mse_loss.argtypes = [vp, vp, i64, f32, vp, vp, vp]
             l.hcp_sumsq.argtypes = [vp, i64, vp, vp]

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
                     tc_fence_after();
                     issue_pv(t, j);
                     if (t == p.nq - 1) umma_commit(&kv_done[st]);      // K_j / V_j no longer needed once these retire
-                    if (j + 1 < nkv) {
+                    if (S > 1 && j + 1 < nkv) {                         // next tile is already resident: keep the pipe busy
                         if (t == 0) {
                             mbar_wait(&kv_full[(j + 1) % S], ((j + 1) / S) & 1);
                             tc_fence_after();
@@ -375,6 +375,11 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
                 if (j + S < nkv) {                                      // refill the stage tile j used
                     mbar_wait(&kv_done[st], (j / S) & 1);
                     load_kv(j + S);
+                }
+                if (S == 1 && j + 1 < nkv) {                            // single stage (d > 128): load, then issue
+                    mbar_wait(&kv_full[0], (j + 1) & 1);
+                    tc_fence_after();
+                    for (int t = 0; t < p.nq; ++t) issue_s(t, j + 1);
                 }
             }
             umma_commit(o_full);

@@ -61,6 +61,9 @@ struct alignas(64) GemmKParams {
     int64_t ldr;
     __nv_bfloat16* out;
     int64_t ldo;
+    // split-K: CTA (x, y) reduces the k-blocks [y*kb_per_split, (y+1)*kb_per_split) and stores raw fp32 partials
+    int32_t splits, kb_per_split;
+    float* ws;                         // [splits, M, N] fp32
 };
 
 template <int BN>
@@ -89,6 +92,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const int n_tile = blockIdx.x % p.tiles_n;
     const int m_tile = blockIdx.x / p.tiles_n;
     const int n0 = n_tile * BN;
+    const int kb_lo = blockIdx.y * p.kb_per_split;
+    const int kb_hi = kb_lo + p.kb_per_split;
 
     // tile origin
     int m0 = m_tile * BLOCK_M;
@@ -131,10 +136,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            int it = 0;
             for (int s = 0; s < p.nseg; ++s) {
                 const int ntap = (p.conv && s == 0) ? p.ntaps : 1;
                 for (int t = 0; t < ntap; ++t) {
-                    for (int kb = 0; kb < p.nkb[s]; ++kb) {
+                    for (int kb = 0; kb < p.nkb[s]; ++kb, ++it) {
+                        if (it < kb_lo || it >= kb_hi) continue;
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
                         void* dA = sA + stage * A_STAGE_BYTES;
@@ -164,10 +171,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             uint32_t accum = 0;
+            int it = 0;
             for (int s = 0; s < p.nseg; ++s) {
                 const int ntap = (p.conv && s == 0) ? p.ntaps : 1;
                 for (int t = 0; t < ntap; ++t) {
-                    for (int kb = 0; kb < p.nkb[s]; ++kb) {
+                    for (int kb = 0; kb < p.nkb[s]; ++kb, ++it) {
+                        if (it < kb_lo || it >= kb_hi) continue;
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
                         const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * A_STAGE_BYTES), 16, 1024);
@@ -223,6 +232,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                         float f[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+                        if (p.splits > 1) {      // raw partial; bias / residual are applied by splitk_finalize_kernel
+                            float* dst = p.ws + ((int64_t)blockIdx.y * p.M + grow) * p.N + col;
+                            *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+                            *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                            continue;
+                        }
                         if (p.bias) {
                             const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
                             const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
@@ -261,6 +276,167 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+
+// out = sum_s ws[s] + bias + rowbias + residual  (bf16), 8 columns per thread
+__global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits, int64_t M, int N, const float* __restrict__ bias,
+                                       const float* __restrict__ rowbias, int rows_per_group, int64_t rowbias_ld,
+                                       const __nv_bfloat16* __restrict__ residual, int64_t ldr, __nv_bfloat16* __restrict__ out, int64_t ldo) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int nv = N / 8;
+    if (i >= M * nv) return;
+    const int64_t row = i / nv;
+    const int col = (int)(i % nv) * 8;
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < splits; ++s) {
+        const float* src = ws + ((int64_t)s * M + row) * N + col;
+        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+        f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+    }
+    if (bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += bias[col + j];
+    }
+    if (rowbias) {
+        const float* rb = rowbias + (rows_per_group > 0 ? row / rows_per_group : 0) * rowbias_ld + col;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += rb[j];
+    }
+    if (residual) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(residual + row * ldr + col);
+        float2 t;
+        t = unpack_bf16x2(rv.x); f[0] += t.x; f[1] += t.y;
+        t = unpack_bf16x2(rv.y); f[2] += t.x; f[3] += t.y;
+        t = unpack_bf16x2(rv.z); f[4] += t.x; f[5] += t.y;
+        t = unpack_bf16x2(rv.w); f[6] += t.x; f[7] += t.y;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + row * ldo + col) = o;
+}
+
+// number of K-splits for a launch with `ctas` output tiles and `total_kb` 64-wide k-blocks (1 = no split)
+static int plan_splits(int64_t ctas, int64_t total_kb) {
+    if (ctas >= 96 || total_kb < 8) return 1;
+    int64_t s = (148 + ctas - 1) / ctas;
+    if (s > total_kb / 4) s = total_kb / 4;
+    if (s > 16) s = 16;
+    return s < 2 ? 1 : (int)s;
+}
+
+// =============================================================================================
+// LoRA gradients on the tensor pipe:  D[n, j] = sum_m X[m, n] * S[m, j]   (reduction over the M token rows)
+//   dW_down[j, k] = sum_m U[m, c0+j] x[m, k]          S = U = dY . (alpha B),  X = x
+//   dW_up[o, j]   = alpha * sum_m dY[m, o0+o] T[m, c0+j]   S = T = x . A^T,        X = dY
+// Both operands are read straight from their row-major [M, *] tensors as MN-major UMMA operands (TMA boxes of 64 columns x
+// 128 rows), so no transpose ever exists.  One CTA owns 128 columns of X and a slice of the rows (split-K); the 128 x 64
+// fp32 accumulator is reduced into the flat gradient buffer with red.global.
+// =============================================================================================
+constexpr int LG_STAGES = 3;
+constexpr int LG_STAGE_BYTES = 3 * 128 * 128;      // two X boxes + one S box
+constexpr int LG_SMEM_BYTES = LG_STAGES * LG_STAGE_BYTES + 256 + 1024;
+constexpr int LG_MAX_BLOCKS = 8;
+
+struct LGBlock {
+    int32_t n_lo, n_hi, c0, rank, transpose_out, dst_ld;
+    float scale;
+    float* dst;
+};
+struct alignas(64) LoraGradParams {
+    CUtensorMap tmX, tmS;
+    int32_t M, n_begin, n_end, tiles_per_cta, nblocks;
+    LGBlock blk[LG_MAX_BLOCKS];
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1) lora_grad_tc_kernel(const __grid_constant__ LoraGradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + LG_STAGES * LG_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + LG_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + LG_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncol0 = p.n_begin + blockIdx.x * 128;
+    const int total_tiles = (p.M + 127) / 128;
+    const int t0 = blockIdx.y * p.tiles_per_cta;
+    const int t1 = min(total_tiles, t0 + p.tiles_per_cta);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 64); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full_bar[stage], LG_STAGE_BYTES);
+                uint8_t* base = smem + stage * LG_STAGE_BYTES;
+                tma_load_2d(base, &p.tmX, &full_bar[stage], ncol0, t * 128);
+                tma_load_2d(base + 128 * 128, &p.tmX, &full_bar[stage], ncol0 + 64, t * 128);
+                tma_load_2d(base + 2 * 128 * 128, &p.tmS, &full_bar[stage], 0, t * 128);
+                if (++stage == LG_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);     // A (X^T) and B (S^T) both MN-major
+            int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t xb = smem_u32(smem + stage * LG_STAGE_BYTES);
+                const uint32_t sb = xb + 2 * 128 * 128;
+                for (int ks = 0; ks < 8; ++ks) {                         // 16 token rows per k-step = 2048 B
+                    umma_ss(tmem_base, make_smem_desc(xb + ks * 2048, 128 * 128, 1024), make_smem_desc(sb + ks * 2048, 128 * 128, 1024),
+                            idesc, accum);
+                    accum = 1;
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == LG_STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int n = ncol0 + quarter * 32 + lane;                       // this thread's column of X
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[16];
+            tmem_ld16(trow + c * 16, v);
+            tmem_wait_ld();
+            if (t1 > t0 && n < p.n_end) {
+                for (int b = 0; b < p.nblocks; ++b) {
+                    const LGBlock& k = p.blk[b];
+                    if (n < k.n_lo || n >= k.n_hi) continue;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int j = c * 16 + e - k.c0;
+                        if (j >= 0 && j < k.rank) {
+                            const float val = __uint_as_float(v[e]) * k.scale;
+                            float* dst = k.transpose_out ? k.dst + (int64_t)(n - k.n_lo) * k.dst_ld + j
+                                                         : k.dst + (int64_t)j * k.dst_ld + (n - k.n_lo);
+                            atomicAdd(dst, val);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -274,7 +450,7 @@ static int launch_gemm(const GemmKParams& kp, int m_tiles, cudaStream_t stream) 
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
         configured = true;
     }
-    dim3 grid(kp.tiles_n * m_tiles);
+    dim3 grid(kp.tiles_n * m_tiles, kp.splits);
     gemm_tc_kernel<BN><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(kp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "gemm launch");
@@ -300,9 +476,44 @@ static int dispatch_gemm(int bn, const GemmKParams& kp, int m_tiles, cudaStream_
     }
 }
 
+// plain or split-K launch (+ finalize).  `ws` may be NULL / too small: then the launch is not split.
+static int run_gemm(int bn, GemmKParams& kp, int m_tiles, int64_t total_kb, float* ws, size_t ws_bytes, bool allow_split,
+                    cudaStream_t stream) {
+    int splits = allow_split ? plan_splits((int64_t)m_tiles * kp.tiles_n, total_kb) : 1;
+    if (splits > 1 && (!ws || ws_bytes < (size_t)splits * kp.M * kp.N * sizeof(float))) splits = 1;
+    if (splits > 1) {
+        kp.kb_per_split = (int)((total_kb + splits - 1) / splits);
+        splits = (int)((total_kb + kp.kb_per_split - 1) / kp.kb_per_split);
+    }
+    if (splits <= 1) {
+        kp.splits = 1;
+        kp.kb_per_split = 1 << 30;
+        kp.ws = nullptr;
+        return dispatch_gemm(bn, kp, m_tiles, stream);
+    }
+    kp.splits = splits;
+    kp.ws = ws;
+    int rc = dispatch_gemm(bn, kp, m_tiles, stream);
+    if (rc) return rc;
+    const int64_t n = (int64_t)kp.M * (kp.N / 8);
+    splitk_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ws, splits, kp.M, kp.N, kp.bias, kp.rowbias,
+                                                                            kp.conv ? kp.oH * kp.oW : kp.rows_per_group, kp.rowbias_ld,
+                                                                            kp.residual, kp.ldr, kp.out, kp.ldo);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "splitk finalize launch");
+    return HCP_OK;
+}
+
 }  // namespace hcp
 
 using namespace hcp;
+
+extern "C" size_t hcp_splitk_workspace_bytes(int64_t M, int64_t N, int64_t total_k) {
+    const int bn = pick_bn(N);
+    const int64_t ctas = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
+    const int splits = plan_splits(ctas, (total_k + BLOCK_K - 1) / BLOCK_K);
+    return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
+}
 
 extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     if (!a || a->nseg < 1 || a->nseg > HCP_GEMM_MAX_SEG) return set_error(HCP_ERR_INVALID, "gemm: nseg");
@@ -338,7 +549,9 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     kp.out = (__nv_bfloat16*)a->out;
     kp.ldo = a->ldo;
     const int m_tiles = (int)((a->M + BLOCK_M - 1) / BLOCK_M);
-    return dispatch_gemm(bn, kp, m_tiles, (cudaStream_t)stream_);
+    int64_t total_kb = 0;
+    for (int s = 0; s < a->nseg; ++s) total_kb += kp.nkb[s];
+    return run_gemm(bn, kp, m_tiles, total_kb, a->workspace, a->workspace_bytes, true, (cudaStream_t)stream_);
 }
 
 extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_) {
@@ -410,7 +623,7 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
                 t.wk_off = (int)((kh * 3 + kw) * Cin);
             }
         kp.sh = kp.sw = 1; kp.oh0 = kp.ow0 = 0;
-        return dispatch_gemm(bn, kp, m_tiles, stream);
+        return run_gemm(bn, kp, m_tiles, (int64_t)9 * kp.nkb[0], a->workspace, a->workspace_bytes, true, stream);
     }
     if (a->mode == 0 && a->stride == 2) {
         // view x as [B][Hin/2][2][Win/2][2*Cin]: input row ih = 2*oh + kh - 1 -> (phase, index)
@@ -433,7 +646,7 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
                 t.wk_off = (int)((kh * 3 + kw) * Cin);
             }
         kp.sh = kp.sw = 1; kp.oh0 = kp.ow0 = 0;
-        return dispatch_gemm(bn, kp, m_tiles, stream);
+        return run_gemm(bn, kp, m_tiles, (int64_t)9 * kp.nkb[0], a->workspace, a->workspace_bytes, true, stream);
     }
     // mode 1: dgrad of the stride-2 conv.  x = dY [B, Hin, Win, Cin] (Cin = Cout of the fwd conv),
     // out = dX [B, 2Hin, 2Win, Cout].  Output pixel (2i+ph, 2j+pw) gathers dY[i+dh, j+dw] over the taps whose
@@ -464,8 +677,47 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
             }
             kp.ntaps = nt;
             kp.oh0 = ph; kp.ow0 = pw;
-            rc = dispatch_gemm(bn, kp, m_tiles, stream);
+            rc = run_gemm(bn, kp, m_tiles, 0, nullptr, 0, false, stream);
             if (rc) return rc;
         }
+    return HCP_OK;
+}
+
+extern "C" int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t M, int64_t n_begin, int64_t n_end,
+                             const hcp_lora_grad_block* blocks, int32_t nblocks, hcp_stream_t stream_) {
+    if (!S || !X || !blocks || nblocks < 1) return set_error(HCP_ERR_INVALID, "lora_grad: null pointer");
+    if (M <= 0 || n_end <= n_begin || (ldx % 8) != 0 || (n_begin % 8) != 0) return set_error(HCP_ERR_INVALID, "lora_grad: shape");
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(lora_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_SMEM_BYTES);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(lora_grad)");
+        configured = true;
+    }
+    const int col_chunks = (int)((n_end - n_begin + 127) / 128);
+    const int total_tiles = (int)((M + 127) / 128);
+    int splits = (296 + col_chunks - 1) / col_chunks;
+    if (splits > total_tiles) splits = total_tiles;
+    const int tiles_per_cta = (total_tiles + splits - 1) / splits;
+    splits = (total_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    for (int b0 = 0; b0 < nblocks; b0 += LG_MAX_BLOCKS) {
+        LoraGradParams p;
+        memset(&p, 0, sizeof(p));
+        int rc = make_tmap_2d(&p.tmX, X, (uint64_t)ldx, (uint64_t)M, (uint64_t)ldx, 64, 128);
+        if (rc) return rc;
+        rc = make_tmap_2d(&p.tmS, S, 64, (uint64_t)M, 64, 64, 128);
+        if (rc) return rc;
+        p.M = (int)M; p.n_begin = (int)n_begin; p.n_end = (int)n_end; p.tiles_per_cta = tiles_per_cta;
+        p.nblocks = (nblocks - b0 < LG_MAX_BLOCKS) ? (nblocks - b0) : LG_MAX_BLOCKS;
+        for (int i = 0; i < p.nblocks; ++i) {
+            const hcp_lora_grad_block& k = blocks[b0 + i];
+            if (k.rank < 1 || k.c0 < 0 || k.c0 + k.rank > 64 || !k.dst) return set_error(HCP_ERR_INVALID, "lora_grad: block descriptor");
+            p.blk[i].n_lo = (int)k.n_lo; p.blk[i].n_hi = (int)k.n_hi; p.blk[i].c0 = k.c0; p.blk[i].rank = k.rank;
+            p.blk[i].transpose_out = k.transpose_out; p.blk[i].dst_ld = (int)k.dst_ld; p.blk[i].scale = k.scale; p.blk[i].dst = k.dst;
+        }
+        dim3 grid(col_chunks, splits);
+        lora_grad_tc_kernel<<<grid, kGemmThreads, LG_SMEM_BYTES, (cudaStream_t)stream_>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return set_cuda_error(e, "lora_grad launch");
+    }
     return HCP_OK;
 }

@@ -211,57 +211,6 @@ __global__ void lora_pack_kernel(const hcp_lora_job* __restrict__ jobs, int njob
 }
 
 // ---------------------------------------------------------------------------------------------
-// LoRA gradients.  out[j, n] += scale * sum_m S[m, c0 + j] * X[m, n]   for j < r, n < N
-//   dW_down[j, k]  : S = U (= dY . Bl) [M,64],  X = x  [M,in]    -> dst[j*N + n]        (transpose_out = 0)
-//   dW_up[o, j]    : S = T (= x . A^T) [M,64],  X = dY [M,out]   -> dst[n*r + j] * alpha (transpose_out = 1)
-// CTA: 256 rows x 64 columns of X; thread (col, row-quarter) accumulates r partial sums, quarters are combined in
-// shared memory, one fp32 atomicAdd per output element and CTA.
-// ---------------------------------------------------------------------------------------------
-constexpr int LG_ROWS = 256;
-constexpr int LG_MAX_R = 32;
-__global__ void __launch_bounds__(256) lora_grad_kernel(const __nv_bfloat16* __restrict__ S, const __nv_bfloat16* __restrict__ X,
-                                                        int64_t ldx, int M, int N, int n_off, int c0, int r, float scale,
-                                                        int transpose_out, float* __restrict__ dst) {
-    __shared__ float sbuf[LG_ROWS * (LG_MAX_R + 1)];            // S tile, later reused for the cross-quarter reduction
-    float (*sS)[LG_MAX_R + 1] = reinterpret_cast<float (*)[LG_MAX_R + 1]>(sbuf);
-    float (*sred)[64][LG_MAX_R + 1] = reinterpret_cast<float (*)[64][LG_MAX_R + 1]>(sbuf);
-    const int m0 = blockIdx.y * LG_ROWS;
-    const int n0 = blockIdx.x * 64;
-    for (int i = threadIdx.x; i < LG_ROWS * r; i += 256) {
-        const int rr = i / r, j = i % r;
-        sS[rr][j] = (m0 + rr < M) ? __bfloat162float(S[(int64_t)(m0 + rr) * 64 + c0 + j]) : 0.f;
-    }
-    __syncthreads();
-    const int col = threadIdx.x & 63, q = threadIdx.x >> 6;
-    const int n = n0 + col;
-    float acc[LG_MAX_R];
-#pragma unroll
-    for (int j = 0; j < LG_MAX_R; ++j) acc[j] = 0.f;
-    if (n < N) {
-        for (int rr = q * 64; rr < q * 64 + 64; ++rr) {
-            if (m0 + rr >= M) break;
-            const float xv = __bfloat162float(X[(int64_t)(m0 + rr) * ldx + n_off + n]);
-#pragma unroll
-            for (int j = 0; j < LG_MAX_R; ++j)
-                if (j < r) acc[j] += sS[rr][j] * xv;
-        }
-    }
-    __syncthreads();   // everyone is done reading sS
-#pragma unroll
-    for (int j = 0; j < LG_MAX_R; ++j)
-        if (j < r) sred[q][col][j] = acc[j];
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * r; i += 256) {
-        const int cc = i % 64, j = i / 64;
-        if (n0 + cc < N) {
-            const float v = (sred[0][cc][j] + sred[1][cc][j] + sred[2][cc][j] + sred[3][cc][j]) * scale;
-            if (transpose_out) atomicAdd(dst + (int64_t)(n0 + cc) * r + j, v);
-            else atomicAdd(dst + (int64_t)j * N + n0 + cc, v);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // loss = mean((pred - target)^2) (fp32, reference train_ac.py:506-515 with loss.type == 'eps'), dpred = 2(pred-target)/n
 // ---------------------------------------------------------------------------------------------
 __global__ void mse_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n, float grad_scale,
@@ -410,17 +359,6 @@ extern "C" int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp
     dim3 grid(16, (unsigned)njobs);
     lora_pack_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(jobs_device, (int)njobs);
     LAUNCH_CHECK("lora_pack launch");
-    return HCP_OK;
-}
-
-extern "C" int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t M, int64_t N, int64_t n_off, int64_t c0, int64_t r,
-                             float scale, int transpose_out, float* dst, hcp_stream_t st) {
-    if (!S || !X || !dst) return set_error(HCP_ERR_INVALID, "lora_grad: null pointer");
-    if (r < 1 || r > LG_MAX_R || c0 + r > 64) return set_error(HCP_ERR_INVALID, "lora_grad: rank must be in [1,32] and fit the 64-wide T/U buffer");
-    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + LG_ROWS - 1) / LG_ROWS));
-    lora_grad_kernel<<<grid, 256, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)S, (const __nv_bfloat16*)X, ldx, (int)M, (int)N, (int)n_off,
-                                                        (int)c0, (int)r, scale, transpose_out, dst);
-    LAUNCH_CHECK("lora_grad launch");
     return HCP_OK;
 }
 

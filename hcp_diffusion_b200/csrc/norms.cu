@@ -29,13 +29,18 @@ __device__ __forceinline__ float gelu_grad(float x) {
 // Pass A: per-(image, pixel-chunk) partial sums per group.  Pass B: finalise the statistics of the image
 // (every CTA re-reduces the few partials), then normalise / back-propagate its own pixel chunk.
 // =============================================================================================
-constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_THREADS = 1024;
 constexpr int GN_MAX_G = 32;
+constexpr int GN_MAX_PT = 4;          // channel pairs per thread (C <= 8192)
 
+// Thread mapping: a CTA owns `rows_per_cta` pixels of one image.  Its threads form a [R row-lanes] x [TP channel-pair
+// columns] grid (TP = C/2/PT, R = blockDim/TP): lane (r, tp) walks rows r, r+R, ... and always touches the same PT channel
+// pairs, so gamma/beta/group statistics stay in registers and one warp reads 128 contiguous bytes of a pixel row.
 struct GNParams {
     const __nv_bfloat16* x1; const __nv_bfloat16* x2;
     int C1, C2, C, G, cg;
     int B, HW, rows_per_cta, nchunks;
+    int TP, R, PT;
     const float* gamma; const float* beta;
     float eps; int silu;
     float* partial;            // [B, nchunks, G, 2]
@@ -53,68 +58,81 @@ __device__ __forceinline__ float2 gn_load2(const GNParams& p, int64_t pix, int c
     return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src));
 }
 
-constexpr int GN_MAX_PAIRS = 2048;   // C <= 4096
-
 template <bool BWD>
-__global__ void __launch_bounds__(GN_THREADS) gn_partial_kernel(const GNParams p) {
-    // per-channel-pair partial sums, then ONE thread per group adds them in a fixed order: the result is deterministic
+__global__ void __launch_bounds__(GN_MAX_THREADS) gn_partial_kernel(const GNParams p) {
+    // per-(row-lane, channel-pair) partial sums, then ONE thread per group adds them in a fixed order: deterministic
     // (no floating-point atomics), which the batch-invariance property test relies on.
-    __shared__ float s_pair[GN_MAX_PAIRS][2];
+    extern __shared__ float s_pair[];     // [R][C/2][2]
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int r0 = chunk * p.rows_per_cta;
     const int r1 = min(p.HW, r0 + p.rows_per_cta);
     const int npair = p.C / 2;
+    const int tp = threadIdx.x % p.TP, rl = threadIdx.x / p.TP;
     const float* st = BWD ? p.stats + (int64_t)b * p.G * 2 : nullptr;
-    for (int cp = threadIdx.x; cp < npair; cp += GN_THREADS) {
-        const int c = cp * 2;
-        const int g = c / p.cg;           // cg is even for every UNet layer, so a pair never straddles two groups
-        float a0 = 0.f, a1 = 0.f;
-        float gm0 = 0.f, gm1 = 0.f, bt0 = 0.f, bt1 = 0.f, mean = 0.f, rstd = 0.f;
-        if (BWD) {
-            gm0 = p.gamma[c]; gm1 = p.gamma[c + 1]; bt0 = p.beta[c]; bt1 = p.beta[c + 1];
-            mean = st[g * 2]; rstd = st[g * 2 + 1];
+    float a0[GN_MAX_PT], a1[GN_MAX_PT];
+    float gm0[GN_MAX_PT], gm1[GN_MAX_PT], bt0[GN_MAX_PT], bt1[GN_MAX_PT], mean[GN_MAX_PT], rstd[GN_MAX_PT];
+#pragma unroll
+    for (int k = 0; k < GN_MAX_PT; ++k) {
+        a0[k] = a1[k] = 0.f;
+        if (BWD && k < p.PT) {
+            const int c = (tp + k * p.TP) * 2;
+            const int g = c / p.cg;
+            gm0[k] = p.gamma[c]; gm1[k] = p.gamma[c + 1]; bt0[k] = p.beta[c]; bt1[k] = p.beta[c + 1];
+            mean[k] = st[g * 2]; rstd[k] = st[g * 2 + 1];
         }
-        for (int r = r0; r < r1; ++r) {
-            const int64_t pix = (int64_t)b * p.HW + r;
-            const float2 v = gn_load2(p, pix, c);
-            if (!BWD) {
-                a0 += v.x + v.y;
-                a1 += v.x * v.x + v.y * v.y;
-            } else {
-                const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.dy + pix * p.C + c));
-                const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd;
-                float g0 = d.x * gm0, g1 = d.y * gm1;
-                if (p.silu) {
-                    g0 *= silu_grad(xh0 * gm0 + bt0);
-                    g1 *= silu_grad(xh1 * gm1 + bt1);
+    }
+    for (int r = r0 + rl; r < r1; r += p.R) {
+        const int64_t pix = (int64_t)b * p.HW + r;
+#pragma unroll
+        for (int k = 0; k < GN_MAX_PT; ++k) {
+            if (k < p.PT) {
+                const int c = (tp + k * p.TP) * 2;
+                const float2 v = gn_load2(p, pix, c);
+                if (!BWD) {
+                    a0[k] += v.x + v.y;
+                    a1[k] += v.x * v.x + v.y * v.y;
+                } else {
+                    const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.dy + pix * p.C + c));
+                    const float xh0 = (v.x - mean[k]) * rstd[k], xh1 = (v.y - mean[k]) * rstd[k];
+                    float g0 = d.x * gm0[k], g1 = d.y * gm1[k];
+                    if (p.silu) {
+                        g0 *= silu_grad(xh0 * gm0[k] + bt0[k]);
+                        g1 *= silu_grad(xh1 * gm1[k] + bt1[k]);
+                    }
+                    a0[k] += g0 + g1;
+                    a1[k] += g0 * xh0 + g1 * xh1;
                 }
-                a0 += g0 + g1;
-                a1 += g0 * xh0 + g1 * xh1;
             }
         }
-        s_pair[cp][0] = a0;
-        s_pair[cp][1] = a1;
     }
+#pragma unroll
+    for (int k = 0; k < GN_MAX_PT; ++k)
+        if (k < p.PT) {
+            const int cp = tp + k * p.TP;
+            s_pair[(rl * npair + cp) * 2] = a0[k];
+            s_pair[(rl * npair + cp) * 2 + 1] = a1[k];
+        }
     __syncthreads();
     float* out = p.partial + ((int64_t)b * p.nchunks + chunk) * p.G * 2;
     const int ppg = p.cg / 2;             // pairs per group
-    for (int i = threadIdx.x; i < p.G * 2; i += GN_THREADS) {
+    for (int i = threadIdx.x; i < p.G * 2; i += blockDim.x) {
         const int g = i >> 1, which = i & 1;
         float acc = 0.f;
-        for (int k = 0; k < ppg; ++k) acc += s_pair[g * ppg + k][which];
+        for (int r = 0; r < p.R; ++r)
+            for (int k = 0; k < ppg; ++k) acc += s_pair[(r * npair + g * ppg + k) * 2 + which];
         out[i] = acc;
     }
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GNParams p) {
+__global__ void __launch_bounds__(GN_MAX_THREADS) gn_apply_kernel(const GNParams p) {
     __shared__ float s_a[GN_MAX_G], s_b[GN_MAX_G];
     const int b = blockIdx.y, chunk = blockIdx.x;
     const float n = (float)p.HW * (float)p.cg;
-    // finalise: warp w reduces group w, w+8, ... over the chunk partials with a shuffle reduction
+    // finalise: warp w reduces group w, w+nwarps, ... over the chunk partials with a shuffle reduction
     {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int g = warp; g < p.G; g += GN_THREADS / 32) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        for (int g = warp; g < p.G; g += nwarps) {
             float a0 = 0.f, a1 = 0.f;
             for (int ch = lane; ch < p.nchunks; ch += 32) {
                 const float* src = p.partial + (((int64_t)b * p.nchunks + ch) * p.G + g) * 2;
@@ -144,37 +162,40 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GNParams p) 
     __syncthreads();
     const int r0 = chunk * p.rows_per_cta;
     const int r1 = min(p.HW, r0 + p.rows_per_cta);
-    const int npair = p.C / 2;
+    const int tp = threadIdx.x % p.TP, rl = threadIdx.x / p.TP;
     const float* st = BWD ? p.stats + (int64_t)b * p.G * 2 : nullptr;
-    for (int cp = threadIdx.x; cp < npair; cp += GN_THREADS) {
-        const int c = cp * 2;
-        const int g = c / p.cg;
-        const float gm0 = p.gamma[c], gm1 = p.gamma[c + 1], bt0 = p.beta[c], bt1 = p.beta[c + 1];
-        if (!BWD) {
-            const float mean = s_a[g], rstd = s_b[g];
-            for (int r = r0; r < r1; ++r) {
-                const int64_t pix = (int64_t)b * p.HW + r;
-                const float2 v = gn_load2(p, pix, c);
-                float z0 = (v.x - mean) * rstd * gm0 + bt0;
-                float z1 = (v.y - mean) * rstd * gm1 + bt1;
+    float gm0[GN_MAX_PT], gm1[GN_MAX_PT], bt0[GN_MAX_PT], bt1[GN_MAX_PT], sa[GN_MAX_PT], sb[GN_MAX_PT], mean[GN_MAX_PT], rstd[GN_MAX_PT];
+#pragma unroll
+    for (int k = 0; k < GN_MAX_PT; ++k)
+        if (k < p.PT) {
+            const int c = (tp + k * p.TP) * 2;
+            const int g = c / p.cg;
+            gm0[k] = p.gamma[c]; gm1[k] = p.gamma[c + 1]; bt0[k] = p.beta[c]; bt1[k] = p.beta[c + 1];
+            sa[k] = s_a[g]; sb[k] = s_b[g];
+            if (BWD) { mean[k] = st[g * 2]; rstd[k] = st[g * 2 + 1]; }
+        }
+    for (int r = r0 + rl; r < r1; r += p.R) {
+        const int64_t pix = (int64_t)b * p.HW + r;
+#pragma unroll
+        for (int k = 0; k < GN_MAX_PT; ++k) {
+            if (k >= p.PT) continue;
+            const int c = (tp + k * p.TP) * 2;
+            const float2 v = gn_load2(p, pix, c);
+            if (!BWD) {
+                float z0 = (v.x - sa[k]) * sb[k] * gm0[k] + bt0[k];
+                float z1 = (v.y - sa[k]) * sb[k] * gm1[k] + bt1[k];
                 if (p.silu) { z0 = silu_f(z0); z1 = silu_f(z1); }
                 *reinterpret_cast<__nv_bfloat162*>(p.y + pix * p.C + c) = __floats2bfloat162_rn(z0, z1);
-            }
-        } else {
-            const float mean = st[g * 2], rstd = st[g * 2 + 1];
-            const float m1 = s_a[g], m2 = s_b[g];
-            for (int r = r0; r < r1; ++r) {
-                const int64_t pix = (int64_t)b * p.HW + r;
-                const float2 v = gn_load2(p, pix, c);
+            } else {
                 const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.dy + pix * p.C + c));
-                const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd;
-                float g0 = d.x * gm0, g1 = d.y * gm1;
+                const float xh0 = (v.x - mean[k]) * rstd[k], xh1 = (v.y - mean[k]) * rstd[k];
+                float g0 = d.x * gm0[k], g1 = d.y * gm1[k];
                 if (p.silu) {
-                    g0 *= silu_grad(xh0 * gm0 + bt0);
-                    g1 *= silu_grad(xh1 * gm1 + bt1);
+                    g0 *= silu_grad(xh0 * gm0[k] + bt0[k]);
+                    g1 *= silu_grad(xh1 * gm1[k] + bt1[k]);
                 }
-                float o0 = rstd * (g0 - m1 - xh0 * m2);
-                float o1 = rstd * (g1 - m1 - xh1 * m2);
+                float o0 = rstd[k] * (g0 - sa[k] - xh0 * sb[k]);
+                float o1 = rstd[k] * (g1 - sa[k] - xh1 * sb[k]);
                 __nv_bfloat16* dst;
                 const __nv_bfloat16* add;
                 if (c < p.C1) {
@@ -200,7 +221,10 @@ static int gn_geometry(const hcp_groupnorm_args* a, GNParams& p) {
     if (a->G <= 0 || a->G > GN_MAX_G || C % a->G != 0) return set_error(HCP_ERR_INVALID, "groupnorm: groups");
     const int64_t cg = C / a->G;
     if ((cg & 1) || (a->C1 & 1) || (a->C2 & 1)) return set_error(HCP_ERR_INVALID, "groupnorm: channels per group must be even");
-    if (C / 2 > GN_MAX_PAIRS) return set_error(HCP_ERR_INVALID, "groupnorm: more than 4096 channels");
+    const int npair = (int)(C / 2);
+    int PT = (npair + GN_MAX_THREADS - 1) / GN_MAX_THREADS;
+    while (PT <= GN_MAX_PT && npair % PT != 0) ++PT;
+    if (PT > GN_MAX_PT) return set_error(HCP_ERR_INVALID, "groupnorm: unsupported channel count");
     if (a->C2 > 0 && !a->x2) return set_error(HCP_ERR_INVALID, "groupnorm: x2");
     memset(&p, 0, sizeof(p));
     p.x1 = (const __nv_bfloat16*)a->x1; p.x2 = (const __nv_bfloat16*)a->x2;
@@ -213,6 +237,11 @@ static int gn_geometry(const hcp_groupnorm_args* a, GNParams& p) {
     if (rows > a->HW) rows = (int)a->HW;
     p.rows_per_cta = rows;
     p.nchunks = (int)((a->HW + rows - 1) / rows);
+    p.PT = PT;
+    p.TP = npair / PT;
+    p.R = GN_MAX_THREADS / p.TP;
+    if (p.R > rows) p.R = rows;
+    if (p.R < 1) p.R = 1;
     p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
     p.partial = a->workspace; p.stats = a->stats;
     if (a->workspace_bytes < (size_t)a->B * p.nchunks * p.G * 2 * sizeof(float)) return set_error(HCP_ERR_INVALID, "groupnorm: workspace too small");
@@ -461,8 +490,10 @@ extern "C" int hcp_groupnorm_fwd_bf16(const hcp_groupnorm_args* a, hcp_stream_t 
     if (!a->y) return set_error(HCP_ERR_INVALID, "groupnorm_fwd: y");
     p.y = (__nv_bfloat16*)a->y;
     dim3 grid(p.nchunks, p.B);
-    gn_partial_kernel<false><<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>(p);
-    gn_apply_kernel<false><<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>(p);
+    const int threads = p.TP * p.R;
+    const size_t smem = (size_t)p.R * (p.C / 2) * 2 * sizeof(float);
+    gn_partial_kernel<false><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
+    gn_apply_kernel<false><<<grid, threads, 0, (cudaStream_t)stream_>>>(p);
     LAUNCH_CHECK("groupnorm_fwd launch");
     return HCP_OK;
 }
@@ -476,8 +507,10 @@ extern "C" int hcp_groupnorm_bwd_bf16(const hcp_groupnorm_args* a, hcp_stream_t 
     p.add1 = (const __nv_bfloat16*)a->add1; p.add2 = (const __nv_bfloat16*)a->add2;
     p.dx1 = (__nv_bfloat16*)a->dx1; p.dx2 = (__nv_bfloat16*)a->dx2;
     dim3 grid(p.nchunks, p.B);
-    gn_partial_kernel<true><<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>(p);
-    gn_apply_kernel<true><<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>(p);
+    const int threads = p.TP * p.R;
+    const size_t smem = (size_t)p.R * (p.C / 2) * 2 * sizeof(float);
+    gn_partial_kernel<true><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
+    gn_apply_kernel<true><<<grid, threads, 0, (cudaStream_t)stream_>>>(p);
     LAUNCH_CHECK("groupnorm_bwd launch");
     return HCP_OK;
 }

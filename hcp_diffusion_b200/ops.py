@@ -53,6 +53,11 @@ def gemm_raw(a_list: Sequence[Tuple[torch.Tensor, int, int]], b_list: Sequence[T
     g.ldr = ldr
     g.out = out.data_ptr()
     g.ldo = ldo
+    wsb = _lib.lib().hcp_splitk_workspace_bytes(M, N, sum(k for _, _, k in a_list))
+    if wsb:
+        ws = torch.empty((wsb // 4,), dtype=torch.float32, device=out.device)
+        g.workspace, g.workspace_bytes = ws.data_ptr(), wsb
+        _lib.launch_count += 1
     call("hcp_gemm_bf16", C.byref(g), stream_ptr())
 
 
@@ -65,6 +70,13 @@ def conv3x3_raw(x: torch.Tensor, w: torch.Tensor, B: int, Hin: int, Win: int, Ci
     a.bias, a.rowbias, a.residual = ptr(bias), ptr(rowbias), ptr(residual)
     a.rowbias_ld = rowbias_ld
     a.out = out.data_ptr()
+    if mode == 0:
+        Mo = B * (Hin // stride) * (Win // stride)
+        wsb = _lib.lib().hcp_splitk_workspace_bytes(Mo, Cout, 9 * Cin)
+        if wsb:
+            ws = torch.empty((wsb // 4,), dtype=torch.float32, device=out.device)
+            a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
+            _lib.launch_count += 1
     call("hcp_conv3x3_bf16", C.byref(a), stream_ptr())
     if mode == 1:
         _lib.launch_count += 3
@@ -192,11 +204,19 @@ class FusedLinearFn(torch.autograd.Function):
             x, T = ctx.saved_tensors
             U = torch.empty((M, 64), dtype=BF16, device=dy.device)
             gemm_raw([(dy, N, N)], [(pack.BlT, N, pack.r_tot, 0)], M, 64, U, 64)
-            for b in pack.lora:
+            nb = len(pack.lora)
+            down = (_lib.LoraGradBlock * nb)()
+            up = (_lib.LoraGradBlock * nb)()
+            for i, b in enumerate(pack.lora):
                 gd = b.g_down if b.g_down is not None else _acc_grad(b.w_down)
                 gu = b.g_up if b.g_up is not None else _acc_grad(b.w_up)
-                call("hcp_lora_grad", U.data_ptr(), x.data_ptr(), ks[0], M, ks[0], 0, b.c0, b.rank, 1.0, 0, gd.data_ptr(), stream_ptr())
-                call("hcp_lora_grad", T.data_ptr(), dy.data_ptr(), N, M, b.out_dim, b.o0, b.c0, b.rank, b.alpha, 1, gu.data_ptr(), stream_ptr())
+                down[i].n_lo, down[i].n_hi, down[i].c0, down[i].rank = 0, ks[0], b.c0, b.rank
+                down[i].scale, down[i].transpose_out, down[i].dst, down[i].dst_ld = 1.0, 0, gd.data_ptr(), ks[0]
+                up[i].n_lo, up[i].n_hi, up[i].c0, up[i].rank = b.o0, b.o0 + b.out_dim, b.c0, b.rank
+                up[i].scale, up[i].transpose_out, up[i].dst, up[i].dst_ld = b.alpha, 1, gu.data_ptr(), b.rank
+            # dW_down = U^T x ;  dW_up = alpha * dY^T T   (tensor-core TN GEMMs, all blocks of the group per launch)
+            call("hcp_lora_grad", U.data_ptr(), x.data_ptr(), ks[0], M, 0, ks[0], down, nb, stream_ptr())
+            call("hcp_lora_grad", T.data_ptr(), dy.data_ptr(), N, M, 0, N, up, nb, stream_ptr())
         grads = []
         off = 0
         for i, k in enumerate(ks):

@@ -68,9 +68,14 @@ typedef struct hcp_gemm_args {
     void* out;                             /* bf16 [M,N] pitch ldo */
     int64_t ldo;
     int32_t flags;                         /* reserved, 0 */
+    float* workspace;                      /* optional split-K scratch (see hcp_splitk_workspace_bytes); NULL = never split */
+    size_t workspace_bytes;
 } hcp_gemm_args;
 
 int hcp_gemm_bf16(const hcp_gemm_args* args, hcp_stream_t stream);
+/* Bytes of fp32 scratch that let a GEMM / conv with this output and total reduction extent (sum of K over segments;
+ * 9*Cin for a 3x3 conv) split its reduction over several CTAs when the output alone cannot fill 148 SMs; 0 = no split. */
+size_t hcp_splitk_workspace_bytes(int64_t M, int64_t N, int64_t total_k);
 
 /* ------------------------------------------------------------------------------------------------
  * 3x3 convolution as implicit GEMM (tcgen05; the im2col gather is done by 4D/5D TMA boxes with
@@ -94,6 +99,8 @@ typedef struct hcp_conv3x3_args {
     int64_t rowbias_ld;  /* row pitch of rowbias in floats (0 -> Cout) */
     const void* residual;/* bf16 [B,Hout,Wout,Cout] or NULL */
     void* out;           /* bf16 [B,Hout,Wout,Cout] */
+    float* workspace;    /* optional split-K scratch, hcp_splitk_workspace_bytes(B*Hout*Wout, Cout, 9*Cin) */
+    size_t workspace_bytes;
 } hcp_conv3x3_args;
 
 int hcp_conv3x3_bf16(const hcp_conv3x3_args* args, hcp_stream_t stream);
@@ -224,10 +231,20 @@ typedef struct hcp_lora_job {
 } hcp_lora_job;
 
 int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp_stream_t stream);
-/* dst += scale * S[:, c0:c0+r]^T . X[:, n_off:n_off+N]   (S bf16 [M,64], X bf16 [M,ldx]);
- * transpose_out = 0: dst fp32 [r,N];  1: dst fp32 [N,r]. */
-int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t M, int64_t N, int64_t n_off, int64_t c0, int64_t r,
-                  float scale, int transpose_out, float* dst, hcp_stream_t stream);
+/* Gradients of the LoRA factors on the tensor pipe: for every block b and every column n in [n_lo_b, n_hi_b) of X,
+ *     D[n, j] = scale_b * sum_m X[m, n] * S[m, c0_b + j],   j < rank_b      (S bf16 [M,64], X bf16 [M,ldx])
+ * is ACCUMULATED (fp32 atomics) into  dst_b[j*dst_ld + (n-n_lo)]  (transpose_out = 0: dW_down[r,in], S = dY.(alpha B), X = x)
+ *                               or   dst_b[(n-n_lo)*dst_ld + j]  (transpose_out = 1: dW_up[out,r],  S = x.A^T, X = dY). */
+typedef struct hcp_lora_grad_block {
+    int64_t n_lo, n_hi;
+    int32_t c0, rank;
+    float scale;
+    int32_t transpose_out;
+    float* dst;
+    int64_t dst_ld;
+} hcp_lora_grad_block;
+int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t M, int64_t n_begin, int64_t n_end,
+                  const hcp_lora_grad_block* blocks, int32_t nblocks, hcp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * The step either side of the UNet call (reference hcpdiff/train_ac.py:437-447, 485-494, 506-515).
