@@ -404,24 +404,23 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
             tmem_ld32(tS + lb + c0, v0);
             tmem_ld32(tS + lb + c0 + 32, v1);
             tmem_wait_ld();
-            float sv[64];
+            float sc = p.scale_log2;
+            if (special) {                 // masked / biased tile: move to the scaled domain in place, then sc = 1
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                sv[e] = __uint_as_float(v0[e]) * p.scale_log2;
-                sv[32 + e] = __uint_as_float(v1[e]) * p.scale_log2;
-            }
-            if (special) {
-#pragma unroll
-                for (int e = 0; e < 64; ++e) {
-                    const int col = c0 + e;
-                    float s = sv[e];
-                    if (bias && col < ncols) s += bias[kv0 + col] * kLog2e;
-                    sv[e] = (col < ncols) ? s : -INFINITY;
+                for (int e = 0; e < 32; ++e) {
+                    float a = __uint_as_float(v0[e]) * p.scale_log2, c = __uint_as_float(v1[e]) * p.scale_log2;
+                    const int ca = c0 + e, cb = c0 + 32 + e;
+                    if (bias && ca < ncols) a += bias[kv0 + ca] * kLog2e;
+                    if (bias && cb < ncols) c += bias[kv0 + cb] * kLog2e;
+                    v0[e] = __float_as_uint(ca < ncols ? a : -INFINITY);
+                    v1[e] = __float_as_uint(cb < ncols ? c : -INFINITY);
                 }
+                sc = 1.f;
             }
-            float mx = sv[0];
+            float mx = fmaxf(__uint_as_float(v0[0]), __uint_as_float(v1[0]));
 #pragma unroll
-            for (int e = 1; e < 64; ++e) mx = fmaxf(mx, sv[e]);
+            for (int e = 1; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
+            mx *= sc;                      // the scale is positive: max commutes with it
             float* xch = sx + (((j & 1) * 2 + t) * 2) * 128;
             xch[half * 128 + row] = mx;
             named_bar_sync(1 + t, 256);
@@ -446,13 +445,21 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
                     m = m_new;
                 }
             }
+            const float negm = -m;
             uint32_t pk[32];
+            float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-            for (int e = 0; e < 64; e += 2) {
-                const float p0 = fast_exp2(sv[e] - m), p1 = fast_exp2(sv[e + 1] - m);
-                l += p0 + p1;
+            for (int e = 0; e < 32; e += 2) {
+                const float p0 = fast_exp2(fmaf(__uint_as_float(v0[e]), sc, negm));
+                const float p1 = fast_exp2(fmaf(__uint_as_float(v0[e + 1]), sc, negm));
+                const float p2 = fast_exp2(fmaf(__uint_as_float(v1[e]), sc, negm));
+                const float p3 = fast_exp2(fmaf(__uint_as_float(v1[e + 1]), sc, negm));
+                l0 += p0 + p1;
+                l1 += p2 + p3;
                 pk[e >> 1] = pack_bf16x2(p0, p1);
+                pk[16 + (e >> 1)] = pack_bf16x2(p2, p3);
             }
+            l += l0 + l1;
             tmem_st32(tS + lb + half * 32, pk);      // P (bf16) over the S columns every warp of this tile has already consumed
             tmem_wait_st();
             tc_fence_before();
@@ -641,12 +648,21 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
         const int row = quarter * 32 + lane;
         const uint32_t lb = lane_base(quarter);
         const float* bias = p.kv_bias ? p.kv_bias + (int64_t)b * p.Lkv : nullptr;
+        const bool special = (bias != nullptr) || (ncols < 128);
+        const int64_t stat_base = ((int64_t)b * p.H + h) * p.Lq;
+        float lse_nx = (row < p.Lq) ? p.lse[stat_base + row] : 0.f;          // software-prefetched one q tile ahead
+        float dlt_nx = (row < p.Lq) ? p.delta[stat_base + row] : 0.f;
         for (int i = 0; i < nq; ++i) {
             const int qrow = i * 128 + row;
             const bool qok = qrow < p.Lq;
-            const int64_t stat_idx = ((int64_t)b * p.H + h) * p.Lq + qrow;
-            const float lse2 = qok ? p.lse[stat_idx] * kLog2e : 0.f;
-            const float dlt = qok ? p.delta[stat_idx] : 0.f;
+            const int64_t stat_idx = stat_base + qrow;
+            const float neg_lse2 = -lse_nx * kLog2e;
+            const float neg_dlt_s = -dlt_nx * p.scale;
+            if (i + 1 < nq) {
+                const int qn = qrow + 128;
+                lse_nx = (qn < p.Lq) ? p.lse[stat_base + qn] : 0.f;
+                dlt_nx = (qn < p.Lq) ? p.delta[stat_base + qn] : 0.f;
+            }
             mbar_wait(sdp_full, i & 1);
             tc_fence_after();
             // ---- P = exp2(S*c - lse), dS = P * (dP - delta) * scale -> smem (K-major [q][kv], SWIZZLE_128B,
@@ -660,20 +676,32 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                     if (do_ds) tmem_ld32(tdP + lb + c * 32, w);
                     tmem_wait_ld();
                     uint32_t pk[16], dk[16];
+                    if (!special && qok) {
 #pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        float pe[2], de[2];
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            const int col = c * 32 + e + t;
-                            float s = __uint_as_float(v[e + t]) * p.scale_log2;
-                            if (bias && col < ncols) s += bias[kv0 + col] * kLog2e;
-                            const float pv = (qok && col < ncols) ? fast_exp2(s - lse2) : 0.f;
-                            pe[t] = pv;
-                            de[t] = do_ds ? pv * (__uint_as_float(w[e + t]) - dlt) * p.scale : 0.f;
+                        for (int e = 0; e < 32; e += 2) {
+                            const float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), p.scale_log2, neg_lse2));
+                            const float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, neg_lse2));
+                            pk[e >> 1] = pack_bf16x2(p0, p1);
+                            dk[e >> 1] = do_ds ? pack_bf16x2(p0 * fmaf(__uint_as_float(w[e]), p.scale, neg_dlt_s),
+                                                             p1 * fmaf(__uint_as_float(w[e + 1]), p.scale, neg_dlt_s))
+                                               : 0u;
                         }
-                        pk[e >> 1] = pack_bf16x2(pe[0], pe[1]);
-                        dk[e >> 1] = pack_bf16x2(de[0], de[1]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) {
+                            float pe[2], de[2];
+#pragma unroll
+                            for (int t = 0; t < 2; ++t) {
+                                const int col = c * 32 + e + t;
+                                float s2 = fmaf(__uint_as_float(v[e + t]), p.scale_log2, neg_lse2);
+                                if (bias && col < ncols) s2 += bias[kv0 + col] * kLog2e;
+                                const float pv = (qok && col < ncols) ? fast_exp2(s2) : 0.f;
+                                pe[t] = pv;
+                                de[t] = do_ds ? pv * fmaf(__uint_as_float(w[e + t]), p.scale, neg_dlt_s) : 0.f;
+                            }
+                            pk[e >> 1] = pack_bf16x2(pe[0], pe[1]);
+                            dk[e >> 1] = pack_bf16x2(de[0], de[1]);
+                        }
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {

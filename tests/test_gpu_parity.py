@@ -337,16 +337,20 @@ def test_sd15_lora_r8_forward_backward():
 
 
 def test_batch_invariance_and_zero_lora_identity():
-    """Size-independent properties at the benchmark shape: every image of a batch gets bit-identical results to running it
-    alone (no cross-image coupling in any kernel), and a LoRA whose W_up is zero is exactly the base model."""
+    """Size-independent properties at the benchmark shape.  (1) Repeating a call is bit-exact (the forward has no
+    floating-point atomics).  (2) An image gets the same result alone or inside a batch of 4 -- up to the summation order of
+    split-K, whose plan depends on the launch size: tolerance 2e-3 instead of bit equality.  (3) A LoRA whose W_up is zero (the
+    reference initialisation) is EXACTLY the base model, although it runs the extra low-rank K-segment."""
     sd = U.init_params(U.SD15)
     unet, group, _ = build_product_unet(U.SD15, sd, 0)
     lat, noise, t, ehs = U.synthetic_batch(4, U.SD15)
     x = lat.to(DEV)
     with torch.no_grad():
         full = unet(x, t.to(DEV), ehs.to(DEV)).sample
+        again = unet(x, t.to(DEV), ehs.to(DEV)).sample
+        assert torch.equal(full, again)
         one = unet(x[2:3], t[2:3].to(DEV), ehs[2:3].to(DEV)).sample
-        assert torch.equal(full[2:3], one)
+        assert rel_l2(one, full[2:3]) < 2e-3
         _, group = make_hcpdiff(unet, None, [{"rank": 8, "layers": [r"re:.*\.attn.?$"]}])     # reference init: W_up == 0
         with_lora = unet(x, t.to(DEV), ehs.to(DEV)).sample
         assert torch.equal(with_lora, full)
