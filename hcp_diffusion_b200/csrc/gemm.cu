@@ -43,7 +43,7 @@ struct alignas(64) GemmKParams {
     int32_t klast[HCP_GEMM_MAX_SEG];   // 16-wide k-steps issued in the last k-block of the segment (1..4)
     int32_t nseg;
     int32_t M, N;
-    int32_t tiles_n;
+    int32_t tiles_n, tiles_m;
     // convolution geometry (conv == 0: plain GEMM)
     int32_t conv;                      // 0 none, 4 = 4D A map, 5 = 5D A map
     int32_t ntaps;
@@ -68,12 +68,54 @@ struct alignas(64) GemmKParams {
 
 template <int BN>
 struct GemmCfg {
-    static constexpr int STAGES = (BN <= 64) ? 4 : 3;
+    static constexpr int STAGES = 4;
     static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
-    static constexpr int TMEM_COLS = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
-    static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 /*barriers*/ + 1024 /*align*/;
+    static constexpr int ACC_STRIDE = 256;                         // TMEM columns between the two accumulators
+    static constexpr int STG_PITCH = BN * 2 + 16;                  // staging row pitch in bytes: odd number of 16-byte units
+    static constexpr int STG_BYTES = BLOCK_M * STG_PITCH;
+    static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + STG_BYTES + 256 /*barriers*/ + 1024 /*align*/;
 };
 
+struct TileOrigin {
+    int m0, img0, h0, w0;
+};
+
+__device__ __forceinline__ TileOrigin tile_origin(const GemmKParams& p, int m_tile) {
+    TileOrigin o{m_tile * BLOCK_M, 0, 0, 0};
+    if (p.conv) {
+        if (p.bn == 1) {
+            const int per_img = p.tiles_w * p.tiles_h;
+            o.img0 = m_tile / per_img;
+            const int r = m_tile % per_img;
+            o.h0 = (r / p.tiles_w) * p.bh;
+            o.w0 = (r % p.tiles_w) * p.bw;
+        } else {
+            o.img0 = m_tile * p.bn;
+        }
+    }
+    return o;
+}
+// row r of the tile -> row of `out` (and the per-image bias group)
+__device__ __forceinline__ int64_t tile_row(const GemmKParams& p, const TileOrigin& o, int r, int& group) {
+    if (p.conv) {
+        const int per = p.bw * p.bh;
+        const int im = o.img0 + r / per;
+        const int rr = r % per;
+        const int hh = o.h0 + rr / p.bw;
+        const int ww = o.w0 + rr % p.bw;
+        group = im;
+        return (int64_t)im * p.oH * p.oW + (int64_t)(hh * p.sh + p.oh0) * p.oW + (ww * p.sw + p.ow0);
+    }
+    const int64_t g = o.m0 + r;
+    group = p.rows_per_group > 0 ? (int)(g / p.rows_per_group) : 0;
+    return g;
+}
+
+// Persistent kernel: grid = min(#work items, #SMs); a work item is (split, m_tile, n_tile) with n fastest so that the CTAs
+// running concurrently share A tiles in L2.  Two TMEM accumulators: the epilogue of item i overlaps the main loop of i+1.
+// Epilogue: the residual tile is prefetched into a padded smem staging buffer with coalesced loads, each thread (== row) adds
+// bias / per-image bias / residual to its TMEM row and writes bf16 back into the staging buffer, then the tile leaves with
+// coalesced 16-byte stores (full 32-byte sectors instead of one 16-byte fragment per row and instruction).
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
     using Cfg = GemmCfg<BN>;
@@ -82,40 +124,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_STAGE_BYTES);
+    uint8_t* sStg = sB + STAGES * Cfg::B_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStg + Cfg::STG_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x % p.tiles_n;
-    const int m_tile = blockIdx.x / p.tiles_n;
-    const int n0 = n_tile * BN;
-    const int kb_lo = blockIdx.y * p.kb_per_split;
-    const int kb_hi = kb_lo + p.kb_per_split;
-
-    // tile origin
-    int m0 = m_tile * BLOCK_M;
-    int img0 = 0, h0 = 0, w0 = 0;
-    if (p.conv) {
-        if (p.bn == 1) {
-            const int per_img = p.tiles_w * p.tiles_h;
-            img0 = m_tile / per_img;
-            const int r = m_tile % per_img;
-            h0 = (r / p.tiles_w) * p.bh;
-            w0 = (r % p.tiles_w) * p.bw;
-        } else {
-            img0 = m_tile * p.bn;
-        }
-    }
+    const int tiles_mn = p.tiles_n * p.tiles_m;
+    const int total_work = tiles_mn * p.splits;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], 128);
+        }
         fence_mbar_init();
         for (int s = 0; s < p.nseg; ++s) {
             tma_prefetch_desc(&p.tmA[s]);
@@ -123,7 +152,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -136,30 +165,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int s = 0; s < p.nseg; ++s) {
-                const int ntap = (p.conv && s == 0) ? p.ntaps : 1;
-                for (int t = 0; t < ntap; ++t) {
-                    for (int kb = 0; kb < p.nkb[s]; ++kb, ++it) {
-                        if (it < kb_lo || it >= kb_hi) continue;
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
-                        void* dA = sA + stage * A_STAGE_BYTES;
-                        void* dB = sB + stage * Cfg::B_STAGE_BYTES;
-                        if (p.conv && s == 0) {
-                            const TapEntry& te = p.taps[t];
-                            if (p.conv == 4)
-                                tma_load_4d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, w0 + te.dw,
-                                            h0 + te.dh, img0);
-                            else
-                                tma_load_5d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, w0 + te.dw,
-                                            te.c2, h0 + te.dh, img0);
-                            tma_load_2d(dB, &p.tmB[0], &full_bar[stage], te.wk_off + kb * BLOCK_K, n0);
-                        } else {
-                            tma_load_2d(dA, &p.tmA[s], &full_bar[stage], kb * BLOCK_K, m0);
-                            tma_load_2d(dB, &p.tmB[s], &full_bar[stage], kb * BLOCK_K, n0);
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int split = w / tiles_mn, mn = w % tiles_mn;
+                const int n0 = (mn % p.tiles_n) * BN;
+                const TileOrigin o = tile_origin(p, mn / p.tiles_n);
+                const int kb_lo = split * p.kb_per_split, kb_hi = kb_lo + p.kb_per_split;
+                int it = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const int ntap = (p.conv && s == 0) ? p.ntaps : 1;
+                    for (int t = 0; t < ntap; ++t) {
+                        for (int kb = 0; kb < p.nkb[s]; ++kb, ++it) {
+                            if (it < kb_lo || it >= kb_hi) continue;
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+                            void* dA = sA + stage * A_STAGE_BYTES;
+                            void* dB = sB + stage * Cfg::B_STAGE_BYTES;
+                            if (p.conv && s == 0) {
+                                const TapEntry& te = p.taps[t];
+                                if (p.conv == 4)
+                                    tma_load_4d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o.w0 + te.dw, o.h0 + te.dh, o.img0);
+                                else
+                                    tma_load_5d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o.w0 + te.dw, te.c2, o.h0 + te.dh,
+                                                o.img0);
+                                tma_load_2d(dB, &p.tmB[0], &full_bar[stage], te.wk_off + kb * BLOCK_K, n0);
+                            } else {
+                                tma_load_2d(dA, &p.tmA[s], &full_bar[stage], kb * BLOCK_K, o.m0);
+                                tma_load_2d(dB, &p.tmB[s], &full_bar[stage], kb * BLOCK_K, n0);
+                            }
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -170,112 +204,143 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t accum = 0;
-            int it = 0;
-            for (int s = 0; s < p.nseg; ++s) {
-                const int ntap = (p.conv && s == 0) ? p.ntaps : 1;
-                for (int t = 0; t < ntap; ++t) {
-                    for (int kb = 0; kb < p.nkb[s]; ++kb, ++it) {
-                        if (it < kb_lo || it >= kb_hi) continue;
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * A_STAGE_BYTES), 16, 1024);
-                        const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * Cfg::B_STAGE_BYTES), 16, 1024);
-                        const int ksteps = (kb == p.nkb[s] - 1) ? p.klast[s] : (BLOCK_K / 16);
-                        for (int k = 0; k < ksteps; ++k) {
-                            // +32 bytes (= 2 in descriptor units) per 16-element k-step inside the swizzle atom
-                            umma_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
-                            accum = 1;
+            int item = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
+                const int split = w / tiles_mn;
+                const int kb_lo = split * p.kb_per_split, kb_hi = kb_lo + p.kb_per_split;
+                const int as = item & 1;
+                mbar_wait(&tmem_empty_bar[as], ((item >> 1) & 1) ^ 1);       // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t acc = tmem_base + as * Cfg::ACC_STRIDE;
+                uint32_t accum = 0;
+                int it = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const int ntap = (p.conv && s == 0) ? p.ntaps : 1;
+                    for (int t = 0; t < ntap; ++t) {
+                        for (int kb = 0; kb < p.nkb[s]; ++kb, ++it) {
+                            if (it < kb_lo || it >= kb_hi) continue;
+                            mbar_wait(&full_bar[stage], phase);
+                            tc_fence_after();
+                            const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * A_STAGE_BYTES), 16, 1024);
+                            const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * Cfg::B_STAGE_BYTES), 16, 1024);
+                            const int ksteps = (kb == p.nkb[s] - 1) ? p.klast[s] : (BLOCK_K / 16);
+                            for (int k = 0; k < ksteps; ++k) {
+                                // +32 bytes (= 2 in descriptor units) per 16-element k-step inside the swizzle atom
+                                umma_ss(acc, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                                accum = 1;
+                            }
+                            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
-                        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
+                umma_commit(&tmem_full_bar[as]);
             }
-            umma_commit(tmem_full_bar);
         }
     } else {
         // ===================================== epilogue ==========================================
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int r = quarter * 32 + lane;            // row inside the tile
-        int64_t grow;                                 // row of `out`
-        bool row_ok;
-        int group;
-        if (p.conv) {
-            const int per = p.bw * p.bh;
-            const int im = img0 + r / per;
-            const int rr = r % per;
-            const int hh = h0 + rr / p.bw;
-            const int ww = w0 + rr % p.bw;
-            const int64_t opix = (int64_t)(hh * p.sh + p.oh0) * p.oW + (ww * p.sw + p.ow0);
-            grow = (int64_t)im * p.oH * p.oW + opix;
-            row_ok = grow < (int64_t)p.M;
-            group = im;
-        } else {
-            grow = m0 + r;
-            row_ok = grow < (int64_t)p.M;
-            group = p.rows_per_group > 0 ? (int)(grow / p.rows_per_group) : 0;
-        }
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int et = threadIdx.x - 64;              // 0..127 among the epilogue threads
+        constexpr int UNITS = BN / 8;                 // 16-byte units per tile row
+        int item = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
+            const int split = w / tiles_mn, mn = w % tiles_mn;
+            const int n0 = (mn % p.tiles_n) * BN;
+            const TileOrigin o = tile_origin(p, mn / p.tiles_n);
+            const int as = item & 1;
+            const bool staged = (p.splits == 1);
+            if (staged && p.residual) {
+                // coalesced prefetch of the residual tile into the staging buffer (overlaps the main loop)
+                for (int u = et; u < BLOCK_M * UNITS; u += 128) {
+                    const int rr = u / UNITS, cu = u % UNITS;
+                    int grp;
+                    const int64_t g = tile_row(p, o, rr, grp);
+                    const int col = n0 + cu * 8;
+                    if (g < (int64_t)p.M && col < p.N)
+                        *reinterpret_cast<uint4*>(sStg + rr * Cfg::STG_PITCH + cu * 16) =
+                            *reinterpret_cast<const uint4*>(p.residual + g * p.ldr + col);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            int group;
+            const int64_t grow = tile_row(p, o, r, group);
+            const bool row_ok = grow < (int64_t)p.M;
+            mbar_wait(&tmem_full_bar[as], (item >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + as * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(trow + c * 32, v);
-            tmem_wait_ld();
-            if (row_ok) {
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(trow + c * 32, v);
+                tmem_wait_ld();
+                if (row_ok) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int col = n0 + c * 32 + g * 8;
-                    if (col < p.N) {
-                        float f[8];
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = n0 + c * 32 + g * 8;
+                        if (col < p.N) {
+                            float f[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-                        if (p.splits > 1) {      // raw partial; bias / residual are applied by splitk_finalize_kernel
-                            float* dst = p.ws + ((int64_t)blockIdx.y * p.M + grow) * p.N + col;
-                            *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
-                            *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                            continue;
+                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+                            if (!staged) {      // split-K: raw partial; bias / residual are applied by splitk_finalize_kernel
+                                float* dst = p.ws + ((int64_t)split * p.M + grow) * p.N + col;
+                                *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+                                *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                                continue;
+                            }
+                            if (p.bias) {
+                                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+                                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            }
+                            if (p.rowbias) {
+                                const float* rb = p.rowbias + (int64_t)group * p.rowbias_ld + col;
+                                const float4 b0 = *reinterpret_cast<const float4*>(rb);
+                                const float4 b1 = *reinterpret_cast<const float4*>(rb + 4);
+                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            }
+                            uint4* slot = reinterpret_cast<uint4*>(sStg + r * Cfg::STG_PITCH + (c * 4 + g) * 16);
+                            if (p.residual) {
+                                const uint4 rv = *slot;
+                                float2 t;
+                                t = unpack_bf16x2(rv.x); f[0] += t.x; f[1] += t.y;
+                                t = unpack_bf16x2(rv.y); f[2] += t.x; f[3] += t.y;
+                                t = unpack_bf16x2(rv.z); f[4] += t.x; f[5] += t.y;
+                                t = unpack_bf16x2(rv.w); f[6] += t.x; f[7] += t.y;
+                            }
+                            uint4 ov;
+                            ov.x = pack_bf16x2(f[0], f[1]);
+                            ov.y = pack_bf16x2(f[2], f[3]);
+                            ov.z = pack_bf16x2(f[4], f[5]);
+                            ov.w = pack_bf16x2(f[6], f[7]);
+                            *slot = ov;
                         }
-                        if (p.bias) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-                            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                        }
-                        if (p.rowbias) {
-                            const float* rb = p.rowbias + (int64_t)group * p.rowbias_ld + col;
-                            const float4 b0 = *reinterpret_cast<const float4*>(rb);
-                            const float4 b1 = *reinterpret_cast<const float4*>(rb + 4);
-                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                        }
-                        if (p.residual) {
-                            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + grow * p.ldr + col);
-                            float2 t;
-                            t = unpack_bf16x2(rv.x); f[0] += t.x; f[1] += t.y;
-                            t = unpack_bf16x2(rv.y); f[2] += t.x; f[3] += t.y;
-                            t = unpack_bf16x2(rv.z); f[4] += t.x; f[5] += t.y;
-                            t = unpack_bf16x2(rv.w); f[6] += t.x; f[7] += t.y;
-                        }
-                        uint4 o;
-                        o.x = pack_bf16x2(f[0], f[1]);
-                        o.y = pack_bf16x2(f[2], f[3]);
-                        o.z = pack_bf16x2(f[4], f[5]);
-                        o.w = pack_bf16x2(f[6], f[7]);
-                        *reinterpret_cast<uint4*>(p.out + grow * p.ldo + col) = o;
                     }
                 }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty_bar[as]);                      // accumulator free: the MMA warp may start item+2
+            if (staged) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int u = et; u < BLOCK_M * UNITS; u += 128) {     // coalesced 16-byte stores
+                    const int rr = u / UNITS, cu = u % UNITS;
+                    int grp;
+                    const int64_t g = tile_row(p, o, rr, grp);
+                    const int col = n0 + cu * 8;
+                    if (g < (int64_t)p.M && col < p.N)
+                        *reinterpret_cast<uint4*>(p.out + g * p.ldo + col) = *reinterpret_cast<const uint4*>(sStg + rr * Cfg::STG_PITCH + cu * 16);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");     // staging buffer reusable
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
-
 
 // out = sum_s ws[s] + bias + rowbias + residual  (bf16), 8 columns per thread
 __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits, int64_t M, int N, const float* __restrict__ bias,
@@ -317,7 +382,7 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits,
 // number of K-splits for a launch with `ctas` output tiles and `total_kb` 64-wide k-blocks (1 = no split)
 static int plan_splits(int64_t ctas, int64_t total_kb) {
     if (ctas >= 96 || total_kb < 8) return 1;
-    int64_t s = (148 + ctas - 1) / ctas;
+    int64_t s = 148 / ctas;                 // persistent grid: keep the work items within one wave of 148 SMs
     if (s > total_kb / 4) s = total_kb / 4;
     if (s > 16) s = 16;
     return s < 2 ? 1 : (int)s;
@@ -441,16 +506,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) lora_grad_tc_kernel(const __g
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int BN>
-static int launch_gemm(const GemmKParams& kp, int m_tiles, cudaStream_t stream) {
+static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     static bool configured = false;
+    static int num_sms = 148;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         configured = true;
     }
-    dim3 grid(kp.tiles_n * m_tiles, kp.splits);
+    const int total = kp.tiles_n * kp.tiles_m * kp.splits;
+    dim3 grid(total < num_sms ? total : num_sms);
     gemm_tc_kernel<BN><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(kp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "gemm launch");
@@ -466,12 +535,13 @@ static int pick_bn(int64_t N) {
     return 128;
 }
 
-static int dispatch_gemm(int bn, const GemmKParams& kp, int m_tiles, cudaStream_t stream) {
+static int dispatch_gemm(int bn, GemmKParams& kp, int m_tiles, cudaStream_t stream) {
+    kp.tiles_m = m_tiles;
     switch (bn) {
-        case 32: return launch_gemm<32>(kp, m_tiles, stream);
-        case 64: return launch_gemm<64>(kp, m_tiles, stream);
-        case 128: return launch_gemm<128>(kp, m_tiles, stream);
-        case 160: return launch_gemm<160>(kp, m_tiles, stream);
+        case 32: return launch_gemm<32>(kp, stream);
+        case 64: return launch_gemm<64>(kp, stream);
+        case 128: return launch_gemm<128>(kp, stream);
+        case 160: return launch_gemm<160>(kp, stream);
         default: return set_error(HCP_ERR_INVALID, "unsupported BLOCK_N");
     }
 }
