@@ -25,7 +25,8 @@ namespace hcp {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;        // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue (two per TMEM lane quarter)
+constexpr int kGemmEpiThreads = 256;
 constexpr int kMaxTaps = 9;
 
 struct TapEntry {
@@ -68,7 +69,7 @@ struct alignas(64) GemmKParams {
 
 template <int BN>
 struct GemmCfg {
-    static constexpr int STAGES = 4;
+    static constexpr int STAGES = (BN > 64) ? 5 : 8;     // one CTA per SM: the ring must cover the TMA latency alone
     static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
     static constexpr int ACC_STRIDE = 256;                         // TMEM columns between the two accumulators
     static constexpr int STG_PITCH = BN * 2 + 16;                  // staging row pitch in bytes: odd number of 16-byte units
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], 128);
+            mbar_init(&tmem_empty_bar[i], kGemmEpiThreads);
         }
         fence_mbar_init();
         for (int s = 0; s < p.nseg; ++s) {
@@ -240,9 +241,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     } else {
         // ===================================== epilogue ==========================================
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;             // which half of the tile's columns this warp converts
         const int r = quarter * 32 + lane;            // row inside the tile
-        const int et = threadIdx.x - 64;              // 0..127 among the epilogue threads
+        const int et = threadIdx.x - 64;              // 0..255 among the epilogue threads
         constexpr int UNITS = BN / 8;                 // 16-byte units per tile row
+        constexpr int CH16 = BN / 16;                 // 16-column TMEM chunks per row
         int item = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
             const int split = w / tiles_mn, mn = w % tiles_mn;
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             const bool staged = (p.splits == 1);
             if (staged && p.residual) {
                 // coalesced prefetch of the residual tile into the staging buffer (overlaps the main loop)
-                for (int u = et; u < BLOCK_M * UNITS; u += 128) {
+                for (int u = et; u < BLOCK_M * UNITS; u += kGemmEpiThreads) {
                     const int rr = u / UNITS, cu = u % UNITS;
                     int grp;
                     const int64_t g = tile_row(p, o, rr, grp);
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                         *reinterpret_cast<uint4*>(sStg + rr * Cfg::STG_PITCH + cu * 16) =
                             *reinterpret_cast<const uint4*>(p.residual + g * p.ldr + col);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             int group;
             const int64_t grow = tile_row(p, o, r, group);
@@ -270,14 +273,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             tc_fence_after();
             const uint32_t trow = tmem_base + as * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(trow + c * 32, v);
+            for (int c = half * ((CH16 + 1) / 2); c < (half ? CH16 : (CH16 + 1) / 2); ++c) {
+                uint32_t v[16];
+                tmem_ld16(trow + c * 16, v);
                 tmem_wait_ld();
                 if (row_ok) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int col = n0 + c * 32 + g * 8;
+                    for (int g = 0; g < 2; ++g) {
+                        const int col = n0 + c * 16 + g * 8;
                         if (col < p.N) {
                             float f[8];
 #pragma unroll
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                                 f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                                 f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                             }
-                            uint4* slot = reinterpret_cast<uint4*>(sStg + r * Cfg::STG_PITCH + (c * 4 + g) * 16);
+                            uint4* slot = reinterpret_cast<uint4*>(sStg + r * Cfg::STG_PITCH + (c * 2 + g) * 16);
                             if (p.residual) {
                                 const uint4 rv = *slot;
                                 float2 t;
@@ -323,8 +326,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             tc_fence_before();
             mbar_arrive(&tmem_empty_bar[as]);                      // accumulator free: the MMA warp may start item+2
             if (staged) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int u = et; u < BLOCK_M * UNITS; u += 128) {     // coalesced 16-byte stores
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int u = et; u < BLOCK_M * UNITS; u += kGemmEpiThreads) {     // coalesced 16-byte stores
                     const int rr = u / UNITS, cu = u % UNITS;
                     int grp;
                     const int64_t g = tile_row(p, o, rr, grp);
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                     if (g < (int64_t)p.M && col < p.N)
                         *reinterpret_cast<uint4*>(p.out + g * p.ldo + col) = *reinterpret_cast<const uint4*>(sStg + rr * Cfg::STG_PITCH + cu * 16);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");     // staging buffer reusable
+                asm volatile("bar.sync 1, 256;" ::: "memory");     // staging buffer reusable
             }
         }
     }
@@ -396,6 +399,7 @@ static int plan_splits(int64_t ctas, int64_t total_kb) {
 // 128 rows), so no transpose ever exists.  One CTA owns 128 columns of X and a slice of the rows (split-K); the 128 x 64
 // fp32 accumulator is reduced into the flat gradient buffer with red.global.
 // =============================================================================================
+constexpr int kLgThreads = 192;   // warp 0: TMA, warp 1: MMA, warps 2-5: reduction epilogue
 constexpr int LG_STAGES = 3;
 constexpr int LG_STAGE_BYTES = 3 * 128 * 128;      // two X boxes + one S box
 constexpr int LG_SMEM_BYTES = LG_STAGES * LG_STAGE_BYTES + 256 + 1024;
@@ -412,7 +416,7 @@ struct alignas(64) LoraGradParams {
     LGBlock blk[LG_MAX_BLOCKS];
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 1) lora_grad_tc_kernel(const __grid_constant__ LoraGradParams p) {
+__global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __grid_constant__ LoraGradParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + LG_STAGES * LG_STAGE_BYTES);
@@ -785,7 +789,7 @@ extern "C" int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t 
             p.blk[i].transpose_out = k.transpose_out; p.blk[i].dst_ld = (int)k.dst_ld; p.blk[i].scale = k.scale; p.blk[i].dst = k.dst;
         }
         dim3 grid(col_chunks, splits);
-        lora_grad_tc_kernel<<<grid, kGemmThreads, LG_SMEM_BYTES, (cudaStream_t)stream_>>>(p);
+        lora_grad_tc_kernel<<<grid, kLgThreads, LG_SMEM_BYTES, (cudaStream_t)stream_>>>(p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return set_cuda_error(e, "lora_grad launch");
     }
