@@ -24,6 +24,19 @@ __device__ __forceinline__ float gelu_grad(float x) {
     return cdf + x * pdf;
 }
 
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+    float2 t;
+    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* o) {
+    uint4 w;
+    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+    return w;
+}
+
 // =============================================================================================
 // GroupNorm.  x is the channel-concatenation of x1 [B,HW,C1] and (optionally) x2 [B,HW,C2].
 // Pass A: per-(image, pixel-chunk) partial sums per group.  Pass B: finalise the statistics of the image
@@ -40,7 +53,7 @@ struct GNParams {
     const __nv_bfloat16* x1; const __nv_bfloat16* x2;
     int C1, C2, C, G, cg;
     int B, HW, rows_per_cta, nchunks;
-    int TP, R, PT;
+    int TP, R, PT, vec8;
     const float* gamma; const float* beta;
     float eps; int silu;
     float* partial;            // [B, nchunks, G, 2]
@@ -215,6 +228,178 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn_apply_kernel(const GNParams
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 16-byte-vector variant (8 channels per thread and row) for layers with >= 8 channels per group.  A vector may straddle
+// ONE group boundary: its first `nb` channels belong to group g_lo, the rest to g_lo + 1; both sets of statistics live in
+// registers.  Same two-pass structure and the same deterministic fixed-order reductions as the scalar-pair kernels.
+// ---------------------------------------------------------------------------------------------
+struct GN8Thread {
+    int c0, g_lo, nb;      // first channel, its group, number of channels (of 8) that belong to g_lo
+};
+__device__ __forceinline__ GN8Thread gn8_thread(const GNParams& p, int vec) {
+    GN8Thread t;
+    t.c0 = vec * 8;
+    t.g_lo = t.c0 / p.cg;
+    t.nb = min(8, (t.g_lo + 1) * p.cg - t.c0);
+    return t;
+}
+__device__ __forceinline__ void gn8_load(const GNParams& p, int64_t pix, int c0, float* f) {
+    const __nv_bfloat16* src = (c0 < p.C1) ? p.x1 + pix * p.C1 + c0 : p.x2 + pix * p.C2 + (c0 - p.C1);
+    unpack8(*reinterpret_cast<const uint4*>(src), f);
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(GN_MAX_THREADS) gn8_partial_kernel(const GNParams p) {
+    extern __shared__ float s_vec[];      // [R][C/8][4] : (lo a0, lo a1, hi a0, hi a1)
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int r0 = chunk * p.rows_per_cta;
+    const int r1 = min(p.HW, r0 + p.rows_per_cta);
+    const int nvec = p.C / 8;
+    const int tv = threadIdx.x % p.TP, rl = threadIdx.x / p.TP;
+    const GN8Thread t = gn8_thread(p, tv);
+    const float* st = BWD ? p.stats + (int64_t)b * p.G * 2 : nullptr;
+    float gm[8], bt[8], mean[2] = {0.f, 0.f}, rstd[2] = {0.f, 0.f};
+    if (BWD) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { gm[e] = p.gamma[t.c0 + e]; bt[e] = p.beta[t.c0 + e]; }
+        mean[0] = st[t.g_lo * 2]; rstd[0] = st[t.g_lo * 2 + 1];
+        if (t.nb < 8) { mean[1] = st[t.g_lo * 2 + 2]; rstd[1] = st[t.g_lo * 2 + 3]; }
+    }
+    float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};
+    for (int r = r0 + rl; r < r1; r += p.R) {
+        const int64_t pix = (int64_t)b * p.HW + r;
+        float x[8];
+        gn8_load(p, pix, t.c0, x);
+        if (!BWD) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = (e < t.nb) ? 0 : 1;
+                a0[k] += x[e];
+                a1[k] += x[e] * x[e];
+            }
+        } else {
+            float d[8];
+            unpack8(*reinterpret_cast<const uint4*>(p.dy + pix * p.C + t.c0), d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = (e < t.nb) ? 0 : 1;
+                const float xh = (x[e] - mean[k]) * rstd[k];
+                float g = d[e] * gm[e];
+                if (p.silu) g *= silu_grad(xh * gm[e] + bt[e]);
+                a0[k] += g;
+                a1[k] += g * xh;
+            }
+        }
+    }
+    float* dst = s_vec + ((size_t)rl * nvec + tv) * 4;
+    dst[0] = a0[0]; dst[1] = a1[0]; dst[2] = a0[1]; dst[3] = a1[1];
+    __syncthreads();
+    float* out = p.partial + ((int64_t)b * p.nchunks + chunk) * p.G * 2;
+    for (int i = threadIdx.x; i < p.G * 2; i += blockDim.x) {
+        const int g = i >> 1, which = i & 1;
+        const int v_lo = (g * p.cg) / 8, v_hi = ((g + 1) * p.cg - 1) / 8;
+        float acc = 0.f;
+        for (int r = 0; r < p.R; ++r)
+            for (int v = v_lo; v <= v_hi; ++v) {
+                const int vg = (v * 8) / p.cg;                    // g_lo of that vector
+                const float* src = s_vec + ((size_t)r * nvec + v) * 4;
+                if (vg == g) acc += src[which];
+                else if (vg + 1 == g) acc += src[2 + which];
+            }
+        out[i] = acc;
+    }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(GN_MAX_THREADS) gn8_apply_kernel(const GNParams p) {
+    __shared__ float s_a[GN_MAX_G], s_b[GN_MAX_G];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const float n = (float)p.HW * (float)p.cg;
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        for (int g = warp; g < p.G; g += nwarps) {
+            float a0 = 0.f, a1 = 0.f;
+            for (int ch = lane; ch < p.nchunks; ch += 32) {
+                const float* src = p.partial + (((int64_t)b * p.nchunks + ch) * p.G + g) * 2;
+                a0 += src[0];
+                a1 += src[1];
+            }
+            a0 = warp_sum(a0);
+            a1 = warp_sum(a1);
+            if (lane == 0) {
+                if (!BWD) {
+                    const float mean = a0 / n;
+                    const float var = fmaxf(a1 / n - mean * mean, 0.f);
+                    const float rstd = rsqrtf(var + p.eps);
+                    s_a[g] = mean;
+                    s_b[g] = rstd;
+                    if (chunk == 0) {
+                        p.stats[((int64_t)b * p.G + g) * 2] = mean;
+                        p.stats[((int64_t)b * p.G + g) * 2 + 1] = rstd;
+                    }
+                } else {
+                    s_a[g] = a0 / n;
+                    s_b[g] = a1 / n;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int r0 = chunk * p.rows_per_cta;
+    const int r1 = min(p.HW, r0 + p.rows_per_cta);
+    const int tv = threadIdx.x % p.TP, rl = threadIdx.x / p.TP;
+    const GN8Thread t = gn8_thread(p, tv);
+    const float* st = BWD ? p.stats + (int64_t)b * p.G * 2 : nullptr;
+    float gm[8], bt[8], sa[2], sb[2], mean[2] = {0.f, 0.f}, rstd[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { gm[e] = p.gamma[t.c0 + e]; bt[e] = p.beta[t.c0 + e]; }
+    const int g_hi = min(t.g_lo + 1, p.G - 1);
+    sa[0] = s_a[t.g_lo]; sb[0] = s_b[t.g_lo]; sa[1] = s_a[g_hi]; sb[1] = s_b[g_hi];
+    if (BWD) { mean[0] = st[t.g_lo * 2]; rstd[0] = st[t.g_lo * 2 + 1]; mean[1] = st[g_hi * 2]; rstd[1] = st[g_hi * 2 + 1]; }
+    for (int r = r0 + rl; r < r1; r += p.R) {
+        const int64_t pix = (int64_t)b * p.HW + r;
+        float x[8], o[8];
+        gn8_load(p, pix, t.c0, x);
+        if (!BWD) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = (e < t.nb) ? 0 : 1;
+                float z = (x[e] - sa[k]) * sb[k] * gm[e] + bt[e];
+                if (p.silu) z = silu_f(z);
+                o[e] = z;
+            }
+            *reinterpret_cast<uint4*>(p.y + pix * p.C + t.c0) = pack8(o);
+        } else {
+            float d[8];
+            unpack8(*reinterpret_cast<const uint4*>(p.dy + pix * p.C + t.c0), d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = (e < t.nb) ? 0 : 1;
+                const float xh = (x[e] - mean[k]) * rstd[k];
+                float g = d[e] * gm[e];
+                if (p.silu) g *= silu_grad(xh * gm[e] + bt[e]);
+                o[e] = rstd[k] * (g - sa[k] - xh * sb[k]);
+            }
+            __nv_bfloat16* dst;
+            const __nv_bfloat16* add;
+            if (t.c0 < p.C1) {
+                dst = p.dx1 + pix * p.C1 + t.c0;
+                add = p.add1 ? p.add1 + pix * p.C1 + t.c0 : nullptr;
+            } else {
+                dst = p.dx2 + pix * p.C2 + (t.c0 - p.C1);
+                add = p.add2 ? p.add2 + pix * p.C2 + (t.c0 - p.C1) : nullptr;
+            }
+            if (add) {
+                float a[8];
+                unpack8(*reinterpret_cast<const uint4*>(add), a);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] += a[e];
+            }
+            *reinterpret_cast<uint4*>(dst) = pack8(o);
+        }
+    }
+}
+
 static int gn_geometry(const hcp_groupnorm_args* a, GNParams& p) {
     if (!a || !a->x1 || !a->gamma || !a->beta || !a->workspace || !a->stats) return set_error(HCP_ERR_INVALID, "groupnorm: null pointer");
     const int64_t C = a->C1 + a->C2;
@@ -237,8 +422,9 @@ static int gn_geometry(const hcp_groupnorm_args* a, GNParams& p) {
     if (rows > a->HW) rows = (int)a->HW;
     p.rows_per_cta = rows;
     p.nchunks = (int)((a->HW + rows - 1) / rows);
+    p.vec8 = (cg >= 8 && (a->C1 % 8) == 0 && (a->C2 % 8) == 0 && C / 8 <= GN_MAX_THREADS) ? 1 : 0;
     p.PT = PT;
-    p.TP = npair / PT;
+    p.TP = p.vec8 ? (int)(C / 8) : npair / PT;
     p.R = GN_MAX_THREADS / p.TP;
     if (p.R > rows) p.R = rows;
     if (p.R < 1) p.R = 1;
@@ -252,19 +438,6 @@ static int gn_geometry(const hcp_groupnorm_args* a, GNParams& p) {
 // LayerNorm: one warp per row, the row lives in registers (C <= 2048)
 // =============================================================================================
 constexpr int LN_MAX_C = 2048;
-
-__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-    float2 t;
-    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
-    t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
-    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
-    t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
-}
-__device__ __forceinline__ uint4 pack8(const float* o) {
-    uint4 w;
-    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-    return w;
-}
 
 // NVPL = ceil((C/8) / 32): 16-byte vectors per lane (compile time so the row stays in registers)
 template <bool BWD, int NVPL>
@@ -491,9 +664,15 @@ extern "C" int hcp_groupnorm_fwd_bf16(const hcp_groupnorm_args* a, hcp_stream_t 
     p.y = (__nv_bfloat16*)a->y;
     dim3 grid(p.nchunks, p.B);
     const int threads = p.TP * p.R;
-    const size_t smem = (size_t)p.R * (p.C / 2) * 2 * sizeof(float);
-    gn_partial_kernel<false><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
-    gn_apply_kernel<false><<<grid, threads, 0, (cudaStream_t)stream_>>>(p);
+    if (p.vec8) {
+        const size_t smem = (size_t)p.R * (p.C / 8) * 4 * sizeof(float);
+        gn8_partial_kernel<false><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
+        gn8_apply_kernel<false><<<grid, threads, 0, (cudaStream_t)stream_>>>(p);
+    } else {
+        const size_t smem = (size_t)p.R * (p.C / 2) * 2 * sizeof(float);
+        gn_partial_kernel<false><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
+        gn_apply_kernel<false><<<grid, threads, 0, (cudaStream_t)stream_>>>(p);
+    }
     LAUNCH_CHECK("groupnorm_fwd launch");
     return HCP_OK;
 }
@@ -508,9 +687,15 @@ extern "C" int hcp_groupnorm_bwd_bf16(const hcp_groupnorm_args* a, hcp_stream_t 
     p.dx1 = (__nv_bfloat16*)a->dx1; p.dx2 = (__nv_bfloat16*)a->dx2;
     dim3 grid(p.nchunks, p.B);
     const int threads = p.TP * p.R;
-    const size_t smem = (size_t)p.R * (p.C / 2) * 2 * sizeof(float);
-    gn_partial_kernel<true><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
-    gn_apply_kernel<true><<<grid, threads, 0, (cudaStream_t)stream_>>>(p);
+    if (p.vec8) {
+        const size_t smem = (size_t)p.R * (p.C / 8) * 4 * sizeof(float);
+        gn8_partial_kernel<true><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
+        gn8_apply_kernel<true><<<grid, threads, 0, (cudaStream_t)stream_>>>(p);
+    } else {
+        const size_t smem = (size_t)p.R * (p.C / 2) * 2 * sizeof(float);
+        gn_partial_kernel<true><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
+        gn_apply_kernel<true><<<grid, threads, 0, (cudaStream_t)stream_>>>(p);
+    }
     LAUNCH_CHECK("groupnorm_bwd launch");
     return HCP_OK;
 }
