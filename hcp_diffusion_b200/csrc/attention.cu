@@ -27,7 +27,9 @@
 namespace hcp {
 
 constexpr int kAttnThreads = 160;          // fwd: warps 0-3: softmax/epilogue rows, warp 4: TMA + MMA control
-constexpr int kAttnBwdThreads = 288;       // bwd: warps 0-7: two per TMEM lane quarter (each owns 64 kv columns), warp 8: control
+constexpr int kBwdParts = 4;               // bwd: softmax warps per TMEM lane quarter (each owns 128/kBwdParts kv columns)
+constexpr int kBwdSoftmaxThreads = 4 * kBwdParts * 32;
+constexpr int kAttnBwdThreads = kBwdSoftmaxThreads + 32;   // + one control warp (the last)
 constexpr int TILE_BYTES = 128 * 128;      // one [128 rows x 64 cols] bf16 box
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -554,15 +556,15 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
         mbar_init(&q_full[0], 1);
         mbar_init(&q_full[1], 1);
         mbar_init(sdp_full, 1);
-        mbar_init(p_ready, 256);
-        mbar_init(ds_ready, 256);
+        mbar_init(p_ready, kBwdSoftmaxThreads);
+        mbar_init(ds_ready, kBwdSoftmaxThreads);
         mbar_init(dv_done, 1);
         mbar_init(dq_full, 1);
-        mbar_init(dq_read, 256);
+        mbar_init(dq_read, kBwdSoftmaxThreads);
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
-    if (warp == 8) {
+    if (warp == 4 * kBwdParts) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
     const uint32_t tmem = *tmem_slot;
     const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem, tdV = tmem + 256, tdK = tmem + 384;
 
-    if (warp == 8) {
+    if (warp == 4 * kBwdParts) {
         if (elect_one()) {
             auto load_q = [&](int i) {
                 const int st = (p.q_stages == 2) ? (i & 1) : 0;
@@ -644,7 +646,8 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
         }
     } else {
         // ------------------------------ thread == query row (S, dP) / kv row (dK, dV) --------------
-        const int quarter = warp & 3, half = warp >> 2;      // lanes [32*quarter, +32), kv columns [64*half, +64)
+        const int quarter = warp & 3, part = warp >> 2;      // lanes [32*quarter, +32), kv columns [128/kBwdParts * part, +...)
+        constexpr int kChunksPerPart = 4 / kBwdParts;        // 32-column TMEM chunks per warp
         const int row = quarter * 32 + lane;
         const uint32_t lb = lane_base(quarter);
         const float* bias = p.kv_bias ? p.kv_bias + (int64_t)b * p.Lkv : nullptr;
@@ -670,7 +673,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             for (int pass = 0; pass < (p.share_pds ? 2 : 1); ++pass) {
                 const bool do_p = (pass == 0);
                 const bool do_ds = !p.share_pds || pass == 1;
-                for (int c = half * 2; c < half * 2 + 2; ++c) {
+                for (int c = part * kChunksPerPart; c < (part + 1) * kChunksPerPart; ++c) {
                     uint32_t v[32], w[32];
                     tmem_ld32(tS + lb + c * 32, v);
                     if (do_ds) tmem_ld32(tdP + lb + c * 32, w);
@@ -723,7 +726,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             mbar_wait(dq_full, i & 1);
             tc_fence_after();
             float* dqrow = p.dq_acc + stat_idx * p.dq_ld + p.col0;
-            for (int c = half; c < p.ncols_out / 16; c += 2) {
+            for (int c = part; c < p.ncols_out / 16; c += kBwdParts) {
                 uint32_t o[16];
                 tmem_ld16(tdQ + lb + c * 16, o);
                 tmem_wait_ld();
@@ -749,7 +752,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             __nv_bfloat16* out = which ? p.dK : p.dV;
             const int64_t ld = which ? p.lddk : p.lddv;
             __nv_bfloat16* orow = out + ((int64_t)b * p.Lkv + kvrow) * ld + (int64_t)h * p.d + p.col0;
-            for (int c = half; c < p.ncols_out / 16; c += 2) {
+            for (int c = part; c < p.ncols_out / 16; c += kBwdParts) {
                 uint32_t o[16];
                 tmem_ld16(t + lb + c * 16, o);
                 tmem_wait_ld();
@@ -772,7 +775,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 512);
+    if (warp == 4 * kBwdParts) tmem_dealloc(tmem, 512);
 }
 
 // delta[b,h,q] = sum_e dO*O ; also zero-fills the fp32 dQ accumulator.  One warp per (b,q,h).

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn_partial_kernel(const GNPara
     const int r1 = min(p.HW, r0 + p.rows_per_cta);
     const int npair = p.C / 2;
     const int tp = threadIdx.x % p.TP, rl = threadIdx.x / p.TP;
+    const bool active = threadIdx.x < p.TP * p.R;          // the block is padded to whole warps
     const float* st = BWD ? p.stats + (int64_t)b * p.G * 2 : nullptr;
     float a0[GN_MAX_PT], a1[GN_MAX_PT];
     float gm0[GN_MAX_PT], gm1[GN_MAX_PT], bt0[GN_MAX_PT], bt1[GN_MAX_PT], mean[GN_MAX_PT], rstd[GN_MAX_PT];
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn_partial_kernel(const GNPara
             mean[k] = st[g * 2]; rstd[k] = st[g * 2 + 1];
         }
     }
-    for (int r = r0 + rl; r < r1; r += p.R) {
+    for (int r = r0 + rl; active && r < r1; r += p.R) {
         const int64_t pix = (int64_t)b * p.HW + r;
 #pragma unroll
         for (int k = 0; k < GN_MAX_PT; ++k) {
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn_partial_kernel(const GNPara
     }
 #pragma unroll
     for (int k = 0; k < GN_MAX_PT; ++k)
-        if (k < p.PT) {
+        if (active && k < p.PT) {
             const int cp = tp + k * p.TP;
             s_pair[(rl * npair + cp) * 2] = a0[k];
             s_pair[(rl * npair + cp) * 2 + 1] = a1[k];
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn_apply_kernel(const GNParams
             sa[k] = s_a[g]; sb[k] = s_b[g];
             if (BWD) { mean[k] = st[g * 2]; rstd[k] = st[g * 2 + 1]; }
         }
-    for (int r = r0 + rl; r < r1; r += p.R) {
+    for (int r = r0 + rl; threadIdx.x < p.TP * p.R && r < r1; r += p.R) {
         const int64_t pix = (int64_t)b * p.HW + r;
 #pragma unroll
         for (int k = 0; k < GN_MAX_PT; ++k) {
@@ -266,7 +267,8 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn8_partial_kernel(const GNPar
         if (t.nb < 8) { mean[1] = st[t.g_lo * 2 + 2]; rstd[1] = st[t.g_lo * 2 + 3]; }
     }
     float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};
-    for (int r = r0 + rl; r < r1; r += p.R) {
+    const bool active = threadIdx.x < p.TP * p.R;          // the block is padded to whole warps
+    for (int r = r0 + rl; active && r < r1; r += p.R) {
         const int64_t pix = (int64_t)b * p.HW + r;
         float x[8];
         gn8_load(p, pix, t.c0, x);
@@ -291,8 +293,10 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn8_partial_kernel(const GNPar
             }
         }
     }
-    float* dst = s_vec + ((size_t)rl * nvec + tv) * 4;
-    dst[0] = a0[0]; dst[1] = a1[0]; dst[2] = a0[1]; dst[3] = a1[1];
+    if (active) {
+        float* dst = s_vec + ((size_t)rl * nvec + tv) * 4;
+        dst[0] = a0[0]; dst[1] = a1[0]; dst[2] = a0[1]; dst[3] = a1[1];
+    }
     __syncthreads();
     float* out = p.partial + ((int64_t)b * p.nchunks + chunk) * p.G * 2;
     for (int i = threadIdx.x; i < p.G * 2; i += blockDim.x) {
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn8_apply_kernel(const GNParam
     const int g_hi = min(t.g_lo + 1, p.G - 1);
     sa[0] = s_a[t.g_lo]; sb[0] = s_b[t.g_lo]; sa[1] = s_a[g_hi]; sb[1] = s_b[g_hi];
     if (BWD) { mean[0] = st[t.g_lo * 2]; rstd[0] = st[t.g_lo * 2 + 1]; mean[1] = st[g_hi * 2]; rstd[1] = st[g_hi * 2 + 1]; }
-    for (int r = r0 + rl; r < r1; r += p.R) {
+    for (int r = r0 + rl; threadIdx.x < p.TP * p.R && r < r1; r += p.R) {
         const int64_t pix = (int64_t)b * p.HW + r;
         float x[8], o[8];
         gn8_load(p, pix, t.c0, x);
@@ -663,7 +667,7 @@ extern "C" int hcp_groupnorm_fwd_bf16(const hcp_groupnorm_args* a, hcp_stream_t 
     if (!a->y) return set_error(HCP_ERR_INVALID, "groupnorm_fwd: y");
     p.y = (__nv_bfloat16*)a->y;
     dim3 grid(p.nchunks, p.B);
-    const int threads = p.TP * p.R;
+    const int threads = (p.TP * p.R + 31) & ~31;          // whole warps: the finalize step uses full-warp shuffles
     if (p.vec8) {
         const size_t smem = (size_t)p.R * (p.C / 8) * 4 * sizeof(float);
         gn8_partial_kernel<false><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
@@ -686,7 +690,7 @@ extern "C" int hcp_groupnorm_bwd_bf16(const hcp_groupnorm_args* a, hcp_stream_t 
     p.add1 = (const __nv_bfloat16*)a->add1; p.add2 = (const __nv_bfloat16*)a->add2;
     p.dx1 = (__nv_bfloat16*)a->dx1; p.dx2 = (__nv_bfloat16*)a->dx2;
     dim3 grid(p.nchunks, p.B);
-    const int threads = p.TP * p.R;
+    const int threads = (p.TP * p.R + 31) & ~31;          // whole warps: the finalize step uses full-warp shuffles
     if (p.vec8) {
         const size_t smem = (size_t)p.R * (p.C / 8) * 4 * sizeof(float);
         gn8_partial_kernel<true><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
