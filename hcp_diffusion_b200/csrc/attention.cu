@@ -27,7 +27,7 @@
 namespace hcp {
 
 constexpr int kAttnThreads = 160;          // fwd: warps 0-3: softmax/epilogue rows, warp 4: TMA + MMA control
-constexpr int kBwdParts = 4;               // bwd: softmax warps per TMEM lane quarter (each owns 128/kBwdParts kv columns)
+constexpr int kBwdParts = 2;               // bwd: softmax warps per TMEM lane quarter (each owns 128/kBwdParts kv columns)
 constexpr int kBwdSoftmaxThreads = 4 * kBwdParts * 32;
 constexpr int kAttnBwdThreads = kBwdSoftmaxThreads + 32;   // + one control warp (the last)
 constexpr int TILE_BYTES = 128 * 128;      // one [128 rows x 64 cols] bf16 box
