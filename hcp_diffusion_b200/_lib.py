@@ -124,7 +124,7 @@ EXPORTS = [
     "hcp_layernorm_fwd_bf16", "hcp_layernorm_bwd_bf16", "hcp_geglu_fwd_bf16", "hcp_geglu_bwd_bf16",
     "hcp_upsample2x_fwd_bf16", "hcp_upsample2x_bwd_bf16", "hcp_add_bf16",
     "hcp_conv_in_f32", "hcp_conv_out_f32", "hcp_conv_out_dgrad_f32", "hcp_skinny_linear", "hcp_cast_f32_to_bf16",
-    "hcp_lora_pack", "hcp_lora_grad", "hcp_add_noise", "hcp_mse_loss", "hcp_sumsq", "hcp_adamw_flat",
+    "hcp_lora_pack", "hcp_lora_grad", "hcp_lora_grad_pair", "hcp_add_noise", "hcp_mse_loss", "hcp_sumsq", "hcp_adamw_flat",
 ]
 
 
@@ -141,7 +141,7 @@ def lib() -> C.CDLL:
             l = C.CDLL(LIB_PATH)
             l.hcp_last_error_string.restype = C.c_char_p
             l.hcp_attn_bwd_workspace_bytes.restype = C.c_size_t
-            l.hcp_attn_bwd_workspace_bytes.argtypes = [C.c_int64] * 4
+            l.hcp_attn_bwd_workspace_bytes.argtypes = [C.c_int64] * 5
             l.hcp_splitk_workspace_bytes.restype = C.c_size_t
             l.hcp_splitk_workspace_bytes.argtypes = [C.c_int64] * 3
             l.hcp_groupnorm_workspace_bytes.restype = C.c_size_t
@@ -167,6 +167,8 @@ def lib() -> C.CDLL:
             l.hcp_cast_f32_to_bf16.argtypes = [vp, i64, vp, vp]
             l.hcp_lora_pack.argtypes = [vp, i64, vp]
             l.hcp_lora_grad.argtypes = [vp, vp, i64, i64, i64, i64, C.POINTER(LoraGradBlock), C.c_int32, vp]
+            l.hcp_lora_grad_pair.argtypes = [vp, vp, i64, i64, C.POINTER(LoraGradBlock), vp, vp, i64, i64, C.POINTER(LoraGradBlock),
+                                             C.c_int32, i64, vp]
             l.hcp_add_noise.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp]
             l.hcp_mse_loss.argtypes = [vp, vp, i64, f32, vp, vp, vp]
             l.hcp_sumsq.argtypes = [vp, i64, vp, vp]

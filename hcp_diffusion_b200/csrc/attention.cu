@@ -519,6 +519,8 @@ struct alignas(64) AttnBwdParams {
     const float* delta;      // [B,H,Lq]  rowsum(dO * O)
     float* dq_acc;           // [B,H,Lq,dq_ld] fp32
     int dq_ld;
+    int qsplit;              // CTAs per kv tile along the query dimension
+    float* dkv_acc;          // [B,H,Lkv,2,dq_ld] fp32 partial dK/dV when qsplit > 1, else nullptr
     __nv_bfloat16 *dK, *dV;
     int64_t lddk, lddv;
 };
@@ -546,8 +548,13 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int nq = (p.Lq + 127) / 128;
+    // blockIdx.x = (kv tile, q split): short-KV problems (cross-attention) have a single kv tile, so the query range is split
+    // over CTAs and the dK/dV partials are reduced with fp32 atomics (dkv_acc) instead of being stored directly.
+    const int jt = blockIdx.x / p.qsplit, qs = blockIdx.x % p.qsplit, h = blockIdx.y, b = blockIdx.z;
+    const int nq_total = (p.Lq + 127) / 128;
+    const int nq_per = (nq_total + p.qsplit - 1) / p.qsplit;
+    const int i0 = qs * nq_per;                                   // first query tile of this CTA
+    const int nq = min(nq_total, i0 + nq_per) - i0;               // >= 1 by construction of qsplit
     const int kv0 = jt * 128;
     const int ncols = min(128, p.Lkv - kv0);
 
@@ -580,8 +587,8 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                 const int st = (p.q_stages == 2) ? (i & 1) : 0;
                 mbar_arrive_expect_tx(&q_full[st], 2 * tile_bytes);
                 for (int bx = 0; bx < p.nbox; ++bx) {
-                    tma_load_4d(sQ + st * tile_bytes + bx * TILE_BYTES, &p.tmQ, &q_full[st], bx * 64, h, i * 128, b);
-                    tma_load_4d(sdO + st * tile_bytes + bx * TILE_BYTES, &p.tmdO, &q_full[st], bx * 64, h, i * 128, b);
+                    tma_load_4d(sQ + st * tile_bytes + bx * TILE_BYTES, &p.tmQ, &q_full[st], bx * 64, h, (i0 + i) * 128, b);
+                    tma_load_4d(sdO + st * tile_bytes + bx * TILE_BYTES, &p.tmdO, &q_full[st], bx * 64, h, (i0 + i) * 128, b);
                 }
             };
             mbar_arrive_expect_tx(kv_full, 2 * tile_bytes);
@@ -653,10 +660,10 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
         const float* bias = p.kv_bias ? p.kv_bias + (int64_t)b * p.Lkv : nullptr;
         const bool special = (bias != nullptr) || (ncols < 128);
         const int64_t stat_base = ((int64_t)b * p.H + h) * p.Lq;
-        float lse_nx = (row < p.Lq) ? p.lse[stat_base + row] : 0.f;          // software-prefetched one q tile ahead
-        float dlt_nx = (row < p.Lq) ? p.delta[stat_base + row] : 0.f;
+        float lse_nx = (i0 * 128 + row < p.Lq) ? p.lse[stat_base + i0 * 128 + row] : 0.f;   // software-prefetched one q tile ahead
+        float dlt_nx = (i0 * 128 + row < p.Lq) ? p.delta[stat_base + i0 * 128 + row] : 0.f;
         for (int i = 0; i < nq; ++i) {
-            const int qrow = i * 128 + row;
+            const int qrow = (i0 + i) * 128 + row;
             const bool qok = qrow < p.Lq;
             const int64_t stat_idx = stat_base + qrow;
             const float neg_lse2 = -lse_nx * kLog2e;
@@ -752,11 +759,20 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             __nv_bfloat16* out = which ? p.dK : p.dV;
             const int64_t ld = which ? p.lddk : p.lddv;
             __nv_bfloat16* orow = out + ((int64_t)b * p.Lkv + kvrow) * ld + (int64_t)h * p.d + p.col0;
+            float* arow = p.dkv_acc ? p.dkv_acc + ((((int64_t)b * p.H + h) * p.Lkv + kvrow) * 2 + which) * p.dq_ld + p.col0 : nullptr;
             for (int c = part; c < p.ncols_out / 16; c += kBwdParts) {
                 uint32_t o[16];
                 tmem_ld16(t + lb + c * 16, o);
                 tmem_wait_ld();
-                if (kvrow < p.Lkv) {
+                if (kvrow < p.Lkv && arow) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = p.col0 + c * 16 + g * 4;
+                        if (col < p.d)
+                            red_add_v4(arow + c * 16 + g * 4, __uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]),
+                                       __uint_as_float(o[g * 4 + 2]), __uint_as_float(o[g * 4 + 3]));
+                    }
+                } else if (kvrow < p.Lkv) {
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
                         const int col = p.col0 + c * 16 + g * 8;
@@ -781,8 +797,11 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
 // delta[b,h,q] = sum_e dO*O ; also zero-fills the fp32 dQ accumulator.  One warp per (b,q,h).
 __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, int64_t ldo, const __nv_bfloat16* __restrict__ dO,
                                      int64_t lddo, int B, int H, int Lq, int d, float* __restrict__ delta,
-                                     float* __restrict__ dq_acc, int dq_ld) {
-    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+                                     float* __restrict__ dq_acc, int dq_ld, float* __restrict__ dkv_acc, int64_t dkv_n) {
+    const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (dkv_acc)
+        for (int64_t i = gtid; i < dkv_n; i += (int64_t)gridDim.x * blockDim.x) dkv_acc[i] = 0.f;
+    const int64_t w = gtid >> 5;
     const int lane = threadIdx.x & 31;
     const int64_t total = (int64_t)B * Lq * H;
     if (w >= total) return;
@@ -823,6 +842,29 @@ __global__ void attn_bwd_post_kernel(const float* __restrict__ dq_acc, int dq_ld
     o.x = pack_bf16x2(v.x, v.y);
     o.y = pack_bf16x2(v.z, v.w);
     *reinterpret_cast<uint2*>(dQ + bq * lddq + (int64_t)h * d + e) = o;
+}
+
+// dK / dV bf16 [B, Lkv, ld] <- fp32 partial sums [B,H,Lkv,2,dq_ld]  (only when the query range was split)
+__global__ void attn_bwd_post_kv_kernel(const float* __restrict__ acc, int dq_ld, int B, int H, int Lkv, int d,
+                                        __nv_bfloat16* __restrict__ dK, int64_t lddk, __nv_bfloat16* __restrict__ dV, int64_t lddv) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int d4 = d / 4;
+    const int64_t total = (int64_t)B * Lkv * H * 2 * d4;
+    if (i >= total) return;
+    const int e = (int)(i % d4) * 4;
+    int64_t r = i / d4;
+    const int which = (int)(r % 2); r /= 2;
+    const int h = (int)(r % H);
+    const int64_t bk = r / H;
+    const int kv = (int)(bk % Lkv);
+    const int b = (int)(bk / Lkv);
+    const float4 v = *reinterpret_cast<const float4*>(acc + ((((int64_t)b * H + h) * Lkv + kv) * 2 + which) * dq_ld + e);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    __nv_bfloat16* dst = which ? dK : dV;
+    const int64_t ld = which ? lddk : lddv;
+    *reinterpret_cast<uint2*>(dst + bk * ld + (int64_t)h * d + e) = o;
 }
 
 static int make_head_map(CUtensorMap* m, const void* base, int64_t ld, int64_t B, int64_t H, int64_t L, int64_t d) {
@@ -904,9 +946,21 @@ extern "C" int hcp_attn_fwd_bf16(const hcp_attn_args* a, hcp_stream_t stream_) {
     return HCP_OK;
 }
 
-extern "C" size_t hcp_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq, int64_t d) {
+static int plan_qsplit(int64_t B, int64_t H, int64_t Lq, int64_t Lkv) {
+    const int64_t base = ((Lkv + 127) / 128) * H * B;
+    const int64_t nq = (Lq + 127) / 128;
+    if (base >= 120 || nq < 2) return 1;
+    int64_t qs = (296 + base - 1) / base;
+    if (qs > nq) qs = nq;
+    const int64_t per = (nq + qs - 1) / qs;
+    return (int)((nq + per - 1) / per);                 // every split owns at least one query tile
+}
+
+extern "C" size_t hcp_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq, int64_t Lkv, int64_t d) {
     const int64_t dq_ld = (d + 3) / 4 * 4;
-    return (size_t)(B * H * Lq * (dq_ld + 1)) * sizeof(float);
+    size_t n = (size_t)(B * H * Lq * (dq_ld + 1));
+    if (plan_qsplit(B, H, Lq, Lkv) > 1) n += (size_t)(B * H * Lkv * 2 * dq_ld);
+    return n * sizeof(float);
 }
 
 extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream_) {
@@ -914,19 +968,22 @@ extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream
         return set_error(HCP_ERR_INVALID, "attn_bwd: null pointer");
     int rc = check_common(a->B, a->H, a->Lq, a->Lkv, a->d);
     if (rc) return rc;
-    if (a->workspace_bytes < hcp_attn_bwd_workspace_bytes(a->B, a->H, a->Lq, a->d))
+    if (a->workspace_bytes < hcp_attn_bwd_workspace_bytes(a->B, a->H, a->Lq, a->Lkv, a->d))
         return set_error(HCP_ERR_INVALID, "attn_bwd: workspace too small");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int dq_ld = (int)((a->d + 3) / 4 * 4);
     float* delta = a->workspace;
     float* dq_acc = a->workspace + a->B * a->H * a->Lq;
+    const int qsplit = plan_qsplit(a->B, a->H, a->Lq, a->Lkv);
+    const int64_t dkv_n = qsplit > 1 ? a->B * a->H * a->Lkv * 2 * dq_ld : 0;
+    float* dkv_acc = qsplit > 1 ? dq_acc + a->B * a->H * a->Lq * dq_ld : nullptr;
     {
         const int64_t warps = a->B * a->Lq * a->H;
         const int threads = 256;
         const int64_t blocks = (warps * 32 + threads - 1) / threads;
         attn_bwd_prep_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const __nv_bfloat16*)a->o, a->ldo,
                                                                        (const __nv_bfloat16*)a->dout, a->lddo, (int)a->B,
-                                                                       (int)a->H, (int)a->Lq, (int)a->d, delta, dq_acc, dq_ld);
+                                                                       (int)a->H, (int)a->Lq, (int)a->d, delta, dq_acc, dq_ld, dkv_acc, dkv_n);
     }
     AttnBwdParams p;
     memset(&p, 0, sizeof(p));
@@ -944,6 +1001,8 @@ extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream
     p.delta = delta;
     p.dq_acc = dq_acc;
     p.dq_ld = dq_ld;
+    p.qsplit = qsplit;
+    p.dkv_acc = dkv_acc;
     p.dK = (__nv_bfloat16*)a->dk; p.lddk = a->lddk;
     p.dV = (__nv_bfloat16*)a->dv; p.lddv = a->lddv;
     p.q_stages = (p.nbox == 1) ? 2 : 1;
@@ -956,7 +1015,7 @@ extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream
         configured = true;
     }
     if (smem > 227 * 1024) return set_error(HCP_ERR_INVALID, "attn_bwd: shared memory budget exceeded");
-    dim3 grid((unsigned)((a->Lkv + 127) / 128), (unsigned)a->H, (unsigned)a->B);
+    dim3 grid((unsigned)(((a->Lkv + 127) / 128) * qsplit), (unsigned)a->H, (unsigned)a->B);
     // output column slices: at most 128 columns per launch, each starting on a 64-column box boundary
     for (int col0 = 0; col0 < p.dn; col0 += 128) {
         p.col0 = col0;
@@ -969,6 +1028,11 @@ extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream
         const int64_t n = a->B * a->Lq * a->H * (a->d / 4);
         attn_bwd_post_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dq_acc, dq_ld, (int)a->B, (int)a->H, (int)a->Lq,
                                                                              (int)a->d, (__nv_bfloat16*)a->dq, a->lddq);
+    }
+    if (qsplit > 1) {
+        const int64_t n = a->B * a->Lkv * a->H * 2 * (a->d / 4);
+        attn_bwd_post_kv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dkv_acc, dq_ld, (int)a->B, (int)a->H, (int)a->Lkv, (int)a->d,
+                                                                                (__nv_bfloat16*)a->dk, a->lddk, (__nv_bfloat16*)a->dv, a->lddv);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd post launch");

@@ -383,8 +383,10 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits,
 }
 
 // number of K-splits for a launch with `ctas` output tiles and `total_kb` 64-wide k-blocks (1 = no split)
-static int plan_splits(int64_t ctas, int64_t total_kb) {
-    if (ctas >= 96 || total_kb < 8) return 1;
+static int plan_splits(int64_t ctas, int64_t total_kb, int64_t N) {
+    // splitting costs a second (finalize) launch and an fp32 round trip: only worth it when the output tiles alone would
+    // leave two thirds of the SMs idle, and never for the skinny LoRA projections
+    if (ctas >= 48 || total_kb < 8 || N <= 64) return 1;
     int64_t s = 148 / ctas;                 // persistent grid: keep the work items within one wave of 148 SMs
     if (s > total_kb / 4) s = total_kb / 4;
     if (s > 16) s = 16;
@@ -410,10 +412,14 @@ struct LGBlock {
     float scale;
     float* dst;
 };
-struct alignas(64) LoraGradParams {
-    CUtensorMap tmX, tmS;
-    int32_t M, n_begin, n_end, tiles_per_cta, nblocks;
+struct LGProblem {
+    int32_t n_begin, n_end, tiles_per_cta, nblocks, col_chunks, splits;
     LGBlock blk[LG_MAX_BLOCKS];
+};
+struct alignas(64) LoraGradParams {
+    CUtensorMap tmX[2], tmS[2];        // up to two independent problems per launch (dW_down and dW_up of one group)
+    int32_t M, nprob;
+    LGProblem prob[2];
 };
 
 __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __grid_constant__ LoraGradParams p) {
@@ -424,10 +430,16 @@ __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __gri
     uint64_t* tmem_full_bar = empty_bar + LG_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ncol0 = p.n_begin + blockIdx.x * 128;
+    // flat grid over (problem, column chunk, row split)
+    int bid = blockIdx.x, z = 0;
+    if (p.nprob == 2 && bid >= p.prob[0].col_chunks * p.prob[0].splits) { bid -= p.prob[0].col_chunks * p.prob[0].splits; z = 1; }
+    const LGProblem& q = p.prob[z];
+    const CUtensorMap* tmX = &p.tmX[z];
+    const CUtensorMap* tmS = &p.tmS[z];
+    const int ncol0 = q.n_begin + (bid % q.col_chunks) * 128;
     const int total_tiles = (p.M + 127) / 128;
-    const int t0 = blockIdx.y * p.tiles_per_cta;
-    const int t1 = min(total_tiles, t0 + p.tiles_per_cta);
+    const int t0 = (bid / q.col_chunks) * q.tiles_per_cta;
+    const int t1 = min(total_tiles, t0 + q.tiles_per_cta);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < LG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -447,9 +459,9 @@ __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __gri
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full_bar[stage], LG_STAGE_BYTES);
                 uint8_t* base = smem + stage * LG_STAGE_BYTES;
-                tma_load_2d(base, &p.tmX, &full_bar[stage], ncol0, t * 128);
-                tma_load_2d(base + 128 * 128, &p.tmX, &full_bar[stage], ncol0 + 64, t * 128);
-                tma_load_2d(base + 2 * 128 * 128, &p.tmS, &full_bar[stage], 0, t * 128);
+                tma_load_2d(base, tmX, &full_bar[stage], ncol0, t * 128);
+                tma_load_2d(base + 128 * 128, tmX, &full_bar[stage], ncol0 + 64, t * 128);
+                tma_load_2d(base + 2 * 128 * 128, tmS, &full_bar[stage], 0, t * 128);
                 if (++stage == LG_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -483,9 +495,9 @@ __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __gri
             uint32_t v[16];
             tmem_ld16(trow + c * 16, v);
             tmem_wait_ld();
-            if (t1 > t0 && n < p.n_end) {
-                for (int b = 0; b < p.nblocks; ++b) {
-                    const LGBlock& k = p.blk[b];
+            if (t1 > t0 && n < q.n_end) {
+                for (int b = 0; b < q.nblocks; ++b) {
+                    const LGBlock& k = q.blk[b];
                     if (n < k.n_lo || n >= k.n_hi) continue;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
@@ -553,7 +565,7 @@ static int dispatch_gemm(int bn, GemmKParams& kp, int m_tiles, cudaStream_t stre
 // plain or split-K launch (+ finalize).  `ws` may be NULL / too small: then the launch is not split.
 static int run_gemm(int bn, GemmKParams& kp, int m_tiles, int64_t total_kb, float* ws, size_t ws_bytes, bool allow_split,
                     cudaStream_t stream) {
-    int splits = allow_split ? plan_splits((int64_t)m_tiles * kp.tiles_n, total_kb) : 1;
+    int splits = allow_split ? plan_splits((int64_t)m_tiles * kp.tiles_n, total_kb, kp.N) : 1;
     if (splits > 1 && (!ws || ws_bytes < (size_t)splits * kp.M * kp.N * sizeof(float))) splits = 1;
     if (splits > 1) {
         kp.kb_per_split = (int)((total_kb + splits - 1) / splits);
@@ -585,7 +597,7 @@ using namespace hcp;
 extern "C" size_t hcp_splitk_workspace_bytes(int64_t M, int64_t N, int64_t total_k) {
     const int bn = pick_bn(N);
     const int64_t ctas = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
-    const int splits = plan_splits(ctas, (total_k + BLOCK_K - 1) / BLOCK_K);
+    const int splits = plan_splits(ctas, (total_k + BLOCK_K - 1) / BLOCK_K, N);
     return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
 }
 
@@ -757,41 +769,68 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
     return HCP_OK;
 }
 
-extern "C" int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t M, int64_t n_begin, int64_t n_end,
-                             const hcp_lora_grad_block* blocks, int32_t nblocks, hcp_stream_t stream_) {
-    if (!S || !X || !blocks || nblocks < 1) return set_error(HCP_ERR_INVALID, "lora_grad: null pointer");
-    if (M <= 0 || n_end <= n_begin || (ldx % 8) != 0 || (n_begin % 8) != 0) return set_error(HCP_ERR_INVALID, "lora_grad: shape");
+static int lg_fill(LoraGradParams& p, int z, const void* S, const void* X, int64_t ldx, int64_t M, int64_t n_begin, int64_t n_end,
+                   const hcp_lora_grad_block* blocks, int32_t nblocks) {
+    if (!S || !X || !blocks || nblocks < 1 || nblocks > LG_MAX_BLOCKS) return set_error(HCP_ERR_INVALID, "lora_grad: 1..8 blocks per problem");
+    if (n_end <= n_begin || (ldx % 8) != 0 || (n_begin % 8) != 0) return set_error(HCP_ERR_INVALID, "lora_grad: shape");
+    int rc = make_tmap_2d(&p.tmX[z], X, (uint64_t)ldx, (uint64_t)M, (uint64_t)ldx, 64, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&p.tmS[z], S, 64, (uint64_t)M, 64, 64, 128);
+    if (rc) return rc;
+    LGProblem& q = p.prob[z];
+    q.n_begin = (int)n_begin; q.n_end = (int)n_end; q.nblocks = nblocks;
+    q.col_chunks = (int)((n_end - n_begin + 127) / 128);
+    const int total_tiles = (int)((M + 127) / 128);
+    int splits = (148 + q.col_chunks - 1) / q.col_chunks;
+    if (splits > total_tiles) splits = total_tiles;
+    q.tiles_per_cta = (total_tiles + splits - 1) / splits;
+    q.splits = (total_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
+    for (int i = 0; i < nblocks; ++i) {
+        const hcp_lora_grad_block& k = blocks[i];
+        if (k.rank < 1 || k.c0 < 0 || k.c0 + k.rank > 64 || !k.dst) return set_error(HCP_ERR_INVALID, "lora_grad: block descriptor");
+        q.blk[i].n_lo = (int)k.n_lo; q.blk[i].n_hi = (int)k.n_hi; q.blk[i].c0 = k.c0; q.blk[i].rank = k.rank;
+        q.blk[i].transpose_out = k.transpose_out; q.blk[i].dst_ld = (int)k.dst_ld; q.blk[i].scale = k.scale; q.blk[i].dst = k.dst;
+    }
+    return HCP_OK;
+}
+
+static int lg_launch(LoraGradParams& p, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(lora_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_SMEM_BYTES);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(lora_grad)");
         configured = true;
     }
-    const int col_chunks = (int)((n_end - n_begin + 127) / 128);
-    const int total_tiles = (int)((M + 127) / 128);
-    int splits = (296 + col_chunks - 1) / col_chunks;
-    if (splits > total_tiles) splits = total_tiles;
-    const int tiles_per_cta = (total_tiles + splits - 1) / splits;
-    splits = (total_tiles + tiles_per_cta - 1) / tiles_per_cta;
-    for (int b0 = 0; b0 < nblocks; b0 += LG_MAX_BLOCKS) {
-        LoraGradParams p;
-        memset(&p, 0, sizeof(p));
-        int rc = make_tmap_2d(&p.tmX, X, (uint64_t)ldx, (uint64_t)M, (uint64_t)ldx, 64, 128);
-        if (rc) return rc;
-        rc = make_tmap_2d(&p.tmS, S, 64, (uint64_t)M, 64, 64, 128);
-        if (rc) return rc;
-        p.M = (int)M; p.n_begin = (int)n_begin; p.n_end = (int)n_end; p.tiles_per_cta = tiles_per_cta;
-        p.nblocks = (nblocks - b0 < LG_MAX_BLOCKS) ? (nblocks - b0) : LG_MAX_BLOCKS;
-        for (int i = 0; i < p.nblocks; ++i) {
-            const hcp_lora_grad_block& k = blocks[b0 + i];
-            if (k.rank < 1 || k.c0 < 0 || k.c0 + k.rank > 64 || !k.dst) return set_error(HCP_ERR_INVALID, "lora_grad: block descriptor");
-            p.blk[i].n_lo = (int)k.n_lo; p.blk[i].n_hi = (int)k.n_hi; p.blk[i].c0 = k.c0; p.blk[i].rank = k.rank;
-            p.blk[i].transpose_out = k.transpose_out; p.blk[i].dst_ld = (int)k.dst_ld; p.blk[i].scale = k.scale; p.blk[i].dst = k.dst;
-        }
-        dim3 grid(col_chunks, splits);
-        lora_grad_tc_kernel<<<grid, kLgThreads, LG_SMEM_BYTES, (cudaStream_t)stream_>>>(p);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return set_cuda_error(e, "lora_grad launch");
-    }
+    int ctas = 0;
+    for (int z = 0; z < p.nprob; ++z) ctas += p.prob[z].col_chunks * p.prob[z].splits;
+    lora_grad_tc_kernel<<<ctas, kLgThreads, LG_SMEM_BYTES, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "lora_grad launch");
     return HCP_OK;
+}
+
+extern "C" int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t M, int64_t n_begin, int64_t n_end,
+                             const hcp_lora_grad_block* blocks, int32_t nblocks, hcp_stream_t stream_) {
+    if (M <= 0) return set_error(HCP_ERR_INVALID, "lora_grad: M");
+    LoraGradParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)M; p.nprob = 1;
+    int rc = lg_fill(p, 0, S, X, ldx, M, n_begin, n_end, blocks, nblocks);
+    if (rc) return rc;
+    return lg_launch(p, (cudaStream_t)stream_);
+}
+
+// dW_down and dW_up of one LoRA group in ONE launch (two independent TN GEMMs over the same M token rows).
+extern "C" int hcp_lora_grad_pair(const void* U, const void* x, int64_t ldx, int64_t K, const hcp_lora_grad_block* down,
+                                  const void* T, const void* dy, int64_t lddy, int64_t N, const hcp_lora_grad_block* up,
+                                  int32_t nblocks, int64_t M, hcp_stream_t stream_) {
+    if (M <= 0) return set_error(HCP_ERR_INVALID, "lora_grad_pair: M");
+    LoraGradParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)M; p.nprob = 2;
+    int rc = lg_fill(p, 0, U, x, ldx, M, 0, K, down, nblocks);
+    if (rc) return rc;
+    rc = lg_fill(p, 1, T, dy, lddy, M, 0, N, up, nblocks);
+    if (rc) return rc;
+    return lg_launch(p, (cudaStream_t)stream_);
 }

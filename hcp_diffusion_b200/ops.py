@@ -215,8 +215,16 @@ class FusedLinearFn(torch.autograd.Function):
                 up[i].n_lo, up[i].n_hi, up[i].c0, up[i].rank = b.o0, b.o0 + b.out_dim, b.c0, b.rank
                 up[i].scale, up[i].transpose_out, up[i].dst, up[i].dst_ld = b.alpha, 1, gu.data_ptr(), b.rank
             # dW_down = U^T x ;  dW_up = alpha * dY^T T   (tensor-core TN GEMMs, all blocks of the group per launch)
-            call("hcp_lora_grad", U.data_ptr(), x.data_ptr(), ks[0], M, 0, ks[0], down, nb, stream_ptr())
-            call("hcp_lora_grad", T.data_ptr(), dy.data_ptr(), N, M, 0, N, up, nb, stream_ptr())
+            if nb <= 8:
+                call("hcp_lora_grad_pair", U.data_ptr(), x.data_ptr(), ks[0], ks[0], down, T.data_ptr(), dy.data_ptr(), N, N, up, nb, M,
+                     stream_ptr())
+            else:
+                for b0 in range(0, nb, 8):
+                    n8 = min(8, nb - b0)
+                    call("hcp_lora_grad", U.data_ptr(), x.data_ptr(), ks[0], M, 0, ks[0], C.cast(C.byref(down[b0]), C.POINTER(_lib.LoraGradBlock)),
+                         n8, stream_ptr())
+                    call("hcp_lora_grad", T.data_ptr(), dy.data_ptr(), N, M, 0, N, C.cast(C.byref(up[b0]), C.POINTER(_lib.LoraGradBlock)), n8,
+                         stream_ptr())
         grads = []
         off = 0
         for i, k in enumerate(ks):
@@ -440,7 +448,7 @@ class AttentionFn(torch.autograd.Function):
         # gradients are written straight into buffers with the layout of the sources
         dq_src = torch.empty_like(q_src)
         dkv = dq_src if same else torch.empty_like(kvt)
-        wsb = _lib.lib().hcp_attn_bwd_workspace_bytes(B, heads, Lq, d)
+        wsb = _lib.lib().hcp_attn_bwd_workspace_bytes(B, heads, Lq, Lkv, d)
         ws = torch.empty((wsb // 4,), dtype=torch.float32, device=do.device)
         a = AttnBwdArgs()
         a.q, a.ldq = q_src.data_ptr() + 2 * offs[0], ldq
@@ -455,6 +463,8 @@ class AttentionFn(torch.autograd.Function):
         a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
         call("hcp_attn_bwd_bf16", C.byref(a), stream_ptr())
         if d > 128:
+            _lib.launch_count += 1
+        if Lkv <= 128 and Lq > 128:
             _lib.launch_count += 1
         return None, None, None, None, dq_src, (None if same else dkv)
 

@@ -142,11 +142,11 @@ typedef struct hcp_attn_bwd_args {
     void* dq; int64_t lddq;
     void* dk; int64_t lddk;
     void* dv; int64_t lddv;
-    float* workspace;            /* >= hcp_attn_bwd_workspace_bytes(B,H,Lq,d) bytes, caller-owned scratch */
+    float* workspace;            /* >= hcp_attn_bwd_workspace_bytes(B,H,Lq,Lkv,d) bytes, caller-owned scratch */
     size_t workspace_bytes;
 } hcp_attn_bwd_args;
 
-size_t hcp_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq, int64_t d);
+size_t hcp_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq, int64_t Lkv, int64_t d);
 int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* args, hcp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -244,7 +244,11 @@ typedef struct hcp_lora_grad_block {
     int64_t dst_ld;
 } hcp_lora_grad_block;
 int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t M, int64_t n_begin, int64_t n_end,
-                  const hcp_lora_grad_block* blocks, int32_t nblocks, hcp_stream_t stream);
+                  const hcp_lora_grad_block* blocks, int32_t nblocks, hcp_stream_t stream);     /* nblocks <= 8 */
+/* Both gradients of one LoRA group in a single launch: dW_down from (U [M,64], x [M,K]) and dW_up from (T [M,64], dY [M,N]). */
+int hcp_lora_grad_pair(const void* U, const void* x, int64_t ldx, int64_t K, const hcp_lora_grad_block* down,
+                       const void* T, const void* dy, int64_t lddy, int64_t N, const hcp_lora_grad_block* up,
+                       int32_t nblocks, int64_t M, hcp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * The step either side of the UNet call (reference hcpdiff/train_ac.py:437-447, 485-494, 506-515).

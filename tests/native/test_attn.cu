@@ -191,7 +191,7 @@ static void run_attn_case(const AttnCase& c, int* pass, int* fail) {
         CK(cudaMalloc(&bias, (size_t)c.B * c.Lkv * 4));
         afill_f32<<<(unsigned)((c.B * c.Lkv + 255) / 256), 256>>>(bias, (size_t)c.B * c.Lkv, 24, 2.0f, 0.f);
     }
-    size_t wsb = hcp_attn_bwd_workspace_bytes(c.B, c.H, c.Lq, c.d);
+    size_t wsb = hcp_attn_bwd_workspace_bytes(c.B, c.H, c.Lq, c.Lkv, c.d);
     CK(cudaMalloc(&ws, wsb));
     const float scale = 1.f / sqrtf((float)c.d);
 
