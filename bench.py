@@ -39,6 +39,19 @@ def measured_peaks():
     return 1400.0, 1590.0, 6650.0, "fallback"
 
 
+def usable_cores() -> int:
+    """Host threads this process may really use: the scheduler affinity mask capped by the cgroup CPU quota (a box that
+    shows 128 logical CPUs but grants a 16-CPU quota thrashes with 128 threads)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -88,7 +101,7 @@ def cpu_reference_steps(max_steps: int, warmup: int, budget_s: float):
     """One step = ONE image (B=1, 64x64 latent, 77 tokens) through the reference step order (train_ac.py:467-504): forward ->
     MSE(eps) -> backward -> clip 1.0 -> AdamW -> zero_grad, fp32, all host threads.  Steps stop early when `budget_s` is spent."""
     from oracle import unet_ref as U
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     spec = U.SD15
     sd = U.init_params(spec)
@@ -309,6 +322,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout: rank 0 prints ONE json line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
         run_product_arm(args, rank, world, local_rank)

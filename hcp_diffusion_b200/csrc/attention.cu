@@ -519,6 +519,7 @@ struct alignas(64) AttnBwdParams {
     const float* delta;      // [B,H,Lq]  rowsum(dO * O)
     float* dq_acc;           // [B,H,Lq,dq_ld] fp32
     int dq_ld;
+    int early_sdp;           // 1: dQ un-aliased + double-buffered Q/dO -> S/dP of the next tile are issued early
     int qsplit;              // CTAs per kv tile along the query dimension
     float* dkv_acc;          // [B,H,Lkv,2,dq_ld] fp32 partial dK/dV when qsplit > 1, else nullptr
     __nv_bfloat16 *dK, *dV;
@@ -579,7 +580,11 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem, tdV = tmem + 256, tdK = tmem + 384;
+    // TMEM columns: S [0,128), dP [128,256), then the accumulators.  dQ aliases S unless `early_sdp` (it then has its own columns).
+    const uint32_t tS = tmem, tdP = tmem + 128;
+    const uint32_t tdV = tmem + 256;
+    const uint32_t tdK = p.early_sdp ? tmem + 256 + p.ncols_out : tmem + 384;
+    const uint32_t tdQ = p.early_sdp ? tmem + 256 + 2 * p.ncols_out : tmem;
 
     if (warp == 4 * kBwdParts) {
         if (elect_one()) {
@@ -602,15 +607,10 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             const uint32_t idesc_acc = make_idesc_bf16(128, p.ncols_out, 1, 1);   // dV, dK: A and B MN-major
             const uint32_t idesc_dq = make_idesc_bf16(128, p.ncols_out, 0, 1);    // dQ: A K-major, B MN-major
             const uint32_t box0 = (p.col0 / 64) * TILE_BYTES;                     // first box of the output slice
-            for (int i = 0; i < nq; ++i) {
-                const int st = (p.q_stages == 2) ? (i & 1) : 0;
-                const uint32_t ph = (p.q_stages == 2) ? ((i >> 1) & 1) : (i & 1);
-                if (p.q_stages == 2 && i + 1 < nq) load_q(i + 1);   // stage (i+1)&1 was released by dq_full of i-1
-                mbar_wait(&q_full[st], ph);
-                tc_fence_after();
+            const uint32_t kb = smem_u32(sK), vb = smem_u32(sV);
+            const uint32_t pb = smem_u32(sP), dsb = smem_u32(sdS);
+            auto issue_sdp = [&](int st) {          // S = Q K^T, dP = dO V^T  (contraction over d)
                 const uint32_t qb = smem_u32(sQ + st * tile_bytes), dob = smem_u32(sdO + st * tile_bytes);
-                const uint32_t kb = smem_u32(sK), vb = smem_u32(sV);
-                // S = Q K^T, dP = dO V^T  (contraction over d)
                 for (int ks = 0; ks < p.dn / 16; ++ks) {
                     const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
                     umma_ss(tS, make_smem_desc(qb + off, 16, 1024), make_smem_desc(kb + off, 16, 1024), idesc_s, ks > 0);
@@ -620,34 +620,80 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                     umma_ss(tdP, make_smem_desc(dob + off, 16, 1024), make_smem_desc(vb + off, 16, 1024), idesc_s, ks > 0);
                 }
                 umma_commit(sdp_full);
-                // dV += P^T dO   (M = kv, K = q rows: both operands MN-major, k-step = 16 q rows = 2048 B)
-                mbar_wait(p_ready, i & 1);
-                tc_fence_after();
-                const uint32_t pb = smem_u32(sP), dsb = smem_u32(sdS);
-                for (int ks = 0; ks < 8; ++ks) {
-                    umma_ss(tdV, make_smem_desc(pb + ks * 2048, TILE_BYTES, 1024),
-                            make_smem_desc(dob + box0 + ks * 2048, TILE_BYTES, 1024), idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
-                }
+            };
+            auto issue_dv = [&](int st, bool acc) {  // dV += P^T dO   (M = kv, K = q rows: both operands MN-major, 2048 B per k-step)
+                const uint32_t dob = smem_u32(sdO + st * tile_bytes);
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_ss(tdV, make_smem_desc(pb + ks * 2048, TILE_BYTES, 1024), make_smem_desc(dob + box0 + ks * 2048, TILE_BYTES, 1024),
+                            idesc_acc, (acc || ks > 0) ? 1u : 0u);
                 umma_commit(dv_done);
-                // dK += dS^T Q ;  dQ_i = dS K
-                mbar_wait(ds_ready, i & 1);
-                tc_fence_after();
+            };
+            auto issue_dk = [&](int st, bool acc) {  // dK += dS^T Q
+                const uint32_t qb = smem_u32(sQ + st * tile_bytes);
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_ss(tdK, make_smem_desc(dsb + ks * 2048, TILE_BYTES, 1024), make_smem_desc(qb + box0 + ks * 2048, TILE_BYTES, 1024),
+                            idesc_acc, (acc || ks > 0) ? 1u : 0u);
+            };
+            auto issue_dq = [&]() {                  // dQ_i = dS K: dS K-major (two 64-wide boxes), K_j MN-major
                 for (int ks = 0; ks < 8; ++ks) {
-                    umma_ss(tdK, make_smem_desc(dsb + ks * 2048, TILE_BYTES, 1024),
-                            make_smem_desc(qb + box0 + ks * 2048, TILE_BYTES, 1024), idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
-                }
-                for (int ks = 0; ks < 8; ++ks) {   // contraction over kv: dS K-major (two 64-wide boxes), K_j MN-major
                     const uint32_t aoff = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
-                    umma_ss(tdQ, make_smem_desc(dsb + aoff, 16, 1024),
-                            make_smem_desc(kb + box0 + ks * 2048, TILE_BYTES, 1024), idesc_dq, ks > 0);
+                    umma_ss(tdQ, make_smem_desc(dsb + aoff, 16, 1024), make_smem_desc(kb + box0 + ks * 2048, TILE_BYTES, 1024), idesc_dq,
+                            ks > 0);
                 }
                 umma_commit(dq_full);
-                if (p.q_stages == 1 && i + 1 < nq) {
-                    mbar_wait(dq_full, i & 1);      // Q/dO tile consumed
-                    load_q(i + 1);
-                }
-                mbar_wait(dq_read, i & 1);          // S/dP/dQ columns free again
+            };
+            if (p.early_sdp) {
+                // dQ has its own TMEM columns and Q/dO are double buffered: S/dP of tile i+1 are issued as soon as the softmax
+                // warps have consumed S/dP of tile i, so they run while dK/dQ of tile i execute and dQ_i is drained.
+                if (nq > 1) load_q(1);
+                mbar_wait(&q_full[0], 0);
                 tc_fence_after();
+                issue_sdp(0);
+                for (int i = 0; i < nq; ++i) {
+                    const int st = i & 1;
+                    mbar_wait(p_ready, i & 1);
+                    tc_fence_after();
+                    issue_dv(st, i > 0);
+                    mbar_wait(ds_ready, i & 1);
+                    tc_fence_after();
+                    if (i + 1 < nq) {
+                        mbar_wait(&q_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+                        tc_fence_after();
+                        issue_sdp((i + 1) & 1);
+                    }
+                    issue_dk(st, i > 0);
+                    if (i > 0) {
+                        mbar_wait(dq_read, (i - 1) & 1);     // dQ_{i-1} drained from TMEM
+                        tc_fence_after();
+                    }
+                    issue_dq();
+                    if (i + 2 < nq) {
+                        mbar_wait(dq_full, i & 1);           // every MMA reading Q_i / dO_i has retired
+                        load_q(i + 2);
+                    }
+                }
+            } else {
+                for (int i = 0; i < nq; ++i) {
+                    const int st = (p.q_stages == 2) ? (i & 1) : 0;
+                    const uint32_t ph = (p.q_stages == 2) ? ((i >> 1) & 1) : (i & 1);
+                    if (p.q_stages == 2 && i + 1 < nq) load_q(i + 1);   // stage (i+1)&1 was released by dq_full of i-1
+                    mbar_wait(&q_full[st], ph);
+                    tc_fence_after();
+                    issue_sdp(st);
+                    mbar_wait(p_ready, i & 1);
+                    tc_fence_after();
+                    issue_dv(st, i > 0);
+                    mbar_wait(ds_ready, i & 1);
+                    tc_fence_after();
+                    issue_dk(st, i > 0);
+                    issue_dq();
+                    if (p.q_stages == 1 && i + 1 < nq) {
+                        mbar_wait(dq_full, i & 1);      // Q/dO tile consumed
+                        load_q(i + 1);
+                    }
+                    mbar_wait(dq_read, i & 1);          // S/dP/dQ columns free again
+                    tc_fence_after();
+                }
             }
             umma_commit(acc_full);
         }
@@ -1007,6 +1053,7 @@ extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream
     p.dV = (__nv_bfloat16*)a->dv; p.lddv = a->lddv;
     p.q_stages = (p.nbox == 1) ? 2 : 1;
     p.share_pds = (p.nbox >= 3) ? 1 : 0;
+    p.early_sdp = (p.q_stages == 2 && 256 + 3 * p.dn <= 512 && getenv("HCP_ATTN_BWD_NO_EARLY") == nullptr) ? 1 : 0;
     const int smem = (2 + 2 * p.q_stages) * p.nbox * TILE_BYTES + (p.share_pds ? 2 : 4) * TILE_BYTES + 256 + 1024;
     static bool configured = false;
     if (!configured) {
