@@ -706,6 +706,23 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
         const float* bias = p.kv_bias ? p.kv_bias + (int64_t)b * p.Lkv : nullptr;
         const bool special = (bias != nullptr) || (ncols < 128);
         const int64_t stat_base = ((int64_t)b * p.H + h) * p.Lq;
+        auto drain_dq = [&](int qr) {            // TMEM dQ tile -> fp32 accumulator (vector red.global)
+            float* dqrow = p.dq_acc + (stat_base + qr) * p.dq_ld + p.col0;
+            for (int c = part; c < p.ncols_out / 16; c += kBwdParts) {
+                uint32_t o[16];
+                tmem_ld16(tdQ + lb + c * 16, o);
+                tmem_wait_ld();
+                if (qr < p.Lq) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = p.col0 + c * 16 + g * 4;
+                        if (col < p.d)
+                            red_add_v4(dqrow + c * 16 + g * 4, __uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]),
+                                       __uint_as_float(o[g * 4 + 2]), __uint_as_float(o[g * 4 + 3]));
+                    }
+                }
+            }
+        };
         float lse_nx = (i0 * 128 + row < p.Lq) ? p.lse[stat_base + i0 * 128 + row] : 0.f;   // software-prefetched one q tile ahead
         float dlt_nx = (i0 * 128 + row < p.Lq) ? p.delta[stat_base + i0 * 128 + row] : 0.f;
         for (int i = 0; i < nq; ++i) {
@@ -731,6 +748,10 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                     tmem_ld32(tS + lb + c * 32, v);
                     if (do_ds) tmem_ld32(tdP + lb + c * 32, w);
                     tmem_wait_ld();
+                    if (p.early_sdp && i > 0 && c == part * kChunksPerPart) {
+                        mbar_wait(dq_full, (i - 1) & 1);    // dK/dQ of the previous tile have finished reading sP / sdS
+                        tc_fence_after();
+                    }
                     uint32_t pk[16], dk[16];
                     if (!special && qok) {
 #pragma unroll
@@ -775,26 +796,25 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             tc_fence_before();
             fence_proxy_async_smem();
             mbar_arrive(ds_ready);
-            // ---- drain dQ_i into the fp32 accumulator
-            mbar_wait(dq_full, i & 1);
-            tc_fence_after();
-            float* dqrow = p.dq_acc + stat_idx * p.dq_ld + p.col0;
-            for (int c = part; c < p.ncols_out / 16; c += kBwdParts) {
-                uint32_t o[16];
-                tmem_ld16(tdQ + lb + c * 16, o);
-                tmem_wait_ld();
-                if (qok) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int col = p.col0 + c * 16 + g * 4;
-                        if (col < p.d)
-                            red_add_v4(dqrow + c * 16 + g * 4, __uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]),
-                                       __uint_as_float(o[g * 4 + 2]), __uint_as_float(o[g * 4 + 3]));
-                    }
-                }
+            if (!p.early_sdp) {
+                // ---- drain dQ_i into the fp32 accumulator
+                mbar_wait(dq_full, i & 1);
+                tc_fence_after();
+                drain_dq(qrow);
+                tc_fence_before();
+                mbar_arrive(dq_read);
+            } else if (i > 0) {
+                // dQ of the PREVIOUS tile: its MMAs retired long ago (waited above), so this never blocks, and the tensor pipe is
+                // meanwhile busy with dV_i, S/dP_{i+1}, dK_i
+                drain_dq(qrow - 128);
+                tc_fence_before();
+                mbar_arrive(dq_read);
             }
-            tc_fence_before();
-            mbar_arrive(dq_read);
+        }
+        if (p.early_sdp) {
+            mbar_wait(dq_full, (nq - 1) & 1);
+            tc_fence_after();
+            drain_dq((i0 + nq - 1) * 128 + row);
         }
         // ---- dK, dV of this kv tile: thread == kv row
         mbar_wait(acc_full, 0);
