@@ -296,7 +296,9 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
     uint64_t* s_full = bars + 7;      // [2]
     uint64_t* p_ready = bars + 9;     // [2]
     uint64_t* o_full = bars + 11;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* s_free = bars + 12;     // [2] every softmax thread of the tile holds its logits in registers
+    uint64_t* pv_done = bars + 14;    // [2] PV of the previous kv tile has retired (P / O may be touched again)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.y, b = blockIdx.z;
@@ -307,7 +309,10 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
         for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_done[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 256); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 256);
+            mbar_init(&s_free[i], 256); mbar_init(&pv_done[i], 1);
+        }
         mbar_init(o_full, 1);
         fence_mbar_init();
     }
@@ -319,6 +324,9 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // TMEM columns of query tile t: S fp32 [t*256, +128), P bf16 (packed) [t*256+128, +64), O fp32 [t*256+192, +dn).
+    // P has its own columns, so S of the NEXT kv tile can be issued as soon as the softmax warps hold the current logits in
+    // registers: QK^T(j+1) runs on the tensor pipe while the exponentials of tile j are computed.
 
     if (warp == 16) {
         if (elect_one()) {
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
                 const uint32_t qb = smem_u32(sQ + t * tile_bytes), kb = smem_u32(sK + st * tile_bytes);
                 for (int ks = 0; ks < p.dn / 16; ++ks) {
                     const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
-                    umma_ss(tmem + t * 128, make_smem_desc(qb + off, 16, 1024), make_smem_desc(kb + off, 16, 1024), idesc, ks > 0);
+                    umma_ss(tmem + t * 256, make_smem_desc(qb + off, 16, 1024), make_smem_desc(kb + off, 16, 1024), idesc, ks > 0);
                 }
                 umma_commit(&s_full[t]);
             };
@@ -347,8 +355,9 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
                 const uint32_t idesc = make_idesc_bf16(128, p.dn, 0, 1);
                 const uint32_t vb = smem_u32(sV + st * tile_bytes);
                 for (int ks = 0; ks < ((ncols + 15) >> 4); ++ks)
-                    umma_ts(tmem + 256 + t * 128, tmem + t * 128 + ks * 8, make_smem_desc(vb + ks * 2048, TILE_BYTES, 1024), idesc,
+                    umma_ts(tmem + t * 256 + 192, tmem + t * 256 + 128 + ks * 8, make_smem_desc(vb + ks * 2048, TILE_BYTES, 1024), idesc,
                             (j > 0 || ks > 0) ? 1u : 0u);
+                umma_commit(&pv_done[t]);
             };
             mbar_arrive_expect_tx(q_full, p.nq * tile_bytes);
             for (int t = 0; t < p.nq; ++t)
@@ -361,18 +370,20 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
             for (int t = 0; t < p.nq; ++t) issue_s(t, 0);
             for (int j = 0; j < nkv; ++j) {
                 const int st = j % S;
+                if (S > 1 && j + 1 < nkv) {                             // next K tile is resident: issue S(j+1) early
+                    mbar_wait(&kv_full[(j + 1) % S], ((j + 1) / S) & 1);
+                    tc_fence_after();
+                    for (int t = 0; t < p.nq; ++t) {
+                        mbar_wait(&s_free[t], j & 1);                   // logits of tile j are in registers
+                        tc_fence_after();
+                        issue_s(t, j + 1);
+                    }
+                }
                 for (int t = 0; t < p.nq; ++t) {
                     mbar_wait(&p_ready[t], j & 1);
                     tc_fence_after();
                     issue_pv(t, j);
                     if (t == p.nq - 1) umma_commit(&kv_done[st]);      // K_j / V_j no longer needed once these retire
-                    if (S > 1 && j + 1 < nkv) {                         // next tile is already resident: keep the pipe busy
-                        if (t == 0) {
-                            mbar_wait(&kv_full[(j + 1) % S], ((j + 1) / S) & 1);
-                            tc_fence_after();
-                        }
-                        issue_s(t, j + 1);
-                    }
                 }
                 if (j + S < nkv) {                                      // refill the stage tile j used
                     mbar_wait(&kv_done[st], (j / S) & 1);
@@ -392,7 +403,7 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
         const int row = quarter * 32 + lane;
         const int qrow = q0 + t * 128 + row;
         const uint32_t lb = lane_base(quarter);
-        const uint32_t tS = tmem + t * 128, tO = tmem + 256 + t * 128;
+        const uint32_t tS = tmem + t * 256, tP = tS + 128, tO = tS + 192;
         const float* bias = p.kv_bias ? p.kv_bias + (int64_t)b * p.Lkv : nullptr;
         float m = -INFINITY, l = 0.f;
         for (int j = 0; j < nkv; ++j) {
@@ -426,6 +437,7 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
             float* xch = sx + (((j & 1) * 2 + t) * 2) * 128;
             xch[half * 128 + row] = mx;
             named_bar_sync(1 + t, 256);
+            mbar_arrive(&s_free[t]);                 // S columns may be overwritten by QK^T of the next kv tile
             mx = fmaxf(mx, xch[(half ^ 1) * 128 + row]);
             if (j == 0) {
                 m = (mx == -INFINITY) ? 0.f : mx;
@@ -435,6 +447,8 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
                     const float alpha = fast_exp2(m - m_new);
                     l *= alpha;
                     if (half == 0) {
+                        mbar_wait(&pv_done[t], (j - 1) & 1);      // O is stable: PV of the previous tile retired
+                        tc_fence_after();
                         for (int c = 0; c < p.dn / 16; ++c) {
                             uint32_t o[16];
                             tmem_ld16(tO + lb + c * 16, o);
@@ -462,7 +476,11 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
                 pk[16 + (e >> 1)] = pack_bf16x2(p2, p3);
             }
             l += l0 + l1;
-            tmem_st32(tS + lb + half * 32, pk);      // P (bf16) over the S columns every warp of this tile has already consumed
+            if (j > 0) {
+                mbar_wait(&pv_done[t], (j - 1) & 1);  // the tensor pipe has finished reading the previous P
+                tc_fence_after();
+            }
+            tmem_st32(tP + lb + half * 32, pk);       // P (bf16, packed pairs) into its own TMEM columns
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&p_ready[t]);
@@ -964,7 +982,7 @@ extern "C" int hcp_attn_fwd_bf16(const hcp_attn_args* a, hcp_stream_t stream_) {
         p.B = (int)a->B; p.H = (int)a->H; p.Lq = (int)a->Lq; p.Lkv = (int)a->Lkv; p.d = (int)a->d;
         p.nbox = (int)((a->d + 63) / 64);
         p.dn = (int)((a->d + 15) / 16 * 16);
-        p.nq = (p.dn <= 128 && a->Lq > 128) ? 2 : 1;
+        p.nq = (p.dn <= 64 && a->Lq > 128) ? 2 : 1;      // two tiles need 2 x (128 S + 64 P + dn O) <= 512 TMEM columns
         p.kv_stages = (p.nbox == 1) ? 3 : (p.nbox == 2 ? 2 : 1);
         p.scale_log2 = a->scale * kLog2e;
         p.kv_bias = a->kv_bias;
