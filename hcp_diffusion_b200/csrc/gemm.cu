@@ -16,6 +16,7 @@
 // The 3x3 convolution uses the same pipeline: the A tile of tap (kh,kw) and channel block c is a 4D (or 5D
 // for stride 2) TMA box over the NHWC activation at a shifted coordinate; coordinates outside the image are
 // zero-filled by the TMA unit, which IS the padding.  B is the weight matrix [Cout, 9*Cin].
+#include <stdlib.h>
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/hcp_b200.h"
@@ -67,14 +68,18 @@ struct alignas(64) GemmKParams {
     float* ws;                         // [splits, M, N] fp32
 };
 
-template <int BN>
+// MSUB = number of 128-row M tiles one work item covers.  MSUB = 2 halves the B (weight) traffic per FLOP -- the long-K
+// convolutions are bound by the L2 -> SM operand stream, not by the tensor pipe -- at the price of using both TMEM accumulators
+// for one item (no epilogue / main-loop overlap, irrelevant when K is thousands).
+template <int BN, int MSUB = 1>
 struct GemmCfg {
-    static constexpr int STAGES = (BN > 64) ? 5 : 8;     // one CTA per SM: the ring must cover the TMA latency alone
+    static constexpr int STAGES = (MSUB == 2) ? 3 : (BN > 64) ? 5 : 8;     // one CTA per SM: the ring must cover the TMA latency alone
+    static constexpr int A_BYTES = MSUB * A_STAGE_BYTES;
     static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
     static constexpr int ACC_STRIDE = 256;                         // TMEM columns between the two accumulators
     static constexpr int STG_PITCH = BN * 2 + 16;                  // staging row pitch in bytes: odd number of 16-byte units
     static constexpr int STG_BYTES = BLOCK_M * STG_PITCH;
-    static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + STG_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_STAGE_BYTES) + STG_BYTES + 256 /*barriers*/ + 1024 /*align*/;
 };
 
 struct TileOrigin {
@@ -117,14 +122,14 @@ __device__ __forceinline__ int64_t tile_row(const GemmKParams& p, const TileOrig
 // Epilogue: the residual tile is prefetched into a padded smem staging buffer with coalesced loads, each thread (== row) adds
 // bias / per-image bias / residual to its TMEM row and writes bf16 back into the staging buffer, then the tile leaves with
 // coalesced 16-byte stores (full 32-byte sectors instead of one 16-byte fragment per row and instruction).
-template <int BN>
+template <int BN, int MSUB>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, MSUB>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
     uint8_t* sStg = sB + STAGES * Cfg::B_STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStg + Cfg::STG_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tiles_mn = p.tiles_n * p.tiles_m;
+    const int tiles_mn = p.tiles_n * ((p.tiles_m + MSUB - 1) / MSUB);      // work items per split
     const int total_work = tiles_mn * p.splits;
 
     if (threadIdx.x == 0) {
@@ -169,7 +174,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const int split = w / tiles_mn, mn = w % tiles_mn;
                 const int n0 = (mn % p.tiles_n) * BN;
-                const TileOrigin o = tile_origin(p, mn / p.tiles_n);
+                TileOrigin o[MSUB];
+#pragma unroll
+                for (int sub = 0; sub < MSUB; ++sub) o[sub] = tile_origin(p, (mn / p.tiles_n) * MSUB + sub);
                 const int kb_lo = split * p.kb_per_split, kb_hi = kb_lo + p.kb_per_split;
                 int it = 0;
                 for (int s = 0; s < p.nseg; ++s) {
@@ -178,21 +185,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                         for (int kb = 0; kb < p.nkb[s]; ++kb, ++it) {
                             if (it < kb_lo || it >= kb_hi) continue;
                             mbar_wait(&empty_bar[stage], phase ^ 1);
-                            mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
-                            void* dA = sA + stage * A_STAGE_BYTES;
+                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_STAGE_BYTES);
                             void* dB = sB + stage * Cfg::B_STAGE_BYTES;
-                            if (p.conv && s == 0) {
-                                const TapEntry& te = p.taps[t];
-                                if (p.conv == 4)
-                                    tma_load_4d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o.w0 + te.dw, o.h0 + te.dh, o.img0);
-                                else
-                                    tma_load_5d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o.w0 + te.dw, te.c2, o.h0 + te.dh,
-                                                o.img0);
-                                tma_load_2d(dB, &p.tmB[0], &full_bar[stage], te.wk_off + kb * BLOCK_K, n0);
-                            } else {
-                                tma_load_2d(dA, &p.tmA[s], &full_bar[stage], kb * BLOCK_K, o.m0);
-                                tma_load_2d(dB, &p.tmB[s], &full_bar[stage], kb * BLOCK_K, n0);
+#pragma unroll
+                            for (int sub = 0; sub < MSUB; ++sub) {
+                                void* dA = sA + stage * Cfg::A_BYTES + sub * A_STAGE_BYTES;
+                                if (p.conv && s == 0) {
+                                    const TapEntry& te = p.taps[t];
+                                    if (p.conv == 4)
+                                        tma_load_4d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw,
+                                                    o[sub].h0 + te.dh, o[sub].img0);
+                                    else
+                                        tma_load_5d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw, te.c2,
+                                                    o[sub].h0 + te.dh, o[sub].img0);
+                                } else {
+                                    tma_load_2d(dA, &p.tmA[s], &full_bar[stage], kb * BLOCK_K, o[sub].m0);
+                                }
                             }
+                            if (p.conv && s == 0) tma_load_2d(dB, &p.tmB[0], &full_bar[stage], p.taps[t].wk_off + kb * BLOCK_K, n0);
+                            else tma_load_2d(dB, &p.tmB[s], &full_bar[stage], kb * BLOCK_K, n0);
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -209,8 +220,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
                 const int split = w / tiles_mn;
                 const int kb_lo = split * p.kb_per_split, kb_hi = kb_lo + p.kb_per_split;
-                const int as = item & 1;
-                mbar_wait(&tmem_empty_bar[as], ((item >> 1) & 1) ^ 1);       // epilogue drained this accumulator
+                // MSUB == 1: two accumulators alternate between items; MSUB == 2: one item owns both
+                const int as = (MSUB == 1) ? (item & 1) : 0;
+                const uint32_t eph = (MSUB == 1) ? ((item >> 1) & 1) : (item & 1);
+                mbar_wait(&tmem_empty_bar[as], eph ^ 1);                     // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t acc = tmem_base + as * Cfg::ACC_STRIDE;
                 uint32_t accum = 0;
@@ -222,12 +235,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                             if (it < kb_lo || it >= kb_hi) continue;
                             mbar_wait(&full_bar[stage], phase);
                             tc_fence_after();
-                            const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * A_STAGE_BYTES), 16, 1024);
+                            const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * Cfg::A_BYTES), 16, 1024);
                             const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * Cfg::B_STAGE_BYTES), 16, 1024);
                             const int ksteps = (kb == p.nkb[s] - 1) ? p.klast[s] : (BLOCK_K / 16);
                             for (int k = 0; k < ksteps; ++k) {
                                 // +32 bytes (= 2 in descriptor units) per 16-element k-step inside the swizzle atom
-                                umma_ss(acc, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+#pragma unroll
+                                for (int sub = 0; sub < MSUB; ++sub)   // the M sub-tiles share the B operand of this k-step
+                                    umma_ss(acc + sub * Cfg::ACC_STRIDE, adesc + sub * (A_STAGE_BYTES >> 4) + 2 * k, bdesc + 2 * k, idesc, accum);
                                 accum = 1;
                             }
                             umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
@@ -250,9 +265,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
             const int split = w / tiles_mn, mn = w % tiles_mn;
             const int n0 = (mn % p.tiles_n) * BN;
-            const TileOrigin o = tile_origin(p, mn / p.tiles_n);
-            const int as = item & 1;
+            const int as = (MSUB == 1) ? (item & 1) : 0;
+            const uint32_t fph = (MSUB == 1) ? ((item >> 1) & 1) : (item & 1);
             const bool staged = (p.splits == 1);
+#pragma unroll 1
+            for (int sub = 0; sub < MSUB; ++sub) {
+            const TileOrigin o = tile_origin(p, (mn / p.tiles_n) * MSUB + sub);
+            const int acc_idx = (MSUB == 1) ? as : sub;
             if (staged && p.residual) {
                 // coalesced prefetch of the residual tile into the staging buffer (overlaps the main loop)
                 for (int u = et; u < BLOCK_M * UNITS; u += kGemmEpiThreads) {
@@ -269,9 +288,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             int group;
             const int64_t grow = tile_row(p, o, r, group);
             const bool row_ok = grow < (int64_t)p.M;
-            mbar_wait(&tmem_full_bar[as], (item >> 1) & 1);
+            if (sub == 0) mbar_wait(&tmem_full_bar[as], fph);
             tc_fence_after();
-            const uint32_t trow = tmem_base + as * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
+            const uint32_t trow = tmem_base + acc_idx * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
             for (int c = half * ((CH16 + 1) / 2); c < (half ? CH16 : (CH16 + 1) / 2); ++c) {
                 uint32_t v[16];
@@ -324,7 +343,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty_bar[as]);                      // accumulator free: the MMA warp may start item+2
+            if (sub == MSUB - 1) mbar_arrive(&tmem_empty_bar[as]); // accumulator(s) free: the MMA warp may go on
             if (staged) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 for (int u = et; u < BLOCK_M * UNITS; u += kGemmEpiThreads) {     // coalesced 16-byte stores
@@ -337,6 +356,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");     // staging buffer reusable
             }
+            }   // sub
         }
     }
 
@@ -521,22 +541,22 @@ __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __gri
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int MSUB>
 static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, MSUB>;
     static bool configured = false;
     static int num_sms = 148;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
         int dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         configured = true;
     }
-    const int total = kp.tiles_n * kp.tiles_m * kp.splits;
+    const int total = kp.tiles_n * ((kp.tiles_m + MSUB - 1) / MSUB) * kp.splits;
     dim3 grid(total < num_sms ? total : num_sms);
-    gemm_tc_kernel<BN><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(kp);
+    gemm_tc_kernel<BN, MSUB><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(kp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "gemm launch");
     return HCP_OK;
@@ -553,11 +573,17 @@ static int pick_bn(int64_t N) {
 
 static int dispatch_gemm(int bn, GemmKParams& kp, int m_tiles, cudaStream_t stream) {
     kp.tiles_m = m_tiles;
+    // two M tiles per work item when the reduction is long (operand-stream bound) and there are plenty of tiles
+    int64_t total_kb = 0;
+    for (int s = 0; s < kp.nseg; ++s) total_kb += (int64_t)kp.nkb[s] * ((kp.conv && s == 0) ? kp.ntaps : 1);
+    const bool pair = bn == 160 && kp.splits == 1 && total_kb >= 40 && (int64_t)kp.tiles_n * m_tiles >= 200 &&
+                      getenv("HCP_GEMM_NO_MSUB2") == nullptr;
+    if (pair) return launch_gemm<160, 2>(kp, stream);
     switch (bn) {
-        case 32: return launch_gemm<32>(kp, stream);
-        case 64: return launch_gemm<64>(kp, stream);
-        case 128: return launch_gemm<128>(kp, stream);
-        case 160: return launch_gemm<160>(kp, stream);
+        case 32: return launch_gemm<32, 1>(kp, stream);
+        case 64: return launch_gemm<64, 1>(kp, stream);
+        case 128: return launch_gemm<128, 1>(kp, stream);
+        case 160: return launch_gemm<160, 1>(kp, stream);
         default: return set_error(HCP_ERR_INVALID, "unsupported BLOCK_N");
     }
 }

@@ -419,9 +419,9 @@ static int gn_geometry(const hcp_groupnorm_args* a, GNParams& p) {
     p.x1 = (const __nv_bfloat16*)a->x1; p.x2 = (const __nv_bfloat16*)a->x2;
     p.C1 = (int)a->C1; p.C2 = (int)a->C2; p.C = (int)C; p.G = (int)a->G; p.cg = (int)cg;
     p.B = (int)a->B; p.HW = (int)a->HW;
-    // <= 64 pixel chunks per image, at least 4 rows per CTA.  The chunking depends on HW only, never on the batch size, so
+    // <= 32 pixel chunks per image (one wave of ~1000-thread CTAs at batch 4), at least 4 rows per CTA.  The chunking depends on HW only, never on the batch size, so
     // the summation order (and therefore every bit of the result) of one image is independent of its batch neighbours.
-    int rows = (int)((a->HW + 63) / 64);
+    int rows = (int)((a->HW + 31) / 32);
     if (rows < 4) rows = 4;
     if (rows > a->HW) rows = (int)a->HW;
     p.rows_per_cta = rows;
@@ -653,7 +653,7 @@ using namespace hcp;
     } while (0)
 
 extern "C" size_t hcp_groupnorm_workspace_bytes(int64_t B, int64_t HW, int64_t G) {
-    int64_t rows = (HW + 63) / 64;
+    int64_t rows = (HW + 31) / 32;
     if (rows < 4) rows = 4;
     if (rows > HW) rows = HW;
     const int64_t nchunks = (HW + rows - 1) / rows;
