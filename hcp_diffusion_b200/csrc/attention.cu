@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_fwd_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
     const uint32_t tS = tmem;            // S fp32 [128 cols]; P bf16 packed aliases columns [0,64)
     const uint32_t tO = tmem + 128;
 
@@ -324,6 +326,8 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
     // TMEM columns of query tile t: S fp32 [t*256, +128), P bf16 (packed) [t*256+128, +64), O fp32 [t*256+192, +dn).
     // P has its own columns, so S of the NEXT kv tile can be issued as soon as the softmax warps hold the current logits in
     // registers: QK^T(j+1) runs on the tensor pipe while the exponentials of tile j are computed.
@@ -535,8 +539,10 @@ struct alignas(64) AttnBwdParams {
     const float* kv_bias;
     const float* lse;        // [B,H,Lq]
     const float* delta;      // [B,H,Lq]  rowsum(dO * O)
-    float* dq_acc;           // [B,H,Lq,dq_ld] fp32
+    float* dq_acc;           // [B,H,Lq,dq_ld] fp32 (nullptr when dq_direct is set)
     int dq_ld;
+    __nv_bfloat16* dq_direct; // single kv tile (Lkv <= 128): dQ_i is complete after one pass -> stored as bf16, no accumulator
+    int64_t lddq;
     int early_sdp;           // 1: dQ un-aliased + double-buffered Q/dO -> S/dP of the next tile are issued early
     int qsplit;              // CTAs per kv tile along the query dimension
     float* dkv_acc;          // [B,H,Lkv,2,dq_ld] fp32 partial dK/dV when qsplit > 1, else nullptr
@@ -598,6 +604,8 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
     // TMEM columns: S [0,128), dP [128,256), then the accumulators.  dQ aliases S unless `early_sdp` (it then has its own columns).
     const uint32_t tS = tmem, tdP = tmem + 128;
     const uint32_t tdV = tmem + 256;
@@ -724,19 +732,35 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
         const float* bias = p.kv_bias ? p.kv_bias + (int64_t)b * p.Lkv : nullptr;
         const bool special = (bias != nullptr) || (ncols < 128);
         const int64_t stat_base = ((int64_t)b * p.H + h) * p.Lq;
-        auto drain_dq = [&](int qr) {            // TMEM dQ tile -> fp32 accumulator (vector red.global)
-            float* dqrow = p.dq_acc + (stat_base + qr) * p.dq_ld + p.col0;
+        auto drain_dq = [&](int qr) {            // TMEM dQ tile -> fp32 accumulator (vector red.global), or straight to bf16 dQ
+            float* dqrow = p.dq_direct ? nullptr : p.dq_acc + (stat_base + qr) * p.dq_ld + p.col0;
+            __nv_bfloat16* drow = p.dq_direct ? p.dq_direct + ((int64_t)b * p.Lq + qr) * p.lddq + (int64_t)h * p.d + p.col0 : nullptr;
             for (int c = part; c < p.ncols_out / 16; c += kBwdParts) {
                 uint32_t o[16];
                 tmem_ld16(tdQ + lb + c * 16, o);
                 tmem_wait_ld();
                 if (qr < p.Lq) {
+                    if (drow) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int col = p.col0 + c * 16 + g * 4;
-                        if (col < p.d)
-                            red_add_v4(dqrow + c * 16 + g * 4, __uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]),
-                                       __uint_as_float(o[g * 4 + 2]), __uint_as_float(o[g * 4 + 3]));
+                        for (int g = 0; g < 2; ++g) {
+                            const int col = p.col0 + c * 16 + g * 8;
+                            if (col < p.d) {
+                                uint4 w;
+                                w.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
+                                w.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+                                w.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+                                w.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+                                *reinterpret_cast<uint4*>(drow + c * 16 + g * 8) = w;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int col = p.col0 + c * 16 + g * 4;
+                            if (col < p.d)
+                                red_add_v4(dqrow + c * 16 + g * 4, __uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]),
+                                           __uint_as_float(o[g * 4 + 2]), __uint_as_float(o[g * 4 + 3]));
+                        }
                     }
                 }
             }
@@ -878,39 +902,50 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
     if (warp == 4 * kBwdParts) tmem_dealloc(tmem, 512);
 }
 
-// delta[b,h,q] = sum_e dO*O ; also zero-fills the fp32 dQ accumulator.  One warp per (b,q,h).
-__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, int64_t ldo, const __nv_bfloat16* __restrict__ dO,
-                                     int64_t lddo, int B, int H, int Lq, int d, float* __restrict__ delta,
-                                     float* __restrict__ dq_acc, int dq_ld, float* __restrict__ dkv_acc, int64_t dkv_n) {
+// delta[b,h,q] = sum_e dO*O ; also zero-fills the fp32 dQ / dK,dV accumulators (when present).  One thread per (b,q,h): the
+// d elements of a head are contiguous (d % 8 == 0 -> 16-byte loads) and adjacent threads read adjacent heads of the same token
+// row, so a warp streams contiguous memory.
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, int64_t ldo,
+                                                            const __nv_bfloat16* __restrict__ dO, int64_t lddo, int B, int H, int Lq,
+                                                            int d, float* __restrict__ delta, float* __restrict__ dq_acc,
+                                                            int64_t dq_n, float* __restrict__ dkv_acc, int64_t dkv_n) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (dkv_acc)
-        for (int64_t i = gtid; i < dkv_n; i += (int64_t)gridDim.x * blockDim.x) dkv_acc[i] = 0.f;
-    const int64_t w = gtid >> 5;
-    const int lane = threadIdx.x & 31;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    if (dq_acc) {
+        float4* z = reinterpret_cast<float4*>(dq_acc);
+        for (int64_t i = gtid; i < dq_n / 4; i += nthreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (dkv_acc) {
+        float4* z = reinterpret_cast<float4*>(dkv_acc);
+        for (int64_t i = gtid; i < dkv_n / 4; i += nthreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const int64_t total = (int64_t)B * Lq * H;
-    if (w >= total) return;
-    const int h = (int)(w % H);
-    const int64_t bq = w / H;
+    if (gtid >= total) return;
+    const int h = (int)(gtid % H);
+    const int64_t bq = gtid / H;
     const int q = (int)(bq % Lq);
     const int b = (int)(bq / Lq);
-    const __nv_bfloat16* o = O + bq * ldo + (int64_t)h * d;
-    const __nv_bfloat16* g = dO + bq * lddo + (int64_t)h * d;
+    const uint4* o = reinterpret_cast<const uint4*>(O + bq * ldo + (int64_t)h * d);
+    const uint4* g = reinterpret_cast<const uint4*>(dO + bq * lddo + (int64_t)h * d);
     float acc = 0.f;
-    for (int e = lane * 2; e < d; e += 64) {
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + e));
-        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g + e));
-        acc += a.x * c.x + a.y * c.y;
+    for (int e = 0; e < d / 8; ++e) {
+        const uint4 a = o[e], c = g[e];
+        float2 x, y;
+        x = unpack_bf16x2(a.x); y = unpack_bf16x2(c.x); acc += x.x * y.x + x.y * y.y;
+        x = unpack_bf16x2(a.y); y = unpack_bf16x2(c.y); acc += x.x * y.x + x.y * y.y;
+        x = unpack_bf16x2(a.z); y = unpack_bf16x2(c.z); acc += x.x * y.x + x.y * y.y;
+        x = unpack_bf16x2(a.w); y = unpack_bf16x2(c.w); acc += x.x * y.x + x.y * y.y;
     }
-    acc = warp_sum(acc);
-    const int64_t idx = ((int64_t)b * H + h) * Lq + q;
-    if (lane == 0) delta[idx] = acc;
-    float* z = dq_acc + idx * dq_ld;
-    for (int e = lane; e < dq_ld; e += 32) z[e] = 0.f;
+    delta[((int64_t)b * H + h) * Lq + q] = acc;
 }
 
 // dQ bf16 [B, Lq, lddq] <- fp32 accumulator [B,H,Lq,dq_ld]
 __global__ void attn_bwd_post_kernel(const float* __restrict__ dq_acc, int dq_ld, int B, int H, int Lq, int d,
                                      __nv_bfloat16* __restrict__ dQ, int64_t lddq) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per 4 elements
     const int d4 = d / 4;
     const int64_t total = (int64_t)B * Lq * H * d4;
@@ -931,6 +966,8 @@ __global__ void attn_bwd_post_kernel(const float* __restrict__ dq_acc, int dq_ld
 // dK / dV bf16 [B, Lkv, ld] <- fp32 partial sums [B,H,Lkv,2,dq_ld]  (only when the query range was split)
 __global__ void attn_bwd_post_kv_kernel(const float* __restrict__ acc, int dq_ld, int B, int H, int Lkv, int d,
                                         __nv_bfloat16* __restrict__ dK, int64_t lddk, __nv_bfloat16* __restrict__ dV, int64_t lddv) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int d4 = d / 4;
     const int64_t total = (int64_t)B * Lkv * H * 2 * d4;
@@ -997,7 +1034,7 @@ extern "C" int hcp_attn_fwd_bf16(const hcp_attn_args* a, hcp_stream_t stream_) {
         }
         if (smem > 227 * 1024) return set_error(HCP_ERR_INVALID, "attn_fwd: shared memory budget exceeded");
         dim3 grid((unsigned)((a->Lq + 128 * p.nq - 1) / (128 * p.nq)), (unsigned)a->H, (unsigned)a->B);
-        attn_fwd2_kernel<<<grid, kFwd2Threads, smem, (cudaStream_t)stream_>>>(p);
+        launch_k(attn_fwd2_kernel, dim3(grid), dim3(kFwd2Threads), smem, (cudaStream_t)stream_, p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return set_cuda_error(e, "attn_fwd2 launch");
         return HCP_OK;
@@ -1024,7 +1061,7 @@ extern "C" int hcp_attn_fwd_bf16(const hcp_attn_args* a, hcp_stream_t stream_) {
         configured = true;
     }
     dim3 grid((unsigned)((a->Lq + 127) / 128), (unsigned)a->H, (unsigned)a->B);
-    attn_fwd_kernel<<<grid, kAttnThreads, smem, (cudaStream_t)stream_>>>(p);
+    launch_k(attn_fwd_kernel, dim3(grid), dim3(kAttnThreads), smem, (cudaStream_t)stream_, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "attn_fwd launch");
     return HCP_OK;
@@ -1042,7 +1079,7 @@ static int plan_qsplit(int64_t B, int64_t H, int64_t Lq, int64_t Lkv) {
 
 extern "C" size_t hcp_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq, int64_t Lkv, int64_t d) {
     const int64_t dq_ld = (d + 3) / 4 * 4;
-    size_t n = (size_t)(B * H * Lq * (dq_ld + 1));
+    size_t n = (size_t)((B * H * Lq + 3) / 4 * 4) + (size_t)(B * H * Lq * dq_ld);   // delta (padded to 16 bytes) + dQ accumulator
     if (plan_qsplit(B, H, Lq, Lkv) > 1) n += (size_t)(B * H * Lkv * 2 * dq_ld);
     return n * sizeof(float);
 }
@@ -1057,17 +1094,20 @@ extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream
     cudaStream_t stream = (cudaStream_t)stream_;
     const int dq_ld = (int)((a->d + 3) / 4 * 4);
     float* delta = a->workspace;
-    float* dq_acc = a->workspace + a->B * a->H * a->Lq;
+    float* dq_acc = a->workspace + (a->B * a->H * a->Lq + 3) / 4 * 4;
     const int qsplit = plan_qsplit(a->B, a->H, a->Lq, a->Lkv);
     const int64_t dkv_n = qsplit > 1 ? a->B * a->H * a->Lkv * 2 * dq_ld : 0;
     float* dkv_acc = qsplit > 1 ? dq_acc + a->B * a->H * a->Lq * dq_ld : nullptr;
+    // a single kv tile sees every key of a query row at once: dQ is final after one pass and is stored directly as bf16
+    const bool dq_direct = a->Lkv <= 128 && getenv("HCP_ATTN_BWD_NO_DIRECT_DQ") == nullptr;
+    if ((a->ldo % 8) != 0 || (a->lddo % 8) != 0 || (a->lddq % 8) != 0) return set_error(HCP_ERR_INVALID, "attn_bwd: leading dimensions must be multiples of 8");
     {
-        const int64_t warps = a->B * a->Lq * a->H;
+        const int64_t total = a->B * a->Lq * a->H;
         const int threads = 256;
-        const int64_t blocks = (warps * 32 + threads - 1) / threads;
-        attn_bwd_prep_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const __nv_bfloat16*)a->o, a->ldo,
-                                                                       (const __nv_bfloat16*)a->dout, a->lddo, (int)a->B,
-                                                                       (int)a->H, (int)a->Lq, (int)a->d, delta, dq_acc, dq_ld, dkv_acc, dkv_n);
+        const int64_t blocks = (total + threads - 1) / threads;
+        launch_k(attn_bwd_prep_kernel, dim3((unsigned)blocks), dim3(threads), 0, stream, (const __nv_bfloat16*)a->o, a->ldo,
+                 (const __nv_bfloat16*)a->dout, a->lddo, (int)a->B, (int)a->H, (int)a->Lq, (int)a->d, delta,
+                 dq_direct ? (float*)nullptr : dq_acc, (int64_t)(a->B * a->H * a->Lq * dq_ld), dkv_acc, dkv_n);
     }
     AttnBwdParams p;
     memset(&p, 0, sizeof(p));
@@ -1083,8 +1123,10 @@ extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream
     p.kv_bias = a->kv_bias;
     p.lse = a->lse;
     p.delta = delta;
-    p.dq_acc = dq_acc;
+    p.dq_acc = dq_direct ? nullptr : dq_acc;
     p.dq_ld = dq_ld;
+    p.dq_direct = dq_direct ? (__nv_bfloat16*)a->dq : nullptr;
+    p.lddq = a->lddq;
     p.qsplit = qsplit;
     p.dkv_acc = dkv_acc;
     p.dK = (__nv_bfloat16*)a->dk; p.lddk = a->lddk;
@@ -1105,18 +1147,18 @@ extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream
     for (int col0 = 0; col0 < p.dn; col0 += 128) {
         p.col0 = col0;
         p.ncols_out = (p.dn - col0 < 128) ? (p.dn - col0) : 128;
-        attn_bwd_kernel<<<grid, kAttnBwdThreads, smem, stream>>>(p);
+        launch_k(attn_bwd_kernel, dim3(grid), dim3(kAttnBwdThreads), smem, stream, p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd launch");
     }
-    {
+    if (!dq_direct) {
         const int64_t n = a->B * a->Lq * a->H * (a->d / 4);
-        attn_bwd_post_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dq_acc, dq_ld, (int)a->B, (int)a->H, (int)a->Lq,
-                                                                             (int)a->d, (__nv_bfloat16*)a->dq, a->lddq);
+        launch_k(attn_bwd_post_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, dq_acc, dq_ld, (int)a->B, (int)a->H, (int)a->Lq,
+                 (int)a->d, (__nv_bfloat16*)a->dq, a->lddq);
     }
     if (qsplit > 1) {
         const int64_t n = a->B * a->Lkv * a->H * 2 * (a->d / 4);
-        attn_bwd_post_kv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dkv_acc, dq_ld, (int)a->B, (int)a->H, (int)a->Lkv, (int)a->d,
+        launch_k(attn_bwd_post_kv_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, dkv_acc, dq_ld, (int)a->B, (int)a->H, (int)a->Lkv, (int)a->d,
                                                                                 (__nv_bfloat16*)a->dk, a->lddk, (__nv_bfloat16*)a->dv, a->lddv);
     }
     cudaError_t e = cudaGetLastError();

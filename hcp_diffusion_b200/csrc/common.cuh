@@ -30,6 +30,17 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL).  Every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (host_util.h: launch_k), so its CTAs may become resident while the
+// previous kernel of the stream is still draining.  Contract: pdl_wait() before the first global-memory access (it returns
+// once the whole preceding grid has completed and its writes are visible -- covers RAW and WAR hazards on recycled buffers);
+// everything before it (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail.
+// pdl_trigger() lets the NEXT kernel start launching; it only affects scheduling, never visibility.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

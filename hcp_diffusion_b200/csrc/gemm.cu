@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();     // the set-up above overlapped the previous kernel's tail; its results are visible from here on
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -369,6 +371,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits, int64_t M, int N, const float* __restrict__ bias,
                                        const float* __restrict__ rowbias, int rows_per_group, int64_t rowbias_ld,
                                        const __nv_bfloat16* __restrict__ residual, int64_t ldr, __nv_bfloat16* __restrict__ out, int64_t ldo) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int nv = N / 8;
     if (i >= M * nv) return;
@@ -471,6 +475,8 @@ __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         if (elect_one()) {
@@ -556,7 +562,7 @@ static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
     }
     const int total = kp.tiles_n * ((kp.tiles_m + MSUB - 1) / MSUB) * kp.splits;
     dim3 grid(total < num_sms ? total : num_sms);
-    gemm_tc_kernel<BN, MSUB><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(kp);
+    launch_k(gemm_tc_kernel<BN, MSUB>, dim3(grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, stream, kp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "gemm launch");
     return HCP_OK;
@@ -608,7 +614,7 @@ static int run_gemm(int bn, GemmKParams& kp, int m_tiles, int64_t total_kb, floa
     int rc = dispatch_gemm(bn, kp, m_tiles, stream);
     if (rc) return rc;
     const int64_t n = (int64_t)kp.M * (kp.N / 8);
-    splitk_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ws, splits, kp.M, kp.N, kp.bias, kp.rowbias,
+    launch_k(splitk_finalize_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, ws, splits, kp.M, kp.N, kp.bias, kp.rowbias,
                                                                             kp.conv ? kp.oH * kp.oW : kp.rows_per_group, kp.rowbias_ld,
                                                                             kp.residual, kp.ldr, kp.out, kp.ldo);
     cudaError_t e = cudaGetLastError();
@@ -795,19 +801,20 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
     return HCP_OK;
 }
 
-static int lg_fill(LoraGradParams& p, int z, const void* S, const void* X, int64_t ldx, int64_t M, int64_t n_begin, int64_t n_end,
-                   const hcp_lora_grad_block* blocks, int32_t nblocks) {
+static int lg_fill(LoraGradParams& p, int z, const void* S, int64_t lds, const void* X, int64_t ldx, int64_t M, int64_t n_begin,
+                   int64_t n_end, const hcp_lora_grad_block* blocks, int32_t nblocks, int target_ctas) {
     if (!S || !X || !blocks || nblocks < 1 || nblocks > LG_MAX_BLOCKS) return set_error(HCP_ERR_INVALID, "lora_grad: 1..8 blocks per problem");
-    if (n_end <= n_begin || (ldx % 8) != 0 || (n_begin % 8) != 0) return set_error(HCP_ERR_INVALID, "lora_grad: shape");
+    if (n_end <= n_begin || (ldx % 8) != 0 || (n_begin % 8) != 0 || lds < 64 || (lds % 8) != 0) return set_error(HCP_ERR_INVALID, "lora_grad: shape");
     int rc = make_tmap_2d(&p.tmX[z], X, (uint64_t)ldx, (uint64_t)M, (uint64_t)ldx, 64, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(&p.tmS[z], S, 64, (uint64_t)M, 64, 64, 128);
+    rc = make_tmap_2d(&p.tmS[z], S, 64, (uint64_t)M, (uint64_t)lds, 64, 128);     // the 64 columns of S this launch reduces
     if (rc) return rc;
     LGProblem& q = p.prob[z];
     q.n_begin = (int)n_begin; q.n_end = (int)n_end; q.nblocks = nblocks;
     q.col_chunks = (int)((n_end - n_begin + 127) / 128);
     const int total_tiles = (int)((M + 127) / 128);
-    int splits = (148 + q.col_chunks - 1) / q.col_chunks;
+    int splits = target_ctas / q.col_chunks;     // at most one wave of CTAs over all problems of the launch
+    if (splits < 1) splits = 1;
     if (splits > total_tiles) splits = total_tiles;
     q.tiles_per_cta = (total_tiles + splits - 1) / splits;
     q.splits = (total_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
@@ -829,19 +836,19 @@ static int lg_launch(LoraGradParams& p, cudaStream_t stream) {
     }
     int ctas = 0;
     for (int z = 0; z < p.nprob; ++z) ctas += p.prob[z].col_chunks * p.prob[z].splits;
-    lora_grad_tc_kernel<<<ctas, kLgThreads, LG_SMEM_BYTES, stream>>>(p);
+    launch_k(lora_grad_tc_kernel, dim3(ctas), dim3(kLgThreads), LG_SMEM_BYTES, stream, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "lora_grad launch");
     return HCP_OK;
 }
 
-extern "C" int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t M, int64_t n_begin, int64_t n_end,
+extern "C" int hcp_lora_grad(const void* S, int64_t lds, const void* X, int64_t ldx, int64_t M, int64_t n_begin, int64_t n_end,
                              const hcp_lora_grad_block* blocks, int32_t nblocks, hcp_stream_t stream_) {
     if (M <= 0) return set_error(HCP_ERR_INVALID, "lora_grad: M");
     LoraGradParams p;
     memset(&p, 0, sizeof(p));
     p.M = (int)M; p.nprob = 1;
-    int rc = lg_fill(p, 0, S, X, ldx, M, n_begin, n_end, blocks, nblocks);
+    int rc = lg_fill(p, 0, S, lds, X, ldx, M, n_begin, n_end, blocks, nblocks, 148);
     if (rc) return rc;
     return lg_launch(p, (cudaStream_t)stream_);
 }
@@ -849,14 +856,19 @@ extern "C" int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t 
 // dW_down and dW_up of one LoRA group in ONE launch (two independent TN GEMMs over the same M token rows).
 extern "C" int hcp_lora_grad_pair(const void* U, const void* x, int64_t ldx, int64_t K, const hcp_lora_grad_block* down,
                                   const void* T, const void* dy, int64_t lddy, int64_t N, const hcp_lora_grad_block* up,
-                                  int32_t nblocks, int64_t M, hcp_stream_t stream_) {
+                                  int32_t nblocks, int64_t M, int64_t lds, hcp_stream_t stream_) {
     if (M <= 0) return set_error(HCP_ERR_INVALID, "lora_grad_pair: M");
     LoraGradParams p;
     memset(&p, 0, sizeof(p));
     p.M = (int)M; p.nprob = 2;
-    int rc = lg_fill(p, 0, U, x, ldx, M, 0, K, down, nblocks);
+    // split the 148 SMs between the two problems in proportion to their column counts (one CTA per SM: 147 KB of smem each)
+    const int64_t ck = (K + 127) / 128, cn = (N + 127) / 128;
+    int t0 = (int)((148 * ck + (ck + cn) / 2) / (ck + cn));
+    if (t0 < 1) t0 = 1;
+    if (t0 > 147) t0 = 147;
+    int rc = lg_fill(p, 0, U, lds, x, ldx, M, 0, K, down, nblocks, t0);
     if (rc) return rc;
-    rc = lg_fill(p, 1, T, dy, lddy, M, 0, N, up, nblocks);
+    rc = lg_fill(p, 1, T, lds, dy, lddy, M, 0, N, up, nblocks, 148 - t0);
     if (rc) return rc;
     return lg_launch(p, (cudaStream_t)stream_);
 }

@@ -2,6 +2,8 @@
 #include "host_util.h"
 #include "../../include/hcp_b200.h"
 #include <stdio.h>
+#include <stdlib.h>
+#include <atomic>
 #include <mutex>
 
 namespace hcp {
@@ -15,6 +17,19 @@ int set_error(int code, const char* msg) {
 int set_cuda_error(cudaError_t e, const char* where) {
     snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
     return HCP_ERR_CUDA;
+}
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        // measured on B200 (profiles/r01_bench_pdl_ab.json): inside the captured step graph the programmatic edges buy
+        // nothing (24.81 ms off vs 25.15 ms on), so the attribute is opt-in
+        const char* e = getenv("HCP_PDL");
+        return e && e[0] == '1';
+    }();
+    return on;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -78,7 +93,8 @@ int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* d
 
 }  // namespace hcp
 
-extern "C" int hcp_version(void) { return 1; }
+extern "C" int hcp_version(void) { return 2; }
+extern "C" unsigned long long hcp_launch_count(void) { return hcp::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* hcp_last_error_string(void) { return hcp::g_err; }
 extern "C" int hcp_device_check(void) {
     int dev = 0;

@@ -26,4 +26,26 @@ inline int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint
     return make_tmap_nd(out, base, 2, dims, strides, box);
 }
 
+// Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor on the stream drains; every
+// kernel of the library calls pdl_wait() (common.cuh) before touching global memory.  Opt-in: HCP_PDL=1.
+bool pdl_enabled();
+void note_launch();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    note_launch();
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace hcp

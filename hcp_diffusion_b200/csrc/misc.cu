@@ -20,6 +20,8 @@ namespace hcp {
 // ---------------------------------------------------------------------------------------------
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int B,
                                int Cin, int H, int W, int Cout, __nv_bfloat16* __restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)B * H * W * Cout;
     if (i >= total) return;
@@ -49,6 +51,8 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
 template <int COUT>
 __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                 int B, int H, int W, int Cin, float* __restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= (int64_t)B * H * W) return;
@@ -84,6 +88,8 @@ __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, const float
 template <int COUT>
 __global__ void conv_out_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, int B, int H, int W, int Cin,
                                       __nv_bfloat16* __restrict__ dx) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)B * H * W * Cin;
     if (i >= total) return;
@@ -116,6 +122,8 @@ __global__ void conv_out_dgrad_kernel(const float* __restrict__ dy, const float*
 constexpr int SK_MAX_M = 16;
 __global__ void skinny_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ Wt, const float* __restrict__ bias,
                                      int M, int K, int N, int in_mode, int out_silu, float* __restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sx[];   // [M][K] transformed inputs
     for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
         const int m = i / K, k = i % K;
@@ -163,6 +171,8 @@ __global__ void skinny_linear_kernel(const float* __restrict__ x, const __nv_bfl
 // fp32 -> bf16 cast (weights once, encoder_hidden_states per step)
 // ---------------------------------------------------------------------------------------------
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         const float4 v = *reinterpret_cast<const float4*>(x + i);
@@ -184,6 +194,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, int64_t n, __n
 // Buffers are zero-initialised once by the caller; blocks of one fused group tile them block-diagonally.
 // ---------------------------------------------------------------------------------------------
 __global__ void lora_pack_kernel(const hcp_lora_job* __restrict__ jobs, int njobs) {
+    pdl_trigger();
+    pdl_wait();
     const int j = blockIdx.y;
     if (j >= njobs) return;
     const hcp_lora_job jb = jobs[j];
@@ -199,12 +211,12 @@ __global__ void lora_pack_kernel(const hcp_lora_job* __restrict__ jobs, int njob
             const int rr = (int)(i / in), k = (int)(i % in);
             const __nv_bfloat16 v = __float2bfloat16(jb.w_down[i]);
             A[(int64_t)(jb.c0 + rr) * in + k] = v;
-            AT[(int64_t)k * 64 + jb.c0 + rr] = v;
+            AT[(int64_t)k * jb.ld_r + jb.c0 + rr] = v;
         } else {
             const int64_t t = i - n_down;
             const int o = (int)(t / r), rr = (int)(t % r);
             const __nv_bfloat16 v = __float2bfloat16(alpha * jb.w_up[t]);
-            Bl[(int64_t)(jb.o0 + o) * 64 + jb.c0 + rr] = v;
+            Bl[(int64_t)(jb.o0 + o) * jb.ld_r + jb.c0 + rr] = v;
             BlT[(int64_t)(jb.c0 + rr) * jb.out_tot + jb.o0 + o] = v;
         }
     }
@@ -215,6 +227,8 @@ __global__ void lora_pack_kernel(const hcp_lora_job* __restrict__ jobs, int njob
 // ---------------------------------------------------------------------------------------------
 __global__ void mse_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n, float grad_scale,
                                 float* __restrict__ loss_sum, float* __restrict__ dpred) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_part[8];
     float acc = 0.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -235,6 +249,8 @@ __global__ void mse_loss_kernel(const float* __restrict__ pred, const float* __r
 // x_t = sqrt(acp[t]) * x0 + sqrt(1 - acp[t]) * noise   (DDPMScheduler.add_noise, reference train_ac.py:437-447)
 __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const int64_t* __restrict__ t,
                                  const float* __restrict__ acp, int64_t per_image, int64_t n, float* __restrict__ xt) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float a = acp[t[i / per_image]];
@@ -243,6 +259,8 @@ __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __re
 
 // sum of squares of a flat fp32 buffer (for clip_grad_norm_, reference train_ac.py:485-490)
 __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_part[8];
     float acc = 0.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += g[i] * g[i];
@@ -261,6 +279,8 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __re
 __global__ void adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                   int64_t n, const float* __restrict__ lr_ptr, float beta1, float beta2, float eps, float wd,
                                   float gscale, const float* __restrict__ sumsq, float max_norm, const int* __restrict__ step_ptr) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     float clip = 1.f;
@@ -282,7 +302,9 @@ __global__ void adamw_flat_kernel(float* __restrict__ p, const float* __restrict
     w -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
     p[i] = w;
 }
-__global__ void incr_step_kernel(int* step) { *step += 1; }
+__global__ void incr_step_kernel(int* step) {
+    pdl_trigger();
+    pdl_wait(); *step += 1; }
 
 }  // namespace hcp
 
@@ -298,7 +320,7 @@ extern "C" int hcp_conv_in_f32(const float* x, const float* w, const float* bias
                                int64_t Cout, void* y, hcp_stream_t st) {
     if (!x || !w || !y) return set_error(HCP_ERR_INVALID, "conv_in: null pointer");
     const int64_t n = B * H * W * Cout;
-    conv_in_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>(x, w, bias, (int)B, (int)Cin, (int)H, (int)W, (int)Cout,
+    launch_k(conv_in_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)st, x, w, bias, (int)B, (int)Cin, (int)H, (int)W, (int)Cout,
                                                                             (__nv_bfloat16*)y);
     LAUNCH_CHECK("conv_in launch");
     return HCP_OK;
@@ -309,7 +331,7 @@ extern "C" int hcp_conv_out_f32(const void* x, const float* w, const float* bias
     if (!x || !w || !y) return set_error(HCP_ERR_INVALID, "conv_out: null pointer");
     if (Cout != 4 || (Cin & 1)) return set_error(HCP_ERR_INVALID, "conv_out: only Cout == 4, even Cin");
     const int64_t n = B * H * W * 32;
-    conv_out_kernel<4><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, w, bias, (int)B, (int)H, (int)W,
+    launch_k(conv_out_kernel<4>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)st, (const __nv_bfloat16*)x, w, bias, (int)B, (int)H, (int)W,
                                                                                 (int)Cin, y);
     LAUNCH_CHECK("conv_out launch");
     return HCP_OK;
@@ -320,7 +342,7 @@ extern "C" int hcp_conv_out_dgrad_f32(const float* dy, const float* w, int64_t B
     if (!dy || !w || !dx) return set_error(HCP_ERR_INVALID, "conv_out_dgrad: null pointer");
     if (Cout != 4) return set_error(HCP_ERR_INVALID, "conv_out_dgrad: only Cout == 4");
     const int64_t n = B * H * W * Cin;
-    conv_out_dgrad_kernel<4><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>(dy, w, (int)B, (int)H, (int)W, (int)Cin,
+    launch_k(conv_out_dgrad_kernel<4>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)st, dy, w, (int)B, (int)H, (int)W, (int)Cin,
                                                                                       (__nv_bfloat16*)dx);
     LAUNCH_CHECK("conv_out_dgrad launch");
     return HCP_OK;
@@ -339,7 +361,7 @@ extern "C" int hcp_skinny_linear(const float* x, const void* w_bf16, const float
         configured = true;
     }
     const int warps = 8;
-    skinny_linear_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, smem, (cudaStream_t)st>>>(
+    launch_k(skinny_linear_kernel, dim3((unsigned)((N + warps - 1) / warps)), dim3(warps * 32), smem, (cudaStream_t)st, 
         x, (const __nv_bfloat16*)w_bf16, bias, (int)M, (int)K, (int)N, in_mode, out_silu, y);
     LAUNCH_CHECK("skinny_linear launch");
     return HCP_OK;
@@ -349,7 +371,7 @@ extern "C" int hcp_cast_f32_to_bf16(const float* x, int64_t n, void* y, hcp_stre
     if (!x || !y) return set_error(HCP_ERR_INVALID, "cast: null pointer");
     if (n == 0) return HCP_OK;
     const int64_t threads = (n + 3) / 4;
-    cast_f32_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)st>>>(x, n, (__nv_bfloat16*)y);
+    launch_k(cast_f32_bf16_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, (cudaStream_t)st, x, n, (__nv_bfloat16*)y);
     LAUNCH_CHECK("cast launch");
     return HCP_OK;
 }
@@ -357,7 +379,7 @@ extern "C" int hcp_cast_f32_to_bf16(const float* x, int64_t n, void* y, hcp_stre
 extern "C" int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp_stream_t st) {
     if (!jobs_device || njobs <= 0) return set_error(HCP_ERR_INVALID, "lora_pack: jobs");
     dim3 grid(16, (unsigned)njobs);
-    lora_pack_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(jobs_device, (int)njobs);
+    launch_k(lora_pack_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)st, jobs_device, (int)njobs);
     LAUNCH_CHECK("lora_pack launch");
     return HCP_OK;
 }
@@ -367,7 +389,7 @@ extern "C" int hcp_mse_loss(const float* pred, const float* target, int64_t n, f
     if (!pred || !target || !loss_sum) return set_error(HCP_ERR_INVALID, "mse_loss: null pointer");
     int blocks = (int)((n + 255) / 256);
     if (blocks > 592) blocks = 592;
-    mse_loss_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(pred, target, n, grad_scale, loss_sum, dpred);
+    launch_k(mse_loss_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)st, pred, target, n, grad_scale, loss_sum, dpred);
     LAUNCH_CHECK("mse_loss launch");
     return HCP_OK;
 }
@@ -376,7 +398,7 @@ extern "C" int hcp_add_noise(const float* x0, const float* noise, const int64_t*
                              int64_t per_image, float* xt, hcp_stream_t st) {
     if (!x0 || !noise || !t || !alphas_cumprod || !xt) return set_error(HCP_ERR_INVALID, "add_noise: null pointer");
     const int64_t n = B * per_image;
-    add_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>(x0, noise, t, alphas_cumprod, per_image, n, xt);
+    launch_k(add_noise_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)st, x0, noise, t, alphas_cumprod, per_image, n, xt);
     LAUNCH_CHECK("add_noise launch");
     return HCP_OK;
 }
@@ -385,7 +407,7 @@ extern "C" int hcp_sumsq(const float* g, int64_t n, float* out, hcp_stream_t st)
     if (!g || !out) return set_error(HCP_ERR_INVALID, "sumsq: null pointer");
     int blocks = (int)((n + 255) / 256);
     if (blocks > 592) blocks = 592;
-    sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(g, n, out);
+    launch_k(sumsq_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)st, g, n, out);
     LAUNCH_CHECK("sumsq launch");
     return HCP_OK;
 }
@@ -394,8 +416,8 @@ extern "C" int hcp_adamw_flat(float* p, const float* g, float* m, float* v, int6
                               float eps, float weight_decay, float grad_scale, const float* sumsq_device, float max_norm,
                               int* step_device, hcp_stream_t st) {
     if (!p || !g || !m || !v || !lr_device || !step_device) return set_error(HCP_ERR_INVALID, "adamw: null pointer");
-    incr_step_kernel<<<1, 1, 0, (cudaStream_t)st>>>(step_device);
-    adamw_flat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>(p, g, m, v, n, lr_device, beta1, beta2, eps, weight_decay,
+    launch_k(incr_step_kernel, dim3(1), dim3(1), 0, (cudaStream_t)st, step_device);
+    launch_k(adamw_flat_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)st, p, g, m, v, n, lr_device, beta1, beta2, eps, weight_decay,
                                                                                grad_scale, sumsq_device, max_norm, step_device);
     LAUNCH_CHECK("adamw launch");
     return HCP_OK;

@@ -73,6 +73,8 @@ __device__ __forceinline__ float2 gn_load2(const GNParams& p, int64_t pix, int c
 
 template <bool BWD>
 __global__ void __launch_bounds__(GN_MAX_THREADS) gn_partial_kernel(const GNParams p) {
+    pdl_trigger();
+    pdl_wait();
     // per-(row-lane, channel-pair) partial sums, then ONE thread per group adds them in a fixed order: deterministic
     // (no floating-point atomics), which the batch-invariance property test relies on.
     extern __shared__ float s_pair[];     // [R][C/2][2]
@@ -140,6 +142,8 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn_partial_kernel(const GNPara
 
 template <bool BWD>
 __global__ void __launch_bounds__(GN_MAX_THREADS) gn_apply_kernel(const GNParams p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_a[GN_MAX_G], s_b[GN_MAX_G];
     const int b = blockIdx.y, chunk = blockIdx.x;
     const float n = (float)p.HW * (float)p.cg;
@@ -251,6 +255,8 @@ __device__ __forceinline__ void gn8_load(const GNParams& p, int64_t pix, int c0,
 
 template <bool BWD>
 __global__ void __launch_bounds__(GN_MAX_THREADS) gn8_partial_kernel(const GNParams p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float s_vec[];      // [R][C/8][4] : (lo a0, lo a1, hi a0, hi a1)
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int r0 = chunk * p.rows_per_cta;
@@ -316,6 +322,8 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn8_partial_kernel(const GNPar
 
 template <bool BWD>
 __global__ void __launch_bounds__(GN_MAX_THREADS) gn8_apply_kernel(const GNParams p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_a[GN_MAX_G], s_b[GN_MAX_G];
     const int b = blockIdx.y, chunk = blockIdx.x;
     const float n = (float)p.HW * (float)p.cg;
@@ -449,6 +457,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
                                                         const __nv_bfloat16* __restrict__ add, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int64_t M, int C,
                                                         float* __restrict__ stats, __nv_bfloat16* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -538,7 +548,7 @@ static void launch_layernorm(const __nv_bfloat16* x, const __nv_bfloat16* dy, co
                              const float* beta, float eps, int64_t M, int C, float* stats, __nv_bfloat16* out, cudaStream_t st) {
     const unsigned blocks = (unsigned)((M * 32 + 255) / 256);
     const int nvpl = (C / 8 + 31) / 32;
-#define LN_CASE(N) case N: layernorm_kernel<BWD, N><<<blocks, 256, 0, st>>>(x, dy, add, gamma, beta, eps, M, C, stats, out); break;
+#define LN_CASE(N) case N: launch_k(layernorm_kernel<BWD, N>, dim3(blocks), dim3(256), 0, st, x, dy, add, gamma, beta, eps, M, C, stats, out); break;
     switch (nvpl) {
         LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
     }
@@ -549,6 +559,8 @@ static void launch_layernorm(const __nv_bfloat16* x, const __nv_bfloat16* dy, co
 // GEGLU: u = [a | g] (each F wide);  h = a * gelu(g)
 // =============================================================================================
 __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ u, int64_t M, int F, __nv_bfloat16* __restrict__ h) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per 8 outputs
     const int nv = F / 8;
     if (i >= M * nv) return;
@@ -567,6 +579,8 @@ __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ u, int64_t M,
 }
 __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ dh, int64_t M, int F,
                                  __nv_bfloat16* __restrict__ du) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int nv = F / 8;
     if (i >= M * nv) return;
@@ -591,6 +605,8 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv
 // nearest 2x upsample (NHWC) and its backward (sum of the 2x2 block)
 // =============================================================================================
 __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, __nv_bfloat16* __restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per 8 output channels
     const int nv = C / 8;
     const int64_t total = (int64_t)B * 4 * H * W * nv;
@@ -602,6 +618,8 @@ __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B
     *reinterpret_cast<uint4*>(y + pix * C + c) = v;
 }
 __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int B, int H, int W, int C, __nv_bfloat16* __restrict__ dx) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per 8 input channels
     const int nv = C / 8;
     const int64_t total = (int64_t)B * H * W * nv;
@@ -629,6 +647,8 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int 
 // out = a + b (bf16), used where autograd fan-in cannot be folded into a producer kernel
 __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, int64_t n8,
                                 __nv_bfloat16* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n8) return;
     const uint4 x = reinterpret_cast<const uint4*>(a)[i], y = reinterpret_cast<const uint4*>(b)[i];
@@ -670,12 +690,12 @@ extern "C" int hcp_groupnorm_fwd_bf16(const hcp_groupnorm_args* a, hcp_stream_t 
     const int threads = (p.TP * p.R + 31) & ~31;          // whole warps: the finalize step uses full-warp shuffles
     if (p.vec8) {
         const size_t smem = (size_t)p.R * (p.C / 8) * 4 * sizeof(float);
-        gn8_partial_kernel<false><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
-        gn8_apply_kernel<false><<<grid, threads, 0, (cudaStream_t)stream_>>>(p);
+        launch_k(gn8_partial_kernel<false>, dim3(grid), dim3(threads), smem, (cudaStream_t)stream_, p);
+        launch_k(gn8_apply_kernel<false>, dim3(grid), dim3(threads), 0, (cudaStream_t)stream_, p);
     } else {
         const size_t smem = (size_t)p.R * (p.C / 2) * 2 * sizeof(float);
-        gn_partial_kernel<false><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
-        gn_apply_kernel<false><<<grid, threads, 0, (cudaStream_t)stream_>>>(p);
+        launch_k(gn_partial_kernel<false>, dim3(grid), dim3(threads), smem, (cudaStream_t)stream_, p);
+        launch_k(gn_apply_kernel<false>, dim3(grid), dim3(threads), 0, (cudaStream_t)stream_, p);
     }
     LAUNCH_CHECK("groupnorm_fwd launch");
     return HCP_OK;
@@ -693,12 +713,12 @@ extern "C" int hcp_groupnorm_bwd_bf16(const hcp_groupnorm_args* a, hcp_stream_t 
     const int threads = (p.TP * p.R + 31) & ~31;          // whole warps: the finalize step uses full-warp shuffles
     if (p.vec8) {
         const size_t smem = (size_t)p.R * (p.C / 8) * 4 * sizeof(float);
-        gn8_partial_kernel<true><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
-        gn8_apply_kernel<true><<<grid, threads, 0, (cudaStream_t)stream_>>>(p);
+        launch_k(gn8_partial_kernel<true>, dim3(grid), dim3(threads), smem, (cudaStream_t)stream_, p);
+        launch_k(gn8_apply_kernel<true>, dim3(grid), dim3(threads), 0, (cudaStream_t)stream_, p);
     } else {
         const size_t smem = (size_t)p.R * (p.C / 2) * 2 * sizeof(float);
-        gn_partial_kernel<true><<<grid, threads, smem, (cudaStream_t)stream_>>>(p);
-        gn_apply_kernel<true><<<grid, threads, 0, (cudaStream_t)stream_>>>(p);
+        launch_k(gn_partial_kernel<true>, dim3(grid), dim3(threads), smem, (cudaStream_t)stream_, p);
+        launch_k(gn_apply_kernel<true>, dim3(grid), dim3(threads), 0, (cudaStream_t)stream_, p);
     }
     LAUNCH_CHECK("groupnorm_bwd launch");
     return HCP_OK;
@@ -727,14 +747,14 @@ extern "C" int hcp_layernorm_bwd_bf16(const void* x, const void* dy, const void*
 extern "C" int hcp_geglu_fwd_bf16(const void* u, int64_t M, int64_t F, void* h, hcp_stream_t stream_) {
     if (!u || !h || F % 8 != 0) return set_error(HCP_ERR_INVALID, "geglu_fwd");
     const int64_t n = M * (F / 8);
-    geglu_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)u, M, (int)F, (__nv_bfloat16*)h);
+    launch_k(geglu_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream_, (const __nv_bfloat16*)u, M, (int)F, (__nv_bfloat16*)h);
     LAUNCH_CHECK("geglu_fwd launch");
     return HCP_OK;
 }
 extern "C" int hcp_geglu_bwd_bf16(const void* u, const void* dh, int64_t M, int64_t F, void* du, hcp_stream_t stream_) {
     if (!u || !dh || !du || F % 8 != 0) return set_error(HCP_ERR_INVALID, "geglu_bwd");
     const int64_t n = M * (F / 8);
-    geglu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)u, (const __nv_bfloat16*)dh, M,
+    launch_k(geglu_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream_, (const __nv_bfloat16*)u, (const __nv_bfloat16*)dh, M,
                                                                                    (int)F, (__nv_bfloat16*)du);
     LAUNCH_CHECK("geglu_bwd launch");
     return HCP_OK;
@@ -742,7 +762,7 @@ extern "C" int hcp_geglu_bwd_bf16(const void* u, const void* dh, int64_t M, int6
 extern "C" int hcp_upsample2x_fwd_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t C, void* y, hcp_stream_t stream_) {
     if (!x || !y || C % 8 != 0) return set_error(HCP_ERR_INVALID, "upsample2x_fwd");
     const int64_t n = B * 4 * H * W * (C / 8);
-    upsample2x_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, (int)B, (int)H, (int)W,
+    launch_k(upsample2x_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream_, (const __nv_bfloat16*)x, (int)B, (int)H, (int)W,
                                                                                         (int)C, (__nv_bfloat16*)y);
     LAUNCH_CHECK("upsample2x_fwd launch");
     return HCP_OK;
@@ -750,7 +770,7 @@ extern "C" int hcp_upsample2x_fwd_bf16(const void* x, int64_t B, int64_t H, int6
 extern "C" int hcp_upsample2x_bwd_bf16(const void* dy, int64_t B, int64_t H, int64_t W, int64_t C, void* dx, hcp_stream_t stream_) {
     if (!dy || !dx || C % 8 != 0) return set_error(HCP_ERR_INVALID, "upsample2x_bwd");
     const int64_t n = B * H * W * (C / 8);
-    upsample2x_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)dy, (int)B, (int)H, (int)W,
+    launch_k(upsample2x_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream_, (const __nv_bfloat16*)dy, (int)B, (int)H, (int)W,
                                                                                         (int)C, (__nv_bfloat16*)dx);
     LAUNCH_CHECK("upsample2x_bwd launch");
     return HCP_OK;
@@ -758,7 +778,7 @@ extern "C" int hcp_upsample2x_bwd_bf16(const void* dy, int64_t B, int64_t H, int
 extern "C" int hcp_add_bf16(const void* a, const void* b, int64_t n, void* out, hcp_stream_t stream_) {
     if (!a || !b || !out || n % 8 != 0) return set_error(HCP_ERR_INVALID, "add_bf16");
     const int64_t n8 = n / 8;
-    add_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n8,
+    launch_k(add_bf16_kernel, dim3((unsigned)((n8 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream_, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n8,
                                                                                    (__nv_bfloat16*)out);
     LAUNCH_CHECK("add_bf16 launch");
     return HCP_OK;

@@ -11,7 +11,11 @@ hcpdiff/models/lora_layers_patch.py: LoraLayer :21, LinearLayer :25-62, lora_lay
 
 Semantics: y = x @ (W_host + sum_b alpha_b * W_up_b @ W_down_b)^T + bias.  The reference materialises the [out,in] delta
 every forward (lora_base_patch.py:61-62, lora_layers_patch.py:44-45); here the delta stays factored and rides the same
-tensor-core pipeline as extra K-blocks (csrc/gemm.cu).  Supported on this path: nn.Linear hosts, dropout == 0.
+tensor-core pipeline as extra K-blocks (csrc/gemm.cu).
+
+Also here: `Conv2dLayer` (LoCon, lora_layers_patch.py:64-100: W_down [r,in,kh,kw], W_up [out,r,1,1]) and the DreamArtist++
+pair `DAPPLayer` / `DAPPPatchContainer` (lora_layers_patch.py:102-216: 'n' blocks act on the first half of the batch, 'p' blocks
+on the second).  Supported on this path: nn.Linear and Conv2d hosts, dropout == 0, no LoRA bias.
 """
 from __future__ import annotations
 
@@ -50,7 +54,7 @@ class LoraBlock(PatchPluginBlock):
             self.layer = self.LinearLayer(host, rank, bias, self)
         elif isinstance(host, nn.Conv2d):
             self.host_type = "conv"
-            raise NotImplementedError("Conv2d LoRA (locon) is not on the B200 hot path yet; restrict `layers` to Linear layers")
+            self.layer = self.Conv2dLayer(host, rank, bias, self)
         else:
             raise NotImplementedError(f"No lora for {type(host)}")
         if bias:
@@ -76,6 +80,13 @@ class LoraBlock(PatchPluginBlock):
             self.rank = rank
             if isinstance(self.rank, float):
                 self.rank = max(round(host.out_features * self.rank), 1)
+
+    class Conv2dLayer(nn.Module):
+        def __init__(self, host: nn.Conv2d, rank, bias, block):
+            super().__init__()
+            self.rank = rank
+            if isinstance(self.rank, float):
+                self.rank = max(round(host.out_channels * self.rank), 1)
 
     @classmethod
     def wrap_layer(cls, lora_id: int, layer, rank=1, dropout=0.0, alpha=1.0, svd_init=False, bias=False, mask=None, **kwargs):
@@ -129,6 +140,45 @@ class LoraLayer(LoraBlock):
             return self.W_up.data @ self.W_down.data, None
 
 
+    class Conv2dLayer(LoraBlock.Conv2dLayer):
+        def __init__(self, host: nn.Conv2d, rank, bias, block):
+            super().__init__(host, rank, bias, block)
+            if host.groups != 1 or host.dilation != (1, 1):
+                raise NotImplementedError("Conv2d LoRA on grouped / dilated convolutions is not supported on the B200 hot path")
+            dev = host.weight.device
+            self.W_down = nn.Parameter(torch.empty(self.rank, host.in_channels, *host.kernel_size, device=dev))
+            self.W_up = nn.Parameter(torch.empty(host.out_channels, self.rank, 1, 1, device=dev))
+            self.register_parameter("bias", None)
+            self.stride, self.padding, self.dilation, self.groups = host.stride, host.padding, host.dilation, host.groups
+
+        def reset_parameters(self):
+            nn.init.kaiming_uniform_(self.W_down, a=math.sqrt(5))
+            nn.init.zeros_(self.W_up)
+
+        def get_weight(self) -> torch.Tensor:
+            return torch.einsum("or...,ri...->oi...", self.W_up[:, :, 0, 0], self.W_down)
+
+        def get_collapsed_param(self):
+            return torch.einsum("or,rikl->oikl", self.W_up.data[:, :, 0, 0], self.W_down.data), None
+
+
+class DAPPPatchContainer(LoraPatchContainer):
+    """DreamArtist++ container (reference lora_layers_patch.py:102-133): the input batch is [negative half | positive half];
+    rows of the first half get W_host + sum of the branch-'n' deltas, rows of the second half the branch-'p' deltas."""
+
+
+class DAPPLayer(LoraLayer):
+    """LoRA block bound to one CFG branch (reference lora_layers_patch.py:135-216).  Same parameters / checkpoint keys as
+    LoraLayer; `branch` is 'p' (positive prompt half) or 'n' (negative half)."""
+    container_cls = DAPPPatchContainer
+
+    def __init__(self, lora_id: int, host, rank=1, dropout=0.1, alpha=1.0, bias=False, alpha_auto_scale=True, branch="p", **kwargs):
+        if branch not in ("p", "n"):
+            raise ValueError(f"DAPPLayer branch must be 'p' or 'n', got {branch!r}")
+        super().__init__(lora_id, host, rank, dropout, alpha=alpha, bias=bias, alpha_auto_scale=alpha_auto_scale, **kwargs)
+        self.branch = branch
+
+
 class LoraGroup(PluginGroup):
     def set_inplace(self, inplace):
         for item in self.plugin_dict.values():
@@ -137,4 +187,5 @@ class LoraGroup(PluginGroup):
 
 lora_layer_map: Dict[str, type] = {
     "lora": LoraLayer,
+    "dapp": DAPPLayer,
 }

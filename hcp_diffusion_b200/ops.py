@@ -57,7 +57,6 @@ def gemm_raw(a_list: Sequence[Tuple[torch.Tensor, int, int]], b_list: Sequence[T
     if wsb:
         ws = torch.empty((wsb // 4,), dtype=torch.float32, device=out.device)
         g.workspace, g.workspace_bytes = ws.data_ptr(), wsb
-        _lib.launch_count += 1
     call("hcp_gemm_bf16", C.byref(g), stream_ptr())
 
 
@@ -76,30 +75,34 @@ def conv3x3_raw(x: torch.Tensor, w: torch.Tensor, B: int, Hin: int, Win: int, Ci
         if wsb:
             ws = torch.empty((wsb // 4,), dtype=torch.float32, device=out.device)
             a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
-            _lib.launch_count += 1
     call("hcp_conv3x3_bf16", C.byref(a), stream_ptr())
-    if mode == 1:
-        _lib.launch_count += 3
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 # packed weights
 # ----------------------------------------------------------------------------------------------------------------------
 class LoraBlockRef:
-    """One LoRA block inside a fused linear group (see hcp_lora_job in include/hcp_b200.h)."""
-    __slots__ = ("w_down", "w_up", "alpha", "rank", "in_dim", "out_dim", "c0", "o0", "g_down", "g_up")
+    """One LoRA block inside a fused linear group (see hcp_lora_job in include/hcp_b200.h).
+    `branch`: None (applies to every row) or 'p' / 'n' -- DreamArtist++ adapters, reference DAPPPatchContainer.forward
+    (hcpdiff/models/lora_layers_patch.py:102-133): the first half of the batch sees the 'n' blocks, the second half the 'p' blocks."""
+    __slots__ = ("w_down", "w_up", "alpha", "rank", "in_dim", "out_dim", "c0", "o0", "g_down", "g_up", "branch")
 
-    def __init__(self, w_down, w_up, alpha, c0, o0):
+    def __init__(self, w_down, w_up, alpha, o0, branch=None):
         self.w_down, self.w_up, self.alpha = w_down, w_up, float(alpha)
-        self.rank, self.in_dim = w_down.shape
+        self.rank, self.in_dim = w_down.shape[0], w_down.shape[1]     # Linear [r,in] or 1x1 Conv2d [r,in,1,1]
         self.out_dim = w_up.shape[0]
-        self.c0, self.o0 = c0, o0
+        self.c0, self.o0 = 0, o0
+        self.branch = branch
         self.g_down = None   # optional fp32 views into a flat gradient buffer (direct accumulation)
         self.g_up = None
 
 
 class LinearPack:
-    """bf16 operands of one (possibly fused, possibly LoRA-patched) linear group  y = x . W^T + b."""
+    """bf16 operands of one (possibly fused, possibly LoRA-patched) linear group  y = x . W^T + b.
+
+    LoRA blocks of the group share R = 64-padded rank columns: T = x . A^T [M,R] is the extra K-segment of the main GEMM
+    against alpha*W_up packed as Bl [N,R].  A block never straddles a 64-column slab unless its rank exceeds 64 (then it starts
+    on a slab boundary), so the gradient kernel works slab by slab."""
 
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], k_splits: Optional[Sequence[int]] = None):
         # weight fp32/bf16 [N, K]
@@ -109,29 +112,65 @@ class LinearPack:
         self.bias = None if bias is None else bias.detach().float().contiguous()
         self.k_splits = list(k_splits) if k_splits else [self.K]
         self.lora: List[LoraBlockRef] = []
-        self.r_tot = 0
+        self.r_tot = 0          # rank columns in use (incl. alignment gaps)
+        self.R = 0              # r_tot padded to a multiple of 64
+        self.dapp = False
         self.A = self.AT = self.Bl = self.BlT = None
+        self.A_br = self.BlT_br = None      # DAPP: {'n': ..., 'p': ...} row-masked variants of A / BlT
 
     def attach_lora(self, blocks: List[LoraBlockRef]) -> None:
         self.lora = blocks
-        self.r_tot = sum(b.rank for b in blocks)
-        if self.r_tot > 64 or any(b.rank > 32 for b in blocks):
-            raise _lib.HcpError(f"LoRA ranks of one fused linear group must sum to <= 64 (each <= 32), got {[b.rank for b in blocks]}")
+        c = 0
+        for b in blocks:
+            if b.in_dim != self.K:
+                raise _lib.HcpError(f"LoRA block input width {b.in_dim} does not match the layer ({self.K})")
+            if b.rank > 64 or (c % 64) + b.rank > 64:
+                c = (c + 63) // 64 * 64
+            b.c0 = c
+            c += b.rank
+        self.r_tot = c
+        self.R = (c + 63) // 64 * 64
+        if self.R > 1024:
+            raise _lib.HcpError(f"LoRA ranks of one fused linear group sum to {c} (> 1024 columns)")
+        self.dapp = any(b.branch is not None for b in blocks)
         dev = self.W.device
-        self.A = torch.zeros((self.r_tot, self.K), dtype=BF16, device=dev)
-        self.AT = torch.zeros((self.K, 64), dtype=BF16, device=dev)
-        self.Bl = torch.zeros((self.N, 64), dtype=BF16, device=dev)
-        self.BlT = torch.zeros((self.r_tot, self.N), dtype=BF16, device=dev)
+        z = lambda *shape: torch.zeros(shape, dtype=BF16, device=dev)   # noqa: E731
+        self.AT = z(self.K, self.R)
+        self.Bl = z(self.N, self.R)
+        if self.dapp:
+            self.A_br = {"n": z(self.R, self.K), "p": z(self.R, self.K)}
+            self.BlT_br = {"n": z(self.R, self.N), "p": z(self.R, self.N)}
+            self.A = self.BlT = None
+        else:
+            self.A = z(self.R, self.K)
+            self.BlT = z(self.R, self.N)
 
     def jobs(self) -> List[_lib.LoraJob]:
         out = []
         for b in self.lora:
-            j = _lib.LoraJob()
-            j.w_down, j.w_up, j.alpha = b.w_down.data_ptr(), b.w_up.data_ptr(), b.alpha
-            j.rank, j.in_dim, j.out_dim = b.rank, b.in_dim, b.out_dim
-            j.c0, j.o0, j.out_tot = b.c0, b.o0, self.N
-            j.A, j.AT, j.Bl, j.BlT = self.A.data_ptr(), self.AT.data_ptr(), self.Bl.data_ptr(), self.BlT.data_ptr()
-            out.append(j)
+            branches = ([b.branch] if b.branch is not None else ["n", "p"]) if self.dapp else [None]
+            for br in branches:
+                j = _lib.LoraJob()
+                j.w_down, j.w_up, j.alpha = b.w_down.data_ptr(), b.w_up.data_ptr(), b.alpha
+                j.rank, j.in_dim, j.out_dim = b.rank, b.in_dim, b.out_dim
+                j.c0, j.o0, j.out_tot, j.ld_r = b.c0, b.o0, self.N, self.R
+                A, BlT = (self.A, self.BlT) if br is None else (self.A_br[br], self.BlT_br[br])
+                j.A, j.AT, j.Bl, j.BlT = A.data_ptr(), self.AT.data_ptr(), self.Bl.data_ptr(), BlT.data_ptr()
+                out.append(j)
+        return out
+
+    def slabs(self):
+        """[(slab index, [(block, first rank row j0, rows, first column inside the slab)])] for the gradient kernel."""
+        out = []
+        for q in range(self.R // 64):
+            lo, hi = 64 * q, 64 * q + 64
+            pieces = []
+            for b in self.lora:
+                a, e = max(lo, b.c0), min(hi, b.c0 + b.rank)
+                if a < e:
+                    pieces.append((b, a - b.c0, e - a, a - lo))
+            if pieces:
+                out.append((q, pieces))
         return out
 
 
@@ -153,10 +192,49 @@ class ConvPack:
 # ----------------------------------------------------------------------------------------------------------------------
 # linear (+LoRA, + fused residual)
 # ----------------------------------------------------------------------------------------------------------------------
+def _skinny_rows(pack: LinearPack, a_list, b_key: str, M: int, batch: int, out: torch.Tensor, n_out: int) -> None:
+    """out[M, R] = sum_s A_s . B_s^T for the LoRA down-projections (T = x . A^T, U = dY . (alpha B)).  Plain groups: one GEMM.
+    DAPP groups: one GEMM per batch half against the row-masked operand of that half's branch, so T / U come out with zeros
+    in the columns of the other branch and everything downstream (main GEMM segment, dX, gradient kernel) stays unmasked."""
+    R = pack.R
+
+    def b_list_for(t):
+        if b_key == "A":       # [R, K] against the (possibly multi-input) x: column offsets follow the k splits
+            bl, off = [], 0
+            for (_, _, k) in a_list:
+                bl.append((t, pack.K, n_out, off))
+                off += k
+            return bl
+        return [(t, pack.N, n_out, 0)]
+
+    if not pack.dapp:
+        gemm_raw(a_list, b_list_for(pack.A if b_key == "A" else pack.BlT), M, R, out, R)
+        return
+    if batch % 2:
+        raise _lib.HcpError("DreamArtist++ (dapp) layers need an even batch: [negative half | positive half]")
+    Mh = M // 2
+    for half, br in ((0, "n"), (1, "p")):
+        t = (pack.A_br if b_key == "A" else pack.BlT_br)[br]
+        rows = [(_RowView(a, half * Mh * lda), lda, k) for (a, lda, k) in a_list]
+        gemm_raw(rows, b_list_for(t), Mh, R, _RowView(out, half * Mh * R), R)
+
+
+class _RowView:
+    """A row-offset alias of a bf16 matrix for gemm_raw (which only needs data_ptr())."""
+    __slots__ = ("t", "off", "device")
+
+    def __init__(self, t, elem_off: int):
+        self.t, self.off, self.device = t, elem_off, t.device
+
+    def data_ptr(self) -> int:
+        return self.t.data_ptr() + 2 * self.off
+
+
 class FusedLinearFn(torch.autograd.Function):
     """y = cat(xs, -1) . W^T + b (+ T . Bl^T, T = x . A^T)(+ residual).  Reference semantics:
     LoraPatchContainer.forward / LoraBlock.post_forward / LinearLayer.forward (hcpdiff/models/lora_base_patch.py:21-35,
-    68-74, lora_layers_patch.py:44-57) without materialising W + alpha*W_up@W_down."""
+    68-74, lora_layers_patch.py:44-57) and DAPPPatchContainer.forward (lora_layers_patch.py:102-133) without materialising
+    W + alpha*W_up@W_down."""
 
     @staticmethod
     def forward(ctx, pack: LinearPack, residual: Optional[torch.Tensor], n_x: int, *tensors):
@@ -175,17 +253,18 @@ class FusedLinearFn(torch.autograd.Function):
             off += k
         T = None
         if pack.lora:
-            if n_x != 1:
-                raise _lib.HcpError("LoRA on a multi-input linear is not supported")
-            T = torch.empty((M, 64), dtype=BF16, device=xs[0].device)
-            gemm_raw([(xs[0], ks[0], ks[0])], [(pack.A, pack.K, pack.r_tot, 0)], M, 64, T, 64)
-            a_list.append((T, 64, pack.r_tot))
-            b_list.append((pack.Bl, 64, N, 0))
+            if len(a_list) + 1 > _lib.MAX_SEG:
+                raise _lib.HcpError("LoRA on a linear with more than two concatenated inputs is not supported")
+            T = torch.empty((M, pack.R), dtype=BF16, device=xs[0].device)
+            _skinny_rows(pack, list(a_list), "A", M, xs[0].shape[0], T, pack.R)
+            a_list.append((T, pack.R, pack.r_tot))
+            b_list.append((pack.Bl, pack.R, N, 0))
         res = None
         if residual is not None:
             res = _chk(residual, "linear residual")
         gemm_raw(a_list, b_list, M, N, out, N, bias=pack.bias, residual=res, ldr=N)
         ctx.pack, ctx.n_x, ctx.M, ctx.ks = pack, n_x, M, ks
+        ctx.batch = xs[0].shape[0]
         ctx.has_res = residual is not None
         saved = list(xs) if pack.lora else []
         if T is not None:
@@ -198,33 +277,36 @@ class FusedLinearFn(torch.autograd.Function):
     def backward(ctx, dy):
         pack, M, ks = ctx.pack, ctx.M, ctx.ks
         dy = _chk(dy, "linear grad")
-        N = pack.N
+        N, R = pack.N, pack.R
         U = None
         if pack.lora:
-            x, T = ctx.saved_tensors
-            U = torch.empty((M, 64), dtype=BF16, device=dy.device)
-            gemm_raw([(dy, N, N)], [(pack.BlT, N, pack.r_tot, 0)], M, 64, U, 64)
-            nb = len(pack.lora)
-            down = (_lib.LoraGradBlock * nb)()
-            up = (_lib.LoraGradBlock * nb)()
-            for i, b in enumerate(pack.lora):
-                gd = b.g_down if b.g_down is not None else _acc_grad(b.w_down)
-                gu = b.g_up if b.g_up is not None else _acc_grad(b.w_up)
-                down[i].n_lo, down[i].n_hi, down[i].c0, down[i].rank = 0, ks[0], b.c0, b.rank
-                down[i].scale, down[i].transpose_out, down[i].dst, down[i].dst_ld = 1.0, 0, gd.data_ptr(), ks[0]
-                up[i].n_lo, up[i].n_hi, up[i].c0, up[i].rank = b.o0, b.o0 + b.out_dim, b.c0, b.rank
-                up[i].scale, up[i].transpose_out, up[i].dst, up[i].dst_ld = b.alpha, 1, gu.data_ptr(), b.rank
-            # dW_down = U^T x ;  dW_up = alpha * dY^T T   (tensor-core TN GEMMs, all blocks of the group per launch)
-            if nb <= 8:
-                call("hcp_lora_grad_pair", U.data_ptr(), x.data_ptr(), ks[0], ks[0], down, T.data_ptr(), dy.data_ptr(), N, N, up, nb, M,
-                     stream_ptr())
-            else:
-                for b0 in range(0, nb, 8):
-                    n8 = min(8, nb - b0)
-                    call("hcp_lora_grad", U.data_ptr(), x.data_ptr(), ks[0], M, 0, ks[0], C.cast(C.byref(down[b0]), C.POINTER(_lib.LoraGradBlock)),
-                         n8, stream_ptr())
-                    call("hcp_lora_grad", T.data_ptr(), dy.data_ptr(), N, M, 0, N, C.cast(C.byref(up[b0]), C.POINTER(_lib.LoraGradBlock)), n8,
-                         stream_ptr())
+            *xs, T = ctx.saved_tensors
+            U = torch.empty((M, R), dtype=BF16, device=dy.device)
+            _skinny_rows(pack, [(dy, N, N)], "BlT", M, ctx.batch, U, R)
+            # dW_down = U^T x ;  dW_up = alpha * dY^T T   (tensor-core TN GEMMs, one 64-column slab of U / T per launch)
+            for q, pieces in pack.slabs():
+                for p0 in range(0, len(pieces), 8):
+                    chunk = pieces[p0:p0 + 8]
+                    nb = len(chunk)
+                    up = (_lib.LoraGradBlock * nb)()
+                    for i, (b, j0, rows, cs) in enumerate(chunk):
+                        gu = b.g_up if b.g_up is not None else _acc_grad(b.w_up)
+                        up[i].n_lo, up[i].n_hi, up[i].c0, up[i].rank = b.o0, b.o0 + b.out_dim, cs, rows
+                        up[i].scale, up[i].transpose_out, up[i].dst, up[i].dst_ld = b.alpha, 1, gu.data_ptr() + 4 * j0, b.rank
+                    koff = 0
+                    for xi, (x, k) in enumerate(zip(xs, ks)):
+                        down = (_lib.LoraGradBlock * nb)()
+                        for i, (b, j0, rows, cs) in enumerate(chunk):
+                            gd = b.g_down if b.g_down is not None else _acc_grad(b.w_down)
+                            down[i].n_lo, down[i].n_hi, down[i].c0, down[i].rank = 0, k, cs, rows
+                            down[i].scale, down[i].transpose_out = 1.0, 0
+                            down[i].dst, down[i].dst_ld = gd.data_ptr() + 4 * (j0 * pack.K + koff), pack.K
+                        Uq, Tq = U.data_ptr() + 2 * 64 * q, T.data_ptr() + 2 * 64 * q
+                        if xi == 0:
+                            call("hcp_lora_grad_pair", Uq, x.data_ptr(), k, k, down, Tq, dy.data_ptr(), N, N, up, nb, M, R, stream_ptr())
+                        else:
+                            call("hcp_lora_grad", Uq, R, x.data_ptr(), k, M, 0, k, down, nb, stream_ptr())
+                        koff += k
         grads = []
         off = 0
         for i, k in enumerate(ks):
@@ -233,8 +315,8 @@ class FusedLinearFn(torch.autograd.Function):
                 a_list = [(dy, N, N)]
                 b_list = [(pack.WT, N, k, off * N)]
                 if U is not None:
-                    a_list.append((U, 64, pack.r_tot))
-                    b_list.append((pack.AT, 64, k, 0))
+                    a_list.append((U, R, pack.r_tot))
+                    b_list.append((pack.AT, R, k, off * R))
                 gemm_raw(a_list, b_list, M, k, dx, k)
                 grads.append(dx)
             else:
@@ -462,10 +544,6 @@ class AttentionFn(torch.autograd.Function):
         a.dv, a.lddv = dkv.data_ptr() + 2 * offs[2], ldkv
         a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
         call("hcp_attn_bwd_bf16", C.byref(a), stream_ptr())
-        if d > 128:
-            _lib.launch_count += 1
-        if Lkv <= 128 and Lq > 128:
-            _lib.launch_count += 1
         return None, None, None, None, dq_src, (None if same else dkv)
 
 

@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import _lib, ops
-from .models.lora import LoraBlock, LoraPatchContainer
+from .models.lora import DAPPPatchContainer, LoraBlock, LoraPatchContainer
 from .ops import BF16, ConvPack, LinearPack, LoraBlockRef
 
 
@@ -74,12 +74,14 @@ class LinearGroup:
         if any(b is not None for b in biases):
             bias = torch.cat([b if b is not None else torch.zeros(h.weight.shape[0], device=w.device) for (h, _), b in zip(hosts, biases)])
         pack = LinearPack(w, bias, k_splits)
-        refs, c0, o0 = [], 0, 0
-        for host, blocks in hosts:
+        refs, o0 = [], 0
+        for ch, (host, blocks) in zip(self.children, hosts):
+            dapp = isinstance(ch, DAPPPatchContainer)
             for b in blocks:
-                ref = LoraBlockRef(b.layer.W_down, b.layer.W_up, float(b.alpha), c0, o0)
-                refs.append(ref)
-                c0 += ref.rank
+                branch = getattr(b, "branch", None) if dapp else None      # a plain LoraPatchContainer sums every block (ref. :21-35)
+                if dapp and branch not in ("p", "n"):
+                    continue                                               # DAPPPatchContainer.forward only reads 'p' / 'n' blocks
+                refs.append(LoraBlockRef(b.layer.W_down, b.layer.W_up, float(b.alpha), o0, branch))
             o0 += host.weight.shape[0]
         if refs:
             pack.attach_lora(refs)
@@ -91,12 +93,20 @@ class LinearGroup:
         return ops.fused_linear(pack, xs, residual)
 
     def run_standalone(self, x: torch.Tensor) -> torch.Tensor:
-        """Used by LoraPatchContainer.forward: any float dtype in, same dtype out."""
+        """Used by LoraPatchContainer.forward: any float dtype in, same dtype out.  Linear hosts take [..., in]; 1x1 Conv2d hosts
+        take NCHW like the reference layer (the NHWC view is the boundary conversion, the product path inside the UNet never
+        leaves NHWC)."""
         if not x.is_cuda:
             raise _lib.HcpError("hcp_diffusion_b200 has no CPU path: LoRA layers run on a B200 only")
         pack = self.prepare()
         if pack.lora:
             pack_lora([self])
+        host, _ = host_and_blocks(self.children[0])
+        if isinstance(host, nn.Conv2d):
+            B, C_, H, W = x.shape
+            t = x.permute(0, 2, 3, 1).reshape(B, H * W, C_).to(BF16).contiguous()
+            y = ops.fused_linear(pack, [t], None)
+            return y.view(B, H, W, -1).permute(0, 3, 1, 2).to(x.dtype)
         y = ops.fused_linear(pack, [x.to(BF16)], None)
         return y.to(x.dtype)
 

@@ -37,6 +37,9 @@ enum hcp_status {
 int hcp_version(void);                     /* ABI version, bumps on any signature change */
 const char* hcp_last_error_string(void);   /* thread-local, never NULL */
 int hcp_device_check(void);                /* HCP_OK iff the current device is compute capability 10.x */
+/* Number of kernels the library has launched in this process (every launch goes through one counter; kernels captured into a
+ * CUDA graph are counted once, at capture).  bench.py reports differences of this value as `gpu_launches`. */
+unsigned long long hcp_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM family (tcgen05 + TMA).  out[M,N] = sum_s A_s[M,K_s] . B_s[N,K_s]^T  (+ epilogue)
@@ -214,25 +217,27 @@ int hcp_cast_f32_to_bf16(const float* x, int64_t n, void* y, hcp_stream_t stream
  * Replaces LoraBlock.get_weight (alpha * mm(W_up, W_down), reference lora_base_patch.py:61-62,
  * lora_layers_patch.py:44-45) and autograd of W_down / W_up.  One job per LoRA block; blocks that share a fused
  * GEMM (to_q/to_k/to_v on the same input; several stacked blocks on one layer) tile the packed operands
- * block-diagonally via (c0, o0).
+ * block-diagonally via (c0, o0).  c0 is the block's first column inside the group's R-wide T / U buffers.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct hcp_lora_job {
     const float* w_down;     /* fp32 [rank, in_dim]  (LoraLayer.LinearLayer.W_down) */
     const float* w_up;       /* fp32 [out_dim, rank] (W_up) */
     float alpha;             /* LoraBlock.alpha buffer = alpha / rank */
     int32_t rank, in_dim, out_dim;
-    int32_t c0;              /* first rank column of this block inside the group's 64-wide T / U buffers */
+    int32_t c0;              /* first rank column of this block inside the group's R-wide T / U buffers */
     int32_t o0;              /* first output row of this block inside the group's fused output */
     int32_t out_tot;         /* fused output width of the group */
-    void* A;                 /* bf16 [r_tot, in_dim] */
-    void* AT;                /* bf16 [in_dim, 64] */
-    void* Bl;                /* bf16 [out_tot, 64] */
-    void* BlT;               /* bf16 [r_tot, out_tot] */
+    int32_t ld_r;            /* R: rank columns of the group padded to a multiple of 64 (row pitch of AT / Bl, of T / U) */
+    void* A;                 /* bf16 [R, in_dim]   (DAPP: the buffer of this block's branch) */
+    void* AT;                /* bf16 [in_dim, R] */
+    void* Bl;                /* bf16 [out_tot, R] */
+    void* BlT;               /* bf16 [R, out_tot]  (DAPP: the buffer of this block's branch) */
 } hcp_lora_job;
 
 int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp_stream_t stream);
 /* Gradients of the LoRA factors on the tensor pipe: for every block b and every column n in [n_lo_b, n_hi_b) of X,
- *     D[n, j] = scale_b * sum_m X[m, n] * S[m, c0_b + j],   j < rank_b      (S bf16 [M,64], X bf16 [M,ldx])
+ *     D[n, j] = scale_b * sum_m X[m, n] * S[m, c0_b + j],   j < rank_b      (S bf16 [M,64] with row pitch lds >= 64: one 64-column
+ *     slab of the group's T / U buffer -- wider groups call once per slab with S advanced by 64 columns; X bf16 [M,ldx])
  * is ACCUMULATED (fp32 atomics) into  dst_b[j*dst_ld + (n-n_lo)]  (transpose_out = 0: dW_down[r,in], S = dY.(alpha B), X = x)
  *                               or   dst_b[(n-n_lo)*dst_ld + j]  (transpose_out = 1: dW_up[out,r],  S = x.A^T, X = dY). */
 typedef struct hcp_lora_grad_block {
@@ -243,12 +248,12 @@ typedef struct hcp_lora_grad_block {
     float* dst;
     int64_t dst_ld;
 } hcp_lora_grad_block;
-int hcp_lora_grad(const void* S, const void* X, int64_t ldx, int64_t M, int64_t n_begin, int64_t n_end,
+int hcp_lora_grad(const void* S, int64_t lds, const void* X, int64_t ldx, int64_t M, int64_t n_begin, int64_t n_end,
                   const hcp_lora_grad_block* blocks, int32_t nblocks, hcp_stream_t stream);     /* nblocks <= 8 */
 /* Both gradients of one LoRA group in a single launch: dW_down from (U [M,64], x [M,K]) and dW_up from (T [M,64], dY [M,N]). */
 int hcp_lora_grad_pair(const void* U, const void* x, int64_t ldx, int64_t K, const hcp_lora_grad_block* down,
                        const void* T, const void* dy, int64_t lddy, int64_t N, const hcp_lora_grad_block* up,
-                       int32_t nblocks, int64_t M, hcp_stream_t stream);
+                       int32_t nblocks, int64_t M, int64_t lds /* row pitch of U and T */, hcp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * The step either side of the UNet call (reference hcpdiff/train_ac.py:437-447, 485-494, 506-515).

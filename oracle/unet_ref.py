@@ -176,22 +176,25 @@ def init_params(spec: UNetSpec = SD15, seed: int = 0, dtype=torch.float32) -> Di
 # ----------------------------------------------------------------------------------------------------------------------
 @dataclass
 class LoraEntry:
-    """One LoRA block on one Linear layer: W_down [r,in], W_up [out,r], alpha = alpha/rank (a scalar)."""
+    """One LoRA block on one layer.  Linear: W_down [r,in], W_up [out,r]; Conv2d (lora_layers_patch.py:64-100): W_down
+    [r,in,kh,kw], W_up [out,r,1,1].  alpha = alpha/rank (a scalar).  branch: None, or 'p' / 'n' for DreamArtist++ blocks."""
     W_down: Tensor
     W_up: Tensor
     alpha: float
+    branch: Optional[str] = None
 
 
 LoraDict = Dict[str, List[LoraEntry]]   # layer path (e.g. '...attn1.to_q') -> stacked blocks
 
 
-def lora_target_layers(spec: UNetSpec = SD15, pattern: str = r".*\.attn.?$") -> List[str]:
-    """Linear layers hit by a reference `layers: ['re:<pattern>']` item: every nn.Linear below a module whose
-    name matches (reference hcpdiff/utils/cfg_net_tools.py:30-75 + plugin.py:297-315)."""
+def lora_target_layers(spec: UNetSpec = SD15, pattern: str = r".*\.attn.?$", include_conv: bool = False) -> List[str]:
+    """Layers hit by a reference `layers: ['re:<pattern>']` item: every nn.Linear (and, with `include_conv`, nn.Conv2d --
+    LoraBlock.wrapable_classes, lora_base_patch.py:39) below a module whose name matches (reference
+    hcpdiff/utils/cfg_net_tools.py:30-75 + plugin.py:297-315)."""
     rx = re.compile(pattern)
     names = []
     for k, shp in param_shapes(spec).items():
-        if not k.endswith(".weight") or len(shp) != 2:
+        if not k.endswith(".weight") or not (len(shp) == 2 or (include_conv and len(shp) == 4)):
             continue
         layer = k[: -len(".weight")]
         parts = layer.split(".")
@@ -202,33 +205,65 @@ def lora_target_layers(spec: UNetSpec = SD15, pattern: str = r".*\.attn.?$") -> 
 
 
 def init_lora(spec: UNetSpec = SD15, rank: int = 8, alpha: float = 1.0, seed: int = 1, up_std: float = 0.02,
-              pattern: str = r".*\.attn.?$") -> LoraDict:
+              pattern: str = r".*\.attn.?$", include_conv: bool = False, branch: Optional[str] = None) -> LoraDict:
     """W_down: kaiming-uniform(a=sqrt5) like the reference init (lora_layers_patch.py:38-42); W_up ~ N(0, up_std) so the
     delta does not vanish in parity tests (up_std=0 reproduces the reference's zero init)."""
     shapes = param_shapes(spec)
     out: LoraDict = {}
-    for idx, layer in enumerate(lora_target_layers(spec, pattern)):
-        o, i = shapes[layer + ".weight"]
+    for idx, layer in enumerate(lora_target_layers(spec, pattern, include_conv)):
+        shp = shapes[layer + ".weight"]
+        o, i = shp[0], shp[1]
         g = torch.Generator().manual_seed(seed * 7_000_003 + idx)
-        bound = 1.0 / math.sqrt(i)          # kaiming_uniform(a=sqrt(5)) on a [r, in] matrix
-        down = (torch.rand((rank, i), generator=g) * 2 - 1) * bound
-        up = torch.randn((o, rank), generator=g) * up_std
-        out[layer] = [LoraEntry(down, up, alpha / rank)]
+        fan_in = i * (shp[2] * shp[3] if len(shp) == 4 else 1)
+        bound = 1.0 / math.sqrt(fan_in)     # kaiming_uniform(a=sqrt(5)) on [r, in(, kh, kw)]
+        down = (torch.rand((rank, *shp[1:]), generator=g) * 2 - 1) * bound
+        up = torch.randn((o, rank) if len(shp) == 2 else (o, rank, 1, 1), generator=g) * up_std
+        out[layer] = [LoraEntry(down, up, alpha / rank, branch)]
     return out
+
+
+def lora_delta(entries: List[LoraEntry], branch: Optional[str] = None) -> Optional[Tensor]:
+    """sum of alpha * W_up . W_down over the blocks of one layer (of one DAPP branch when `branch` is given)."""
+    dw = None
+    for e in entries:
+        if branch is not None and e.branch != branch:
+            continue
+        if e.W_down.dim() == 2:
+            d = torch.mm(e.W_up, e.W_down) * e.alpha       # lora_layers_patch.py:44-45, lora_base_patch.py:61-62
+        else:                                              # einsum('o r ..., r i ... -> o i ...'), lora_layers_patch.py:91-92
+            d = torch.einsum("or,rikl->oikl", e.W_up[:, :, 0, 0], e.W_down) * e.alpha
+        dw = d if dw is None else dw + d                   # lora_base_patch.py:24-28
+    return dw
+
+
+def _mm(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+    shp = x.shape
+    y = torch.mm(x.reshape(-1, shp[-1]), w.transpose(0, 1)).view(*shp[:-1], -1)   # lora_layers_patch.py:50-57
+    return y if b is None else y + b
 
 
 def _linear(sd: Dict[str, Tensor], lora: Optional[LoraDict], name: str, x: Tensor) -> Tensor:
     w = sd[name + ".weight"]
-    if lora is not None and name in lora:
-        dw = None
-        for e in lora[name]:
-            d = torch.mm(e.W_up, e.W_down) * e.alpha       # lora_layers_patch.py:44-45, lora_base_patch.py:61-62
-            dw = d if dw is None else dw + d               # lora_base_patch.py:24-28
-        w = w + dw                                         # lora_base_patch.py:74 (host_weight + weight)
     b = sd.get(name + ".bias")
-    shp = x.shape
-    y = torch.mm(x.reshape(-1, shp[-1]), w.transpose(0, 1)).view(*shp[:-1], -1)   # lora_layers_patch.py:50-57
-    return y if b is None else y + b
+    entries = lora.get(name) if lora is not None else None
+    if entries and any(e.branch is not None for e in entries):
+        # DAPPPatchContainer.forward (lora_layers_patch.py:102-133): x = [negative half | positive half]
+        B = x.shape[0] // 2
+        y_p = _mm(x[B:], w + lora_delta(entries, "p"), b)
+        y_n = _mm(x[:B], w + lora_delta(entries, "n"), b)
+        return torch.cat([y_n, y_p], dim=0)
+    if entries:
+        w = w + lora_delta(entries)                        # lora_base_patch.py:74 (host_weight + weight)
+    return _mm(x, w, b)
+
+
+def _conv(sd: Dict[str, Tensor], lora: Optional[LoraDict], name: str, x: Tensor, stride: int = 1, padding: int = 0) -> Tensor:
+    """F.conv2d(x, W_host + delta, b) -- LoraLayer.Conv2dLayer.forward (lora_layers_patch.py:97-98) for patched convolutions."""
+    w = sd[name + ".weight"]
+    entries = lora.get(name) if lora is not None else None
+    if entries:
+        w = w + lora_delta(entries)
+    return F.conv2d(x, w, sd.get(name + ".bias"), stride=stride, padding=padding)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -242,15 +277,15 @@ def timestep_embedding(t: Tensor, dim: int) -> Tensor:
     return torch.cat([torch.cos(a), torch.sin(a)], dim=-1)
 
 
-def _resnet(sd, p: str, x: Tensor, emb: Tensor, spec: UNetSpec) -> Tensor:
+def _resnet(sd, p: str, x: Tensor, emb: Tensor, spec: UNetSpec, lora=None) -> Tensor:
     h = F.group_norm(x, spec.norm_groups, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], spec.resnet_eps)
-    h = F.conv2d(F.silu(h), sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding=1)
-    t = F.linear(F.silu(emb), sd[p + ".time_emb_proj.weight"], sd[p + ".time_emb_proj.bias"])
+    h = _conv(sd, lora, p + ".conv1", F.silu(h), padding=1)
+    t = _linear(sd, lora, p + ".time_emb_proj", F.silu(emb))
     h = h + t[:, :, None, None]
     h = F.group_norm(h, spec.norm_groups, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], spec.resnet_eps)
-    h = F.conv2d(F.silu(h), sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=1)
+    h = _conv(sd, lora, p + ".conv2", F.silu(h), padding=1)
     if (p + ".conv_shortcut.weight") in sd:
-        x = F.conv2d(x, sd[p + ".conv_shortcut.weight"], sd[p + ".conv_shortcut.bias"])
+        x = _conv(sd, lora, p + ".conv_shortcut", x)
     return x + h
 
 
@@ -275,7 +310,7 @@ def _transformer(sd, lora, p: str, x: Tensor, ehs: Tensor, bias: Optional[Tensor
     B, C, H, W = x.shape
     res = x
     h = F.group_norm(x, spec.norm_groups, sd[p + ".norm.weight"], sd[p + ".norm.bias"], spec.transformer_norm_eps)
-    h = F.conv2d(h, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
+    h = _conv(sd, lora, p + ".proj_in", h)
     h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
     tb = p + ".transformer_blocks.0"
     n = F.layer_norm(h, (C,), sd[tb + ".norm1.weight"], sd[tb + ".norm1.bias"], spec.layernorm_eps)
@@ -287,7 +322,7 @@ def _transformer(sd, lora, p: str, x: Tensor, ehs: Tensor, bias: Optional[Tensor
     a, g = u.chunk(2, dim=-1)
     h = _linear(sd, lora, tb + ".ff.net.2", a * F.gelu(g)) + h
     h = h.reshape(B, H, W, C).permute(0, 3, 1, 2)
-    return F.conv2d(h, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"]) + res
+    return _conv(sd, lora, p + ".proj_out", h) + res
 
 
 def unet_forward(sd: Dict[str, Tensor], sample: Tensor, timestep: Tensor, encoder_hidden_states: Tensor,
@@ -307,34 +342,34 @@ def unet_forward(sd: Dict[str, Tensor], sample: Tensor, timestep: Tensor, encode
     emb = F.linear(emb, sd["time_embedding.linear_1.weight"], sd["time_embedding.linear_1.bias"])
     emb = F.linear(F.silu(emb), sd["time_embedding.linear_2.weight"], sd["time_embedding.linear_2.bias"])
 
-    h = F.conv2d(sample, sd["conv_in.weight"], sd["conv_in.bias"], padding=1)
+    h = _conv(sd, lora, "conv_in", sample, padding=1)
     skips = [h]
     nblk = len(spec.block_out_channels)
     for i in range(nblk):
         for j in range(spec.layers_per_block):
-            h = _resnet(sd, f"down_blocks.{i}.resnets.{j}", h, emb, spec)
+            h = _resnet(sd, f"down_blocks.{i}.resnets.{j}", h, emb, spec, lora)
             if spec.down_has_attn[i]:
                 h = _transformer(sd, lora, f"down_blocks.{i}.attentions.{j}", h, encoder_hidden_states, bias, spec)
             skips.append(h)
         if i < nblk - 1:
             p = f"down_blocks.{i}.downsamplers.0.conv"
-            h = F.conv2d(h, sd[p + ".weight"], sd[p + ".bias"], stride=2, padding=1)
+            h = _conv(sd, lora, p, h, stride=2, padding=1)
             skips.append(h)
-    h = _resnet(sd, "mid_block.resnets.0", h, emb, spec)
+    h = _resnet(sd, "mid_block.resnets.0", h, emb, spec, lora)
     h = _transformer(sd, lora, "mid_block.attentions.0", h, encoder_hidden_states, bias, spec)
-    h = _resnet(sd, "mid_block.resnets.1", h, emb, spec)
+    h = _resnet(sd, "mid_block.resnets.1", h, emb, spec, lora)
     for i in range(nblk):
         for j in range(spec.layers_per_block + 1):
             h = torch.cat([h, skips.pop()], dim=1)
-            h = _resnet(sd, f"up_blocks.{i}.resnets.{j}", h, emb, spec)
+            h = _resnet(sd, f"up_blocks.{i}.resnets.{j}", h, emb, spec, lora)
             if spec.up_has_attn[i]:
                 h = _transformer(sd, lora, f"up_blocks.{i}.attentions.{j}", h, encoder_hidden_states, bias, spec)
         if i < nblk - 1:
             p = f"up_blocks.{i}.upsamplers.0.conv"
             h = F.interpolate(h, scale_factor=2.0, mode="nearest")
-            h = F.conv2d(h, sd[p + ".weight"], sd[p + ".bias"], padding=1)
+            h = _conv(sd, lora, p, h, padding=1)
     h = F.group_norm(h, spec.norm_groups, sd["conv_norm_out.weight"], sd["conv_norm_out.bias"], spec.resnet_eps)
-    return F.conv2d(F.silu(h), sd["conv_out.weight"], sd["conv_out.bias"], padding=1)
+    return _conv(sd, lora, "conv_out", F.silu(h), padding=1)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -7,6 +7,8 @@ Outputs (small, committed):
   ref_lora_linear.pt      vectors produced by the REAL reference classes hcpdiff.models.lora_layers_patch.LoraLayer /
                           lora_base_patch.LoraPatchContainer / plugin.PluginGroup: inputs, outputs, gradients and the
                           checkpoint key names (the operator the CUDA kernels sit behind)
+  ref_lora_dapp_conv.pt   the same for the DreamArtist++ pair (DAPPLayer / DAPPPatchContainer: batch = [negative | positive]) and
+                          for LoraLayer on Conv2d hosts (3x3 stride 1 / stride 2 and 1x1)
 """
 import importlib
 import json
@@ -152,6 +154,53 @@ def make_lora():
     print("  model keys sample:", [k for k in fx["state_keys_model"] if "to_q" in k][:6])
 
 
+class _DappConvNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.to_k = nn.Linear(24, 32, bias=False)
+        self.ff = nn.Linear(32, 32, bias=True)
+        self.conv = nn.Conv2d(8, 16, 3, padding=1)
+        self.conv_s2 = nn.Conv2d(8, 16, 3, stride=2, padding=1)
+        self.proj = nn.Conv2d(8, 16, 1)
+
+
+def make_dapp_conv():
+    """DreamArtist++ (DAPPLayer / DAPPPatchContainer) and Conv2d LoRA (LoraLayer.Conv2dLayer) vectors from the real reference."""
+    plugin, base, layers = import_reference_lora()
+    torch.manual_seed(1)
+    model = _DappConvNet().float()
+    g = torch.Generator().manual_seed(7)
+    blocks = {}
+    for lname in ("to_k", "ff"):
+        for lora_id, (branch, rank) in enumerate((("p", 4), ("n", 2))):
+            host = getattr(model, lname)
+            blk = layers.DAPPLayer.wrap_layer(lora_id, host, rank=rank, dropout=0.0, alpha=1.0, branch=branch, parent_block=model,
+                                              host_name=lname)
+            blocks[f"{lname}.{branch}"] = blk
+    for lname in ("conv", "conv_s2", "proj"):
+        blk = layers.LoraLayer.wrap_layer(0, getattr(model, lname), rank=4, dropout=0.0, alpha=2.0, parent_block=model, host_name=lname)
+        blocks[lname] = blk
+    for blk in blocks.values():
+        with torch.no_grad():
+            blk.layer.W_up.copy_(torch.randn(blk.layer.W_up.shape, generator=g) * 0.2)
+    fx = {"state_keys_model": sorted(model.state_dict().keys())}
+    fx["state"] = {k: v.clone() for k, v in model.state_dict().items()}
+    fx["container_types"] = {n: type(m).__name__ for n, m in model.named_children()}
+    xk = torch.randn(4, 5, 24, generator=g, requires_grad=True)          # batch 4 = [2 negative | 2 positive]
+    xf = torch.randn(4, 5, 32, generator=g, requires_grad=True)
+    xc = torch.randn(2, 8, 8, 8, generator=g, requires_grad=True)
+    outs = {"to_k": model.to_k(xk), "ff": model.ff(xf), "conv": model.conv(xc), "conv_s2": model.conv_s2(xc), "proj": model.proj(xc)}
+    loss = sum((o ** 2).sum() for o in outs.values())
+    loss.backward()
+    fx["xk"], fx["xf"], fx["xc"] = xk.detach().clone(), xf.detach().clone(), xc.detach().clone()
+    fx["outs"] = {k: v.detach().clone() for k, v in outs.items()}
+    fx["grad_in"] = {"xk": xk.grad.clone(), "xf": xf.grad.clone(), "xc": xc.grad.clone()}
+    fx["grads"] = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None and "lora_block" in n}
+    torch.save(fx, os.path.join(HERE, "ref_lora_dapp_conv.pt"))
+    print("ref_lora_dapp_conv.pt:", fx["container_types"], len(fx["grads"]), "lora grads")
+
+
 if __name__ == "__main__":
     make_struct()
     make_lora()
+    make_dapp_conv()

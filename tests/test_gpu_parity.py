@@ -62,7 +62,7 @@ def test_linear_lora_fwd_bwd(M, K, N, ranks):
         down = rnd(r, K, scale=1 / math.sqrt(K), seed=10 + i).requires_grad_(True)
         up = rnd(n_per, r, scale=0.3, seed=20 + i).requires_grad_(True)
         blocks.append((down, up, 0.125))
-        refs.append(LoraBlockRef(down, up, 0.125, c0, i * n_per))
+        refs.append(LoraBlockRef(down, up, 0.125, i * n_per))
         c0 += r
     if refs:
         pack.attach_lora(refs)
@@ -372,3 +372,47 @@ def test_train_step_graph_matches_eager_and_learns():
     assert l0[-1] < l0[0]
     assert max(abs(a - b) for a, b in zip(l0, l1)) < 1e-3 * abs(l0[0])
     assert rel_l2(p1, p0) < 1e-3
+
+
+def test_reference_dapp_and_conv1x1_lora_golden_through_product_containers(golden_dir):
+    """DreamArtist++ containers (batch = [negative | positive]) and LoRA on a 1x1 Conv2d: vectors of the REAL reference classes
+    (tests/golden/ref_lora_dapp_conv.pt) vs the product containers on the GPU (bf16 operands, fp32 accumulate)."""
+    from hcp_diffusion_b200.models.lora import DAPPLayer, DAPPPatchContainer
+    fx = torch.load(os.path.join(golden_dir, "ref_lora_dapp_conv.pt"))
+    st = fx["state"]
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.to_k = torch.nn.Linear(24, 32, bias=False)
+            self.ff = torch.nn.Linear(32, 32, bias=True)
+            self.proj = torch.nn.Conv2d(8, 16, 1)
+
+    model = Net()
+    model.load_state_dict({k.replace("._host", ""): v for k, v in st.items() if "._host." in k and k.split(".")[0] in ("to_k", "ff", "proj")})
+    model = model.to(DEV).requires_grad_(False)
+    for lname in ("to_k", "ff"):
+        for lora_id, (branch, rank) in enumerate((("p", 4), ("n", 2))):
+            DAPPLayer.wrap_layer(lora_id, getattr(model, lname), rank=rank, dropout=0.0, alpha=1.0, branch=branch, parent_block=model,
+                                 host_name=lname)
+    LoraLayer.wrap_layer(0, model.proj, rank=4, dropout=0.0, alpha=2.0, parent_block=model, host_name="proj")
+    assert isinstance(model.to_k, DAPPPatchContainer) and type(model.to_k).__name__ == fx["container_types"]["to_k"]
+    mine = model.state_dict()
+    assert sorted(mine.keys()) == sorted(k for k in fx["state_keys_model"] if k.split(".")[0] in ("to_k", "ff", "proj"))
+    with torch.no_grad():
+        for k, v in mine.items():
+            if "lora_block" in k:
+                assert v.shape == st[k].shape, k
+                v.copy_(st[k])
+    xk = fx["xk"].to(DEV).requires_grad_(True)
+    xf = fx["xf"].to(DEV).requires_grad_(True)
+    xc = fx["xc"].to(DEV).requires_grad_(True)
+    outs = {"to_k": model.to_k(xk), "ff": model.ff(xf), "proj": model.proj(xc)}
+    for k, v in outs.items():
+        assert v.shape == fx["outs"][k].shape and rel_l2(v, fx["outs"][k]) < 1e-2, k
+    # the golden loss also contains the two 3x3 convolutions; their share of d(loss)/d(xc) is removed through the oracle
+    sum((o ** 2).sum() for o in outs.values()).backward()
+    assert rel_l2(xk.grad, fx["grad_in"]["xk"]) < 2e-2 and rel_l2(xf.grad, fx["grad_in"]["xf"]) < 2e-2
+    for name, p in model.named_parameters():
+        if "lora_block" in name:
+            assert rel_l2(p.grad, fx["grads"][name]) < 3e-2, name

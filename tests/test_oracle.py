@@ -126,3 +126,52 @@ def test_timestep_embedding_layout():
     assert e.shape == (2, 320)
     torch.testing.assert_close(e[0, :160], torch.ones(160))      # cos(0) first (flip_sin_to_cos)
     torch.testing.assert_close(e[0, 160:], torch.zeros(160))
+
+
+def _dapp_conv_oracle(fx):
+    """(state dict of the host layers, LoraDict) of the DAPP / Conv2d-LoRA golden fixture."""
+    sd, lora = {}, {}
+    st = fx["state"]
+    for k, v in st.items():
+        if "._host." in k:
+            sd[k.replace("._host", "")] = v
+    for k in st:
+        if k.endswith(".layer.W_down"):
+            base = k[: -len(".layer.W_down")]                       # '<layer>.lora_block_<id>'
+            layer = base.rsplit(".", 1)[0]
+            branch = None
+            if fx["container_types"][layer] == "DAPPPatchContainer":
+                branch = "p" if base.endswith("lora_block_0") else "n"     # make_golden.py wraps ('p', rank 4) then ('n', rank 2)
+            lora.setdefault(layer, []).append(U.LoraEntry(st[k].clone(), st[base + ".layer.W_up"].clone(), float(st[base + ".alpha"]), branch))
+    return sd, lora
+
+
+def test_oracle_dapp_and_conv_lora_match_reference_golden(golden_dir):
+    """DAPPPatchContainer / DAPPLayer and LoraLayer.Conv2dLayer of the REAL reference (tests/golden/ref_lora_dapp_conv.pt) vs the
+    oracle's `_linear` (batch = [negative | positive]) and `_conv`: outputs, input gradients, parameter gradients."""
+    fx = torch.load(os.path.join(golden_dir, "ref_lora_dapp_conv.pt"))
+    assert fx["container_types"]["to_k"] == "DAPPPatchContainer" and fx["container_types"]["conv"] == "LoraPatchContainer"
+    sd, lora = _dapp_conv_oracle(fx)
+    for blocks in lora.values():
+        for e in blocks:
+            e.W_down.requires_grad_(True)
+            e.W_up.requires_grad_(True)
+    xk, xf, xc = (fx[k].clone().requires_grad_(True) for k in ("xk", "xf", "xc"))
+    outs = {"to_k": U._linear(sd, lora, "to_k", xk), "ff": U._linear(sd, lora, "ff", xf),
+            "conv": U._conv(sd, lora, "conv", xc, padding=1), "conv_s2": U._conv(sd, lora, "conv_s2", xc, stride=2, padding=1),
+            "proj": U._conv(sd, lora, "proj", xc)}
+    for k, v in outs.items():
+        torch.testing.assert_close(v, fx["outs"][k], rtol=1e-5, atol=1e-5)
+    sum((o ** 2).sum() for o in outs.values()).backward()
+    for k, x in (("xk", xk), ("xf", xf), ("xc", xc)):
+        torch.testing.assert_close(x.grad, fx["grad_in"][k], rtol=1e-4, atol=1e-4)
+    n = 0
+    for layer, blocks in lora.items():
+        for e in blocks:
+            bid = 0 if e.branch in (None, "p") else 1
+            torch.testing.assert_close(e.W_down.grad, fx["grads"][f"{layer}.lora_block_{bid}.layer.W_down"], rtol=1e-4, atol=1e-4)
+            torch.testing.assert_close(e.W_up.grad, fx["grads"][f"{layer}.lora_block_{bid}.layer.W_up"], rtol=1e-4, atol=1e-4)
+            n += 2
+    assert n == len(fx["grads"])
+    # the two halves of a DAPP batch really see different weights
+    assert not torch.allclose(outs["to_k"][:2], U._mm(fx["xk"][:2], sd["to_k.weight"] + U.lora_delta(lora["to_k"], "p"), None))

@@ -142,3 +142,44 @@ def test_cpu_call_fails_loudly():
     cont = unet.mid_block.attentions[0].transformer_blocks[0].attn1.to_q
     with pytest.raises(Exception, match="CUDA|CPU"):
         cont(torch.zeros(2, 128))
+
+
+def test_dapp_and_conv_lora_surface_matches_reference_golden(golden_dir):
+    """State-dict keys, parameter shapes and container classes of DAPPLayer / Conv2d LoraLayer equal what the REAL reference
+    classes produced (tests/golden/ref_lora_dapp_conv.pt); `type: dapp` resolves through lora_layer_map like cfg_net_tools.py:114."""
+    import os
+    from hcp_diffusion_b200.models.lora import DAPPLayer, DAPPPatchContainer, LoraLayer, LoraPatchContainer, lora_layer_map
+    fx = torch.load(os.path.join(golden_dir, "ref_lora_dapp_conv.pt"))
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.to_k = torch.nn.Linear(24, 32, bias=False)
+            self.ff = torch.nn.Linear(32, 32, bias=True)
+            self.conv = torch.nn.Conv2d(8, 16, 3, padding=1)
+            self.conv_s2 = torch.nn.Conv2d(8, 16, 3, stride=2, padding=1)
+            self.proj = torch.nn.Conv2d(8, 16, 1)
+
+    model = Net()
+    assert lora_layer_map["dapp"] is DAPPLayer
+    for lname in ("to_k", "ff"):
+        for lora_id, (branch, rank) in enumerate((("p", 4), ("n", 2))):
+            DAPPLayer.wrap_layer(lora_id, getattr(model, lname), rank=rank, dropout=0.0, alpha=1.0, branch=branch, parent_block=model,
+                                 host_name=lname)
+    for lname in ("conv", "conv_s2", "proj"):
+        LoraLayer.wrap_layer(0, getattr(model, lname), rank=4, dropout=0.0, alpha=2.0, parent_block=model, host_name=lname)
+    assert {n: type(m).__name__ for n, m in model.named_children()} == fx["container_types"]
+    assert isinstance(model.to_k, DAPPPatchContainer) and isinstance(model.conv, LoraPatchContainer)
+    sd = model.state_dict()
+    assert sorted(sd.keys()) == fx["state_keys_model"]
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(fx["state"][k].shape), k
+    assert model.to_k.lora_block_0.branch == "p" and model.to_k.lora_block_1.branch == "n"
+    assert abs(float(model.conv.lora_block_0.alpha) - float(fx["state"]["conv.lora_block_0.alpha"])) < 1e-7
+    # get_weight(): the materialised delta of the reference operator
+    blk = model.conv.lora_block_0
+    with torch.no_grad():
+        blk.layer.W_down.copy_(fx["state"]["conv.lora_block_0.layer.W_down"])
+        blk.layer.W_up.copy_(fx["state"]["conv.lora_block_0.layer.W_up"])
+    ref = torch.einsum("or,rikl->oikl", blk.layer.W_up[:, :, 0, 0], blk.layer.W_down) * blk.alpha
+    torch.testing.assert_close(blk.get_weight(), ref)
