@@ -49,7 +49,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                 const uint32_t* box) {
+                 const uint32_t* box, bool swizzle128) {
     // cuTensorMapEncodeTiled is a driver call and needs a context current on THIS thread; autograd worker threads may
     // not have touched the runtime yet (observed: CUDA_ERROR_INVALID_CONTEXT from a backward thread).  cudaSetDevice on
     // the thread's current device binds its primary context (and, unlike cudaFree(0), is legal during stream capture).
@@ -79,7 +79,8 @@ int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* d
         if (gs[i] % 16 != 0) return set_error(HCP_ERR_INVALID, "tensor map: stride not a multiple of 16 bytes");
     }
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[256];

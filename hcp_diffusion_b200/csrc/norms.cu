@@ -6,6 +6,7 @@
 // Replaces (reference module structure cfgs/unet_struct.txt): ResnetBlock2D.norm1/norm2 + nonlinearity (:93-99),
 // Transformer2DModel.norm (:13), conv_norm_out (:929), BasicTransformerBlock.norm1/2/3 (:44-46), GEGLU (:27-30),
 // Upsample2D's F.interpolate(scale_factor=2, mode='nearest') (:392) -- and their autograd backward.
+#include <stdlib.h>
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/hcp_b200.h"
@@ -412,6 +413,283 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn8_apply_kernel(const GNParam
     }
 }
 
+// =============================================================================================
+// Single-pass GroupNorm: one read and one write of the activation (fwd), two reads and one write (bwd).
+//
+// The statistics of a group only involve that group's channels, so the work is cut along CHANNELS first: a channel block is
+// CB = lcm(8, C/G) channels (whole groups AND whole 16-byte vectors: 40 / 80 / 120 channels for the SD widths), and the HW
+// pixels of one (image, channel block) are split over a thread-block cluster of S CTAs.  Each CTA brings its [P pixels x CB
+// channels] slab into shared memory with a few TMA box loads (all in flight at once), reduces it, the S partial sums per
+// group are exchanged through distributed shared memory (fixed rank order -> deterministic and independent of the batch
+// neighbours), and the slab is normalised / back-propagated straight from shared memory.
+// Replaces the two-pass kernels above whenever the concatenation boundary C1 falls on a channel-block boundary.
+// =============================================================================================
+constexpr int GNF_LANES = 64;        // pixel lanes per CTA: blockDim = (CB / 8) * GNF_LANES
+
+struct alignas(64) GNFParams {
+    CUtensorMap tmX1, tmX2, tmDY;    // [B*HW, C*] row-major, box [CB, RB], no swizzle
+    int C1, C2, C, G, cg, CB, V, gpb;
+    int HW, P, RB, nbox, S;
+    float inv_n;                     // 1 / (HW * cg)
+    const float* gamma; const float* beta;
+    float eps; int silu;
+    float* stats;                    // [B, G, 2] (mean, rstd): written by fwd, read by bwd
+    __nv_bfloat16* y;
+    const __nv_bfloat16* add1; const __nv_bfloat16* add2;
+    __nv_bfloat16* dx1; __nv_bfloat16* dx2;
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(1024) gnf_kernel(const __grid_constant__ GNFParams p) {
+    extern __shared__ uint8_t gnf_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gnf_smem_raw) + 127) & ~uintptr_t(127));
+    const int tile_bytes = p.P * p.CB * 2;
+    uint8_t* sX = smem;
+    uint8_t* sDY = sX + tile_bytes;                                     // BWD only
+    float* s_part = reinterpret_cast<float*>(sX + (BWD ? 2 : 1) * tile_bytes);   // [GNF_LANES][V][4]
+    float* s_cta = s_part + GNF_LANES * p.V * 4;                         // [gpb*2] partial sums of this CTA (read by the cluster)
+    float* s_raw = s_cta + 16;                                           // [gpb*2] cluster totals
+    float* s_fin = s_raw + 16;                                           // [gpb*2] (mean, rstd) or (mean g, mean g*xhat)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_fin + 16);
+
+    const int rank = (int)cluster_ctarank();
+    const int cb = blockIdx.y, b = blockIdx.z;
+    const int c0 = cb * p.CB;                                            // first channel of the block (in the concatenation)
+    const int tv = threadIdx.x % p.V, rl = threadIdx.x / p.V;
+    const int64_t row0 = (int64_t)b * p.HW + (int64_t)rank * p.P;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    pdl_trigger();
+    pdl_wait();
+    const bool first = c0 < p.C1;
+    if (threadIdx.x == 0) {
+        const CUtensorMap* tx = first ? &p.tmX1 : &p.tmX2;
+        const int cc = first ? c0 : c0 - p.C1;
+        mbar_arrive_expect_tx(bar, (BWD ? 2 : 1) * tile_bytes);
+        for (int i = 0; i < p.nbox; ++i) {
+            tma_load_2d(sX + (size_t)i * p.RB * p.CB * 2, tx, bar, cc, (int)(row0 + i * p.RB));
+            if (BWD) tma_load_2d(sDY + (size_t)i * p.RB * p.CB * 2, &p.tmDY, bar, c0, (int)(row0 + i * p.RB));
+        }
+    }
+    // per-thread constants: 8 consecutive channels, which may straddle ONE group boundary
+    const int ch = c0 + tv * 8;
+    const int g_lo = (tv * 8) / p.cg;                                    // group index inside the block
+    const int nb = min(8, (g_lo + 1) * p.cg - tv * 8);
+    const int g_hi = min(g_lo + 1, p.gpb - 1);
+    const int gbase = c0 / p.cg;
+    float gm[8], bt[8], mean[2] = {0.f, 0.f}, rstd[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { gm[e] = p.gamma[ch + e]; bt[e] = p.beta[ch + e]; }
+    if (BWD) {
+        const float* st = p.stats + ((int64_t)b * p.G + gbase) * 2;
+        mean[0] = st[g_lo * 2]; rstd[0] = st[g_lo * 2 + 1];
+        mean[1] = st[g_hi * 2]; rstd[1] = st[g_hi * 2 + 1];
+    }
+    mbar_wait(bar, 0);
+
+    // ---- pass 1: partial sums of this CTA's slab
+    float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};
+    for (int pp = rl; pp < p.P; pp += GNF_LANES) {
+        float x[8];
+        unpack8(*reinterpret_cast<const uint4*>(sX + ((size_t)pp * p.CB + tv * 8) * 2), x);
+        if (!BWD) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = (e < nb) ? 0 : 1;
+                a0[k] += x[e];
+                a1[k] += x[e] * x[e];
+            }
+        } else {
+            float d[8];
+            unpack8(*reinterpret_cast<const uint4*>(sDY + ((size_t)pp * p.CB + tv * 8) * 2), d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = (e < nb) ? 0 : 1;
+                const float xh = (x[e] - mean[k]) * rstd[k];
+                float g = d[e] * gm[e];
+                if (p.silu) g *= silu_grad(xh * gm[e] + bt[e]);
+                a0[k] += g;
+                a1[k] += g * xh;
+            }
+        }
+    }
+    {
+        float* dst = s_part + ((size_t)rl * p.V + tv) * 4;
+        dst[0] = a0[0]; dst[1] = a1[0]; dst[2] = a0[1]; dst[3] = a1[1];
+    }
+    __syncthreads();
+    if ((int)(threadIdx.x >> 5) < p.gpb * 2) {                           // one warp per (group, moment); fixed summation tree
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int g = w >> 1, which = w & 1;
+        const int v_lo = (g * p.cg) / 8, v_hi = ((g + 1) * p.cg - 1) / 8;
+        float acc = 0.f;
+#pragma unroll
+        for (int r = lane; r < GNF_LANES; r += 32)
+            for (int v = v_lo; v <= v_hi; ++v) {
+                const int vg = (v * 8) / p.cg;
+                const float* src = s_part + ((size_t)r * p.V + v) * 4;
+                if (vg == g) acc += src[which];
+                else if (vg + 1 == g) acc += src[2 + which];
+            }
+        acc = warp_sum(acc);
+        if (lane == 0) s_cta[w] = acc;
+    }
+    // ---- cluster exchange of the partial sums (rank order: deterministic)
+    cluster_arrive();
+    cluster_wait();
+    if ((int)threadIdx.x < p.gpb * 2) {
+        float tot = 0.f;
+        for (int r = 0; r < p.S; ++r) tot += ld_dsmem_f32(smem_u32(&s_cta[threadIdx.x]), (uint32_t)r);
+        s_raw[threadIdx.x] = tot;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < p.gpb) {
+        const int g = threadIdx.x;
+        if (!BWD) {
+            const float m = s_raw[2 * g] * p.inv_n;
+            const float var = fmaxf(s_raw[2 * g + 1] * p.inv_n - m * m, 0.f);
+            const float rs = rsqrtf(var + p.eps);
+            s_fin[2 * g] = m;
+            s_fin[2 * g + 1] = rs;
+            if (rank == 0) {
+                p.stats[((int64_t)b * p.G + gbase + g) * 2] = m;
+                p.stats[((int64_t)b * p.G + gbase + g) * 2 + 1] = rs;
+            }
+        } else {
+            s_fin[2 * g] = s_raw[2 * g] * p.inv_n;
+            s_fin[2 * g + 1] = s_raw[2 * g + 1] * p.inv_n;
+        }
+    }
+    cluster_arrive();                // this CTA no longer reads its neighbours' shared memory (matched by the wait before exit)
+    __syncthreads();
+
+    // ---- pass 2: normalise / back-propagate the slab from shared memory
+    const float sa[2] = {s_fin[g_lo * 2], s_fin[g_hi * 2]};
+    const float sb[2] = {s_fin[g_lo * 2 + 1], s_fin[g_hi * 2 + 1]};
+    for (int pp = rl; pp < p.P; pp += GNF_LANES) {
+        const int64_t pix = row0 + pp;
+        float x[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(sX + ((size_t)pp * p.CB + tv * 8) * 2), x);
+        if (!BWD) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = (e < nb) ? 0 : 1;
+                float z = (x[e] - sa[k]) * sb[k] * gm[e] + bt[e];
+                if (p.silu) z = silu_f(z);
+                o[e] = z;
+            }
+            *reinterpret_cast<uint4*>(p.y + pix * p.C + ch) = pack8(o);
+        } else {
+            float d[8];
+            unpack8(*reinterpret_cast<const uint4*>(sDY + ((size_t)pp * p.CB + tv * 8) * 2), d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = (e < nb) ? 0 : 1;
+                const float xh = (x[e] - mean[k]) * rstd[k];
+                float g = d[e] * gm[e];
+                if (p.silu) g *= silu_grad(xh * gm[e] + bt[e]);
+                o[e] = rstd[k] * (g - sa[k] - xh * sb[k]);
+            }
+            __nv_bfloat16* dst;
+            const __nv_bfloat16* add;
+            if (first) {
+                dst = p.dx1 + pix * p.C1 + ch;
+                add = p.add1 ? p.add1 + pix * p.C1 + ch : nullptr;
+            } else {
+                dst = p.dx2 + pix * p.C2 + (ch - p.C1);
+                add = p.add2 ? p.add2 + pix * p.C2 + (ch - p.C1) : nullptr;
+            }
+            if (add) {
+                float a[8];
+                unpack8(*reinterpret_cast<const uint4*>(add), a);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] += a[e];
+            }
+            *reinterpret_cast<uint4*>(dst) = pack8(o);
+        }
+    }
+    cluster_wait();                  // nobody in the cluster still reads this CTA's partial sums
+}
+
+static int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+
+// Geometry of the single-pass kernel; returns false when the shape must take the two-pass kernels.
+static bool gnf_plan(const hcp_groupnorm_args* a, bool bwd, GNFParams& p, dim3& grid, int& threads, size_t& smem, int& rc) {
+    rc = HCP_OK;
+    static const bool off = getenv("HCP_GN_TWO_PASS") != nullptr;
+    if (off) return false;
+    const int64_t C = a->C1 + a->C2;
+    if (a->G <= 0 || C % a->G != 0) return false;
+    const int cg = (int)(C / a->G);
+    if (cg < 8 || (cg & 1) || (a->C1 % 8) != 0 || (a->C2 % 8) != 0) return false;
+    const int CB = cg / gcd_int(cg, 8) * 8;                      // lcm(8, cg)
+    if (C % CB != 0 || (a->C2 > 0 && a->C1 % CB != 0)) return false;
+    const int V = CB / 8, gpb = CB / cg;
+    if (V * GNF_LANES > 1024 || gpb > 8 || CB > 256) return false;
+    const int64_t HW = a->HW;
+    if (HW * a->B >= (int64_t)1 << 31) return false;
+    const int nblk = (int)(C / CB);
+    const size_t per_pixel = (size_t)CB * 2 * (bwd ? 2 : 1);
+    // cluster size: a function of HW only (never of the batch), so the summation order -- and every bit of the result -- of one
+    // image does not depend on its batch neighbours; at least one pixel per lane and CTA
+    int S = 1;
+    while (S < 8 && HW % (2 * S) == 0 && HW / (2 * S) >= GNF_LANES) S *= 2;
+    const int P = (int)(HW / S);
+    if (P * per_pixel > 180 * 1024) return false;
+    int RB = P < 256 ? P : 256;                                   // rows per TMA box: a multiple of 8 (128-byte aligned slabs)
+    while (RB >= 8 && (P % RB != 0 || RB % 8 != 0)) --RB;
+    if (RB < 8) return false;
+    memset(&p, 0, sizeof(p));
+    p.C1 = (int)a->C1; p.C2 = (int)a->C2; p.C = (int)C; p.G = (int)a->G; p.cg = cg; p.CB = CB; p.V = V; p.gpb = gpb;
+    p.HW = (int)HW; p.P = P; p.RB = RB; p.nbox = P / RB; p.S = S;
+    p.inv_n = 1.f / ((float)HW * (float)cg);
+    p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
+    p.stats = a->stats;
+    const uint64_t rows = (uint64_t)a->B * HW;
+    {
+        uint64_t dims[2] = {(uint64_t)a->C1, rows};
+        uint64_t strides[1] = {(uint64_t)a->C1 * 2};
+        uint32_t box[2] = {(uint32_t)CB, (uint32_t)RB};
+        if ((rc = make_tmap_nd(&p.tmX1, a->x1, 2, dims, strides, box, false))) return false;
+    }
+    if (a->C2 > 0) {
+        uint64_t dims[2] = {(uint64_t)a->C2, rows};
+        uint64_t strides[1] = {(uint64_t)a->C2 * 2};
+        uint32_t box[2] = {(uint32_t)CB, (uint32_t)RB};
+        if ((rc = make_tmap_nd(&p.tmX2, a->x2, 2, dims, strides, box, false))) return false;
+    } else {
+        p.tmX2 = p.tmX1;
+    }
+    if (bwd) {
+        uint64_t dims[2] = {(uint64_t)C, rows};
+        uint64_t strides[1] = {(uint64_t)C * 2};
+        uint32_t box[2] = {(uint32_t)CB, (uint32_t)RB};
+        if ((rc = make_tmap_nd(&p.tmDY, a->dy, 2, dims, strides, box, false))) return false;
+    } else {
+        p.tmDY = p.tmX1;
+    }
+    grid = dim3((unsigned)S, (unsigned)nblk, (unsigned)a->B);
+    threads = V * GNF_LANES;
+    smem = (size_t)P * per_pixel + (size_t)GNF_LANES * V * 4 * sizeof(float) + 3 * 16 * sizeof(float) + 64 + 128;
+    return true;
+}
+
+template <bool BWD>
+static int gnf_launch(const GNFParams& p, dim3 grid, int threads, size_t smem, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gnf_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gnf)");
+        configured = true;
+    }
+    cudaError_t e = launch_cluster(gnf_kernel<BWD>, grid, dim3(threads), smem, stream, grid.x, p);
+    if (e != cudaSuccess) return set_cuda_error(e, "groupnorm single-pass launch");
+    return HCP_OK;
+}
+
 static int gn_geometry(const hcp_groupnorm_args* a, GNParams& p) {
     if (!a || !a->x1 || !a->gamma || !a->beta || !a->workspace || !a->stats) return set_error(HCP_ERR_INVALID, "groupnorm: null pointer");
     const int64_t C = a->C1 + a->C2;
@@ -685,6 +963,17 @@ extern "C" int hcp_groupnorm_fwd_bf16(const hcp_groupnorm_args* a, hcp_stream_t 
     int rc = gn_geometry(a, p);
     if (rc) return rc;
     if (!a->y) return set_error(HCP_ERR_INVALID, "groupnorm_fwd: y");
+    {
+        GNFParams f;
+        dim3 fgrid;
+        int fthreads = 0, frc = HCP_OK;
+        size_t fsmem = 0;
+        if (gnf_plan(a, false, f, fgrid, fthreads, fsmem, frc)) {
+            f.y = (__nv_bfloat16*)a->y;
+            return gnf_launch<false>(f, fgrid, fthreads, fsmem, (cudaStream_t)stream_);
+        }
+        if (frc) return frc;
+    }
     p.y = (__nv_bfloat16*)a->y;
     dim3 grid(p.nchunks, p.B);
     const int threads = (p.TP * p.R + 31) & ~31;          // whole warps: the finalize step uses full-warp shuffles
@@ -706,6 +995,18 @@ extern "C" int hcp_groupnorm_bwd_bf16(const hcp_groupnorm_args* a, hcp_stream_t 
     int rc = gn_geometry(a, p);
     if (rc) return rc;
     if (!a->dy || !a->dx1 || (a->C2 > 0 && !a->dx2)) return set_error(HCP_ERR_INVALID, "groupnorm_bwd: dy/dx");
+    {
+        GNFParams f;
+        dim3 fgrid;
+        int fthreads = 0, frc = HCP_OK;
+        size_t fsmem = 0;
+        if (gnf_plan(a, true, f, fgrid, fthreads, fsmem, frc)) {
+            f.add1 = (const __nv_bfloat16*)a->add1; f.add2 = (const __nv_bfloat16*)a->add2;
+            f.dx1 = (__nv_bfloat16*)a->dx1; f.dx2 = (__nv_bfloat16*)a->dx2;
+            return gnf_launch<true>(f, fgrid, fthreads, fsmem, (cudaStream_t)stream_);
+        }
+        if (frc) return frc;
+    }
     p.dy = (const __nv_bfloat16*)a->dy;
     p.add1 = (const __nv_bfloat16*)a->add1; p.add2 = (const __nv_bfloat16*)a->add2;
     p.dx1 = (__nv_bfloat16*)a->dx1; p.dx2 = (__nv_bfloat16*)a->dx2;

@@ -9,6 +9,7 @@ Outputs (small, committed):
                           checkpoint key names (the operator the CUDA kernels sit behind)
   ref_lora_dapp_conv.pt   the same for the DreamArtist++ pair (DAPPLayer / DAPPPatchContainer: batch = [negative | positive]) and
                           for LoraLayer on Conv2d hosts (3x3 stride 1 / stride 2 and 1x1)
+  lora_webui_keys.json    hcpdiff <-> webui key maps of the REAL reference LoraConverter for the 160 SD1.5 attention/ff LoRA layers
 """
 import importlib
 import json
@@ -200,7 +201,51 @@ def make_dapp_conv():
     print("ref_lora_dapp_conv.pt:", fx["container_types"], len(fx["grads"]), "lora grads")
 
 
+def make_webui_keys():
+    """Key maps of the REAL reference LoraConverter (hcpdiff/tools/lora_convert.py) for the SD1.5 attention + ff LoRA layers."""
+    import_reference_lora()
+    ck = types.ModuleType("hcpdiff.ckpt_manager")
+    ck.auto_manager = lambda path: None
+    sys.modules["hcpdiff.ckpt_manager"] = ck
+    for name, path in (("hcpdiff.tools", "hcpdiff/tools"), ("hcpdiff.deprecated", "hcpdiff/deprecated")):
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(REF, path)]
+        sys.modules[name] = m
+    dep = importlib.import_module("hcpdiff.deprecated.lora_convert")
+    sys.modules["hcpdiff.deprecated"].convert_to_webui_maybe_old = dep.convert_to_webui_maybe_old
+    sys.modules["hcpdiff.deprecated"].convert_to_webui_xl_maybe_old = dep.convert_to_webui_xl_maybe_old
+    conv = importlib.import_module("hcpdiff.tools.lora_convert").LoraConverter()
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import unet_ref as U
+    layers = U.lora_target_layers(U.SD15, r".*\.attn.?$|.*\.ff$")
+    shapes = U.param_shapes(U.SD15)
+    sd = {}
+    for i, layer in enumerate(layers):
+        o, k = shapes[layer + ".weight"]
+        sd[f"{layer}.___.layer.W_down"] = torch.full((4, 2), float(i))         # tiny stand-ins: only names and the scale rule matter
+        sd[f"{layer}.___.layer.W_up"] = torch.full((2, 4), float(i) + 0.5)
+        sd[f"{layer}.___.alpha"] = torch.tensor(0.25)
+    te = {"text_model.encoder.layers.0.self_attn.q_proj.___.layer.W_down": torch.ones(4, 2),
+          "text_model.encoder.layers.0.self_attn.q_proj.___.layer.W_up": torch.ones(2, 4),
+          "text_model.encoder.layers.0.self_attn.q_proj.___.alpha": torch.tensor(0.5),
+          "text_model.encoder.layers.11.mlp.fc1.___.layer.W_down": torch.ones(4, 2),
+          "text_model.encoder.layers.11.mlp.fc1.___.layer.W_up": torch.ones(2, 4),
+          "text_model.encoder.layers.11.mlp.fc1.___.alpha": torch.tensor(0.5)}
+    web = conv.convert_to_webui(dict(sd), dict(te), auto_scale_alpha=False)
+    web_scaled = conv.convert_to_webui(dict(sd), dict(te), auto_scale_alpha=True)
+    back_te, back_unet = conv.convert_from_webui(dict(web), auto_scale_alpha=False)
+    fx = {"to_webui": {k: wk for k, wk in zip(list(sd) + list(te), web.keys())},
+          "from_webui_unet": sorted(back_unet["lora"].keys()), "from_webui_te": sorted(back_te["lora"].keys()),
+          "scaled_sample": {k: [float(x) for x in web_scaled[k].flatten()[:2]] for k in list(web_scaled)[:6]},
+          "hcp_keys": list(sd) + list(te)}
+    assert sorted(back_unet["lora"].keys()) == sorted(sd.keys())
+    with open(os.path.join(HERE, "lora_webui_keys.json"), "w") as f:
+        json.dump(fx, f, indent=0)
+    print("lora_webui_keys.json:", len(fx["to_webui"]), "keys; sample", list(fx["to_webui"].items())[0])
+
+
 if __name__ == "__main__":
     make_struct()
     make_lora()
     make_dapp_conv()
+    make_webui_keys()
