@@ -282,21 +282,21 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn8_partial_kernel(const GNPar
         if (!BWD) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int k = (e < t.nb) ? 0 : 1;
-                a0[k] += x[e];
-                a1[k] += x[e] * x[e];
+                const bool lo = e < t.nb;     // selects, not runtime-indexed arrays (those live in local memory)
+                if (lo) a0[0] += x[e]; else a0[1] += x[e];
+                if (lo) a1[0] += x[e] * x[e]; else a1[1] += x[e] * x[e];
             }
         } else {
             float d[8];
             unpack8(*reinterpret_cast<const uint4*>(p.dy + pix * p.C + t.c0), d);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int k = (e < t.nb) ? 0 : 1;
-                const float xh = (x[e] - mean[k]) * rstd[k];
+                const bool lo = e < t.nb;     // selects, not runtime-indexed arrays (those live in local memory)
+                const float xh = (x[e] - (lo ? mean[0] : mean[1])) * (lo ? rstd[0] : rstd[1]);
                 float g = d[e] * gm[e];
                 if (p.silu) g *= silu_grad(xh * gm[e] + bt[e]);
-                a0[k] += g;
-                a1[k] += g * xh;
+                if (lo) a0[0] += g; else a0[1] += g;
+                if (lo) a1[0] += g * xh; else a1[1] += g * xh;
             }
         }
     }
@@ -376,8 +376,8 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn8_apply_kernel(const GNParam
         if (!BWD) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int k = (e < t.nb) ? 0 : 1;
-                float z = (x[e] - sa[k]) * sb[k] * gm[e] + bt[e];
+                const bool lo = e < t.nb;     // selects, not runtime-indexed arrays (those live in local memory)
+                float z = (x[e] - (lo ? sa[0] : sa[1])) * (lo ? sb[0] : sb[1]) * gm[e] + bt[e];
                 if (p.silu) z = silu_f(z);
                 o[e] = z;
             }
@@ -387,11 +387,11 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn8_apply_kernel(const GNParam
             unpack8(*reinterpret_cast<const uint4*>(p.dy + pix * p.C + t.c0), d);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int k = (e < t.nb) ? 0 : 1;
-                const float xh = (x[e] - mean[k]) * rstd[k];
+                const bool lo = e < t.nb;     // selects, not runtime-indexed arrays (those live in local memory)
+                const float xh = (x[e] - (lo ? mean[0] : mean[1])) * (lo ? rstd[0] : rstd[1]);
                 float g = d[e] * gm[e];
                 if (p.silu) g *= silu_grad(xh * gm[e] + bt[e]);
-                o[e] = rstd[k] * (g - sa[k] - xh * sb[k]);
+                o[e] = (lo ? rstd[0] : rstd[1]) * (g - (lo ? sa[0] : sa[1]) - xh * (lo ? sb[0] : sb[1]));
             }
             __nv_bfloat16* dst;
             const __nv_bfloat16* add;
@@ -424,12 +424,12 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) gn8_apply_kernel(const GNParam
 // neighbours), and the slab is normalised / back-propagated straight from shared memory.
 // Replaces the two-pass kernels above whenever the concatenation boundary C1 falls on a channel-block boundary.
 // =============================================================================================
-constexpr int GNF_LANES = 64;        // pixel lanes per CTA: blockDim = (CB / 8) * GNF_LANES
+constexpr int GNF_LANES = 64;        // pixel lanes per CTA: blockDim = (CB / 8) * lanes, lanes = 64 (narrow blocks) or 32; <= 512 threads
 
 struct alignas(64) GNFParams {
     CUtensorMap tmX1, tmX2, tmDY;    // [B*HW, C*] row-major, box [CB, RB], no swizzle
     int C1, C2, C, G, cg, CB, V, gpb;
-    int HW, P, RB, nbox, S;
+    int HW, P, RB, nbox, S, lanes;
     float inv_n;                     // 1 / (HW * cg)
     const float* gamma; const float* beta;
     float eps; int silu;
@@ -440,14 +440,14 @@ struct alignas(64) GNFParams {
 };
 
 template <bool BWD>
-__global__ void __launch_bounds__(1024) gnf_kernel(const __grid_constant__ GNFParams p) {
+__global__ void __launch_bounds__(512) gnf_kernel(const __grid_constant__ GNFParams p) {
     extern __shared__ uint8_t gnf_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gnf_smem_raw) + 127) & ~uintptr_t(127));
     const int tile_bytes = p.P * p.CB * 2;
     uint8_t* sX = smem;
     uint8_t* sDY = sX + tile_bytes;                                     // BWD only
     float* s_part = reinterpret_cast<float*>(sX + (BWD ? 2 : 1) * tile_bytes);   // [GNF_LANES][V][4]
-    float* s_cta = s_part + GNF_LANES * p.V * 4;                         // [gpb*2] partial sums of this CTA (read by the cluster)
+    float* s_cta = s_part + p.lanes * p.V * 4;                         // [gpb*2] partial sums of this CTA (read by the cluster)
     float* s_raw = s_cta + 16;                                           // [gpb*2] cluster totals
     float* s_fin = s_raw + 16;                                           // [gpb*2] (mean, rstd) or (mean g, mean g*xhat)
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_fin + 16);
@@ -492,27 +492,27 @@ __global__ void __launch_bounds__(1024) gnf_kernel(const __grid_constant__ GNFPa
 
     // ---- pass 1: partial sums of this CTA's slab
     float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};
-    for (int pp = rl; pp < p.P; pp += GNF_LANES) {
+    for (int pp = rl; pp < p.P; pp += p.lanes) {
         float x[8];
         unpack8(*reinterpret_cast<const uint4*>(sX + ((size_t)pp * p.CB + tv * 8) * 2), x);
         if (!BWD) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int k = (e < nb) ? 0 : 1;
-                a0[k] += x[e];
-                a1[k] += x[e] * x[e];
+                const bool lo = e < nb;       // selects, not runtime-indexed arrays (those live in local memory)
+                if (lo) a0[0] += x[e]; else a0[1] += x[e];
+                if (lo) a1[0] += x[e] * x[e]; else a1[1] += x[e] * x[e];
             }
         } else {
             float d[8];
             unpack8(*reinterpret_cast<const uint4*>(sDY + ((size_t)pp * p.CB + tv * 8) * 2), d);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int k = (e < nb) ? 0 : 1;
-                const float xh = (x[e] - mean[k]) * rstd[k];
+                const bool lo = e < nb;       // selects, not runtime-indexed arrays (those live in local memory)
+                const float xh = (x[e] - (lo ? mean[0] : mean[1])) * (lo ? rstd[0] : rstd[1]);
                 float g = d[e] * gm[e];
                 if (p.silu) g *= silu_grad(xh * gm[e] + bt[e]);
-                a0[k] += g;
-                a1[k] += g * xh;
+                if (lo) a0[0] += g; else a0[1] += g;
+                if (lo) a1[0] += g * xh; else a1[1] += g * xh;
             }
         }
     }
@@ -526,8 +526,7 @@ __global__ void __launch_bounds__(1024) gnf_kernel(const __grid_constant__ GNFPa
         const int g = w >> 1, which = w & 1;
         const int v_lo = (g * p.cg) / 8, v_hi = ((g + 1) * p.cg - 1) / 8;
         float acc = 0.f;
-#pragma unroll
-        for (int r = lane; r < GNF_LANES; r += 32)
+        for (int r = lane; r < p.lanes; r += 32)
             for (int v = v_lo; v <= v_hi; ++v) {
                 const int vg = (v * 8) / p.cg;
                 const float* src = s_part + ((size_t)r * p.V + v) * 4;
@@ -569,15 +568,15 @@ __global__ void __launch_bounds__(1024) gnf_kernel(const __grid_constant__ GNFPa
     // ---- pass 2: normalise / back-propagate the slab from shared memory
     const float sa[2] = {s_fin[g_lo * 2], s_fin[g_hi * 2]};
     const float sb[2] = {s_fin[g_lo * 2 + 1], s_fin[g_hi * 2 + 1]};
-    for (int pp = rl; pp < p.P; pp += GNF_LANES) {
+    for (int pp = rl; pp < p.P; pp += p.lanes) {
         const int64_t pix = row0 + pp;
         float x[8], o[8];
         unpack8(*reinterpret_cast<const uint4*>(sX + ((size_t)pp * p.CB + tv * 8) * 2), x);
         if (!BWD) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int k = (e < nb) ? 0 : 1;
-                float z = (x[e] - sa[k]) * sb[k] * gm[e] + bt[e];
+                const bool lo = e < nb;       // selects, not runtime-indexed arrays (those live in local memory)
+                float z = (x[e] - (lo ? sa[0] : sa[1])) * (lo ? sb[0] : sb[1]) * gm[e] + bt[e];
                 if (p.silu) z = silu_f(z);
                 o[e] = z;
             }
@@ -587,11 +586,11 @@ __global__ void __launch_bounds__(1024) gnf_kernel(const __grid_constant__ GNFPa
             unpack8(*reinterpret_cast<const uint4*>(sDY + ((size_t)pp * p.CB + tv * 8) * 2), d);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int k = (e < nb) ? 0 : 1;
-                const float xh = (x[e] - mean[k]) * rstd[k];
+                const bool lo = e < nb;       // selects, not runtime-indexed arrays (those live in local memory)
+                const float xh = (x[e] - (lo ? mean[0] : mean[1])) * (lo ? rstd[0] : rstd[1]);
                 float g = d[e] * gm[e];
                 if (p.silu) g *= silu_grad(xh * gm[e] + bt[e]);
-                o[e] = rstd[k] * (g - sa[k] - xh * sb[k]);
+                o[e] = (lo ? rstd[0] : rstd[1]) * (g - (lo ? sa[0] : sa[1]) - xh * (lo ? sb[0] : sb[1]));
             }
             __nv_bfloat16* dst;
             const __nv_bfloat16* add;
@@ -628,7 +627,8 @@ static bool gnf_plan(const hcp_groupnorm_args* a, bool bwd, GNFParams& p, dim3& 
     const int CB = cg / gcd_int(cg, 8) * 8;                      // lcm(8, cg)
     if (C % CB != 0 || (a->C2 > 0 && a->C1 % CB != 0)) return false;
     const int V = CB / 8, gpb = CB / cg;
-    if (V * GNF_LANES > 1024 || gpb > 8 || CB > 256) return false;
+    const int lanes = V <= 5 ? GNF_LANES : 32;
+    if (V * lanes > 512 || gpb > 8 || CB > 256) return false;
     const int64_t HW = a->HW;
     if (HW * a->B >= (int64_t)1 << 31) return false;
     const int nblk = (int)(C / CB);
@@ -644,7 +644,7 @@ static bool gnf_plan(const hcp_groupnorm_args* a, bool bwd, GNFParams& p, dim3& 
     if (RB < 8) return false;
     memset(&p, 0, sizeof(p));
     p.C1 = (int)a->C1; p.C2 = (int)a->C2; p.C = (int)C; p.G = (int)a->G; p.cg = cg; p.CB = CB; p.V = V; p.gpb = gpb;
-    p.HW = (int)HW; p.P = P; p.RB = RB; p.nbox = P / RB; p.S = S;
+    p.HW = (int)HW; p.P = P; p.RB = RB; p.nbox = P / RB; p.S = S; p.lanes = lanes;
     p.inv_n = 1.f / ((float)HW * (float)cg);
     p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
     p.stats = a->stats;
@@ -672,8 +672,8 @@ static bool gnf_plan(const hcp_groupnorm_args* a, bool bwd, GNFParams& p, dim3& 
         p.tmDY = p.tmX1;
     }
     grid = dim3((unsigned)S, (unsigned)nblk, (unsigned)a->B);
-    threads = V * GNF_LANES;
-    smem = (size_t)P * per_pixel + (size_t)GNF_LANES * V * 4 * sizeof(float) + 3 * 16 * sizeof(float) + 64 + 128;
+    threads = V * lanes;
+    smem = (size_t)P * per_pixel + (size_t)lanes * V * 4 * sizeof(float) + 3 * 16 * sizeof(float) + 64 + 128;
     return true;
 }
 

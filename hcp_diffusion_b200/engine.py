@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
-from . import _lib
+from . import _lib, ops
 from ._lib import call, stream_ptr
 
 
@@ -63,7 +63,7 @@ class LoraTrainStep:
 
     def __init__(self, unet: nn.Module, params: Iterable[nn.Parameter], lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2, max_grad_norm: float = 1.0, use_cuda_graph: bool = True,
-                 process_group: Optional[dist.ProcessGroup] = None):
+                 process_group: Optional[dist.ProcessGroup] = None, side_stream: bool = True):
         self.unet = unet
         self.flat = FlatParams(list(params))
         dev = self.flat.data.device
@@ -81,6 +81,9 @@ class LoraTrainStep:
         self._static = None
         self._graph_fb = None
         self._graph_opt = None
+        # work off the critical path (LoRA-gradient kernels, text-embedding k/v projections) goes to a side stream inside
+        # _forward_backward and is joined there, before anything reads the gradients (HCP_SIDE_STREAM=0 keeps a single stream)
+        self.side_stream = side_stream
 
     def set_lr(self, lr: float):
         self.lr.fill_(lr)
@@ -90,6 +93,14 @@ class LoraTrainStep:
         """zero_grad, x_t = add_noise, pred = unet(x_t, t, ehs), loss = mse(pred, noise), backward."""
         self.flat.grad.zero_()
         self.loss.zero_()
+        ops.set_side_stream(self.side_stream)
+        try:
+            self._fb_body(latents, noise, t, ehs)
+        finally:
+            ops.join_side()
+            ops.set_side_stream(False)
+
+    def _fb_body(self, latents, noise, t, ehs):
         B = latents.shape[0]
         per_image = latents[0].numel()
         x_t = torch.empty_like(latents)

@@ -119,7 +119,8 @@ class Attention(nn.Module):
         g = self._groups()
         return [g.kv, g.q, g.out] if self.is_cross else [g.qkv, g.out]
 
-    def run(self, x: torch.Tensor, residual: torch.Tensor, context: Optional[torch.Tensor], kv_bias: Optional[torch.Tensor]) -> torch.Tensor:
+    def run(self, x: torch.Tensor, residual: torch.Tensor, context, kv_bias: Optional[torch.Tensor]) -> torch.Tensor:
+        """`context`: the text embedding [B, Lc, ctx] or a `_HoistedKV` holding the k/v projections computed ahead of time."""
         g = self._groups()
         C_ = self.inner_dim
         if not self.is_cross:
@@ -127,9 +128,33 @@ class Attention(nn.Module):
             o = ops.attention(self.heads, C_, (0, C_, 2 * C_), qkv, None, None)
         else:
             q = g.q([x])
-            kv = g.kv([context])                                              # [B, Lc, 2C]
+            kv = context.take(self) if isinstance(context, _HoistedKV) else g.kv([context])   # [B, Lc, 2C]
             o = ops.attention(self.heads, C_, (0, 0, C_), q, kv, kv_bias)
         return g.out([o], residual=residual)
+
+
+class _HoistedKV:
+    """k/v projections of the text embedding for every cross-attention, issued on the side stream at the start of the forward
+    (they depend on nothing but the text embedding, and autograd runs their backward -- incl. the LoRA-gradient kernels -- on
+    the same side stream).  `take` makes the main stream wait for them once, at the first consumer."""
+
+    def __init__(self, ctx: torch.Tensor, attns: Sequence["Attention"]):
+        self.ctx = ctx
+        main = torch.cuda.current_stream()
+        self.side = ops.fork_side(ctx)
+        self.joined = False
+        self.kv = {}
+        with torch.cuda.stream(self.side):
+            for a in attns:
+                t = a._groups().kv([ctx])
+                t.record_stream(main)               # produced on the side stream, consumed (and later freed) on the main one
+                self.kv[id(a)] = t
+
+    def take(self, attn: "Attention") -> torch.Tensor:
+        if not self.joined:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self.joined = True
+        return self.kv.pop(id(attn))
 
 
 class GEGLU(nn.Module):
@@ -422,6 +447,9 @@ class UNet2DConditionModel(nn.Module):
         kv_bias = None
         if encoder_attention_mask is not None:
             kv_bias = ((1.0 - encoder_attention_mask.to(torch.float32)) * -10000.0).contiguous()
+
+        if ops.side_enabled():
+            ctx = _HoistedKV(ctx, [m.attn2 for m in self.modules() if isinstance(m, BasicTransformerBlock)])
 
         h = ops.conv_in(sample, rt.w_in, rt.b_in)                        # bf16 [B, H*W, C0]
         geom = (B, H, W)

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -20,6 +21,44 @@ from . import _lib
 from ._lib import AttnArgs, AttnBwdArgs, ConvArgs, GemmArgs, GroupNormArgs, call, ptr, stream_ptr
 
 BF16 = torch.bfloat16
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# side stream: work that is OFF the critical path of the step (LoRA-gradient kernels, the cross-attention k/v projections of the
+# text embedding) is enqueued on a second stream so that it fills the SMs the small kernels of the main chain leave idle.
+# Opt-in (LoraTrainStep turns it on and joins the stream before the optimizer); plain autograd users keep one stream.
+# ----------------------------------------------------------------------------------------------------------------------
+class _Side:
+    enabled = False
+    stream: Optional["torch.cuda.Stream"] = None
+    used = False
+    keep: list = []          # tensors the side stream reads: kept alive (no allocator reuse) until the join
+
+
+def set_side_stream(on: bool) -> None:
+    _Side.enabled = bool(on) and os.environ.get("HCP_SIDE_STREAM", "1") != "0"
+
+
+def side_enabled() -> bool:
+    return _Side.enabled
+
+
+def fork_side(*keep: torch.Tensor) -> "torch.cuda.Stream":
+    """Side stream, ordered after everything enqueued on the current stream so far."""
+    if _Side.stream is None:
+        _Side.stream = torch.cuda.Stream()
+    _Side.stream.wait_stream(torch.cuda.current_stream())
+    _Side.used = True
+    _Side.keep.extend(t for t in keep if t is not None)
+    return _Side.stream
+
+
+def join_side() -> None:
+    """The current stream waits for the side stream (call before anything consumes the LoRA gradients)."""
+    if _Side.used:
+        torch.cuda.current_stream().wait_stream(_Side.stream)
+        _Side.used = False
+    _Side.keep.clear()
 
 
 def _chk(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -274,6 +313,32 @@ class FusedLinearFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    def _lora_grads(pack, xs, ks, T, U, dy, M, N, R):
+        for q, pieces in pack.slabs():
+            for p0 in range(0, len(pieces), 8):
+                chunk = pieces[p0:p0 + 8]
+                nb = len(chunk)
+                up = (_lib.LoraGradBlock * nb)()
+                for i, (b, j0, rows, cs) in enumerate(chunk):
+                    gu = b.g_up if b.g_up is not None else _acc_grad(b.w_up)
+                    up[i].n_lo, up[i].n_hi, up[i].c0, up[i].rank = b.o0, b.o0 + b.out_dim, cs, rows
+                    up[i].scale, up[i].transpose_out, up[i].dst, up[i].dst_ld = b.alpha, 1, gu.data_ptr() + 4 * j0, b.rank
+                koff = 0
+                for xi, (x, k) in enumerate(zip(xs, ks)):
+                    down = (_lib.LoraGradBlock * nb)()
+                    for i, (b, j0, rows, cs) in enumerate(chunk):
+                        gd = b.g_down if b.g_down is not None else _acc_grad(b.w_down)
+                        down[i].n_lo, down[i].n_hi, down[i].c0, down[i].rank = 0, k, cs, rows
+                        down[i].scale, down[i].transpose_out = 1.0, 0
+                        down[i].dst, down[i].dst_ld = gd.data_ptr() + 4 * (j0 * pack.K + koff), pack.K
+                    Uq, Tq = U.data_ptr() + 2 * 64 * q, T.data_ptr() + 2 * 64 * q
+                    if xi == 0:
+                        call("hcp_lora_grad_pair", Uq, x.data_ptr(), k, k, down, Tq, dy.data_ptr(), N, N, up, nb, M, R, stream_ptr())
+                    else:
+                        call("hcp_lora_grad", Uq, R, x.data_ptr(), k, M, 0, k, down, nb, stream_ptr())
+                    koff += k
+
+    @staticmethod
     def backward(ctx, dy):
         pack, M, ks = ctx.pack, ctx.M, ctx.ks
         dy = _chk(dy, "linear grad")
@@ -283,30 +348,13 @@ class FusedLinearFn(torch.autograd.Function):
             *xs, T = ctx.saved_tensors
             U = torch.empty((M, R), dtype=BF16, device=dy.device)
             _skinny_rows(pack, [(dy, N, N)], "BlT", M, ctx.batch, U, R)
-            # dW_down = U^T x ;  dW_up = alpha * dY^T T   (tensor-core TN GEMMs, one 64-column slab of U / T per launch)
-            for q, pieces in pack.slabs():
-                for p0 in range(0, len(pieces), 8):
-                    chunk = pieces[p0:p0 + 8]
-                    nb = len(chunk)
-                    up = (_lib.LoraGradBlock * nb)()
-                    for i, (b, j0, rows, cs) in enumerate(chunk):
-                        gu = b.g_up if b.g_up is not None else _acc_grad(b.w_up)
-                        up[i].n_lo, up[i].n_hi, up[i].c0, up[i].rank = b.o0, b.o0 + b.out_dim, cs, rows
-                        up[i].scale, up[i].transpose_out, up[i].dst, up[i].dst_ld = b.alpha, 1, gu.data_ptr() + 4 * j0, b.rank
-                    koff = 0
-                    for xi, (x, k) in enumerate(zip(xs, ks)):
-                        down = (_lib.LoraGradBlock * nb)()
-                        for i, (b, j0, rows, cs) in enumerate(chunk):
-                            gd = b.g_down if b.g_down is not None else _acc_grad(b.w_down)
-                            down[i].n_lo, down[i].n_hi, down[i].c0, down[i].rank = 0, k, cs, rows
-                            down[i].scale, down[i].transpose_out = 1.0, 0
-                            down[i].dst, down[i].dst_ld = gd.data_ptr() + 4 * (j0 * pack.K + koff), pack.K
-                        Uq, Tq = U.data_ptr() + 2 * 64 * q, T.data_ptr() + 2 * 64 * q
-                        if xi == 0:
-                            call("hcp_lora_grad_pair", Uq, x.data_ptr(), k, k, down, Tq, dy.data_ptr(), N, N, up, nb, M, R, stream_ptr())
-                        else:
-                            call("hcp_lora_grad", Uq, R, x.data_ptr(), k, M, 0, k, down, nb, stream_ptr())
-                        koff += k
+            # dW_down = U^T x ;  dW_up = alpha * dY^T T   (tensor-core TN GEMMs, one 64-column slab of U / T per launch).
+            # Nothing downstream of this node reads them: with the side stream on they run next to the dX GEMM of the main chain.
+            if side_enabled():
+                with torch.cuda.stream(fork_side(U, T, dy, *xs)):
+                    FusedLinearFn._lora_grads(pack, xs, ks, T, U, dy, M, N, R)
+            else:
+                FusedLinearFn._lora_grads(pack, xs, ks, T, U, dy, M, N, R)
         grads = []
         off = 0
         for i, k in enumerate(ks):

@@ -362,16 +362,18 @@ def test_train_step_graph_matches_eager_and_learns():
     sd = U.init_params(spec)
     lat, noise, t, ehs = U.synthetic_batch(4, spec)
     results = []
-    for use_graph in (False, True):
+    # eager single stream (the plain autograd order) vs eager / captured with the side stream (LoRA-gradient kernels and the
+    # text-embedding k/v projections run concurrently with the main chain and are joined before the optimizer)
+    for use_graph, side in ((False, False), (False, True), (True, True)):
         unet, group, _ = build_product_unet(spec, sd, 4)
         params = [p for b in group.plugin_dict.values() for p in b.parameters()]
-        step = LoraTrainStep(unet, params, lr=1e-3, use_cuda_graph=use_graph)
+        step = LoraTrainStep(unet, params, lr=1e-3, use_cuda_graph=use_graph, side_stream=side)
         losses = [float(step.step(lat, noise, t, ehs).cpu()) for _ in range(6)]
         results.append((losses, step.flat.data.clone()))
-    (l0, p0), (l1, p1) = results
+    (l0, p0), (l1, p1), (l2, p2) = results
     assert l0[-1] < l0[0]
-    assert max(abs(a - b) for a, b in zip(l0, l1)) < 1e-3 * abs(l0[0])
-    assert rel_l2(p1, p0) < 1e-3
+    assert max(abs(a - b) for a, b in zip(l0, l1)) < 1e-3 * abs(l0[0]) and max(abs(a - b) for a, b in zip(l0, l2)) < 1e-3 * abs(l0[0])
+    assert rel_l2(p1, p0) < 1e-3 and rel_l2(p2, p0) < 1e-3
 
 
 def test_reference_dapp_and_conv1x1_lora_golden_through_product_containers(golden_dir):
