@@ -27,7 +27,9 @@
 namespace hcp {
 
 constexpr int kAttnThreads = 160;          // fwd: warps 0-3: softmax/epilogue rows, warp 4: TMA + MMA control
-constexpr int kBwdParts = 2;               // bwd: softmax warps per TMEM lane quarter (each owns 128/kBwdParts kv columns)
+constexpr int kBwdParts = 4;               // bwd: softmax warps per TMEM lane quarter (each owns 128/kBwdParts kv columns): 16 warps hide
+                                           // the TMEM-load / MUFU latencies that 8 warps (2 per scheduler) left exposed (ncu: 2.25 active warps,
+                                           // issue slot used every 3.1 cycles); 16-column register chunks keep them under the 120-register cap
 constexpr int kBwdSoftmaxThreads = 4 * kBwdParts * 32;
 constexpr int kAttnBwdThreads = kBwdSoftmaxThreads + 32;   // + one control warp (the last)
 constexpr int TILE_BYTES = 128 * 128;      // one [128 rows x 64 cols] bf16 box
@@ -786,18 +788,20 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                 const bool do_p = (pass == 0);
                 const bool do_ds = !p.share_pds || pass == 1;
                 for (int c = part * kChunksPerPart; c < (part + 1) * kChunksPerPart; ++c) {
-                    uint32_t v[32], w[32];
-                    tmem_ld32(tS + lb + c * 32, v);
-                    if (do_ds) tmem_ld32(tdP + lb + c * 32, w);
+#pragma unroll 1
+                  for (int hf = 0; hf < 2; ++hf) {                       // 16 kv columns at a time (register budget)
+                    uint32_t v[16], w[16];
+                    tmem_ld16(tS + lb + c * 32 + hf * 16, v);
+                    if (do_ds) tmem_ld16(tdP + lb + c * 32 + hf * 16, w);
                     tmem_wait_ld();
-                    if (p.early_sdp && i > 0 && c == part * kChunksPerPart) {
+                    if (p.early_sdp && i > 0 && c == part * kChunksPerPart && hf == 0) {
                         mbar_wait(dq_full, (i - 1) & 1);    // dK/dQ of the previous tile have finished reading sP / sdS
                         tc_fence_after();
                     }
-                    uint32_t pk[16], dk[16];
+                    uint32_t pk[8], dk[8];
                     if (!special && qok) {
 #pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
+                        for (int e = 0; e < 16; e += 2) {
                             const float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), p.scale_log2, neg_lse2));
                             const float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, neg_lse2));
                             pk[e >> 1] = pack_bf16x2(p0, p1);
@@ -807,11 +811,11 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                         }
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
+                        for (int e = 0; e < 16; e += 2) {
                             float pe[2], de[2];
 #pragma unroll
                             for (int t = 0; t < 2; ++t) {
-                                const int col = c * 32 + e + t;
+                                const int col = c * 32 + hf * 16 + e + t;
                                 float s2 = fmaf(__uint_as_float(v[e + t]), p.scale_log2, neg_lse2);
                                 if (bias && col < ncols) s2 += bias[kv0 + col] * kLog2e;
                                 const float pv = (qok && col < ncols) ? fast_exp2(s2) : 0.f;
@@ -823,11 +827,12 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                         }
                     }
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const uint32_t off = (c >> 1) * TILE_BYTES + sw128_offset(row, (c & 1) * 4 + g);
+                    for (int g = 0; g < 2; ++g) {
+                        const uint32_t off = (c >> 1) * TILE_BYTES + sw128_offset(row, (c & 1) * 4 + hf * 2 + g);
                         if (do_p) *reinterpret_cast<uint4*>(sP + off) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
                         if (do_ds) *reinterpret_cast<uint4*>(sdS + off) = make_uint4(dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
                     }
+                  }
                 }
                 if (do_p) {
                     fence_proxy_async_smem();

@@ -13,6 +13,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
+import hcp_diffusion_b200.models  # noqa: E402,F401  (models first: runtime <-> models import cycle)
 from hcp_diffusion_b200 import ops  # noqa: E402
 from hcp_diffusion_b200.ops import ConvPack, LinearPack, LoraBlockRef  # noqa: E402
 from hcp_diffusion_b200.runtime import pack_lora  # noqa: E402
