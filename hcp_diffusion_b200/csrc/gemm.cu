@@ -275,15 +275,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             const TileOrigin o = tile_origin(p, (mn / p.tiles_n) * MSUB + sub);
             const int acc_idx = (MSUB == 1) ? as : sub;
             if (staged && p.residual) {
-                // coalesced prefetch of the residual tile into the staging buffer (overlaps the main loop)
-                for (int u = et; u < BLOCK_M * UNITS; u += kGemmEpiThreads) {
+                // coalesced prefetch of the residual tile into the staging buffer (overlaps the main loop).  All loads of a thread
+                // are issued before the first store: one L2 round trip per tile instead of one per 16-byte unit.
+                constexpr int NRES = (BLOCK_M * UNITS + kGemmEpiThreads - 1) / kGemmEpiThreads;
+                uint4 rbuf[NRES];
+#pragma unroll
+                for (int it = 0; it < NRES; ++it) {
+                    const int u = et + it * kGemmEpiThreads;
                     const int rr = u / UNITS, cu = u % UNITS;
-                    int grp;
-                    const int64_t g = tile_row(p, o, rr, grp);
-                    const int col = n0 + cu * 8;
-                    if (g < (int64_t)p.M && col < p.N)
-                        *reinterpret_cast<uint4*>(sStg + rr * Cfg::STG_PITCH + cu * 16) =
-                            *reinterpret_cast<const uint4*>(p.residual + g * p.ldr + col);
+                    rbuf[it] = make_uint4(0u, 0u, 0u, 0u);
+                    if (u < BLOCK_M * UNITS) {
+                        int grp;
+                        const int64_t g = tile_row(p, o, rr, grp);
+                        const int col = n0 + cu * 8;
+                        if (g < (int64_t)p.M && col < p.N) rbuf[it] = *reinterpret_cast<const uint4*>(p.residual + g * p.ldr + col);
+                    }
+                }
+#pragma unroll
+                for (int it = 0; it < NRES; ++it) {
+                    const int u = et + it * kGemmEpiThreads;
+                    if (u < BLOCK_M * UNITS) *reinterpret_cast<uint4*>(sStg + (u / UNITS) * Cfg::STG_PITCH + (u % UNITS) * 16) = rbuf[it];
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
@@ -379,10 +390,21 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits,
     const int64_t row = i / nv;
     const int col = (int)(i % nv) * 8;
     float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int s = 0; s < splits; ++s) {
-        const float* src = ws + ((int64_t)s * M + row) * N + col;
-        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-        f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+    for (int s0 = 0; s0 < splits; s0 += 4) {                     // four partials in flight per thread (fixed summation order)
+        float4 a[4], b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int s = (s0 + j < splits) ? s0 + j : s0;         // clamp: the duplicate is not added below
+            const float* src = ws + ((int64_t)s * M + row) * N + col;
+            a[j] = *reinterpret_cast<const float4*>(src);
+            b[j] = *reinterpret_cast<const float4*>(src + 4);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (s0 + j < splits) {
+                f[0] += a[j].x; f[1] += a[j].y; f[2] += a[j].z; f[3] += a[j].w;
+                f[4] += b[j].x; f[5] += b[j].y; f[6] += b[j].z; f[7] += b[j].w;
+            }
     }
     if (bias) {
 #pragma unroll
@@ -408,9 +430,13 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits,
 
 // number of K-splits for a launch with `ctas` output tiles and `total_kb` 64-wide k-blocks (1 = no split)
 static int plan_splits(int64_t ctas, int64_t total_kb, int64_t N) {
-    // splitting costs a second (finalize) launch and an fp32 round trip: only worth it when the output tiles alone would
-    // leave two thirds of the SMs idle, and never for the skinny LoRA projections
-    if (ctas >= 48 || total_kb < 8 || N <= 64) return 1;
+    // splitting costs a second (finalize) launch and an fp32 round trip: never for the skinny LoRA projections or short reductions
+    if (total_kb < 8 || N <= 64) return 1;
+    if (ctas >= 48) {
+        // 48..74 output tiles leave half of the 148 SMs idle for the whole reduction: two K halves fill them, worth it when each
+        // half is still a long main loop (>= 20 k-blocks): the 16x16 / 8x8 level convolutions and the K >= 2560 linears at M = 1024
+        return (ctas <= 74 && total_kb >= 40) ? 2 : 1;
+    }
     int64_t s = 148 / ctas;                 // persistent grid: keep the work items within one wave of 148 SMs
     if (s > total_kb / 4) s = total_kb / 4;
     if (s > 16) s = 16;

@@ -440,7 +440,7 @@ struct alignas(64) GNFParams {
 };
 
 template <bool BWD>
-__global__ void __launch_bounds__(512) gnf_kernel(const __grid_constant__ GNFParams p) {
+__global__ void __maxnreg__(96) gnf_kernel(const __grid_constant__ GNFParams p) {   // <= 512 threads; 96 registers keep two 320-thread CTAs per SM
     extern __shared__ uint8_t gnf_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gnf_smem_raw) + 127) & ~uintptr_t(127));
     const int tile_bytes = p.P * p.CB * 2;
@@ -568,46 +568,52 @@ __global__ void __launch_bounds__(512) gnf_kernel(const __grid_constant__ GNFPar
     // ---- pass 2: normalise / back-propagate the slab from shared memory
     const float sa[2] = {s_fin[g_lo * 2], s_fin[g_hi * 2]};
     const float sb[2] = {s_fin[g_lo * 2 + 1], s_fin[g_hi * 2 + 1]};
-    for (int pp = rl; pp < p.P; pp += p.lanes) {
-        const int64_t pix = row0 + pp;
-        float x[8], o[8];
-        unpack8(*reinterpret_cast<const uint4*>(sX + ((size_t)pp * p.CB + tv * 8) * 2), x);
-        if (!BWD) {
+    for (int pb = rl; pb < p.P; pb += 2 * p.lanes) {
+        uint4 av[2];
+        if (BWD) {                       // residual-branch gradients of two pixels in flight before the first store
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const bool lo = e < nb;       // selects, not runtime-indexed arrays (those live in local memory)
-                float z = (x[e] - (lo ? sa[0] : sa[1])) * (lo ? sb[0] : sb[1]) * gm[e] + bt[e];
-                if (p.silu) z = silu_f(z);
-                o[e] = z;
+            for (int j = 0; j < 2; ++j) {
+                const int pp = pb + j * p.lanes;
+                av[j] = make_uint4(0u, 0u, 0u, 0u);
+                if (pp < p.P) {
+                    const int64_t pix = row0 + pp;
+                    const __nv_bfloat16* add = first ? (p.add1 ? p.add1 + pix * p.C1 + ch : nullptr)
+                                                     : (p.add2 ? p.add2 + pix * p.C2 + (ch - p.C1) : nullptr);
+                    if (add) av[j] = *reinterpret_cast<const uint4*>(add);
+                }
             }
-            *reinterpret_cast<uint4*>(p.y + pix * p.C + ch) = pack8(o);
-        } else {
-            float d[8];
-            unpack8(*reinterpret_cast<const uint4*>(sDY + ((size_t)pp * p.CB + tv * 8) * 2), d);
+        }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const bool lo = e < nb;       // selects, not runtime-indexed arrays (those live in local memory)
-                const float xh = (x[e] - (lo ? mean[0] : mean[1])) * (lo ? rstd[0] : rstd[1]);
-                float g = d[e] * gm[e];
-                if (p.silu) g *= silu_grad(xh * gm[e] + bt[e]);
-                o[e] = (lo ? rstd[0] : rstd[1]) * (g - (lo ? sa[0] : sa[1]) - xh * (lo ? sb[0] : sb[1]));
-            }
-            __nv_bfloat16* dst;
-            const __nv_bfloat16* add;
-            if (first) {
-                dst = p.dx1 + pix * p.C1 + ch;
-                add = p.add1 ? p.add1 + pix * p.C1 + ch : nullptr;
+        for (int j = 0; j < 2; ++j) {
+            const int pp = pb + j * p.lanes;
+            if (pp >= p.P) break;
+            const int64_t pix = row0 + pp;
+            float x[8], o[8];
+            unpack8(*reinterpret_cast<const uint4*>(sX + ((size_t)pp * p.CB + tv * 8) * 2), x);
+            if (!BWD) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const bool lo = e < nb;
+                    float z = (x[e] - (lo ? sa[0] : sa[1])) * (lo ? sb[0] : sb[1]) * gm[e] + bt[e];
+                    if (p.silu) z = silu_f(z);
+                    o[e] = z;
+                }
+                *reinterpret_cast<uint4*>(p.y + pix * p.C + ch) = pack8(o);
             } else {
-                dst = p.dx2 + pix * p.C2 + (ch - p.C1);
-                add = p.add2 ? p.add2 + pix * p.C2 + (ch - p.C1) : nullptr;
-            }
-            if (add) {
-                float a[8];
-                unpack8(*reinterpret_cast<const uint4*>(add), a);
+                float d[8], a[8];
+                unpack8(*reinterpret_cast<const uint4*>(sDY + ((size_t)pp * p.CB + tv * 8) * 2), d);
+                unpack8(av[j], a);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] += a[e];
+                for (int e = 0; e < 8; ++e) {
+                    const bool lo = e < nb;
+                    const float xh = (x[e] - (lo ? mean[0] : mean[1])) * (lo ? rstd[0] : rstd[1]);
+                    float g = d[e] * gm[e];
+                    if (p.silu) g *= silu_grad(xh * gm[e] + bt[e]);
+                    o[e] = (lo ? rstd[0] : rstd[1]) * (g - (lo ? sa[0] : sa[1]) - xh * (lo ? sb[0] : sb[1])) + a[e];
+                }
+                __nv_bfloat16* dst = first ? p.dx1 + pix * p.C1 + ch : p.dx2 + pix * p.C2 + (ch - p.C1);
+                *reinterpret_cast<uint4*>(dst) = pack8(o);
             }
-            *reinterpret_cast<uint4*>(dst) = pack8(o);
         }
     }
     cluster_wait();                  // nobody in the cluster still reads this CTA's partial sums
@@ -801,20 +807,22 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
         }
         s1 = warp_sum(s1) / C;
         s2 = warp_sum(s2) / C;
+        uint4 av[NVPL];                                   // all residual-gradient loads in flight before the first store
+#pragma unroll
+        for (int k = 0; k < NVPL; ++k) {
+            const int i = lane + 32 * k;
+            av[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (add && i < nv) av[k] = *reinterpret_cast<const uint4*>(add + row * C + i * 8);
+        }
 #pragma unroll
         for (int k = 0; k < NVPL; ++k) {
             const int i = lane + 32 * k;
             if (i < nv) {
                 const int c = i * 8;
-                float o[8];
+                float o[8], a[8];
+                unpack8(av[k], a);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = rstd * (g[k][e] - s1 - v[k][e] * s2);
-                if (add) {
-                    float a[8];
-                    unpack8(*reinterpret_cast<const uint4*>(add + row * C + c), a);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] += a[e];
-                }
+                for (int e = 0; e < 8; ++e) o[e] = rstd * (g[k][e] - s1 - v[k][e] * s2) + a[e];
                 *reinterpret_cast<uint4*>(out + row * C + c) = pack8(o);
             }
         }

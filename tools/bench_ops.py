@@ -196,9 +196,22 @@ def linear_bwd_case(M, K, N, rank):
     bench(f"linear+lora fwd+bwd (5 GEMMs + grad kernel) M{M} K{K} N{N} r{rank}", make, flops=4.0 * M * N * K)
 
 
+def tiny_case():
+    """Launch floor: a 1-CTA elementwise kernel, back to back in the graph."""
+    from hcp_diffusion_b200._lib import call, stream_ptr
+    a, b, o = (torch.zeros(64, device=DEV, dtype=BF) for _ in range(3))
+
+    def make(i):
+        return lambda: call("hcp_add_bf16", a.data_ptr(), b.data_ptr(), 64, o.data_ptr(), stream_ptr())
+    bench("tiny kernel (add_bf16 on 64 elements): graph launch floor", make)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     B = 4
+    tiny_case()
+    gemm_case(16384, 320, 320, res=True)
+    gemm_case(16384, 320, 320, rank=8)
     for M, K, N in [(16384, 320, 320), (4096, 640, 640), (1024, 1280, 1280), (256, 1280, 1280), (16384, 320, 64), (4096, 640, 64), (1024, 1280, 64),
                     (16384, 320, 2560), (16384, 1280, 320), (16384, 2560, 320), (4096, 640, 5120), (1024, 1280, 10240), (1024, 5120, 1280),
                     (1024, 10240, 1280)]:
