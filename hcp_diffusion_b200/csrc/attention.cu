@@ -373,7 +373,16 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
             mbar_wait(q_full, 0);
             mbar_wait(&kv_full[0], 0);
             tc_fence_after();
-            for (int t = 0; t < p.nq; ++t) issue_s(t, 0);
+            // The two query tiles are started half an iteration apart: tile 1 gets its first logits only when tile 0 has pulled
+            // its own into registers and enters the exponential phase.  Each tile's chain (logits -> max -> exp -> P) is strictly
+            // sequential, so the offset persists and the MUFU pipe serves one tile's exponentials while the other tile loads /
+            // reduces / stores (ncu, in-phase start: XU pipe 49 % busy, both tiles contending in the same window).
+            issue_s(0, 0);
+            if (p.nq == 2) {
+                mbar_wait(&s_free[0], 0);
+                tc_fence_after();
+                issue_s(1, 0);
+            }
             for (int j = 0; j < nkv; ++j) {
                 const int st = j % S;
                 if (S > 1 && j + 1 < nkv) {                             // next K tile is resident: issue S(j+1) early
@@ -572,7 +581,10 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
     uint64_t* dq_full = bars + 7;    // dK, dQ MMAs retired
     uint64_t* dq_read = bars + 8;    // dQ drained from TMEM (128 arrivals)
     uint64_t* acc_full = bars + 9;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* sdp_free = bars + 10;  // every softmax thread holds its S / dP values of the tile in registers
+    uint64_t* q_full2 = bars + 11;   // third Q/dO stage (early_sdp)
+    uint64_t* dp_free = bars + 12;   // ... and its dP values (S and dP are released separately: 32 live registers each)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // blockIdx.x = (kv tile, q split): short-KV problems (cross-attention) have a single kv tile, so the query range is split
@@ -596,6 +608,9 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
         mbar_init(dq_full, 1);
         mbar_init(dq_read, kBwdSoftmaxThreads);
         mbar_init(acc_full, 1);
+        mbar_init(sdp_free, kBwdSoftmaxThreads);
+        mbar_init(q_full2, 1);
+        mbar_init(dp_free, kBwdSoftmaxThreads);
         fence_mbar_init();
     }
     if (warp == 4 * kBwdParts) {
@@ -616,12 +631,13 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
 
     if (warp == 4 * kBwdParts) {
         if (elect_one()) {
+            auto qbar = [&](int st) { return st == 2 ? q_full2 : &q_full[st]; };
             auto load_q = [&](int i) {
-                const int st = (p.q_stages == 2) ? (i & 1) : 0;
-                mbar_arrive_expect_tx(&q_full[st], 2 * tile_bytes);
+                const int st = i % p.q_stages;
+                mbar_arrive_expect_tx(qbar(st), 2 * tile_bytes);
                 for (int bx = 0; bx < p.nbox; ++bx) {
-                    tma_load_4d(sQ + st * tile_bytes + bx * TILE_BYTES, &p.tmQ, &q_full[st], bx * 64, h, (i0 + i) * 128, b);
-                    tma_load_4d(sdO + st * tile_bytes + bx * TILE_BYTES, &p.tmdO, &q_full[st], bx * 64, h, (i0 + i) * 128, b);
+                    tma_load_4d(sQ + st * tile_bytes + bx * TILE_BYTES, &p.tmQ, qbar(st), bx * 64, h, (i0 + i) * 128, b);
+                    tma_load_4d(sdO + st * tile_bytes + bx * TILE_BYTES, &p.tmdO, qbar(st), bx * 64, h, (i0 + i) * 128, b);
                 }
             };
             mbar_arrive_expect_tx(kv_full, 2 * tile_bytes);
@@ -637,18 +653,22 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             const uint32_t box0 = (p.col0 / 64) * TILE_BYTES;                     // first box of the output slice
             const uint32_t kb = smem_u32(sK), vb = smem_u32(sV);
             const uint32_t pb = smem_u32(sP), dsb = smem_u32(sdS);
-            auto issue_sdp = [&](int st) {          // S = Q K^T, dP = dO V^T  (contraction over d)
-                const uint32_t qb = smem_u32(sQ + st * tile_bytes), dob = smem_u32(sdO + st * tile_bytes);
+            auto issue_s = [&](int st) {            // S = Q K^T  (contraction over d)
+                const uint32_t qb = smem_u32(sQ + st * tile_bytes);
                 for (int ks = 0; ks < p.dn / 16; ++ks) {
                     const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
                     umma_ss(tS, make_smem_desc(qb + off, 16, 1024), make_smem_desc(kb + off, 16, 1024), idesc_s, ks > 0);
                 }
+            };
+            auto issue_dp = [&](int st) {           // dP = dO V^T, then signal "S and dP ready"
+                const uint32_t dob = smem_u32(sdO + st * tile_bytes);
                 for (int ks = 0; ks < p.dn / 16; ++ks) {
                     const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
                     umma_ss(tdP, make_smem_desc(dob + off, 16, 1024), make_smem_desc(vb + off, 16, 1024), idesc_s, ks > 0);
                 }
                 umma_commit(sdp_full);
             };
+            auto issue_sdp = [&](int st) { issue_s(st); issue_dp(st); };
             auto issue_dv = [&](int st, bool acc) {  // dV += P^T dO   (M = kv, K = q rows: both operands MN-major, 2048 B per k-step)
                 const uint32_t dob = smem_u32(sdO + st * tile_bytes);
                 for (int ks = 0; ks < 8; ++ks)
@@ -671,33 +691,42 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                 umma_commit(dq_full);
             };
             if (p.early_sdp) {
-                // dQ has its own TMEM columns and Q/dO are double buffered: S/dP of tile i+1 are issued as soon as the softmax
-                // warps have consumed S/dP of tile i, so they run while dK/dQ of tile i execute and dQ_i is drained.
+                // dQ has its own TMEM columns and Q/dO have three stages.  The softmax threads pull their S / dP values of tile i
+                // into registers first (sdp_free), so S/dP of tile i+1 are issued while the exponentials of tile i are computed;
+                // dV_i, dK_i, dQ_i follow as their operands appear.  The tensor pipe and the softmax warps never wait for each
+                // other except for true data dependencies.
                 if (nq > 1) load_q(1);
+                if (nq > 2) load_q(2);
                 mbar_wait(&q_full[0], 0);
                 tc_fence_after();
                 issue_sdp(0);
                 for (int i = 0; i < nq; ++i) {
-                    const int st = i & 1;
+                    const int st = i % 3;
+                    if (i + 1 < nq) {
+                        mbar_wait(sdp_free, i & 1);          // S_i is in registers: S_{i+1} may overwrite the columns
+                        mbar_wait(qbar((i + 1) % 3), ((i + 1) / 3) & 1);
+                        tc_fence_after();
+                        issue_s((i + 1) % 3);
+                    }
                     mbar_wait(p_ready, i & 1);
                     tc_fence_after();
                     issue_dv(st, i > 0);
+                    if (i + 1 < nq) {
+                        mbar_wait(dp_free, i & 1);           // dP_i is in registers
+                        tc_fence_after();
+                        issue_dp((i + 1) % 3);
+                    }
                     mbar_wait(ds_ready, i & 1);
                     tc_fence_after();
-                    if (i + 1 < nq) {
-                        mbar_wait(&q_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
-                        tc_fence_after();
-                        issue_sdp((i + 1) & 1);
-                    }
                     issue_dk(st, i > 0);
                     if (i > 0) {
                         mbar_wait(dq_read, (i - 1) & 1);     // dQ_{i-1} drained from TMEM
                         tc_fence_after();
                     }
                     issue_dq();
-                    if (i + 2 < nq) {
-                        mbar_wait(dq_full, i & 1);           // every MMA reading Q_i / dO_i has retired
-                        load_q(i + 2);
+                    if (i + 3 < nq) {
+                        mbar_wait(dq_full, i & 1);           // every MMA reading Q_i / dO_i has retired: the stage is free
+                        load_q(i + 3);
                     }
                 }
             } else {
@@ -783,7 +812,110 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             mbar_wait(sdp_full, i & 1);
             tc_fence_after();
             // ---- P = exp2(S*c - lse), dS = P * (dP - delta) * scale -> smem (K-major [q][kv], SWIZZLE_128B,
-            //      two 64-wide boxes each).  One pass unless P and dS must share a buffer (d > 128).
+            //      two 64-wide boxes each), 16 kv columns at a time.
+            auto emit16 = [&](const uint32_t (&v)[16], const uint32_t (&w)[16], int c, int hf, bool do_p, bool do_ds) {
+                uint32_t pk[8], dk[8];
+                if (!special && qok) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), p.scale_log2, neg_lse2));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, neg_lse2));
+                        pk[e >> 1] = pack_bf16x2(p0, p1);
+                        dk[e >> 1] = do_ds ? pack_bf16x2(p0 * fmaf(__uint_as_float(w[e]), p.scale, neg_dlt_s),
+                                                         p1 * fmaf(__uint_as_float(w[e + 1]), p.scale, neg_dlt_s))
+                                           : 0u;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        float pe[2], de[2];
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            const int col = c * 32 + hf * 16 + e + t;
+                            float s2 = fmaf(__uint_as_float(v[e + t]), p.scale_log2, neg_lse2);
+                            if (bias && col < ncols) s2 += bias[kv0 + col] * kLog2e;
+                            const float pv = (qok && col < ncols) ? fast_exp2(s2) : 0.f;
+                            pe[t] = pv;
+                            de[t] = do_ds ? pv * fmaf(__uint_as_float(w[e + t]), p.scale, neg_dlt_s) : 0.f;
+                        }
+                        pk[e >> 1] = pack_bf16x2(pe[0], pe[1]);
+                        dk[e >> 1] = pack_bf16x2(de[0], de[1]);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t off = (c >> 1) * TILE_BYTES + sw128_offset(row, (c & 1) * 4 + hf * 2 + g);
+                    if (do_p) *reinterpret_cast<uint4*>(sP + off) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+                    if (do_ds) *reinterpret_cast<uint4*>(sdS + off) = make_uint4(dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
+                }
+            };
+            if (p.early_sdp) {
+                // The 32 logits of this thread go to registers and the S columns are released to the next tile's Q K^T at once;
+                // P is produced (and dV may start) before the 32 dP values are pulled in and released the same way.
+                static_assert(kChunksPerPart == 1, "the register-resident path assumes one 32-column chunk per warp");
+                const int c = part;
+                uint32_t pk[16];
+                {
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(tS + lb + c * 32, v0);
+                    tmem_ld16(tS + lb + c * 32 + 16, v1);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(sdp_free);
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        float q0 = fmaf(__uint_as_float(v0[e]), p.scale_log2, neg_lse2), q1 = fmaf(__uint_as_float(v0[e + 1]), p.scale_log2, neg_lse2);
+                        float q2 = fmaf(__uint_as_float(v1[e]), p.scale_log2, neg_lse2), q3 = fmaf(__uint_as_float(v1[e + 1]), p.scale_log2, neg_lse2);
+                        if (special) {
+                            const int col = c * 32 + e;
+                            if (bias) {
+                                if (col < ncols) q0 += bias[kv0 + col] * kLog2e;
+                                if (col + 1 < ncols) q1 += bias[kv0 + col + 1] * kLog2e;
+                                if (col + 16 < ncols) q2 += bias[kv0 + col + 16] * kLog2e;
+                                if (col + 17 < ncols) q3 += bias[kv0 + col + 17] * kLog2e;
+                            }
+                            q0 = (col < ncols) ? q0 : -INFINITY;
+                            q1 = (col + 1 < ncols) ? q1 : -INFINITY;
+                            q2 = (col + 16 < ncols) ? q2 : -INFINITY;
+                            q3 = (col + 17 < ncols) ? q3 : -INFINITY;
+                        }
+                        if (!qok) q0 = q1 = q2 = q3 = -INFINITY;           // exp2(-inf) == 0
+                        pk[e >> 1] = pack_bf16x2(fast_exp2(q0), fast_exp2(q1));
+                        pk[8 + (e >> 1)] = pack_bf16x2(fast_exp2(q2), fast_exp2(q3));
+                    }
+                }
+                if (i > 0) {
+                    mbar_wait(dq_full, (i - 1) & 1);        // dK/dQ of the previous tile have finished reading sP / sdS
+                    tc_fence_after();
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint4*>(sP + (c >> 1) * TILE_BYTES + sw128_offset(row, (c & 1) * 4 + g)) =
+                        make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+                fence_proxy_async_smem();
+                mbar_arrive(p_ready);
+                {
+                    uint32_t w0[16], w1[16];
+                    tmem_ld16(tdP + lb + c * 32, w0);
+                    tmem_ld16(tdP + lb + c * 32 + 16, w1);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(dp_free);
+                    // dS = P (dP - delta) scale, with the bf16-rounded P the tensor pipe sees in dV
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        const float2 pa = unpack_bf16x2(pk[e >> 1]), pb2 = unpack_bf16x2(pk[8 + (e >> 1)]);
+                        pk[e >> 1] = pack_bf16x2(pa.x * fmaf(__uint_as_float(w0[e]), p.scale, neg_dlt_s),
+                                                 pa.y * fmaf(__uint_as_float(w0[e + 1]), p.scale, neg_dlt_s));
+                        pk[8 + (e >> 1)] = pack_bf16x2(pb2.x * fmaf(__uint_as_float(w1[e]), p.scale, neg_dlt_s),
+                                                       pb2.y * fmaf(__uint_as_float(w1[e + 1]), p.scale, neg_dlt_s));
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint4*>(sdS + (c >> 1) * TILE_BYTES + sw128_offset(row, (c & 1) * 4 + g)) =
+                        make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+            } else {
             for (int pass = 0; pass < (p.share_pds ? 2 : 1); ++pass) {
                 const bool do_p = (pass == 0);
                 const bool do_ds = !p.share_pds || pass == 1;
@@ -794,44 +926,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                     tmem_ld16(tS + lb + c * 32 + hf * 16, v);
                     if (do_ds) tmem_ld16(tdP + lb + c * 32 + hf * 16, w);
                     tmem_wait_ld();
-                    if (p.early_sdp && i > 0 && c == part * kChunksPerPart && hf == 0) {
-                        mbar_wait(dq_full, (i - 1) & 1);    // dK/dQ of the previous tile have finished reading sP / sdS
-                        tc_fence_after();
-                    }
-                    uint32_t pk[8], dk[8];
-                    if (!special && qok) {
-#pragma unroll
-                        for (int e = 0; e < 16; e += 2) {
-                            const float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), p.scale_log2, neg_lse2));
-                            const float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, neg_lse2));
-                            pk[e >> 1] = pack_bf16x2(p0, p1);
-                            dk[e >> 1] = do_ds ? pack_bf16x2(p0 * fmaf(__uint_as_float(w[e]), p.scale, neg_dlt_s),
-                                                             p1 * fmaf(__uint_as_float(w[e + 1]), p.scale, neg_dlt_s))
-                                               : 0u;
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 16; e += 2) {
-                            float pe[2], de[2];
-#pragma unroll
-                            for (int t = 0; t < 2; ++t) {
-                                const int col = c * 32 + hf * 16 + e + t;
-                                float s2 = fmaf(__uint_as_float(v[e + t]), p.scale_log2, neg_lse2);
-                                if (bias && col < ncols) s2 += bias[kv0 + col] * kLog2e;
-                                const float pv = (qok && col < ncols) ? fast_exp2(s2) : 0.f;
-                                pe[t] = pv;
-                                de[t] = do_ds ? pv * fmaf(__uint_as_float(w[e + t]), p.scale, neg_dlt_s) : 0.f;
-                            }
-                            pk[e >> 1] = pack_bf16x2(pe[0], pe[1]);
-                            dk[e >> 1] = pack_bf16x2(de[0], de[1]);
-                        }
-                    }
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const uint32_t off = (c >> 1) * TILE_BYTES + sw128_offset(row, (c & 1) * 4 + hf * 2 + g);
-                        if (do_p) *reinterpret_cast<uint4*>(sP + off) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-                        if (do_ds) *reinterpret_cast<uint4*>(sdS + off) = make_uint4(dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
-                    }
+                    emit16(v, w, c, hf, do_p, do_ds);
                   }
                 }
                 if (do_p) {
@@ -839,6 +934,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                     mbar_arrive(p_ready);
                     if (p.share_pds) mbar_wait(dv_done, i & 1);   // P consumed before dS overwrites the buffer
                 }
+            }
             }
             tc_fence_before();
             fence_proxy_async_smem();
@@ -1139,6 +1235,7 @@ extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream
     p.q_stages = (p.nbox == 1) ? 2 : 1;
     p.share_pds = (p.nbox >= 3) ? 1 : 0;
     p.early_sdp = (p.q_stages == 2 && 256 + 3 * p.dn <= 512 && getenv("HCP_ATTN_BWD_NO_EARLY") == nullptr) ? 1 : 0;
+    if (p.early_sdp) p.q_stages = 3;
     const int smem = (2 + 2 * p.q_stages) * p.nbox * TILE_BYTES + (p.share_pds ? 2 : 4) * TILE_BYTES + 256 + 1024;
     static bool configured = false;
     if (!configured) {

@@ -24,10 +24,10 @@ void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 bool pdl_enabled() {
     static const bool on = [] {
-        // measured on B200 (profiles/r01_bench_pdl_ab.json): inside the captured step graph the programmatic edges buy
-        // nothing (24.81 ms off vs 25.15 ms on), so the attribute is opt-in
+        // measured on B200 inside the captured step graph: 22.67 ms with the programmatic edges vs 23.02 ms without
+        // (profiles/r01_bench_v11*.json; ~0.8 us per kernel boundary in tools/bench_ops.py).  HCP_PDL=0 turns them off.
         const char* e = getenv("HCP_PDL");
-        return e && e[0] == '1';
+        return !(e && e[0] == '0');
     }();
     return on;
 }

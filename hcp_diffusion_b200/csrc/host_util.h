@@ -27,7 +27,7 @@ inline int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint
 }
 
 // Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor on the stream drains; every
-// kernel of the library calls pdl_wait() (common.cuh) before touching global memory.  Opt-in: HCP_PDL=1.
+// kernel of the library calls pdl_wait() (common.cuh) before touching global memory.  HCP_PDL=0 turns the attribute off.
 bool pdl_enabled();
 void note_launch();
 
