@@ -64,6 +64,7 @@ class ConvArgs(C.Structure):
         ("stride", C.c_int32), ("mode", C.c_int32),
         ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_ld", C.c_int64), ("residual", C.c_void_p), ("out", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("lora_t", C.c_void_p), ("lora_b", C.c_void_p), ("lora_r", C.c_int64), ("lora_ld", C.c_int64),
     ]
 
 
@@ -106,6 +107,13 @@ class LoraJob(C.Structure):
     ]
 
 
+class LoraConvJob(C.Structure):
+    _fields_ = [
+        ("w_down", C.c_void_p), ("rank", C.c_int32), ("cin", C.c_int32), ("c0", C.c_int32), ("ld_r", C.c_int32), ("flip", C.c_int32),
+        ("pad_", C.c_int32), ("wt", C.c_void_p), ("wd", C.c_void_p),
+    ]
+
+
 class LoraGradBlock(C.Structure):
     _fields_ = [
         ("n_lo", C.c_int64), ("n_hi", C.c_int64), ("c0", C.c_int32), ("rank", C.c_int32), ("scale", C.c_float),
@@ -124,7 +132,7 @@ EXPORTS = [
     "hcp_layernorm_fwd_bf16", "hcp_layernorm_bwd_bf16", "hcp_geglu_fwd_bf16", "hcp_geglu_bwd_bf16",
     "hcp_upsample2x_fwd_bf16", "hcp_upsample2x_bwd_bf16", "hcp_add_bf16",
     "hcp_conv_in_f32", "hcp_conv_out_f32", "hcp_conv_out_dgrad_f32", "hcp_skinny_linear", "hcp_cast_f32_to_bf16",
-    "hcp_lora_pack", "hcp_lora_grad", "hcp_lora_grad_pair", "hcp_add_noise", "hcp_mse_loss", "hcp_sumsq", "hcp_adamw_flat",
+    "hcp_lora_pack", "hcp_lora_pack_conv", "hcp_lora_grad", "hcp_lora_grad_pair", "hcp_lora_grad_conv3x3", "hcp_add_noise", "hcp_mse_loss", "hcp_sumsq", "hcp_adamw_flat",
 ]
 
 
@@ -168,6 +176,8 @@ def lib() -> C.CDLL:
             l.hcp_skinny_linear.argtypes = [vp, vp, vp, i64, i64, i64, i32, i32, vp, vp]
             l.hcp_cast_f32_to_bf16.argtypes = [vp, i64, vp, vp]
             l.hcp_lora_pack.argtypes = [vp, i64, vp]
+            l.hcp_lora_pack_conv.argtypes = [vp, i64, vp]
+            l.hcp_lora_grad_conv3x3.argtypes = [vp, i64, vp, i64, i64, i64, i64, C.c_int32, C.POINTER(LoraGradBlock), C.c_int32, vp]
             l.hcp_lora_grad.argtypes = [vp, i64, vp, i64, i64, i64, i64, C.POINTER(LoraGradBlock), C.c_int32, vp]
             l.hcp_lora_grad_pair.argtypes = [vp, vp, i64, i64, C.POINTER(LoraGradBlock), vp, vp, i64, i64, C.POINTER(LoraGradBlock),
                                              C.c_int32, i64, i64, vp]

@@ -459,8 +459,15 @@ constexpr int LG_MAX_BLOCKS = 8;
 
 struct LGBlock {
     int32_t n_lo, n_hi, c0, rank, transpose_out, dst_ld;
+    int32_t n_stride;        // element stride of the X-column index in the destination (1; 9 for the taps of a 3x3 W_down)
     float scale;
     float* dst;
+};
+// X operand = shifted im2col box of a 3x3 convolution (dW_down of a Conv2d LoRA): same boxes as the forward conv's A operand
+struct LGConv {
+    int32_t rank;            // 0: plain [M, ldx] matrix; 4 / 5: rank of the NHWC tensor map
+    int32_t bw, bh, bn, tiles_w, tiles_h;
+    int32_t c0_off, dw, dh, c2;
 };
 struct LGProblem {
     int32_t n_begin, n_end, tiles_per_cta, nblocks, col_chunks, splits;
@@ -470,6 +477,7 @@ struct alignas(64) LoraGradParams {
     CUtensorMap tmX[2], tmS[2];        // up to two independent problems per launch (dW_down and dW_up of one group)
     int32_t M, nprob;
     LGProblem prob[2];
+    LGConv conv;
 };
 
 __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __grid_constant__ LoraGradParams p) {
@@ -511,8 +519,26 @@ __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __gri
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full_bar[stage], LG_STAGE_BYTES);
                 uint8_t* base = smem + stage * LG_STAGE_BYTES;
-                tma_load_2d(base, tmX, &full_bar[stage], ncol0, t * 128);
-                tma_load_2d(base + 128 * 128, tmX, &full_bar[stage], ncol0 + 64, t * 128);
+                if (p.conv.rank == 0) {
+                    tma_load_2d(base, tmX, &full_bar[stage], ncol0, t * 128);
+                    tma_load_2d(base + 128 * 128, tmX, &full_bar[stage], ncol0 + 64, t * 128);
+                } else {
+                    const LGConv& cv = p.conv;
+                    int img0, h0 = 0, w0 = 0;
+                    if (cv.bn == 1) {
+                        const int per_img = cv.tiles_w * cv.tiles_h, r = t % per_img;
+                        img0 = t / per_img;
+                        h0 = (r / cv.tiles_w) * cv.bh;
+                        w0 = (r % cv.tiles_w) * cv.bw;
+                    } else {
+                        img0 = t * cv.bn;
+                    }
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int c = cv.c0_off + ncol0 + hf * 64;
+                        if (cv.rank == 4) tma_load_4d(base + hf * 128 * 128, tmX, &full_bar[stage], c, w0 + cv.dw, h0 + cv.dh, img0);
+                        else tma_load_5d(base + hf * 128 * 128, tmX, &full_bar[stage], c, w0 + cv.dw, cv.c2, h0 + cv.dh, img0);
+                    }
+                }
                 tma_load_2d(base + 2 * 128 * 128, tmS, &full_bar[stage], 0, t * 128);
                 if (++stage == LG_STAGES) { stage = 0; phase ^= 1; }
             }
@@ -557,7 +583,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __gri
                         if (j >= 0 && j < k.rank) {
                             const float val = __uint_as_float(v[e]) * k.scale;
                             float* dst = k.transpose_out ? k.dst + (int64_t)(n - k.n_lo) * k.dst_ld + j
-                                                         : k.dst + (int64_t)j * k.dst_ld + (n - k.n_lo);
+                                                         : k.dst + (int64_t)j * k.dst_ld + (int64_t)(n - k.n_lo) * k.n_stride;
                             atomicAdd(dst, val);
                         }
                     }
@@ -698,6 +724,21 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     return run_gemm(bn, kp, m_tiles, total_kb, a->workspace, a->workspace_bytes, true, (cudaStream_t)stream_);
 }
 
+// Conv2d LoRA: out += T . Bl^T as K-segment 1 (plain 2D operands; the rows of an M tile of the convolution are contiguous pixels)
+static int conv_lora_segment(const hcp_conv3x3_args* a, GemmKParams& kp, int bn) {
+    if (!a->lora_t) return HCP_OK;
+    if (!a->lora_b || a->lora_r <= 0 || a->lora_r > a->lora_ld || (a->lora_ld % 8) != 0)
+        return set_error(HCP_ERR_INVALID, "conv3x3: LoRA segment (lora_b / lora_r / lora_ld)");
+    int rc = make_tmap_2d(&kp.tmA[1], a->lora_t, (uint64_t)a->lora_r, (uint64_t)kp.M, (uint64_t)a->lora_ld, BLOCK_K, BLOCK_M);
+    if (rc) return rc;
+    rc = make_tmap_2d(&kp.tmB[1], a->lora_b, (uint64_t)a->lora_r, (uint64_t)a->Cout, (uint64_t)a->lora_ld, BLOCK_K, bn);
+    if (rc) return rc;
+    kp.nseg = 2;
+    kp.nkb[1] = (int)((a->lora_r + BLOCK_K - 1) / BLOCK_K);
+    kp.klast[1] = (int)((a->lora_r - (int64_t)(kp.nkb[1] - 1) * BLOCK_K + 15) / 16);
+    return HCP_OK;
+}
+
 extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_) {
     if (!a || !a->x || !a->w || !a->out) return set_error(HCP_ERR_INVALID, "conv3x3: null pointer");
     if (a->Cin % 64 != 0 || a->Cout % 8 != 0) return set_error(HCP_ERR_INVALID, "conv3x3: Cin %% 64, Cout %% 8 required");
@@ -767,7 +808,8 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
                 t.wk_off = (int)((kh * 3 + kw) * Cin);
             }
         kp.sh = kp.sw = 1; kp.oh0 = kp.ow0 = 0;
-        return run_gemm(bn, kp, m_tiles, (int64_t)9 * kp.nkb[0], a->workspace, a->workspace_bytes, true, stream);
+        if ((rc = conv_lora_segment(a, kp, bn))) return rc;
+        return run_gemm(bn, kp, m_tiles, (int64_t)9 * kp.nkb[0] + (kp.nseg > 1 ? kp.nkb[1] : 0), a->workspace, a->workspace_bytes, true, stream);
     }
     if (a->mode == 0 && a->stride == 2) {
         // view x as [B][Hin/2][2][Win/2][2*Cin]: input row ih = 2*oh + kh - 1 -> (phase, index)
@@ -790,8 +832,10 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
                 t.wk_off = (int)((kh * 3 + kw) * Cin);
             }
         kp.sh = kp.sw = 1; kp.oh0 = kp.ow0 = 0;
-        return run_gemm(bn, kp, m_tiles, (int64_t)9 * kp.nkb[0], a->workspace, a->workspace_bytes, true, stream);
+        if ((rc = conv_lora_segment(a, kp, bn))) return rc;
+        return run_gemm(bn, kp, m_tiles, (int64_t)9 * kp.nkb[0] + (kp.nseg > 1 ? kp.nkb[1] : 0), a->workspace, a->workspace_bytes, true, stream);
     }
+    if (a->lora_t) return set_error(HCP_ERR_INVALID, "conv3x3: the LoRA segment is only available in mode 0");
     // mode 1: dgrad of the stride-2 conv.  x = dY [B, Hin, Win, Cin] (Cin = Cout of the fwd conv),
     // out = dX [B, 2Hin, 2Win, Cout].  Output pixel (2i+ph, 2j+pw) gathers dY[i+dh, j+dw] over the taps whose
     // parity matches:  ph=0: kh=1 (dh=0);  ph=1: kh=0 (dh=+1), kh=2 (dh=0).   w[co][kh][kw][ci] here is the
@@ -849,6 +893,7 @@ static int lg_fill(LoraGradParams& p, int z, const void* S, int64_t lds, const v
         if (k.rank < 1 || k.c0 < 0 || k.c0 + k.rank > 64 || !k.dst) return set_error(HCP_ERR_INVALID, "lora_grad: block descriptor");
         q.blk[i].n_lo = (int)k.n_lo; q.blk[i].n_hi = (int)k.n_hi; q.blk[i].c0 = k.c0; q.blk[i].rank = k.rank;
         q.blk[i].transpose_out = k.transpose_out; q.blk[i].dst_ld = (int)k.dst_ld; q.blk[i].scale = k.scale; q.blk[i].dst = k.dst;
+        q.blk[i].n_stride = 1;
     }
     return HCP_OK;
 }
@@ -877,6 +922,76 @@ extern "C" int hcp_lora_grad(const void* S, int64_t lds, const void* X, int64_t 
     int rc = lg_fill(p, 0, S, lds, X, ldx, M, n_begin, n_end, blocks, nblocks, 148);
     if (rc) return rc;
     return lg_launch(p, (cudaStream_t)stream_);
+}
+
+// dW_down of a Conv2d LoRA: nine launches (one per tap) of the gradient kernel with the shifted NHWC box as X operand.
+extern "C" int hcp_lora_grad_conv3x3(const void* S, int64_t lds, const void* x, int64_t B, int64_t Hin, int64_t Win, int64_t Cin,
+                                     int32_t stride, const hcp_lora_grad_block* blocks, int32_t nblocks, hcp_stream_t stream_) {
+    if (!S || !x || !blocks || nblocks < 1 || nblocks > LG_MAX_BLOCKS) return set_error(HCP_ERR_INVALID, "lora_grad_conv: arguments");
+    if (Cin % 64 != 0 || (stride != 1 && stride != 2) || lds < 64 || (lds % 8) != 0) return set_error(HCP_ERR_INVALID, "lora_grad_conv: shape");
+    if (stride == 2 && ((Hin | Win) & 1)) return set_error(HCP_ERR_INVALID, "lora_grad_conv: odd extent with stride 2");
+    const int64_t oH = Hin / stride, oW = Win / stride;
+    int bw, bh, bnimg;                       // same 128-pixel tiles as hcp_conv3x3_bf16 (mode 0)
+    if (oW >= 128) { bw = 128; bh = 1; bnimg = 1; if (oW % 128) return set_error(HCP_ERR_INVALID, "lora_grad_conv: W"); }
+    else {
+        bw = (int)oW;
+        if (128 % bw) return set_error(HCP_ERR_INVALID, "lora_grad_conv: W must divide 128");
+        bh = 128 / bw;
+        if (bh <= oH) { if (oH % bh) return set_error(HCP_ERR_INVALID, "lora_grad_conv: H tiling"); bnimg = 1; }
+        else { bh = (int)oH; if (128 % (bw * bh)) return set_error(HCP_ERR_INVALID, "lora_grad_conv: H*W must divide 128"); bnimg = 128 / (bw * bh); }
+    }
+    LoraGradParams p;
+    memset(&p, 0, sizeof(p));
+    const int64_t M = B * oH * oW;
+    p.M = (int)M; p.nprob = 1;
+    int rc;
+    if (stride == 1) {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
+        uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+        uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnimg};
+        rc = make_tmap_nd(&p.tmX[0], x, 4, dims, strides, box);
+        p.conv.rank = 4;
+    } else {
+        uint64_t dims[5] = {(uint64_t)(2 * Cin), (uint64_t)(Win / 2), 2, (uint64_t)(Hin / 2), (uint64_t)B};
+        uint64_t strides[4] = {(uint64_t)(2 * Cin) * 2, (uint64_t)Win * Cin * 2, (uint64_t)(2 * Win * Cin) * 2, (uint64_t)Hin * Win * Cin * 2};
+        uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bnimg};
+        rc = make_tmap_nd(&p.tmX[0], x, 5, dims, strides, box);
+        p.conv.rank = 5;
+    }
+    if (rc) return rc;
+    rc = make_tmap_2d(&p.tmS[0], S, 64, (uint64_t)M, (uint64_t)lds, 64, 128);
+    if (rc) return rc;
+    p.conv.bw = bw; p.conv.bh = bh; p.conv.bn = bnimg;
+    p.conv.tiles_w = (int)(oW / bw); p.conv.tiles_h = (int)(oH / bh);
+    LGProblem& q = p.prob[0];
+    q.n_begin = 0; q.n_end = (int)Cin; q.nblocks = nblocks;
+    q.col_chunks = (int)((Cin + 127) / 128);
+    const int total_tiles = (int)((M + 127) / 128);
+    int splits = 148 / q.col_chunks;
+    if (splits < 1) splits = 1;
+    if (splits > total_tiles) splits = total_tiles;
+    q.tiles_per_cta = (total_tiles + splits - 1) / splits;
+    q.splits = (total_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
+    for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+            if (stride == 1) { p.conv.c0_off = 0; p.conv.dw = kw - 1; p.conv.dh = kh - 1; p.conv.c2 = 0; }
+            else {          // input row 2*oh + kh - 1 -> (phase, index) of the [H/2][2][W/2][2C] view, as in the forward conv
+                p.conv.c0_off = (int)(((kw == 1) ? 0 : 1) * Cin);
+                p.conv.dw = (kw == 0) ? -1 : 0;
+                p.conv.c2 = (kh == 1) ? 0 : 1;
+                p.conv.dh = (kh == 0) ? -1 : 0;
+            }
+            for (int i = 0; i < nblocks; ++i) {
+                const hcp_lora_grad_block& k = blocks[i];
+                if (k.rank < 1 || k.c0 < 0 || k.c0 + k.rank > 64 || !k.dst) return set_error(HCP_ERR_INVALID, "lora_grad_conv: block descriptor");
+                q.blk[i].n_lo = 0; q.blk[i].n_hi = (int)Cin; q.blk[i].c0 = k.c0; q.blk[i].rank = k.rank;
+                q.blk[i].transpose_out = 0; q.blk[i].dst_ld = (int)(Cin * 9); q.blk[i].n_stride = 9;
+                q.blk[i].scale = k.scale; q.blk[i].dst = k.dst + (kh * 3 + kw);
+            }
+            rc = lg_launch(p, (cudaStream_t)stream_);
+            if (rc) return rc;
+        }
+    return HCP_OK;
 }
 
 // dW_down and dW_up of one LoRA group in ONE launch (two independent TN GEMMs over the same M token rows).

@@ -15,8 +15,9 @@
 namespace hcp {
 
 // ---------------------------------------------------------------------------------------------
-// conv_in: x NCHW fp32 [B,Cin(<=8),H,W] -> y NHWC bf16 [B,H,W,Cout];  w fp32 [Cout,Cin,3,3]
-// one thread per (pixel, output channel): the 9*Cin input taps are shared by the warp through L1
+// conv_in: x NCHW fp32 [B,Cin(<=8),H,W] -> y NHWC bf16 [B,H,W,Cout];  w fp32 TAP-MAJOR [Cin,3,3,Cout]
+// one thread per (pixel, output channel): the 9*Cin input taps are broadcast loads shared by the warp, the weights of a tap
+// are contiguous over the output channels (coalesced; the [Cout,Cin,3,3] parameter layout made them 144-byte strided)
 // ---------------------------------------------------------------------------------------------
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int B,
                                int Cin, int H, int W, int Cout, __nv_bfloat16* __restrict__ y) {
@@ -38,14 +39,14 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
             for (int kw = 0; kw < 3; ++kw) {
                 const int iw = xw + kw - 1;
                 if (iw < 0 || iw >= W) continue;
-                acc += x[(((int64_t)b * Cin + ci) * H + ih) * W + iw] * w[((co * Cin + ci) * 3 + kh) * 3 + kw];
+                acc += x[(((int64_t)b * Cin + ci) * H + ih) * W + iw] * w[((ci * 3 + kh) * 3 + kw) * Cout + co];
             }
         }
     y[i] = __float2bfloat16(acc);
 }
 
 // ---------------------------------------------------------------------------------------------
-// conv_out: x NHWC bf16 [B,H,W,Cin] -> y NCHW fp32 [B,Cout(<=8),H,W];  w fp32 [Cout,Cin,3,3]
+// conv_out: x NHWC bf16 [B,H,W,Cin] -> y NCHW fp32 [B,Cout(<=8),H,W];  w fp32 TAP-MAJOR [3,3,Cout,Cin] (contiguous over ci)
 // one warp per output pixel: lanes split the channels, shuffle-reduce the Cout partial sums
 // ---------------------------------------------------------------------------------------------
 template <int COUT>
@@ -71,8 +72,8 @@ __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, const float
                 const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xp + ci));
 #pragma unroll
                 for (int c = 0; c < COUT; ++c) {
-                    const float* wp = w + ((c * Cin + ci) * 3 + kh) * 3 + kw;
-                    acc[c] += v.x * wp[0] + v.y * wp[9];
+                    const float2 wv = *reinterpret_cast<const float2*>(w + ((kh * 3 + kw) * COUT + c) * Cin + ci);
+                    acc[c] += v.x * wv.x + v.y * wv.y;
                 }
             }
         }
@@ -84,7 +85,7 @@ __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, const float
     }
 }
 
-// dgrad of conv_out: dy NCHW fp32 [B,Cout,H,W] -> dx NHWC bf16 [B,H,W,Cin]; one thread per (pixel, ci)
+// dgrad of conv_out: dy NCHW fp32 [B,Cout,H,W] -> dx NHWC bf16 [B,H,W,Cin]; one thread per (pixel, ci); w TAP-MAJOR [3,3,Cout,Cin]
 template <int COUT>
 __global__ void conv_out_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, int B, int H, int W, int Cin,
                                       __nv_bfloat16* __restrict__ dx) {
@@ -108,7 +109,7 @@ __global__ void conv_out_dgrad_kernel(const float* __restrict__ dy, const float*
             if (ow < 0 || ow >= W) continue;
 #pragma unroll
             for (int c = 0; c < COUT; ++c)
-                acc += dy[(((int64_t)b * COUT + c) * H + oh) * W + ow] * w[((c * Cin + ci) * 3 + kh) * 3 + kw];
+                acc += dy[(((int64_t)b * COUT + c) * H + oh) * W + ow] * w[((kh * 3 + kw) * COUT + c) * Cin + ci];
         }
     }
     dx[i] = __float2bfloat16(acc);
@@ -219,6 +220,28 @@ __global__ void lora_pack_kernel(const hcp_lora_job* __restrict__ jobs, int njob
             Bl[(int64_t)(jb.o0 + o) * jb.ld_r + jb.c0 + rr] = v;
             BlT[(int64_t)(jb.c0 + rr) * jb.out_tot + jb.o0 + o] = v;
         }
+    }
+}
+
+// Conv2d LoRA down-projection: fp32 [rank, Cin, 3, 3] -> bf16 wt [R,3,3,Cin] (rows c0..) and wd [Cin,3,3,R] (columns c0..);
+// wd is the dgrad arrangement: taps flipped for the stride-1 conv, as-is for the stride-2 phase kernels (hcp_conv3x3_bf16 mode 1)
+__global__ void lora_pack_conv_kernel(const hcp_lora_conv_job* __restrict__ jobs, int njobs) {
+    pdl_trigger();
+    pdl_wait();
+    const int j = blockIdx.y;
+    if (j >= njobs) return;
+    const hcp_lora_conv_job jb = jobs[j];
+    const int64_t n = (int64_t)jb.rank * jb.cin * 9;
+    __nv_bfloat16* wt = (__nv_bfloat16*)jb.wt;
+    __nv_bfloat16* wd = (__nv_bfloat16*)jb.wd;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % 9);
+        const int ci = (int)((i / 9) % jb.cin);
+        const int rr = (int)(i / (9 * (int64_t)jb.cin));
+        const __nv_bfloat16 v = __float2bfloat16(jb.w_down[i]);
+        wt[((int64_t)(jb.c0 + rr) * 9 + tap) * jb.cin + ci] = v;
+        const int tap_d = jb.flip ? 8 - tap : tap;
+        wd[((int64_t)ci * 9 + tap_d) * jb.ld_r + jb.c0 + rr] = v;
     }
 }
 
@@ -381,6 +404,14 @@ extern "C" int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp
     dim3 grid(16, (unsigned)njobs);
     launch_k(lora_pack_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)st, jobs_device, (int)njobs);
     LAUNCH_CHECK("lora_pack launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_lora_pack_conv(const hcp_lora_conv_job* jobs_device, int64_t njobs, hcp_stream_t st) {
+    if (!jobs_device || njobs <= 0) return set_error(HCP_ERR_INVALID, "lora_pack_conv: jobs");
+    dim3 grid(16, (unsigned)njobs);
+    launch_k(lora_pack_conv_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)st, jobs_device, (int)njobs);
+    LAUNCH_CHECK("lora_pack_conv launch");
     return HCP_OK;
 }
 

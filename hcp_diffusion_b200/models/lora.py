@@ -32,10 +32,12 @@ class LoraPatchContainer(PatchPluginContainer):
     def forward(self, x, *args, **kwargs):
         """Stand-alone call of one patched layer (inside the UNet the parent block fuses several layers into one GEMM and
         does not come through here).  Extra positional arguments (diffusers' `scale`) are ignored like in the reference."""
-        from ..runtime import LinearGroup  # local import: runtime imports this module
+        from ..runtime import ConvGroup, LinearGroup  # local import: runtime imports this module
         grp = self.__dict__.get("_hcp_group")
         if grp is None:
-            grp = LinearGroup([self])
+            host = self._host
+            is3x3 = isinstance(host, nn.Conv2d) and host.kernel_size == (3, 3)
+            grp = ConvGroup(self) if is3x3 else LinearGroup([self])
             self.__dict__["_hcp_group"] = grp
         return grp.run_standalone(x)
 

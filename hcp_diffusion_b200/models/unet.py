@@ -57,6 +57,7 @@ class ResnetBlock2D(nn.Module):
         if in_channels != out_channels:
             self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1, stride=1, padding=0)
         self.in_channels, self.out_channels = in_channels, out_channels
+        self.in_split = None              # (C_h, C_skip) when the block is fed the concatenation of two tensors (up blocks)
         self.__dict__["_g"] = None
 
     def _groups(self):
@@ -69,6 +70,8 @@ class ResnetBlock2D(nn.Module):
         g.conv1.conv, g.conv2.conv = self.conv1, self.conv2
         if g.shortcut is not None:
             g.shortcut.children = [self.conv_shortcut]
+            if self.in_split is not None and g.shortcut._k_splits is None:
+                g.shortcut._k_splits = list(self.in_split)     # known at construction: the packs are built once, before the first call
         return g
 
     def run(self, xs: Sequence[torch.Tensor], geom, temb: torch.Tensor) -> torch.Tensor:
@@ -246,12 +249,15 @@ class Downsample2D(nn.Module):
         self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=1)
         self.__dict__["_g"] = None
 
-    def run(self, x, geom):
+    def _group(self) -> ConvGroup:
         if self.__dict__["_g"] is None:
             self.__dict__["_g"] = ConvGroup(self.conv)
         g = self.__dict__["_g"]
         g.conv = self.conv
-        return ops.conv3x3(g.prepare(), x, geom)
+        return g
+
+    def run(self, x, geom):
+        return ops.conv3x3(self._group().prepare(), x, geom)
 
 
 class Upsample2D(nn.Module):
@@ -260,14 +266,17 @@ class Upsample2D(nn.Module):
         self.conv = nn.Conv2d(channels, channels, 3, stride=1, padding=1)
         self.__dict__["_g"] = None
 
-    def run(self, x, geom):
+    def _group(self) -> ConvGroup:
         if self.__dict__["_g"] is None:
             self.__dict__["_g"] = ConvGroup(self.conv)
         g = self.__dict__["_g"]
         g.conv = self.conv
+        return g
+
+    def run(self, x, geom):
         B, H, W = geom
         up = ops.Upsample2xFn.apply(geom, x)
-        return ops.conv3x3(g.prepare(), up, (B, 2 * H, 2 * W))
+        return ops.conv3x3(self._group().prepare(), up, (B, 2 * H, 2 * W))
 
 
 class DownBlock(nn.Module):
@@ -296,7 +305,9 @@ class UpBlock(nn.Module):
         super().__init__()
         if has_attn:
             self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, ctx_dim, groups) for _ in in_chs])
-        self.resnets = nn.ModuleList([ResnetBlock2D(c, cout, temb, groups) for c in in_chs])
+        self.resnets = nn.ModuleList([ResnetBlock2D(a + b, cout, temb, groups) for a, b in in_chs])
+        for r, split in zip(self.resnets, in_chs):
+            r.in_split = tuple(split)
         if add_up:
             self.upsamplers = nn.ModuleList([Upsample2D(cout)])
         self.has_attn, self.gradient_checkpointing = has_attn, False
@@ -338,7 +349,7 @@ class UNet2DConditionModel(nn.Module):
             has_attn = up_block_types[i].startswith("CrossAttn")
             in_chs = []
             for _ in range(layers_per_block + 1):
-                in_chs.append(cprev + skip_ch.pop())
+                in_chs.append((cprev, skip_ch.pop()))
                 cprev = c
             self.up_blocks.append(UpBlock(in_chs, c, temb, has_attn, heads, cross_attention_dim, i < len(ch) - 1, g))
         self.conv_norm_out = nn.GroupNorm(g, ch[0], eps=1e-5)
@@ -378,6 +389,20 @@ class UNet2DConditionModel(nn.Module):
         for m in self.modules():
             if isinstance(m, (Attention, FeedForward, Transformer2DModel)):
                 out += m.linear_groups()
+            elif isinstance(m, ResnetBlock2D):
+                g = m._groups()
+                if g.shortcut is not None:
+                    out.append(g.shortcut)
+        return out
+
+    def conv_groups(self) -> List[ConvGroup]:
+        out = []
+        for m in self.modules():
+            if isinstance(m, ResnetBlock2D):
+                g = m._groups()
+                out += [g.conv1, g.conv2]
+            elif isinstance(m, (Downsample2D, Upsample2D)):
+                out.append(m._group())
         return out
 
     # ---- time embedding: three skinny-linear launches for the whole network --------------------------------------------
@@ -405,9 +430,9 @@ class UNet2DConditionModel(nn.Module):
                 offs.append((o, o + r.out_channels))
                 o += r.out_channels
             rt.offs = offs
-            rt.w_in = self.conv_in.weight.detach().float().contiguous()
+            rt.w_in = self.conv_in.weight.detach().float().permute(1, 2, 3, 0).contiguous()       # tap-major [Cin,3,3,Cout]
             rt.b_in = self.conv_in.bias.detach().float().contiguous()
-            rt.w_out = self.conv_out.weight.detach().float().contiguous()
+            rt.w_out = self.conv_out.weight.detach().float().permute(2, 3, 0, 1).contiguous()     # tap-major [3,3,Cout,Cin]
             rt.b_out = self.conv_out.bias.detach().float().contiguous()
             rt.jobs = _JobTable()
             self.__dict__["_rt"] = rt
@@ -430,8 +455,11 @@ class UNet2DConditionModel(nn.Module):
         # LoRA operands: every group is (re)built if stale, then ONE launch re-packs all low-rank factors from the fp32 params
         groups = self.linear_groups()
         for g in groups:
+            g.prepare(g._k_splits)
+        cgroups = self.conv_groups()
+        for g in cgroups:
             g.prepare()
-        pack_lora(groups, rt.jobs)
+        pack_lora(groups + cgroups, rt.jobs)
 
         # time embedding -> per-resnet bias rows [B, sum(C)] fp32
         t = torch.as_tensor(timestep, device=dev)

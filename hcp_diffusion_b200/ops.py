@@ -100,7 +100,8 @@ def gemm_raw(a_list: Sequence[Tuple[torch.Tensor, int, int]], b_list: Sequence[T
 
 
 def conv3x3_raw(x: torch.Tensor, w: torch.Tensor, B: int, Hin: int, Win: int, Cin: int, Cout: int, stride: int, mode: int,
-                out: torch.Tensor, bias=None, rowbias=None, residual=None, rowbias_ld: int = 0) -> None:
+                out: torch.Tensor, bias=None, rowbias=None, residual=None, rowbias_ld: int = 0, lora=None) -> None:
+    """`lora`: (T [M,R] bf16, Bl [Cout,R] bf16, r_used, R) -- the Conv2d-LoRA K-segment of a forward convolution."""
     a = ConvArgs()
     a.x, a.w = x.data_ptr(), w.data_ptr()
     a.B, a.Hin, a.Win, a.Cin, a.Cout = B, Hin, Win, Cin, Cout
@@ -108,9 +109,11 @@ def conv3x3_raw(x: torch.Tensor, w: torch.Tensor, B: int, Hin: int, Win: int, Ci
     a.bias, a.rowbias, a.residual = ptr(bias), ptr(rowbias), ptr(residual)
     a.rowbias_ld = rowbias_ld
     a.out = out.data_ptr()
+    if lora is not None:
+        a.lora_t, a.lora_b, a.lora_r, a.lora_ld = lora[0].data_ptr(), lora[1].data_ptr(), lora[2], lora[3]
     if mode == 0:
         Mo = B * (Hin // stride) * (Win // stride)
-        wsb = _lib.lib().hcp_splitk_workspace_bytes(Mo, Cout, 9 * Cin)
+        wsb = _lib.lib().hcp_splitk_workspace_bytes(Mo, Cout, 9 * Cin + (lora[3] if lora is not None else 0))
         if wsb:
             ws = torch.empty((wsb // 4,), dtype=torch.float32, device=out.device)
             a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
@@ -213,8 +216,21 @@ class LinearPack:
         return out
 
 
+class ConvLoraRef:
+    """One LoRA block on a 3x3 convolution (reference LoraLayer.Conv2dLayer, lora_layers_patch.py:64-100):
+    W_down fp32 [r, Cin, 3, 3], W_up fp32 [Cout, r, 1, 1], alpha."""
+    __slots__ = ("w_down", "w_up", "alpha", "rank", "c0")
+
+    def __init__(self, w_down, w_up, alpha):
+        self.w_down, self.w_up, self.alpha = w_down, w_up, float(alpha)
+        self.rank = w_down.shape[0]
+        self.c0 = 0
+
+
 class ConvPack:
-    """bf16 operands of one 3x3 convolution (weights [Cout,Cin,3,3] fp32 -> tap-major K-major matrices)."""
+    """bf16 operands of one 3x3 convolution (weights [Cout,Cin,3,3] fp32 -> tap-major K-major matrices), optionally with LoCon
+    blocks: y = conv(x, W) + T . (alpha W_up)^T with T = conv3x3(x, W_down) -- the reference's conv(x, W + W_up x W_down)
+    (lora_layers_patch.py:91-98) without materialising the [Cout,Cin,3,3] delta."""
 
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int):
         self.Cout, self.Cin = weight.shape[0], weight.shape[1]
@@ -226,6 +242,61 @@ class ConvPack:
         else:
             self.Wd = w.permute(1, 2, 3, 0).contiguous()                     # stride-2 dgrad arrangement (not flipped)
         self.bias = None if bias is None else bias.detach().float().contiguous()
+        self.lora: List[ConvLoraRef] = []
+        self.r_tot = self.R = 0
+        self.Wt = self.Wdl = self.Bl = self.BlT = None
+
+    def attach_lora(self, blocks: List[ConvLoraRef]) -> None:
+        self.lora = blocks
+        c = 0
+        for b in blocks:
+            if b.w_down.shape[1] != self.Cin or tuple(b.w_down.shape[2:]) != (3, 3) or b.w_up.shape[0] != self.Cout:
+                raise _lib.HcpError("Conv2d LoRA block does not match its 3x3 host convolution")
+            if b.rank > 64 or (c % 64) + b.rank > 64:
+                c = (c + 63) // 64 * 64
+            b.c0 = c
+            c += b.rank
+        self.r_tot, self.R = c, (c + 63) // 64 * 64
+        dev = self.W.device
+        z = lambda *shape: torch.zeros(shape, dtype=BF16, device=dev)   # noqa: E731
+        self.Wt = z(self.R, 3, 3, self.Cin)          # forward weights of T = conv3x3(x, W_down)
+        self.Wdl = z(self.Cin, 3, 3, self.R)         # dgrad arrangement of the same taps
+        self.Bl = z(self.Cout, self.R)
+        self.BlT = z(self.R, self.Cout)
+
+    def jobs(self) -> List[_lib.LoraJob]:
+        out = []
+        for b in self.lora:                          # up-projection only (in_dim = 0): alpha*W_up -> Bl / BlT
+            j = _lib.LoraJob()
+            j.w_down, j.w_up, j.alpha = b.w_up.data_ptr(), b.w_up.data_ptr(), b.alpha
+            j.rank, j.in_dim, j.out_dim = b.rank, 0, self.Cout
+            j.c0, j.o0, j.out_tot, j.ld_r = b.c0, 0, self.Cout, self.R
+            j.A, j.AT, j.Bl, j.BlT = self.Bl.data_ptr(), self.Bl.data_ptr(), self.Bl.data_ptr(), self.BlT.data_ptr()
+            out.append(j)
+        return out
+
+    def conv_jobs(self) -> List[_lib.LoraConvJob]:
+        out = []
+        for b in self.lora:
+            j = _lib.LoraConvJob()
+            j.w_down, j.rank, j.cin, j.c0, j.ld_r = b.w_down.data_ptr(), b.rank, self.Cin, b.c0, self.R
+            j.flip = 1 if self.stride == 1 else 0
+            j.wt, j.wd = self.Wt.data_ptr(), self.Wdl.data_ptr()
+            out.append(j)
+        return out
+
+    def slabs(self):
+        out = []
+        for q in range(self.R // 64):
+            lo, hi = 64 * q, 64 * q + 64
+            pieces = []
+            for b in self.lora:
+                a, e = max(lo, b.c0), min(hi, b.c0 + b.rank)
+                if a < e:
+                    pieces.append((b, a - b.c0, e - a, a - lo))
+            if pieces:
+                out.append((q, pieces))
+        return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -396,7 +467,7 @@ def fused_linear(pack: LinearPack, xs: Sequence[torch.Tensor], residual: Optiona
 class Conv3x3Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pack: ConvPack, geom: Tuple[int, int, int], rowbias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
-                x: torch.Tensor):
+                x: torch.Tensor, *lora_params):
         B, H, W = geom
         x = _chk(x, "conv input")
         s = pack.stride
@@ -408,9 +479,18 @@ class Conv3x3Fn(torch.autograd.Function):
             if rowbias.dtype != torch.float32 or rowbias.stride(-1) != 1:
                 raise _lib.HcpError("conv rowbias must be fp32 with unit inner stride")
             rb_ld = rowbias.stride(0)
-        conv3x3_raw(x, pack.W, B, H, W, pack.Cin, pack.Cout, s, 0, out, bias=pack.bias, rowbias=rowbias, residual=res, rowbias_ld=rb_ld)
+        T, lora = None, None
+        if pack.lora:
+            T = torch.empty((B, Ho * Wo, pack.R), dtype=BF16, device=x.device)
+            conv3x3_raw(x, pack.Wt, B, H, W, pack.Cin, pack.R, s, 0, T)                   # T = conv3x3(x, W_down)
+            lora = (T, pack.Bl, pack.r_tot, pack.R)
+        conv3x3_raw(x, pack.W, B, H, W, pack.Cin, pack.Cout, s, 0, out, bias=pack.bias, rowbias=rowbias, residual=res, rowbias_ld=rb_ld,
+                    lora=lora)
         ctx.pack, ctx.geom = pack, geom
         ctx.has_res = residual is not None
+        ctx.n_extra = len(lora_params)
+        if pack.lora:
+            ctx.save_for_backward(x, T)
         return out
 
     @staticmethod
@@ -418,19 +498,49 @@ class Conv3x3Fn(torch.autograd.Function):
         pack = ctx.pack
         B, H, W = ctx.geom
         dy = _chk(dy, "conv grad")
+        s = pack.stride
+        M = B * (H // s) * (W // s)
+        U = None
+        if pack.lora:
+            x, T = ctx.saved_tensors
+            R, N = pack.R, pack.Cout
+            U = torch.empty((M, R), dtype=BF16, device=dy.device)
+            gemm_raw([(dy, N, N)], [(pack.BlT, N, R, 0)], M, R, U, R)                       # U = dY . (alpha W_up)
+            for q, pieces in pack.slabs():
+                for p0 in range(0, len(pieces), 8):
+                    chunk = pieces[p0:p0 + 8]
+                    nb = len(chunk)
+                    up = (_lib.LoraGradBlock * nb)()
+                    down = (_lib.LoraGradBlock * nb)()
+                    for i, (b, j0, rows, cs) in enumerate(chunk):
+                        gu, gd = _acc_grad(b.w_up), _acc_grad(b.w_down)
+                        up[i].n_lo, up[i].n_hi, up[i].c0, up[i].rank = 0, N, cs, rows
+                        up[i].scale, up[i].transpose_out, up[i].dst, up[i].dst_ld = b.alpha, 1, gu.data_ptr() + 4 * j0, b.rank
+                        down[i].c0, down[i].rank, down[i].scale = cs, rows, 1.0
+                        down[i].dst = gd.data_ptr() + 4 * j0 * pack.Cin * 9
+                    # dW_up = alpha dY^T T ;  dW_down[., ., kh, kw] = U^T x_shifted(kh, kw)
+                    call("hcp_lora_grad", T.data_ptr() + 2 * 64 * q, R, dy.data_ptr(), N, M, 0, N, up, nb, stream_ptr())
+                    call("hcp_lora_grad_conv3x3", U.data_ptr() + 2 * 64 * q, R, x.data_ptr(), B, H, W, pack.Cin, s, down, nb, stream_ptr())
         dx = None
         if ctx.needs_input_grad[4]:
             dx = torch.empty((B, H * W, pack.Cin), dtype=BF16, device=dy.device)
-            if pack.stride == 1:
+            if s == 1:
                 conv3x3_raw(dy, pack.Wd, B, H, W, pack.Cout, pack.Cin, 1, 0, dx)
+                if U is not None:                                                           # + dgrad through W_down
+                    conv3x3_raw(U, pack.Wdl, B, H, W, pack.R, pack.Cin, 1, 0, dx, residual=dx)
             else:
                 conv3x3_raw(dy, pack.Wd, B, H // 2, W // 2, pack.Cout, pack.Cin, 2, 1, dx)
+                if U is not None:
+                    conv3x3_raw(U, pack.Wdl, B, H // 2, W // 2, pack.R, pack.Cin, 2, 1, dx, residual=dx)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None
-        return None, None, None, dres, dx
+        return (None, None, None, dres, dx, *([None] * ctx.n_extra))
 
 
 def conv3x3(pack: ConvPack, x: torch.Tensor, geom, rowbias=None, residual=None) -> torch.Tensor:
-    return Conv3x3Fn.apply(pack, geom, rowbias, residual, x)
+    extra = []
+    for b in pack.lora:          # autograd inputs so the node exists even when x carries no gradient
+        extra += [b.w_down, b.w_up]
+    return Conv3x3Fn.apply(pack, geom, rowbias, residual, x, *extra)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -672,7 +782,7 @@ class ConvOutFn(torch.autograd.Function):
     def forward(ctx, w: torch.Tensor, bias: Optional[torch.Tensor], geom, x):
         B, H, W = geom
         x = _chk(x, "conv_out input")
-        Cin, Cout = x.shape[-1], w.shape[0]
+        Cin, Cout = x.shape[-1], w.shape[2]            # w: tap-major [3,3,Cout,Cin]
         y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device)
         call("hcp_conv_out_f32", x.data_ptr(), w.data_ptr(), ptr(bias), B, H, W, Cin, Cout, y.data_ptr(), stream_ptr())
         ctx.w, ctx.geom, ctx.Cin = w, geom, Cin
@@ -683,7 +793,7 @@ class ConvOutFn(torch.autograd.Function):
         B, H, W = ctx.geom
         dy = dy.float().contiguous()
         dx = torch.empty((B, H * W, ctx.Cin), dtype=BF16, device=dy.device)
-        call("hcp_conv_out_dgrad_f32", dy.data_ptr(), ctx.w.data_ptr(), B, H, W, ctx.Cin, ctx.w.shape[0], dx.data_ptr(), stream_ptr())
+        call("hcp_conv_out_dgrad_f32", dy.data_ptr(), ctx.w.data_ptr(), B, H, W, ctx.Cin, ctx.w.shape[2], dx.data_ptr(), stream_ptr())
         return None, None, None, dx
 
 
@@ -691,7 +801,7 @@ def conv_in(x_nchw: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor])
     """fp32 NCHW latent -> bf16 NHWC [B, H*W, Cout] (no gradient: the latent is data, conv_in is frozen)."""
     x = x_nchw.float().contiguous()
     B, Cin, H, W = x.shape
-    Cout = w.shape[0]
+    Cout = w.shape[3]                                  # w: tap-major [Cin,3,3,Cout]
     y = torch.empty((B, H * W, Cout), dtype=BF16, device=x.device)
     call("hcp_conv_in_f32", x.data_ptr(), w.data_ptr(), ptr(bias), B, Cin, H, W, Cout, y.data_ptr(), stream_ptr())
     return y

@@ -15,7 +15,7 @@ from torch import nn
 
 from . import _lib, ops
 from .models.lora import DAPPPatchContainer, LoraBlock, LoraPatchContainer
-from .ops import BF16, ConvPack, LinearPack, LoraBlockRef
+from .ops import BF16, ConvLoraRef, ConvPack, LinearPack, LoraBlockRef
 
 
 def host_and_blocks(child: nn.Module) -> Tuple[nn.Module, List[LoraBlock]]:
@@ -114,33 +114,42 @@ class LinearGroup:
 class _JobTable:
     def __init__(self):
         self.key = None
-        self.dev = None
-        self.n = 0
+        self.dev = self.cdev = None
+        self.n = self.cn = 0
 
 
 _job_table = _JobTable()
 
 
-def pack_lora(groups: Sequence[LinearGroup], table: Optional[_JobTable] = None) -> None:
-    """One kernel launch that refreshes the packed low-rank operands of every LoRA-carrying group from the fp32 parameters."""
+def pack_lora(groups: Sequence, table: Optional[_JobTable] = None) -> None:
+    """One kernel launch that refreshes the packed low-rank operands of every LoRA-carrying group (LinearGroup / ConvGroup) from
+    the fp32 parameters, plus one for the 3x3 down-projections of Conv2d LoRA blocks."""
     table = table or _JobTable()
-    jobs = []
+    jobs, cjobs = [], []
     for g in groups:
         if g.pack is not None and g.pack.lora:
             jobs += g.pack.jobs()
+            if isinstance(g.pack, ConvPack):
+                cjobs += g.pack.conv_jobs()
     if not jobs:
         return
-    key = tuple((j.w_down, j.w_up, j.A, j.alpha) for j in jobs)
+    key = tuple((j.w_down, j.w_up, j.A, j.BlT, j.alpha) for j in jobs) + tuple((j.w_down, j.wt) for j in cjobs)
     if table.key != key:
         arr = (_lib.LoraJob * len(jobs))(*jobs)
-        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-        table.dev = host.cuda()
-        table.key, table.n = key, len(jobs)
+        table.dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).cuda()
+        table.cdev = None
+        if cjobs:
+            carr = (_lib.LoraConvJob * len(cjobs))(*cjobs)
+            table.cdev = torch.frombuffer(bytearray(bytes(carr)), dtype=torch.uint8).cuda()
+        table.key, table.n, table.cn = key, len(jobs), len(cjobs)
     _lib.call("hcp_lora_pack", table.dev.data_ptr(), table.n, _lib.stream_ptr())
+    if table.cdev is not None:
+        _lib.call("hcp_lora_pack_conv", table.cdev.data_ptr(), table.cn, _lib.stream_ptr())
 
 
 class ConvGroup:
-    """Packed operands of one 3x3 convolution layer (frozen base weights; LoRA on 3x3 convolutions is not on this path)."""
+    """Packed operands of one 3x3 convolution layer: a frozen nn.Conv2d, or a LoraPatchContainer around one (LoCon: LoraLayer
+    blocks with W_down [r,Cin,3,3] / W_up [Cout,r,1,1], reference lora_layers_patch.py:64-100)."""
 
     def __init__(self, conv: nn.Module):
         self.conv = conv
@@ -148,10 +157,13 @@ class ConvGroup:
         self._sig = None
 
     def prepare(self) -> ConvPack:
-        conv = self.conv
+        child = self.conv
+        if isinstance(child, DAPPPatchContainer):
+            raise NotImplementedError("DreamArtist++ (dapp) blocks on 3x3 convolutions are not supported on the B200 hot path")
+        conv, blocks = host_and_blocks(child)
         if not isinstance(conv, nn.Conv2d):
-            raise NotImplementedError(f"{type(conv).__name__} on a 3x3 convolution of the hot path is not supported (LoRA/locon on Conv2d pending)")
-        sig = (id(conv), conv.weight._version, conv.weight.data_ptr())
+            raise NotImplementedError(f"{type(conv).__name__} on a 3x3 convolution of the hot path is not supported")
+        sig = (id(child), id(conv), conv.weight._version, conv.weight.data_ptr(), tuple(id(b) for b in blocks))
         if self.pack is None or sig != self._sig:
             if conv.weight.requires_grad:
                 raise NotImplementedError("training base convolution weights needs the wgrad kernels, which are not built yet")
@@ -159,6 +171,21 @@ class ConvGroup:
                 raise _lib.HcpError("hcp_diffusion_b200 runs on CUDA only (there is no CPU path)")
             if conv.kernel_size != (3, 3) or conv.padding != (1, 1) or conv.stride[0] not in (1, 2):
                 raise NotImplementedError("only 3x3 / pad 1 / stride 1|2 convolutions are supported")
-            self.pack = ConvPack(conv.weight, conv.bias, conv.stride[0])
-            self._sig = sig
+            pack = ConvPack(conv.weight, conv.bias, conv.stride[0])
+            if blocks:
+                pack.attach_lora([ConvLoraRef(b.layer.W_down, b.layer.W_up, float(b.alpha)) for b in blocks])
+            self.pack, self._sig = pack, sig
         return self.pack
+
+    def run_standalone(self, x: torch.Tensor) -> torch.Tensor:
+        """LoraPatchContainer.forward on a 3x3 host: NCHW in / out like the reference layer."""
+        if not x.is_cuda:
+            raise _lib.HcpError("hcp_diffusion_b200 has no CPU path: LoRA layers run on a B200 only")
+        pack = self.prepare()
+        if pack.lora:
+            pack_lora([self])
+        B, C_, H, W = x.shape
+        t = x.permute(0, 2, 3, 1).reshape(B, H * W, C_).to(BF16).contiguous()
+        y = ops.conv3x3(pack, t, (B, H, W))
+        s = pack.stride
+        return y.view(B, H // s, W // s, -1).permute(0, 3, 1, 2).to(x.dtype)

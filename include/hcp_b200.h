@@ -104,6 +104,12 @@ typedef struct hcp_conv3x3_args {
     void* out;           /* bf16 [B,Hout,Wout,Cout] */
     float* workspace;    /* optional split-K scratch, hcp_splitk_workspace_bytes(B*Hout*Wout, Cout, 9*Cin) */
     size_t workspace_bytes;
+    /* Conv2d LoRA (LoCon, reference lora_layers_patch.py:64-100), mode 0 only: out += T . Bl^T as one more K-segment, where
+     * T = conv3x3(x, W_down) [B*Hout*Wout, lora_ld] was produced by a previous call and Bl = alpha*W_up [Cout, lora_ld]. */
+    const void* lora_t;  /* bf16 or NULL */
+    const void* lora_b;  /* bf16 */
+    int64_t lora_r;      /* rank columns in use (<= lora_ld) */
+    int64_t lora_ld;     /* row pitch of lora_t / lora_b: the 64-padded rank */
 } hcp_conv3x3_args;
 
 int hcp_conv3x3_bf16(const hcp_conv3x3_args* args, hcp_stream_t stream);
@@ -198,7 +204,9 @@ int hcp_add_bf16(const void* a, const void* b, int64_t n, void* out, hcp_stream_
 
 /* ------------------------------------------------------------------------------------------------
  * Module-boundary kernels: the UNet call takes NCHW fp32 latents and returns NCHW fp32 noise_pred
- * (reference hcpdiff/models/wrapper.py:29); inside everything is bf16 NHWC.
+ * (reference hcpdiff/models/wrapper.py:29); inside everything is bf16 NHWC.  Weights are fp32 and TAP-MAJOR so that a warp reads
+ * them contiguously: conv_in  w[Cin][3][3][Cout]  (= nn.Conv2d weight.permute(1,2,3,0));
+ *                    conv_out w[3][3][Cout][Cin]  (= weight.permute(2,3,0,1)), also for its dgrad.
  * ---------------------------------------------------------------------------------------------- */
 int hcp_conv_in_f32(const float* x_nchw, const float* w, const float* bias, int64_t B, int64_t Cin, int64_t H, int64_t W,
                     int64_t Cout, void* y_nhwc_bf16, hcp_stream_t stream);
@@ -235,6 +243,17 @@ typedef struct hcp_lora_job {
 } hcp_lora_job;
 
 int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp_stream_t stream);
+/* Conv2d LoRA down-projection W_down fp32 [rank, Cin, 3, 3] -> the two bf16 operands the 3x3 kernels take:
+ *   wt [R, 3, 3, Cin]  forward weights of T = conv3x3(x, W_down) (rows c0 .. c0+rank of the group's R-row matrix)
+ *   wd [Cin, 3, 3, R]  dgrad arrangement of the same taps (flipped for stride 1, as-is for the stride-2 phase kernels)
+ * (the up-projection [Cout, rank, 1, 1] goes through hcp_lora_pack with in_dim = 0). */
+typedef struct hcp_lora_conv_job {
+    const float* w_down;
+    int32_t rank, cin, c0, ld_r, flip, pad_;
+    void* wt;
+    void* wd;
+} hcp_lora_conv_job;
+int hcp_lora_pack_conv(const hcp_lora_conv_job* jobs_device, int64_t njobs, hcp_stream_t stream);
 /* Gradients of the LoRA factors on the tensor pipe: for every block b and every column n in [n_lo_b, n_hi_b) of X,
  *     D[n, j] = scale_b * sum_m X[m, n] * S[m, c0_b + j],   j < rank_b      (S bf16 [M,64] with row pitch lds >= 64: one 64-column
  *     slab of the group's T / U buffer -- wider groups call once per slab with S advanced by 64 columns; X bf16 [M,ldx])
@@ -250,6 +269,13 @@ typedef struct hcp_lora_grad_block {
 } hcp_lora_grad_block;
 int hcp_lora_grad(const void* S, int64_t lds, const void* X, int64_t ldx, int64_t M, int64_t n_begin, int64_t n_end,
                   const hcp_lora_grad_block* blocks, int32_t nblocks, hcp_stream_t stream);     /* nblocks <= 8 */
+/* dW_down of a Conv2d LoRA: for every tap (kh,kw) and block b,
+ *     dst_b[(j*Cin + n)*9 + kh*3 + kw] += sum_m S[m, c0_b + j] * x[pixel(m) shifted by the tap, n]
+ * S = U = dY . (alpha W_up) bf16 [B*Hout*Wout, lds]; x bf16 NHWC [B,Hin,Win,Cin]; zero padding and stride as in the forward conv.
+ * Nine launches of the gradient kernel whose X operand is the shifted 4-D / 5-D TMA box of the convolution.  Block fields used:
+ * c0, rank, scale, dst (fp32 [rank, Cin, 3, 3]); n_lo/n_hi/transpose_out/dst_ld are ignored. */
+int hcp_lora_grad_conv3x3(const void* S, int64_t lds, const void* x, int64_t B, int64_t Hin, int64_t Win, int64_t Cin, int32_t stride,
+                          const hcp_lora_grad_block* blocks, int32_t nblocks, hcp_stream_t stream);
 /* Both gradients of one LoRA group in a single launch: dW_down from (U [M,64], x [M,K]) and dW_up from (T [M,64], dY [M,N]). */
 int hcp_lora_grad_pair(const void* U, const void* x, int64_t ldx, int64_t K, const hcp_lora_grad_block* down,
                        const void* T, const void* dy, int64_t lddy, int64_t N, const hcp_lora_grad_block* up,

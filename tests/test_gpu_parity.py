@@ -418,3 +418,148 @@ def test_reference_dapp_and_conv1x1_lora_golden_through_product_containers(golde
     for name, p in model.named_parameters():
         if "lora_block" in name:
             assert rel_l2(p.grad, fx["grads"][name]) < 3e-2, name
+
+
+def test_tiny_unet_dapp_and_conv1x1_lora_forward_backward():
+    """BASELINE config 5 topology at test size: DreamArtist++ pairs (type dapp, branch p rank 4 / branch n rank 2) on every
+    Linear of the cross-attentions and feed-forwards, UNet batch = [negative half | positive half] (reference
+    cfgs/train/examples/DreamArtist++.yaml, lora_layers_patch.py:102-133), plus a plain rank-4 LoRA on the 1x1 proj_in / proj_out
+    convolutions (LoCon on 1x1 hosts).  noise_pred and every LoRA gradient against the fp32 oracle, whose DAPP / Conv2d semantics
+    are pinned to the reference.  (The `layers` patterns name the PARENT modules: like in the reference, two config items that
+    both match a leaf Linear by name re-wrap the stale leaf and orphan the first item's container -- cfg_net_tools.py:108-121.)"""
+    spec = U.TINY
+    sd = U.init_params(spec)
+    unet = UNet2DConditionModel(sample_size=spec.sample_size, block_out_channels=spec.block_out_channels,
+                                attention_head_dim=spec.num_heads, cross_attention_dim=spec.cross_attention_dim)
+    unet.load_state_dict(sd)
+    unet = unet.to(DEV).requires_grad_(False).eval()
+    pat = r".*\.attn2$|.*\.ff$"
+    cfg = [{"type": "dapp", "branch": "p", "rank": 4, "alpha": 1.0, "dropout": 0.0, "layers": ["re:" + pat]},
+           {"type": "dapp", "branch": "n", "rank": 2, "alpha": 1.0, "dropout": 0.0, "layers": ["re:" + pat]},
+           {"rank": 4, "alpha": 2.0, "dropout": 0.0, "layers": [r"re:.*\.proj_in$", r"re:.*\.proj_out$"]}]
+    _, group = make_hcpdiff(unet, None, cfg)
+    lora = {}
+    for idx, (branch, rank, alpha, patt, conv) in enumerate((("p", 4, 1.0, pat, False), ("n", 2, 1.0, pat, False),
+                                                             (None, 4, 2.0, r".*\.proj_in$|.*\.proj_out$", True))):
+        part = U.init_lora(spec, rank=rank, alpha=alpha, seed=11 + idx, up_std=0.05, pattern=patt, include_conv=conv, branch=branch)
+        for layer, entries in part.items():
+            lora.setdefault(layer, []).extend(entries)
+    # copy the oracle factors into the product blocks: lora_block_<id> of a layer is the block of cfg item <id>
+    named = dict(unet.named_modules())
+    n_blocks = 0
+    with torch.no_grad():
+        for layer, entries in lora.items():
+            cont = named[layer]
+            for e in entries:
+                bid = {"p": 0, "n": 1, None: 2}[e.branch]
+                blk = getattr(cont, f"lora_block_{bid}")
+                assert blk.layer.W_down.shape == e.W_down.shape and abs(float(blk.alpha) - e.alpha) < 1e-7, layer
+                blk.layer.W_down.copy_(e.W_down)
+                blk.layer.W_up.copy_(e.W_up)
+                n_blocks += 1
+    assert n_blocks == sum(1 for m in unet.modules() if isinstance(m, LoraLayer))
+    lat, noise, t, ehs = U.synthetic_batch(4, spec)
+    loss_ref, pred_ref, grads_ref = U.lora_step_loss_and_grads(sd, lora, lat, noise, t, ehs, spec)
+    x_t = U.add_noise(lat, noise, t, U.ddpm_alphas_cumprod())
+    pred = unet(x_t.to(DEV), t.to(DEV), ehs.to(DEV)).sample
+    assert rel_l2(pred, pred_ref) < 2e-2
+    # the two halves must really have used different adapters: swapping the halves of the batch changes the result
+    loss = F.mse_loss(pred, noise.to(DEV), reduction="none").mean()
+    loss.backward()
+    num = den = 0.0
+    for layer, entries in lora.items():
+        cont = named[layer]
+        for e, (gd, gu) in zip(entries, grads_ref[layer]):
+            blk = getattr(cont, f"lora_block_{ {'p': 0, 'n': 1, None: 2}[e.branch] }")
+            for got, ref in ((blk.layer.W_down.grad, gd), (blk.layer.W_up.grad, gu)):
+                num += float((got.cpu().double() - ref.double()).pow(2).sum())
+                den += float(ref.double().pow(2).sum())
+    assert math.sqrt(num / den) < 5e-2
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,stride,ranks", [(2, 16, 64, 128, 1, (4,)), (2, 16, 128, 64, 2, (4, 8)), (1, 32, 64, 64, 1, (8,))])
+def test_conv3x3_lora_fwd_bwd(B, H, Cin, Cout, stride, ranks):
+    """Conv2d LoRA (LoCon) on a 3x3 convolution: y = conv(x, W + sum_b alpha_b W_up_b x W_down_b) (reference
+    lora_layers_patch.py:91-98) through the factored kernels vs the materialised fp32 formula; x, W_down and W_up gradients."""
+    from hcp_diffusion_b200.ops import ConvLoraRef
+    x = rnd(B, H * H, Cin, seed=1).to(BF).requires_grad_(True)
+    w = rnd(Cout, Cin, 3, 3, scale=1 / math.sqrt(9 * Cin), seed=2)
+    b = rnd(Cout, scale=0.1, seed=3)
+    pack = ConvPack(w, b, stride)
+    blocks = []
+    for i, r in enumerate(ranks):
+        down = rnd(r, Cin, 3, 3, scale=1 / math.sqrt(9 * Cin), seed=10 + i).requires_grad_(True)
+        up = rnd(Cout, r, 1, 1, scale=0.3, seed=20 + i).requires_grad_(True)
+        blocks.append(ConvLoraRef(down, up, 0.25))
+    pack.attach_lora(blocks)
+
+    class G:
+        pass
+    g = G()
+    g.pack = pack
+    pack_lora([g])
+    y = ops.conv3x3(pack, x, (B, H, H))
+    xr = x.detach().float().view(B, H, H, Cin).permute(0, 3, 1, 2).requires_grad_(True)
+    refs = [(blk.w_down.detach().clone().requires_grad_(True), blk.w_up.detach().clone().requires_grad_(True)) for blk in blocks]
+    wp = bf(w)
+    for d, u in refs:
+        wp = wp + 0.25 * torch.einsum("or,rikl->oikl", u[:, :, 0, 0], d)
+    yr = F.conv2d(xr, wp, b, stride=stride, padding=1)
+    Ho = H // stride
+    yr_nhwc = yr.permute(0, 2, 3, 1).reshape(B, Ho * Ho, Cout)
+    assert rel_l2(y, yr_nhwc) < 1e-2
+    dy = rnd(B, Ho * Ho, Cout, seed=6).to(BF)
+    y.backward(dy)
+    yr_nhwc.backward(dy.float())
+    assert rel_l2(x.grad, xr.grad.permute(0, 2, 3, 1).reshape(B, H * H, Cin)) < 1e-2
+    for blk, (d, u) in zip(blocks, refs):
+        assert rel_l2(blk.w_down.grad, d.grad) < 2e-2
+        assert rel_l2(blk.w_up.grad, u.grad) < 2e-2
+
+
+def test_conv3x3_lora_container_standalone():
+    """LoraLayer.wrap_layer on a 3x3 nn.Conv2d and a direct call of the container (NCHW in / out, like the reference layer)."""
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(64, 64, 3, padding=1).to(DEV).requires_grad_(False)
+    holder = torch.nn.Module()
+    holder.conv = conv
+    blk = LoraLayer.wrap_layer(0, conv, rank=4, dropout=0.0, alpha=2.0, parent_block=holder, host_name="conv")
+    with torch.no_grad():
+        blk.layer.W_up.normal_(0, 0.2)
+    x = rnd(2, 64, 16, 16, seed=3)
+    y = holder.conv(x)
+    wp = bf(conv.weight) + float(blk.alpha) * torch.einsum("or,rikl->oikl", blk.layer.W_up[:, :, 0, 0], blk.layer.W_down)
+    yr = F.conv2d(bf(x), wp.detach(), conv.bias, padding=1)
+    assert y.shape == yr.shape and rel_l2(y, yr) < 1e-2
+
+
+def test_tiny_unet_locon_forward_backward():
+    """BASELINE config 4's adapter placement at test size: LoRA rank 4 on every 3x3 / 1x1 convolution of the resnets and the
+    down/up-samplers (reference cfgs/train/examples/locon.yaml pattern) -- noise_pred and all LoRA gradients vs the fp32 oracle."""
+    spec = U.TINY
+    sd = U.init_params(spec)
+    unet = UNet2DConditionModel(sample_size=spec.sample_size, block_out_channels=spec.block_out_channels,
+                                attention_head_dim=spec.num_heads, cross_attention_dim=spec.cross_attention_dim)
+    unet.load_state_dict(sd)
+    unet = unet.to(DEV).requires_grad_(False).eval()
+    pat = r".*\.resnets\.\d+\.conv[12]$|.*\.conv_shortcut$|.*samplers\.0\.conv$"
+    _, group = make_hcpdiff(unet, None, [{"rank": 4, "alpha": 1.0, "dropout": 0.0, "layers": ["re:" + pat]}])
+    lora = U.init_lora(spec, rank=4, alpha=1.0, seed=5, up_std=0.05, pattern=pat, include_conv=True)
+    assert set(lora) == set(group.plugin_dict) and len(lora) > 40
+    with torch.no_grad():
+        for layer, entries in lora.items():
+            group[layer].layer.W_down.copy_(entries[0].W_down)
+            group[layer].layer.W_up.copy_(entries[0].W_up)
+    lat, noise, t, ehs = U.synthetic_batch(2, spec)
+    loss_ref, pred_ref, grads_ref = U.lora_step_loss_and_grads(sd, lora, lat, noise, t, ehs, spec)
+    x_t = U.add_noise(lat, noise, t, U.ddpm_alphas_cumprod())
+    pred = unet(x_t.to(DEV), t.to(DEV), ehs.to(DEV)).sample
+    assert rel_l2(pred, pred_ref) < 2e-2
+    F.mse_loss(pred, noise.to(DEV), reduction="none").mean().backward()
+    num = den = 0.0
+    for layer, blocks in grads_ref.items():
+        blk = group[layer]
+        for got, ref in ((blk.layer.W_down.grad, blocks[0][0]), (blk.layer.W_up.grad, blocks[0][1])):
+            num += float((got.cpu().double() - ref.double()).pow(2).sum())
+            den += float(ref.double().pow(2).sum())
+    assert math.sqrt(num / den) < 5e-2
