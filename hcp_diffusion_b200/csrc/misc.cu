@@ -223,6 +223,21 @@ __global__ void lora_pack_kernel(const hcp_lora_job* __restrict__ jobs, int njob
     }
 }
 
+// out[m / per_row, (m % per_row) * dim + j] = cos(x[m] f_j) (j < dim/2) | sin(x[m] f_{j-dim/2}),  f_j = 10000^(-j/(dim/2)):
+// diffusers Timesteps(flip_sin_to_cos=True, downscale_freq_shift=0) for the SDXL `time_ids` (add_time_proj), written straight
+// into the column slot of the add_embedding input
+__global__ void sinusoid_kernel(const float* __restrict__ x, int64_t M, int dim, int per_row, float* __restrict__ out, int64_t ld_out) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= M * dim) return;
+    const int64_t m = i / dim;
+    const int j = (int)(i % dim), half = dim / 2;
+    const int jj = j < half ? j : j - half;
+    const float a = x[m] * expf(-9.210340371976184f * (float)jj / (float)half);
+    out[(m / per_row) * ld_out + (m % per_row) * dim + j] = j < half ? cosf(a) : sinf(a);
+}
+
 // Conv2d LoRA down-projection: fp32 [rank, Cin, 3, 3] -> bf16 wt [R,3,3,Cin] (rows c0..) and wd [Cin,3,3,R] (columns c0..);
 // wd is the dgrad arrangement: taps flipped for the stride-1 conv, as-is for the stride-2 phase kernels (hcp_conv3x3_bf16 mode 1)
 __global__ void lora_pack_conv_kernel(const hcp_lora_conv_job* __restrict__ jobs, int njobs) {
@@ -404,6 +419,14 @@ extern "C" int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp
     dim3 grid(16, (unsigned)njobs);
     launch_k(lora_pack_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)st, jobs_device, (int)njobs);
     LAUNCH_CHECK("lora_pack launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_sinusoid_f32(const float* x, int64_t M, int64_t dim, int64_t per_row, float* out, int64_t ld_out, hcp_stream_t st) {
+    if (!x || !out || M <= 0 || dim <= 0 || (dim & 1) || per_row <= 0) return set_error(HCP_ERR_INVALID, "sinusoid: arguments");
+    const int64_t n = M * dim;
+    launch_k(sinusoid_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)st, x, M, (int)dim, (int)per_row, out, ld_out);
+    LAUNCH_CHECK("sinusoid launch");
     return HCP_OK;
 }
 

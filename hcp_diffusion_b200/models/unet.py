@@ -212,12 +212,16 @@ class BasicTransformerBlock(nn.Module):
 
 
 class Transformer2DModel(nn.Module):
-    def __init__(self, channels: int, heads: int, cross_attention_dim: int, groups: int = 32, eps: float = 1e-6):
+    """GroupNorm -> proj_in -> `depth` BasicTransformerBlocks -> proj_out (+ residual).  proj_in / proj_out are 1x1 Conv2d (SD1.x)
+    or nn.Linear (`use_linear_projection`, SDXL); on NHWC token matrices both are the same GEMM."""
+
+    def __init__(self, channels: int, heads: int, cross_attention_dim: int, groups: int = 32, eps: float = 1e-6, depth: int = 1,
+                 use_linear_projection: bool = False):
         super().__init__()
         self.norm = nn.GroupNorm(groups, channels, eps=eps, affine=True)
-        self.proj_in = nn.Conv2d(channels, channels, 1)
-        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(channels, heads, cross_attention_dim)])
-        self.proj_out = nn.Conv2d(channels, channels, 1)
+        self.proj_in = nn.Linear(channels, channels) if use_linear_projection else nn.Conv2d(channels, channels, 1)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(channels, heads, cross_attention_dim) for _ in range(depth)])
+        self.proj_out = nn.Linear(channels, channels) if use_linear_projection else nn.Conv2d(channels, channels, 1)
         self.__dict__["_g"] = None
 
     def _groups(self):
@@ -282,10 +286,11 @@ class Upsample2D(nn.Module):
 class DownBlock(nn.Module):
     """CrossAttnDownBlock2D / DownBlock2D (has_attn False): resnets [+ attentions] [+ downsamplers]."""
 
-    def __init__(self, cin, cout, temb, n_layers, has_attn, heads, ctx_dim, add_down, groups):
+    def __init__(self, cin, cout, temb, n_layers, has_attn, heads, ctx_dim, add_down, groups, depth=1, linear_proj=False):
         super().__init__()
         if has_attn:
-            self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, ctx_dim, groups) for _ in range(n_layers)])
+            self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, ctx_dim, groups, depth=depth, use_linear_projection=linear_proj)
+                                             for _ in range(n_layers)])
         self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb, groups) for i in range(n_layers)])
         if add_down:
             self.downsamplers = nn.ModuleList([Downsample2D(cout)])
@@ -293,18 +298,19 @@ class DownBlock(nn.Module):
 
 
 class MidBlock(nn.Module):
-    def __init__(self, ch, temb, heads, ctx_dim, groups):
+    def __init__(self, ch, temb, heads, ctx_dim, groups, depth=1, linear_proj=False):
         super().__init__()
-        self.attentions = nn.ModuleList([Transformer2DModel(ch, heads, ctx_dim, groups)])
+        self.attentions = nn.ModuleList([Transformer2DModel(ch, heads, ctx_dim, groups, depth=depth, use_linear_projection=linear_proj)])
         self.resnets = nn.ModuleList([ResnetBlock2D(ch, ch, temb, groups), ResnetBlock2D(ch, ch, temb, groups)])
         self.gradient_checkpointing = False
 
 
 class UpBlock(nn.Module):
-    def __init__(self, in_chs: Sequence[int], cout, temb, has_attn, heads, ctx_dim, add_up, groups):
+    def __init__(self, in_chs: Sequence[Tuple[int, int]], cout, temb, has_attn, heads, ctx_dim, add_up, groups, depth=1, linear_proj=False):
         super().__init__()
         if has_attn:
-            self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, ctx_dim, groups) for _ in in_chs])
+            self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, ctx_dim, groups, depth=depth, use_linear_projection=linear_proj)
+                                             for _ in in_chs])
         self.resnets = nn.ModuleList([ResnetBlock2D(a + b, cout, temb, groups) for a, b in in_chs])
         for r, split in zip(self.resnets, in_chs):
             r.in_split = tuple(split)
@@ -316,32 +322,54 @@ class UpBlock(nn.Module):
 class UNet2DConditionModel(nn.Module):
     def __init__(self, sample_size: int = 64, in_channels: int = 4, out_channels: int = 4,
                  block_out_channels: Sequence[int] = (320, 640, 1280, 1280), layers_per_block: int = 2,
-                 attention_head_dim: int = 8, cross_attention_dim: int = 768, norm_num_groups: int = 32,
+                 attention_head_dim=8, cross_attention_dim: int = 768, norm_num_groups: int = 32,
                  down_block_types: Sequence[str] = ("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
                  up_block_types: Sequence[str] = ("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D"),
+                 transformer_layers_per_block=1, use_linear_projection: bool = False, addition_embed_type: Optional[str] = None,
+                 addition_time_embed_dim: Optional[int] = None, projection_class_embeddings_input_dim: Optional[int] = None,
                  **unused):
+        """Constructor keys of the diffusers config.  Defaults = SD1.x (reference cfgs/unet_struct.txt); the SDXL-base config
+        (3 levels, `attention_head_dim` (5, 10, 20) = heads per level, `transformer_layers_per_block` (1, 2, 10),
+        `use_linear_projection`, `addition_embed_type='text_time'`, 2048-wide context) builds the SDXL UNet the reference reaches
+        through hcpdiff/models/wrapper.py:57-75."""
         super().__init__()
         ch = tuple(block_out_channels)
-        heads = attention_head_dim          # SD1.x quirk: `attention_head_dim` is the number of heads
+        nlev = len(ch)
+        per_level = lambda v: tuple(v) if isinstance(v, (list, tuple)) else (v,) * nlev   # noqa: E731
+        heads = per_level(attention_head_dim)       # SD quirk: `attention_head_dim` is the number of heads
+        depth = per_level(transformer_layers_per_block)
+        if len(down_block_types) != nlev or len(up_block_types) != nlev:
+            raise ValueError("down_block_types / up_block_types must have one entry per level")
+        if addition_embed_type not in (None, "text_time"):
+            raise NotImplementedError(f"addition_embed_type={addition_embed_type!r} is not supported")
         temb = ch[0] * 4
         self.config = SimpleNamespace(sample_size=sample_size, in_channels=in_channels, out_channels=out_channels,
                                       block_out_channels=ch, layers_per_block=layers_per_block, attention_head_dim=attention_head_dim,
                                       cross_attention_dim=cross_attention_dim, norm_num_groups=norm_num_groups,
-                                      down_block_types=tuple(down_block_types), up_block_types=tuple(up_block_types))
+                                      down_block_types=tuple(down_block_types), up_block_types=tuple(up_block_types),
+                                      transformer_layers_per_block=transformer_layers_per_block,
+                                      use_linear_projection=use_linear_projection, addition_embed_type=addition_embed_type,
+                                      addition_time_embed_dim=addition_time_embed_dim,
+                                      projection_class_embeddings_input_dim=projection_class_embeddings_input_dim)
         self.conv_in = nn.Conv2d(in_channels, ch[0], 3, padding=1)
         self.time_proj = Timesteps(ch[0])
         self.time_embedding = TimestepEmbedding(ch[0], temb)
+        if addition_embed_type == "text_time":
+            self.add_time_proj = Timesteps(addition_time_embed_dim)
+            self.add_embedding = TimestepEmbedding(projection_class_embeddings_input_dim, temb)
         g = norm_num_groups
+        lin = use_linear_projection
         self.down_blocks = nn.ModuleList()
         skip_ch = [ch[0]]
         cprev = ch[0]
         for i, c in enumerate(ch):
             has_attn = down_block_types[i].startswith("CrossAttn")
-            last = i == len(ch) - 1
-            self.down_blocks.append(DownBlock(cprev, c, temb, layers_per_block, has_attn, heads, cross_attention_dim, not last, g))
+            last = i == nlev - 1
+            self.down_blocks.append(DownBlock(cprev, c, temb, layers_per_block, has_attn, heads[i], cross_attention_dim, not last, g,
+                                              depth=depth[i], linear_proj=lin))
             skip_ch += [c] * layers_per_block + ([] if last else [c])
             cprev = c
-        self.mid_block = MidBlock(ch[-1], temb, heads, cross_attention_dim, g)
+        self.mid_block = MidBlock(ch[-1], temb, heads[-1], cross_attention_dim, g, depth=depth[-1], linear_proj=lin)
         self.up_blocks = nn.ModuleList()
         rev = list(reversed(ch))
         cprev = ch[-1]
@@ -351,7 +379,8 @@ class UNet2DConditionModel(nn.Module):
             for _ in range(layers_per_block + 1):
                 in_chs.append((cprev, skip_ch.pop()))
                 cprev = c
-            self.up_blocks.append(UpBlock(in_chs, c, temb, has_attn, heads, cross_attention_dim, i < len(ch) - 1, g))
+            self.up_blocks.append(UpBlock(in_chs, c, temb, has_attn, heads[nlev - 1 - i], cross_attention_dim, i < nlev - 1, g,
+                                          depth=depth[nlev - 1 - i], linear_proj=lin))
         self.conv_norm_out = nn.GroupNorm(g, ch[0], eps=1e-5)
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(ch[0], out_channels, 3, padding=1)
@@ -423,6 +452,18 @@ class UNet2DConditionModel(nn.Module):
             rt.b1 = te.linear_1.bias.detach().float().contiguous()
             rt.w2 = te.linear_2.weight.detach().to(torch.bfloat16).contiguous()
             rt.b2 = te.linear_2.bias.detach().float().contiguous()
+            rt.add = None
+            if hasattr(self, "add_embedding"):
+                # emb = time_embedding(t) + add_embedding(cat[text_embeds, sinusoid(time_ids)]): the two second linears are one
+                # skinny GEMM over the concatenated hidden vectors [e1 | a1] with W = [W2 | Wa2], b = b2 + ba2
+                ae = self.add_embedding
+                for p in (ae.linear_1, ae.linear_2):
+                    if not isinstance(p, nn.Linear) or p.weight.requires_grad:
+                        raise NotImplementedError("plugins / training on the additional-embedding layers are not supported on the B200 hot path")
+                rt.add = SimpleNamespace(
+                    w1=ae.linear_1.weight.detach().to(torch.bfloat16).contiguous(), b1=ae.linear_1.bias.detach().float().contiguous(),
+                    w2cat=torch.cat([te.linear_2.weight.detach(), ae.linear_2.weight.detach()], 1).to(torch.bfloat16).contiguous(),
+                    b2sum=(te.linear_2.bias.detach() + ae.linear_2.bias.detach()).float().contiguous())
             rt.wp = torch.cat([r.time_emb_proj.weight.detach() for r in resnets], 0).to(torch.bfloat16).contiguous()
             rt.bp = torch.cat([r.time_emb_proj.bias.detach() for r in resnets], 0).float().contiguous()
             offs, o = [], 0
@@ -442,9 +483,16 @@ class UNet2DConditionModel(nn.Module):
                 encoder_attention_mask: Optional[torch.Tensor] = None, return_dict: bool = True, **kwargs):
         if not sample.is_cuda:
             raise _lib.HcpError("hcp_diffusion_b200.UNet2DConditionModel runs on a CUDA (sm_100) device only; there is no CPU fallback")
-        for key in ("added_cond_kwargs", "class_labels", "down_block_additional_residuals", "mid_block_additional_residual"):
+        for key in ("class_labels", "down_block_additional_residuals", "mid_block_additional_residual"):
             if kwargs.get(key) is not None:
-                raise NotImplementedError(f"`{key}` is not supported by the SD1.x hot path")
+                raise NotImplementedError(f"`{key}` is not supported by the hot path")
+        added = kwargs.get("added_cond_kwargs")
+        if hasattr(self, "add_embedding"):
+            if not added or "text_embeds" not in added or "time_ids" not in added:
+                raise ValueError("this UNet has addition_embed_type='text_time': pass added_cond_kwargs={'text_embeds', 'time_ids'} "
+                                 "(reference hcpdiff/models/wrapper.py:66)")
+        elif added:
+            raise NotImplementedError("`added_cond_kwargs` given to a UNet without an additional embedding")
         B, _, H, W = sample.shape
         nlev = len(self.config.block_out_channels)
         if H % (1 << (nlev - 1)) or W % (1 << (nlev - 1)):
@@ -467,7 +515,20 @@ class UNet2DConditionModel(nn.Module):
             t = t[None]
         t = t.expand(B).to(torch.float32).contiguous()
         e1 = ops.skinny_linear(t, rt.w1, rt.b1, 2, True)                 # silu(linear_1(sinusoid(t)))
-        emb = ops.skinny_linear(e1, rt.w2, rt.b2, 0, True)               # silu(linear_2(.)): every consumer applies SiLU first
+        if rt.add is None:
+            emb = ops.skinny_linear(e1, rt.w2, rt.b2, 0, True)           # silu(linear_2(.)): every consumer applies SiLU first
+        else:
+            te_, ids = added["text_embeds"], added["time_ids"]
+            cfg = self.config
+            P_, D_ = cfg.projection_class_embeddings_input_dim, cfg.addition_time_embed_dim
+            n_ids = ids.shape[-1]
+            if te_.shape[-1] + n_ids * D_ != P_:
+                raise ValueError(f"text_embeds ({te_.shape[-1]}) + time_ids ({n_ids} x {D_}) do not add up to {P_}")
+            addin = torch.empty((B, P_), dtype=torch.float32, device=dev)
+            addin[:, :te_.shape[-1]].copy_(te_)                           # boundary copy; the sinusoids are written next to it
+            ops.sinusoid(ids.to(dev, torch.float32).reshape(-1).contiguous(), D_, n_ids, addin, te_.shape[-1])
+            a1 = ops.skinny_linear(addin, rt.add.w1, rt.add.b1, 0, True)  # silu(add_embedding.linear_1(.))
+            emb = ops.skinny_linear(torch.cat([e1, a1], 1), rt.add.w2cat, rt.add.b2sum, 0, True)   # silu(linear_2(e1) + add.linear_2(a1))
         temb_all = ops.skinny_linear(emb, rt.wp, rt.bp, 0, False)        # all 22 time_emb_proj layers at once
         tembs = iter([temb_all[:, a:b] for a, b in rt.offs])
 

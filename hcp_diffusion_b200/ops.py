@@ -816,6 +816,11 @@ def skinny_linear(x: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[torch.Te
     return y
 
 
+def sinusoid(x: torch.Tensor, dim: int, per_row: int, out: torch.Tensor, col0: int) -> None:
+    """out[m // per_row, col0 + (m % per_row) * dim + j] = sinusoidal embedding (cos | sin) of x[m]; out fp32 2-D, x fp32 [M]."""
+    call("hcp_sinusoid_f32", x.data_ptr(), x.numel(), dim, per_row, out.data_ptr() + 4 * col0, out.stride(0), stream_ptr())
+
+
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     x = x.float().contiguous()
     y = torch.empty(x.shape, dtype=BF16, device=x.device)

@@ -208,6 +208,10 @@ int hcp_add_bf16(const void* a, const void* b, int64_t n, void* out, hcp_stream_
  * them contiguously: conv_in  w[Cin][3][3][Cout]  (= nn.Conv2d weight.permute(1,2,3,0));
  *                    conv_out w[3][3][Cout][Cin]  (= weight.permute(2,3,0,1)), also for its dgrad.
  * ---------------------------------------------------------------------------------------------- */
+/* Sinusoidal embedding of M scalars (diffusers Timesteps, flip_sin_to_cos, shift 0): element m lands in row m / per_row at
+ * column (m % per_row) * dim of `out` (row pitch ld_out floats) -- the SDXL time_ids slot of the add_embedding input
+ * (diffusers add_time_proj; reference hcpdiff/models/wrapper.py:66 supplies the ids as `crop_info`). */
+int hcp_sinusoid_f32(const float* x, int64_t M, int64_t dim, int64_t per_row, float* out, int64_t ld_out, hcp_stream_t stream);
 int hcp_conv_in_f32(const float* x_nchw, const float* w, const float* bias, int64_t B, int64_t Cin, int64_t H, int64_t W,
                     int64_t Cout, void* y_nhwc_bf16, hcp_stream_t stream);
 int hcp_conv_out_f32(const void* x_nhwc_bf16, const float* w, const float* bias, int64_t B, int64_t H, int64_t W, int64_t Cin,

@@ -29,7 +29,7 @@ from __future__ import annotations
 import math
 import re
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple, Union
 
 import torch
 import torch.nn.functional as F
@@ -39,12 +39,14 @@ Tensor = torch.Tensor
 
 @dataclass(frozen=True)
 class UNetSpec:
-    """Architecture hyper-parameters (defaults = SD1.5, reference cfgs/unet_struct.txt)."""
+    """Architecture hyper-parameters (defaults = SD1.5, reference cfgs/unet_struct.txt).  The SDXL fields follow the diffusers
+    config of stable-diffusion-xl-base-1.0 (the reference only ever sees it through `UNet2DConditionModel.from_pretrained` and
+    the `added_cond_kwargs` of hcpdiff/models/wrapper.py:57-75): restated from knowledge, parity unpinned like the SD1.5 flow."""
     in_channels: int = 4
     out_channels: int = 4
     block_out_channels: Tuple[int, ...] = (320, 640, 1280, 1280)
     layers_per_block: int = 2
-    num_heads: int = 8                      # diffusers' `attention_head_dim=8` is the HEAD COUNT for SD1.x
+    num_heads: Union[int, Tuple[int, ...]] = 8   # diffusers' `attention_head_dim` is the HEAD COUNT (per level for SDXL)
     cross_attention_dim: int = 768
     norm_groups: int = 32
     # which down blocks carry transformers (SD1.5: first three)
@@ -53,6 +55,10 @@ class UNetSpec:
     transformer_norm_eps: float = 1e-6      # unet_struct.txt:13
     layernorm_eps: float = 1e-5             # unet_struct.txt:44
     sample_size: int = 64
+    transformer_depth: Union[int, Tuple[int, ...]] = 1     # BasicTransformerBlocks per Transformer2DModel, per level
+    use_linear_projection: bool = False     # proj_in / proj_out are nn.Linear on the token matrix (SDXL) instead of 1x1 convs
+    addition_time_embed_dim: Optional[int] = None          # SDXL 'text_time' additional embedding: sinusoid width per time id
+    projection_class_embeddings_input_dim: Optional[int] = None   # text_embeds dim + 6 * addition_time_embed_dim
 
     @property
     def time_embed_dim(self) -> int:
@@ -62,10 +68,24 @@ class UNetSpec:
     def up_has_attn(self) -> Tuple[bool, ...]:
         return tuple(reversed(self.down_has_attn))
 
+    def heads(self, level: int) -> int:
+        return self.num_heads if isinstance(self.num_heads, int) else self.num_heads[level]
+
+    def depth(self, level: int) -> int:
+        return self.transformer_depth if isinstance(self.transformer_depth, int) else self.transformer_depth[level]
+
 
 SD15 = UNetSpec()
 # a small topology with the same block structure, for tests that must finish in seconds
 TINY = UNetSpec(block_out_channels=(64, 128, 128, 128), num_heads=2, cross_attention_dim=64, sample_size=16)
+# stable-diffusion-xl-base-1.0: three levels, no attention at the top one, transformer depth 2 / 10, head dim 64 everywhere,
+# linear projections, 2048-wide text context, (pooled text | 6 sinusoidal time ids) additional embedding
+SDXL = UNetSpec(block_out_channels=(320, 640, 1280), num_heads=(5, 10, 20), cross_attention_dim=2048,
+                down_has_attn=(False, True, True), sample_size=128, transformer_depth=(1, 2, 10), use_linear_projection=True,
+                addition_time_embed_dim=256, projection_class_embeddings_input_dim=2816)
+TINY_XL = UNetSpec(block_out_channels=(64, 128, 128), num_heads=(1, 2, 2), cross_attention_dim=64, down_has_attn=(False, True, True),
+                   sample_size=16, transformer_depth=(1, 2, 3), use_linear_projection=True, addition_time_embed_dim=32,
+                   projection_class_embeddings_input_dim=256)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -84,26 +104,28 @@ def _resnet_params(prefix: str, cin: int, cout: int, temb: int) -> List[Tuple[st
     return p
 
 
-def _transformer_params(prefix: str, c: int, ctx: int) -> List[Tuple[str, Tuple[int, ...]]]:
-    tb = f"{prefix}.transformer_blocks.0"
+def _transformer_params(prefix: str, c: int, ctx: int, depth: int = 1, linear_proj: bool = False) -> List[Tuple[str, Tuple[int, ...]]]:
+    proj = (c, c) if linear_proj else (c, c, 1, 1)
     p = [
         (f"{prefix}.norm.weight", (c,)), (f"{prefix}.norm.bias", (c,)),
-        (f"{prefix}.proj_in.weight", (c, c, 1, 1)), (f"{prefix}.proj_in.bias", (c,)),
+        (f"{prefix}.proj_in.weight", proj), (f"{prefix}.proj_in.bias", (c,)),
     ]
-    for attn, kdim in (("attn1", c), ("attn2", ctx)):
+    for k in range(depth):
+        tb = f"{prefix}.transformer_blocks.{k}"
+        for attn, kdim in (("attn1", c), ("attn2", ctx)):
+            p += [
+                (f"{tb}.{attn}.to_q.weight", (c, c)),
+                (f"{tb}.{attn}.to_k.weight", (c, kdim)),
+                (f"{tb}.{attn}.to_v.weight", (c, kdim)),
+                (f"{tb}.{attn}.to_out.0.weight", (c, c)), (f"{tb}.{attn}.to_out.0.bias", (c,)),
+            ]
         p += [
-            (f"{tb}.{attn}.to_q.weight", (c, c)),
-            (f"{tb}.{attn}.to_k.weight", (c, kdim)),
-            (f"{tb}.{attn}.to_v.weight", (c, kdim)),
-            (f"{tb}.{attn}.to_out.0.weight", (c, c)), (f"{tb}.{attn}.to_out.0.bias", (c,)),
+            (f"{tb}.ff.net.0.proj.weight", (8 * c, c)), (f"{tb}.ff.net.0.proj.bias", (8 * c,)),
+            (f"{tb}.ff.net.2.weight", (c, 4 * c)), (f"{tb}.ff.net.2.bias", (c,)),
         ]
-    p += [
-        (f"{tb}.ff.net.0.proj.weight", (8 * c, c)), (f"{tb}.ff.net.0.proj.bias", (8 * c,)),
-        (f"{tb}.ff.net.2.weight", (c, 4 * c)), (f"{tb}.ff.net.2.bias", (c,)),
-    ]
-    for n in ("norm1", "norm2", "norm3"):
-        p += [(f"{tb}.{n}.weight", (c,)), (f"{tb}.{n}.bias", (c,))]
-    p += [(f"{prefix}.proj_out.weight", (c, c, 1, 1)), (f"{prefix}.proj_out.bias", (c,))]
+        for n in ("norm1", "norm2", "norm3"):
+            p += [(f"{tb}.{n}.weight", (c,)), (f"{tb}.{n}.bias", (c,))]
+    p += [(f"{prefix}.proj_out.weight", proj), (f"{prefix}.proj_out.bias", (c,))]
     return p
 
 
@@ -116,6 +138,10 @@ def param_shapes(spec: UNetSpec = SD15) -> Dict[str, Tuple[int, ...]]:
         ("time_embedding.linear_1.weight", (temb, ch[0])), ("time_embedding.linear_1.bias", (temb,)),
         ("time_embedding.linear_2.weight", (temb, temb)), ("time_embedding.linear_2.bias", (temb,)),
     ]
+    if spec.addition_time_embed_dim:
+        out += [("add_embedding.linear_1.weight", (temb, spec.projection_class_embeddings_input_dim)), ("add_embedding.linear_1.bias", (temb,)),
+                ("add_embedding.linear_2.weight", (temb, temb)), ("add_embedding.linear_2.bias", (temb,))]
+    lin = spec.use_linear_projection
     skip_ch = [ch[0]]
     cprev = ch[0]
     nblk = len(ch)
@@ -123,7 +149,7 @@ def param_shapes(spec: UNetSpec = SD15) -> Dict[str, Tuple[int, ...]]:
         for j in range(spec.layers_per_block):
             out += _resnet_params(f"down_blocks.{i}.resnets.{j}", cprev, c, temb)
             if spec.down_has_attn[i]:
-                out += _transformer_params(f"down_blocks.{i}.attentions.{j}", c, spec.cross_attention_dim)
+                out += _transformer_params(f"down_blocks.{i}.attentions.{j}", c, spec.cross_attention_dim, spec.depth(i), lin)
             cprev = c
             skip_ch.append(c)
         if i < nblk - 1:
@@ -132,7 +158,7 @@ def param_shapes(spec: UNetSpec = SD15) -> Dict[str, Tuple[int, ...]]:
             skip_ch.append(c)
     cm = ch[-1]
     out += _resnet_params("mid_block.resnets.0", cm, cm, temb)
-    out += _transformer_params("mid_block.attentions.0", cm, spec.cross_attention_dim)
+    out += _transformer_params("mid_block.attentions.0", cm, spec.cross_attention_dim, spec.depth(nblk - 1), lin)
     out += _resnet_params("mid_block.resnets.1", cm, cm, temb)
     rev = list(reversed(ch))
     cprev = cm
@@ -141,7 +167,7 @@ def param_shapes(spec: UNetSpec = SD15) -> Dict[str, Tuple[int, ...]]:
             cskip = skip_ch.pop()
             out += _resnet_params(f"up_blocks.{i}.resnets.{j}", cprev + cskip, c, temb)
             if spec.up_has_attn[i]:
-                out += _transformer_params(f"up_blocks.{i}.attentions.{j}", c, spec.cross_attention_dim)
+                out += _transformer_params(f"up_blocks.{i}.attentions.{j}", c, spec.cross_attention_dim, spec.depth(nblk - 1 - i), lin)
             cprev = c
         if i < nblk - 1:
             out += [(f"up_blocks.{i}.upsamplers.0.conv.weight", (c, c, 3, 3)),
@@ -306,28 +332,41 @@ def _attention(sd, lora, p: str, x: Tensor, ctx: Tensor, bias: Optional[Tensor],
     return _linear(sd, lora, p + ".to_out.0", o)
 
 
-def _transformer(sd, lora, p: str, x: Tensor, ehs: Tensor, bias: Optional[Tensor], spec: UNetSpec) -> Tensor:
+def _transformer(sd, lora, p: str, x: Tensor, ehs: Tensor, bias: Optional[Tensor], spec: UNetSpec, level: int = 0) -> Tensor:
+    """Transformer2DModel: GroupNorm, proj_in, `depth` BasicTransformerBlocks, proj_out, residual.  With
+    `use_linear_projection` (SDXL) proj_in / proj_out are Linear layers on the token matrix, applied after / before the
+    NCHW <-> token reshape; otherwise 1x1 convolutions applied before / after it."""
     B, C, H, W = x.shape
+    heads = spec.heads(level)
     res = x
     h = F.group_norm(x, spec.norm_groups, sd[p + ".norm.weight"], sd[p + ".norm.bias"], spec.transformer_norm_eps)
-    h = _conv(sd, lora, p + ".proj_in", h)
-    h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
-    tb = p + ".transformer_blocks.0"
-    n = F.layer_norm(h, (C,), sd[tb + ".norm1.weight"], sd[tb + ".norm1.bias"], spec.layernorm_eps)
-    h = _attention(sd, lora, tb + ".attn1", n, n, None, spec.num_heads) + h
-    n = F.layer_norm(h, (C,), sd[tb + ".norm2.weight"], sd[tb + ".norm2.bias"], spec.layernorm_eps)
-    h = _attention(sd, lora, tb + ".attn2", n, ehs, bias, spec.num_heads) + h
-    n = F.layer_norm(h, (C,), sd[tb + ".norm3.weight"], sd[tb + ".norm3.bias"], spec.layernorm_eps)
-    u = _linear(sd, lora, tb + ".ff.net.0.proj", n)
-    a, g = u.chunk(2, dim=-1)
-    h = _linear(sd, lora, tb + ".ff.net.2", a * F.gelu(g)) + h
+    if spec.use_linear_projection:
+        h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
+        h = _linear(sd, lora, p + ".proj_in", h)
+    else:
+        h = _conv(sd, lora, p + ".proj_in", h)
+        h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
+    for k in range(spec.depth(level)):
+        tb = f"{p}.transformer_blocks.{k}"
+        n = F.layer_norm(h, (C,), sd[tb + ".norm1.weight"], sd[tb + ".norm1.bias"], spec.layernorm_eps)
+        h = _attention(sd, lora, tb + ".attn1", n, n, None, heads) + h
+        n = F.layer_norm(h, (C,), sd[tb + ".norm2.weight"], sd[tb + ".norm2.bias"], spec.layernorm_eps)
+        h = _attention(sd, lora, tb + ".attn2", n, ehs, bias, heads) + h
+        n = F.layer_norm(h, (C,), sd[tb + ".norm3.weight"], sd[tb + ".norm3.bias"], spec.layernorm_eps)
+        u = _linear(sd, lora, tb + ".ff.net.0.proj", n)
+        a, g = u.chunk(2, dim=-1)
+        h = _linear(sd, lora, tb + ".ff.net.2", a * F.gelu(g)) + h
+    if spec.use_linear_projection:
+        h = _linear(sd, lora, p + ".proj_out", h)
+        h = h.reshape(B, H, W, C).permute(0, 3, 1, 2)
+        return h + res
     h = h.reshape(B, H, W, C).permute(0, 3, 1, 2)
     return _conv(sd, lora, p + ".proj_out", h) + res
 
 
 def unet_forward(sd: Dict[str, Tensor], sample: Tensor, timestep: Tensor, encoder_hidden_states: Tensor,
                  encoder_attention_mask: Optional[Tensor] = None, lora: Optional[LoraDict] = None,
-                 spec: UNetSpec = SD15) -> Tensor:
+                 spec: UNetSpec = SD15, added_cond_kwargs: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """noise_pred [B, out_ch, H, W] for sample [B,4,H,W], timestep [B] (or scalar), ehs [B,Lc,ctx]."""
     B = sample.shape[0]
     bias = None
@@ -341,6 +380,15 @@ def unet_forward(sd: Dict[str, Tensor], sample: Tensor, timestep: Tensor, encode
     emb = timestep_embedding(t, spec.block_out_channels[0]).to(sample.dtype)
     emb = F.linear(emb, sd["time_embedding.linear_1.weight"], sd["time_embedding.linear_1.bias"])
     emb = F.linear(F.silu(emb), sd["time_embedding.linear_2.weight"], sd["time_embedding.linear_2.bias"])
+    if spec.addition_time_embed_dim:
+        # SDXL 'text_time' (reference wrapper.py:66: added_cond_kwargs = {text_embeds: pooled CLIP-bigG output, time_ids: crop_info}):
+        # aug = add_embedding(cat[text_embeds, sinusoid(time_ids).flatten]), emb = emb + aug
+        te, ids = added_cond_kwargs["text_embeds"], added_cond_kwargs["time_ids"]
+        tid = timestep_embedding(ids.flatten(), spec.addition_time_embed_dim).reshape(B, -1)
+        add = torch.cat([te, tid.to(te.dtype)], dim=-1)
+        aug = F.linear(add, sd["add_embedding.linear_1.weight"], sd["add_embedding.linear_1.bias"])
+        aug = F.linear(F.silu(aug), sd["add_embedding.linear_2.weight"], sd["add_embedding.linear_2.bias"])
+        emb = emb + aug
 
     h = _conv(sd, lora, "conv_in", sample, padding=1)
     skips = [h]
@@ -349,21 +397,21 @@ def unet_forward(sd: Dict[str, Tensor], sample: Tensor, timestep: Tensor, encode
         for j in range(spec.layers_per_block):
             h = _resnet(sd, f"down_blocks.{i}.resnets.{j}", h, emb, spec, lora)
             if spec.down_has_attn[i]:
-                h = _transformer(sd, lora, f"down_blocks.{i}.attentions.{j}", h, encoder_hidden_states, bias, spec)
+                h = _transformer(sd, lora, f"down_blocks.{i}.attentions.{j}", h, encoder_hidden_states, bias, spec, i)
             skips.append(h)
         if i < nblk - 1:
             p = f"down_blocks.{i}.downsamplers.0.conv"
             h = _conv(sd, lora, p, h, stride=2, padding=1)
             skips.append(h)
     h = _resnet(sd, "mid_block.resnets.0", h, emb, spec, lora)
-    h = _transformer(sd, lora, "mid_block.attentions.0", h, encoder_hidden_states, bias, spec)
+    h = _transformer(sd, lora, "mid_block.attentions.0", h, encoder_hidden_states, bias, spec, nblk - 1)
     h = _resnet(sd, "mid_block.resnets.1", h, emb, spec, lora)
     for i in range(nblk):
         for j in range(spec.layers_per_block + 1):
             h = torch.cat([h, skips.pop()], dim=1)
             h = _resnet(sd, f"up_blocks.{i}.resnets.{j}", h, emb, spec, lora)
             if spec.up_has_attn[i]:
-                h = _transformer(sd, lora, f"up_blocks.{i}.attentions.{j}", h, encoder_hidden_states, bias, spec)
+                h = _transformer(sd, lora, f"up_blocks.{i}.attentions.{j}", h, encoder_hidden_states, bias, spec, nblk - 1 - i)
         if i < nblk - 1:
             p = f"up_blocks.{i}.upsamplers.0.conv"
             h = F.interpolate(h, scale_factor=2.0, mode="nearest")
@@ -398,7 +446,20 @@ def synthetic_batch(batch: int, spec: UNetSpec = SD15, seed: int = 1234, ctx_len
     return latents, noise, t, ehs
 
 
-def lora_step_loss_and_grads(sd, lora: LoraDict, latents, noise, t, ehs, spec: UNetSpec = SD15):
+def synthetic_added_cond(batch: int, spec: UNetSpec, seed: int = 4321) -> Optional[Dict[str, Tensor]]:
+    """SDXL `added_cond_kwargs` with the statistics of the real inputs: pooled text embedding ~ N(0,1), time ids =
+    (orig_h, orig_w, crop_top, crop_left, target_h, target_w) in pixels (reference data/pair_dataset crop_info)."""
+    if not spec.addition_time_embed_dim:
+        return None
+    g = torch.Generator().manual_seed(seed)
+    te_dim = spec.projection_class_embeddings_input_dim - 6 * spec.addition_time_embed_dim
+    px = spec.sample_size * 8
+    ids = torch.tensor([[px, px, 0, 0, px, px]], dtype=torch.float32).repeat(batch, 1)
+    ids[:, 2:4] = torch.randint(0, 64, (batch, 2), generator=g).float()
+    return {"text_embeds": torch.randn((batch, te_dim), generator=g), "time_ids": ids}
+
+
+def lora_step_loss_and_grads(sd, lora: LoraDict, latents, noise, t, ehs, spec: UNetSpec = SD15, added_cond_kwargs=None):
     """One reference training forward/backward: eps-prediction MSE (train_ac.py:506-515, reduction mean) and the
     gradients of every LoRA parameter.  Returns (loss, noise_pred, {layer: [(dW_down, dW_up), ...]})."""
     leaves = []
@@ -410,7 +471,7 @@ def lora_step_loss_and_grads(sd, lora: LoraDict, latents, noise, t, ehs, spec: U
             e.W_up.grad = None
             leaves += [e.W_down, e.W_up]
     x_t = add_noise(latents, noise, t, ddpm_alphas_cumprod())
-    pred = unet_forward(sd, x_t, t, ehs, lora=lora, spec=spec)
+    pred = unet_forward(sd, x_t, t, ehs, lora=lora, spec=spec, added_cond_kwargs=added_cond_kwargs)
     loss = F.mse_loss(pred.float(), noise.float(), reduction="none").mean()
     loss.backward()
     grads = {layer: [(e.W_down.grad.clone(), e.W_up.grad.clone()) for e in blocks] for layer, blocks in lora.items()}

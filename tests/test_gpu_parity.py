@@ -563,3 +563,58 @@ def test_tiny_unet_locon_forward_backward():
             num += float((got.cpu().double() - ref.double()).pow(2).sum())
             den += float(ref.double().pow(2).sum())
     assert math.sqrt(num / den) < 5e-2
+
+
+def unet_for_spec(spec):
+    """Product UNet with the diffusers config keys of an oracle spec (SD1.x or SDXL topology)."""
+    down = tuple("CrossAttnDownBlock2D" if a else "DownBlock2D" for a in spec.down_has_attn)
+    up = tuple("CrossAttnUpBlock2D" if a else "UpBlock2D" for a in spec.up_has_attn)
+    return UNet2DConditionModel(
+        sample_size=spec.sample_size, block_out_channels=spec.block_out_channels, attention_head_dim=spec.num_heads,
+        cross_attention_dim=spec.cross_attention_dim, down_block_types=down, up_block_types=up,
+        transformer_layers_per_block=spec.transformer_depth, use_linear_projection=spec.use_linear_projection,
+        addition_embed_type="text_time" if spec.addition_time_embed_dim else None, addition_time_embed_dim=spec.addition_time_embed_dim,
+        projection_class_embeddings_input_dim=spec.projection_class_embeddings_input_dim)
+
+
+@pytest.mark.parametrize("rank", [0, 4])
+def test_tiny_sdxl_unet_forward_backward(rank):
+    """SDXL topology (SURVEY 8f-4 / BASELINE config 4) at test size: no attention at the top level, transformer depth (2, 3),
+    head dim 64, Linear proj_in/proj_out, `added_cond_kwargs` = {text_embeds, time_ids} (reference wrapper.py:57-75), LoRA on every
+    attn / ff Linear (cfgs/train/examples/lora_sdxl.yaml) -- noise_pred and LoRA gradients against the fp32 oracle."""
+    spec = U.TINY_XL
+    sd = U.init_params(spec)
+    unet = unet_for_spec(spec)
+    unet.load_state_dict(sd)
+    unet = unet.to(DEV).requires_grad_(False).eval()
+    lat, noise, t, ehs = U.synthetic_batch(2, spec)
+    added = U.synthetic_added_cond(2, spec)
+    added_dev = {k: v.to(DEV) for k, v in added.items()}
+    x_t = U.add_noise(lat, noise, t, U.ddpm_alphas_cumprod())
+    if rank == 0:
+        with torch.no_grad():
+            pred_ref = U.unet_forward(sd, x_t, t, ehs, spec=spec, added_cond_kwargs=added)
+            pred = unet(x_t.to(DEV), t.to(DEV), ehs.to(DEV), added_cond_kwargs=added_dev).sample
+        assert rel_l2(pred, pred_ref) < 2e-2
+        with pytest.raises(ValueError):
+            unet(x_t.to(DEV), t.to(DEV), ehs.to(DEV))                 # the additional embedding is not optional
+        return
+    pat = r".*\.attn.?$|.*\.ff$"
+    _, group = make_hcpdiff(unet, None, [{"rank": rank, "alpha": 1.0, "dropout": 0.0, "layers": ["re:" + pat]}])
+    lora = U.init_lora(spec, rank=rank, seed=3, pattern=pat)
+    assert set(lora) == set(group.plugin_dict)
+    with torch.no_grad():
+        for layer, entries in lora.items():
+            group[layer].layer.W_down.copy_(entries[0].W_down)
+            group[layer].layer.W_up.copy_(entries[0].W_up)
+    loss_ref, pred_ref, grads_ref = U.lora_step_loss_and_grads(sd, lora, lat, noise, t, ehs, spec, added)
+    pred = unet(x_t.to(DEV), t.to(DEV), ehs.to(DEV), added_cond_kwargs=added_dev).sample
+    assert rel_l2(pred, pred_ref) < 2e-2
+    F.mse_loss(pred, noise.to(DEV), reduction="none").mean().backward()
+    num = den = 0.0
+    for layer, blocks in grads_ref.items():
+        blk = group[layer]
+        for got, ref in ((blk.layer.W_down.grad, blocks[0][0]), (blk.layer.W_up.grad, blocks[0][1])):
+            num += float((got.cpu().double() - ref.double()).pow(2).sum())
+            den += float(ref.double().pow(2).sum())
+    assert math.sqrt(num / den) < 5e-2

@@ -183,3 +183,27 @@ def test_dapp_and_conv_lora_surface_matches_reference_golden(golden_dir):
         blk.layer.W_up.copy_(fx["state"]["conv.lora_block_0.layer.W_up"])
     ref = torch.einsum("or,rikl->oikl", blk.layer.W_up[:, :, 0, 0], blk.layer.W_down) * blk.alpha
     torch.testing.assert_close(blk.get_weight(), ref)
+
+
+def test_sdxl_config_builds_the_sdxl_module_tree():
+    """The diffusers SDXL-base config keys build the SDXL UNet: 2,567,463,684 parameters, names and shapes equal to the oracle's
+    inventory (depth-2 / depth-10 transformers, Linear projections, add_embedding), on the meta device (no 10 GB allocation)."""
+    from oracle import unet_ref as U
+    from hcp_diffusion_b200.models import UNet2DConditionModel
+    with torch.device("meta"):
+        unet = UNet2DConditionModel(sample_size=128, block_out_channels=(320, 640, 1280), attention_head_dim=(5, 10, 20),
+                                    cross_attention_dim=2048, down_block_types=("DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"),
+                                    up_block_types=("CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"),
+                                    transformer_layers_per_block=(1, 2, 10), use_linear_projection=True, addition_embed_type="text_time",
+                                    addition_time_embed_dim=256, projection_class_embeddings_input_dim=2816)
+    shapes = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+    ref = U.param_shapes(U.SDXL)
+    assert shapes == {k: tuple(v) for k, v in ref.items()}
+    assert sum(torch.Size(v).numel() for v in shapes.values()) == 2_567_463_684
+    assert isinstance(unet.down_blocks[1].attentions[0].proj_in, torch.nn.Linear)
+    assert len(unet.mid_block.attentions[0].transformer_blocks) == 10 and unet.mid_block.attentions[0].transformer_blocks[0].attn1.heads == 20
+    assert not hasattr(unet.down_blocks[0], "attentions") and not hasattr(unet.up_blocks[2], "attentions")
+    # the lora_sdxl.yaml layer selection resolves on it
+    from hcp_diffusion_b200.utils.cfg_net_tools import get_match_layers
+    named = dict(unet.named_modules())
+    assert len(get_match_layers([r"re:.*\.attn.?$", r"re:.*\.ff$"], named)) == 3 * 70
