@@ -634,7 +634,8 @@ static int dispatch_gemm(int bn, GemmKParams& kp, int m_tiles, cudaStream_t stre
     // two M tiles per work item when the reduction is long (operand-stream bound) and there are plenty of tiles
     int64_t total_kb = 0;
     for (int s = 0; s < kp.nseg; ++s) total_kb += (int64_t)kp.nkb[s] * ((kp.conv && s == 0) ? kp.ntaps : 1);
-    const bool pair = bn == 160 && kp.splits == 1 && total_kb >= 40 && (int64_t)kp.tiles_n * m_tiles >= 200 &&
+    static const int msub2_min_kb = [] { const char* e = getenv("HCP_MSUB2_MIN_KB"); return e ? atoi(e) : 40; }();
+    const bool pair = bn == 160 && kp.splits == 1 && total_kb >= msub2_min_kb && (int64_t)kp.tiles_n * m_tiles >= 200 &&
                       getenv("HCP_GEMM_NO_MSUB2") == nullptr;
     if (pair) return launch_gemm<160, 2>(kp, stream);
     switch (bn) {

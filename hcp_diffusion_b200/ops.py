@@ -570,6 +570,7 @@ class GroupNormFn(torch.autograd.Function):
         a.stats, a.workspace, a.workspace_bytes = stats.data_ptr(), ws.data_ptr(), wsb
         a.y = y.data_ptr()
         call("hcp_groupnorm_fwd_bf16", C.byref(a), stream_ptr())
+        ctx.set_materialize_grads(False)      # an unused alias output must arrive as None in backward, not as a zero-filled tensor
         ctx.save_for_backward(x1, x2, stats, gamma, beta)
         ctx.cfg = (groups, eps, silu)
         if x2 is None:
@@ -620,6 +621,7 @@ class LayerNormFn(torch.autograd.Function):
         stats = torch.empty((M, 2), dtype=torch.float32, device=x.device)
         call("hcp_layernorm_fwd_bf16", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, M, C_, stats.data_ptr(), y.data_ptr(),
              stream_ptr())
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, stats, gamma)
         return y, x
 
