@@ -89,24 +89,24 @@ class LoraTrainStep:
         self.lr.fill_(lr)
 
     # ---- pieces ------------------------------------------------------------------------------------------------------
-    def _forward_backward(self, latents, noise, t, ehs):
+    def _forward_backward(self, latents, noise, t, ehs, added=None):
         """zero_grad, x_t = add_noise, pred = unet(x_t, t, ehs), loss = mse(pred, noise), backward."""
         self.flat.grad.zero_()
         self.loss.zero_()
         ops.set_side_stream(self.side_stream)
         try:
-            self._fb_body(latents, noise, t, ehs)
+            self._fb_body(latents, noise, t, ehs, added)
         finally:
             ops.join_side()
             ops.set_side_stream(False)
 
-    def _fb_body(self, latents, noise, t, ehs):
+    def _fb_body(self, latents, noise, t, ehs, added=None):
         B = latents.shape[0]
         per_image = latents[0].numel()
         x_t = torch.empty_like(latents)
         call("hcp_add_noise", latents.data_ptr(), noise.data_ptr(), t.data_ptr(), self.acp.data_ptr(), B, per_image, x_t.data_ptr(),
              stream_ptr())
-        pred = self.unet(x_t, t, ehs).sample
+        pred = (self.unet(x_t, t, ehs, added_cond_kwargs=added) if added is not None else self.unet(x_t, t, ehs)).sample
         dpred = torch.empty_like(pred)
         call("hcp_mse_loss", pred.data_ptr(), noise.data_ptr(), pred.numel(), 1.0, self.loss.data_ptr(), dpred.data_ptr(), stream_ptr())
         pred.backward(dpred)
@@ -124,23 +124,29 @@ class LoraTrainStep:
             dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)   # averaged by grad_scale = 1/world in AdamW
 
     # ---- public ------------------------------------------------------------------------------------------------------
-    def step(self, latents: torch.Tensor, noise: torch.Tensor, t: torch.Tensor, ehs: torch.Tensor) -> torch.Tensor:
-        """latents/noise fp32 [B,4,H,W], t int64 [B], ehs fp32 [B,L,768] (host-pinned or device).  Returns the device loss
-        tensor (shape [1]); reading it is the caller's D2H."""
+    def step(self, latents: torch.Tensor, noise: torch.Tensor, t: torch.Tensor, ehs: torch.Tensor,
+             added_cond_kwargs: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+        """latents/noise fp32 [B,4,H,W], t int64 [B], ehs fp32 [B,L,ctx] (host-pinned or device); `added_cond_kwargs`
+        ({'text_embeds' [B,P], 'time_ids' [B,6]}) for SDXL UNets (reference wrapper.py:66).  Returns the device loss tensor
+        (shape [1]); reading it is the caller's D2H."""
+        dev = self.flat.data.device
         if not self.use_graph:
-            dev = self.flat.data.device
+            added = None if added_cond_kwargs is None else {k: v.to(dev, non_blocking=True) for k, v in added_cond_kwargs.items()}
             self._forward_backward(latents.to(dev, non_blocking=True), noise.to(dev, non_blocking=True), t.to(dev, non_blocking=True),
-                                   ehs.to(dev, non_blocking=True))
+                                   ehs.to(dev, non_blocking=True), added)
             self._all_reduce()
             self._optimizer()
             return self.loss
         if self._static is None:
-            self._capture(latents, noise, t, ehs)
+            self._capture(latents, noise, t, ehs, added_cond_kwargs)
         s = self._static
         s["latents"].copy_(latents, non_blocking=True)
         s["noise"].copy_(noise, non_blocking=True)
         s["t"].copy_(t, non_blocking=True)
         s["ehs"].copy_(ehs, non_blocking=True)
+        if s["added"] is not None:
+            for k, v in s["added"].items():
+                v.copy_(added_cond_kwargs[k], non_blocking=True)
         self._graph_fb.replay()
         self._all_reduce()
         self._graph_opt.replay()
@@ -155,11 +161,12 @@ class LoraTrainStep:
         self._graph_opt.replay()
         return self.loss
 
-    def _capture(self, latents, noise, t, ehs):
+    def _capture(self, latents, noise, t, ehs, added=None):
         dev = self.flat.data.device
         self._static = {
             "latents": latents.to(dev).float().contiguous().clone(), "noise": noise.to(dev).float().contiguous().clone(),
             "t": t.to(dev).long().contiguous().clone(), "ehs": ehs.to(dev).float().contiguous().clone(),
+            "added": None if added is None else {k: v.to(dev).float().contiguous().clone() for k, v in added.items()},
         }
         s = self._static
         # warm-up on a side stream (builds the packed weights, tensor maps, autograd metadata) -- parameters are restored
@@ -168,7 +175,7 @@ class LoraTrainStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                self._forward_backward(s["latents"], s["noise"], s["t"], s["ehs"])
+                self._forward_backward(s["latents"], s["noise"], s["t"], s["ehs"], s["added"])
                 self._optimizer()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -176,7 +183,7 @@ class LoraTrainStep:
         before = _lib.launch_count
         self._graph_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_fb):
-            self._forward_backward(s["latents"], s["noise"], s["t"], s["ehs"])
+            self._forward_backward(s["latents"], s["noise"], s["t"], s["ehs"], s["added"])
         self._graph_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_opt):
             self._optimizer()
