@@ -286,7 +286,8 @@ def run_product_arm(args, rank, world, local_rank):
                                "77 tokens; step = add_noise + UNet fwd + MSE + bwd + grad all-reduce + clip + AdamW" % n_lora,
                    "global_batch": world * B, "per_gpu_batch": B, "lora_rank": LORA_RANK, "parallelism": f"dp{world}",
                    "l2": "working set (1.7 GB bf16 weights + activations) is far larger than the 126 MB L2; no explicit flush",
-                   "cuda_graph": True, "grad_checkpointing": False},
+                   "cuda_graph": True, "grad_checkpointing": False,
+                   "side_stream": os.environ.get("HCP_SIDE_STREAM", "1") != "0", "pdl": os.environ.get("HCP_PDL", "1") != "0"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": step.launches_per_step * args.steps,
