@@ -323,7 +323,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout: rank 0 prints ONE json line
+        # rank 0 prints ONE json line on stdout: NCCL's version banner / debug lines (whatever NCCL_DEBUG the box exports) go to stderr
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
         run_product_arm(args, rank, world, local_rank)

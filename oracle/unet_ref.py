@@ -479,3 +479,28 @@ def lora_step_loss_and_grads(sd, lora: LoraDict, latents, noise, t, ehs, spec: U
         p.requires_grad_(False)
         p.grad = None
     return loss.detach(), pred.detach(), grads
+
+
+def ddim_cfg_sample(sd, latents: Tensor, prompt_embeds: Tensor, negative_embeds: Tensor, num_inference_steps: int, guidance_scale: float,
+                    spec: UNetSpec = SD15, lora: Optional[LoraDict] = None, added_cond_kwargs=None, num_train_timesteps: int = 1000) -> Tensor:
+    """The reference text-to-image denoising loop (hcpdiff/utils/pipe_hook.py:115-150) with the DDIM (eta = 0, leading spacing,
+    steps_offset 1, set_alpha_to_one False) update, around the oracle UNet: one forward per step on [negative | positive]."""
+    acp = ddpm_alphas_cumprod(num_train_timesteps)
+    ratio = num_train_timesteps // num_inference_steps
+    steps = (torch.arange(0, num_inference_steps) * ratio).flip(0) + 1
+    x = latents.clone()
+    B = x.shape[0]
+    ehs2 = torch.cat([negative_embeds, prompt_embeds], 0)
+    with torch.no_grad():
+        for t in steps.tolist():
+            t = min(t, num_train_timesteps - 1)
+            tt = torch.full((2 * B,), t, dtype=torch.int64)
+            eps2 = unet_forward(sd, torch.cat([x, x], 0), tt, ehs2, lora=lora, spec=spec, added_cond_kwargs=added_cond_kwargs)
+            e_u, e_c = eps2.chunk(2)
+            eps = e_u + guidance_scale * (e_c - e_u)
+            a_t = acp[t]
+            t_prev = t - ratio
+            a_prev = acp[t_prev] if t_prev >= 0 else acp[0]
+            x0 = (x - (1 - a_t).sqrt() * eps) / a_t.sqrt()
+            x = a_prev.sqrt() * x0 + (1 - a_prev).sqrt() * eps
+    return x

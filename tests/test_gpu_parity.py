@@ -618,3 +618,20 @@ def test_tiny_sdxl_unet_forward_backward(rank):
             num += float((got.cpu().double() - ref.double()).pow(2).sum())
             den += float(ref.double().pow(2).sum())
     assert math.sqrt(num / den) < 5e-2
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_cfg_denoising_loop_matches_oracle(use_graph):
+    """Forward-only reuse: the reference's CFG denoising loop (pipe_hook.py:115-150) with DDIM updates, 4 steps on the
+    TINY UNet with a LoRA loaded, batch [negative | positive]; eager and captured-graph forwards against the oracle loop."""
+    from hcp_diffusion_b200.sampling import CFGDenoiser
+    spec = U.TINY
+    sd = U.init_params(spec)
+    unet, group, lora = build_product_unet(spec, sd, 4)
+    g = torch.Generator().manual_seed(7)
+    lat = torch.randn((2, 4, spec.sample_size, spec.sample_size), generator=g)
+    pos = torch.randn((2, 77, spec.cross_attention_dim), generator=g)
+    neg = torch.randn((2, 77, spec.cross_attention_dim), generator=g)
+    ref = U.ddim_cfg_sample(sd, lat, pos, neg, 4, 5.0, spec=spec, lora=lora)
+    out = CFGDenoiser(unet).sample(lat.to(DEV), pos.to(DEV), neg.to(DEV), num_inference_steps=4, guidance_scale=5.0, use_cuda_graph=use_graph)
+    assert out.shape == ref.shape and rel_l2(out, ref) < 5e-2
