@@ -21,7 +21,7 @@ kern = [(re.sub(r"\(.*", "", r["Kernel Name"]), float(r["Metric Value"].replace(
 SEQ = {
     "hcp_gemm_bf16": [("gemm_tc_kernel", 1, 1), ("splitk_finalize", 0, 1)],
     "hcp_attn_fwd_bf16": [("attn_fwd", 1, 1)],
-    "hcp_attn_bwd_bf16": [("attn_bwd_prep", 1, 1), ("attn_bwd_kernel", 1, 2), ("attn_bwd_post_kernel", 1, 1), ("attn_bwd_post_kv", 0, 1)],
+    "hcp_attn_bwd_bf16": [("attn_bwd_prep", 1, 1), ("attn_bwd_kernel", 1, 2), ("attn_bwd_post_kernel", 0, 1), ("attn_bwd_post_kv", 0, 1)],
     "hcp_groupnorm_fwd_bf16": [("gn", 1, 3)],
     "hcp_groupnorm_bwd_bf16": [("gn", 1, 3)],
     "hcp_lora_grad_pair": [("lora_grad", 1, 1)],
