@@ -79,7 +79,8 @@ struct GemmCfg {
     static constexpr int ACC_STRIDE = 256;                         // TMEM columns between the two accumulators
     static constexpr int STG_PITCH = BN * 2 + 16;                  // staging row pitch in bytes: odd number of 16-byte units
     static constexpr int STG_BYTES = BLOCK_M * STG_PITCH;
-    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_STAGE_BYTES) + STG_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+    static constexpr int BIAS_BYTES = ((BN * 4 + 127) / 128) * 128;  // bias slice of the tile's columns, staged once per work item
+    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_STAGE_BYTES) + STG_BYTES + BIAS_BYTES + 256 /*barriers*/ + 1024 /*align*/;
 };
 
 struct TileOrigin {
@@ -131,7 +132,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
     uint8_t* sStg = sB + STAGES * Cfg::B_STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStg + Cfg::STG_BYTES);
+    float* sBias = reinterpret_cast<float*>(sStg + Cfg::STG_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStg + Cfg::STG_BYTES + Cfg::BIAS_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
@@ -270,6 +272,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             const int as = (MSUB == 1) ? (item & 1) : 0;
             const uint32_t fph = (MSUB == 1) ? ((item >> 1) & 1) : (item & 1);
             const bool staged = (p.splits == 1);
+            if (staged && p.bias) {
+                // the bias slice of this item's columns goes to shared memory once (ncu: the per-chunk global bias loads were the
+                // top stall of the epilogue, 25 % of the samples of the K=320 N=2560 GEMM); the previous item's trailing bar.sync
+                // guarantees nobody still reads the old slice
+                for (int c = et; c < BN / 4; c += kGemmEpiThreads)
+                    reinterpret_cast<float4*>(sBias)[c] = (n0 + c * 4 < p.N) ? *reinterpret_cast<const float4*>(p.bias + n0 + c * 4)
+                                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
 #pragma unroll 1
             for (int sub = 0; sub < MSUB; ++sub) {
             const TileOrigin o = tile_origin(p, (mn / p.tiles_n) * MSUB + sub);
@@ -324,8 +335,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                                 continue;
                             }
                             if (p.bias) {
-                                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-                                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+                                const float4 b0 = *reinterpret_cast<const float4*>(sBias + c * 16 + g * 8);
+                                const float4 b1 = *reinterpret_cast<const float4*>(sBias + c * 16 + g * 8 + 4);
                                 f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                                 f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                             }

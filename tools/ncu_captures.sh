@@ -16,6 +16,6 @@ run gemm_first14 'gemm_tc_kernel' 0 14        # #0 conv 320->320 @64x64 (MSUB 2)
 run conv8x8 'gemm_tc_kernel' 101 1            # conv 1280->1280 @8x8, split-K
 run attn_fwd 'attn_fwd2_kernel' 0 1           # self-attention L4096 d40
 run attn_bwd 'attn_bwd_kernel' 1 1            # self-attention L4096 d40 backward
-run gnf_fwd 'gnf_kernel<0>' 0 1               # single-pass GroupNorm forward C320 HW4096
-run gnf_bwd 'gnf_kernel<1>' 0 1               # single-pass GroupNorm backward C320 HW4096
+run gnf_fwd 'gnf_kernel' 0 1                  # single-pass GroupNorm forward C320 HW4096 (first launch of the step)
+run gnf_bwd 'gnf_kernel' 57 1                 # single-pass GroupNorm backward C320 HW4096 (the 57 forward launches come first)
 run lora_grad 'lora_grad_tc_kernel' 0 1       # LoRA gradients of the first group of the backward
