@@ -315,12 +315,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             if (sub == 0) mbar_wait(&tmem_full_bar[as], fph);
             tc_fence_after();
             const uint32_t trow = tmem_base + acc_idx * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-            for (int c = half * ((CH16 + 1) / 2); c < (half ? CH16 : (CH16 + 1) / 2); ++c) {
-                uint32_t v[16];
-                tmem_ld16(trow + c * 16, v);
-                tmem_wait_ld();
-                if (row_ok) {
+            // all TMEM chunks of this thread are pulled into registers with ONE wait, and the accumulator is handed back to the MMA
+            // warp before any of the epilogue arithmetic / staging stores (it used to be held until the last chunk was written)
+            constexpr int NCH = (CH16 + 1) / 2;
+            uint32_t vv[NCH][16];
+#pragma unroll
+            for (int cl = 0; cl < NCH; ++cl)
+                if (half * NCH + cl < CH16) tmem_ld16(trow + (half * NCH + cl) * 16, vv[cl]);
+            tmem_wait_ld();
+            tc_fence_before();
+            if (sub == MSUB - 1) mbar_arrive(&tmem_empty_bar[as]); // accumulator(s) free: the MMA warp may go on
+#pragma unroll
+            for (int cl = 0; cl < NCH; ++cl) {
+                const int c = half * NCH + cl;
+                const uint32_t (&v)[16] = vv[cl];
+                if (c < CH16 && row_ok) {
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
                         const int col = n0 + c * 16 + g * 8;
@@ -366,8 +375,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                     }
                 }
             }
-            tc_fence_before();
-            if (sub == MSUB - 1) mbar_arrive(&tmem_empty_bar[as]); // accumulator(s) free: the MMA warp may go on
             if (staged) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 for (int u = et; u < BLOCK_M * UNITS; u += kGemmEpiThreads) {     // coalesced 16-byte stores
