@@ -550,7 +550,7 @@ struct alignas(64) AttnBwdParams {
     const float* kv_bias;
     const float* lse;        // [B,H,Lq]
     const float* delta;      // [B,H,Lq]  rowsum(dO * O)
-    float* dq_acc;           // [B,H,Lq,dq_ld] fp32 (nullptr when dq_direct is set)
+    float* dq_acc;           // [B,H,dq_ld/4,Lq,4] fp32 (nullptr when dq_direct is set)
     int dq_ld;
     __nv_bfloat16* dq_direct; // single kv tile (Lkv <= 128): dQ_i is complete after one pass -> stored as bf16, no accumulator
     int64_t lddq;
@@ -764,7 +764,10 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
         const bool special = (bias != nullptr) || (ncols < 128);
         const int64_t stat_base = ((int64_t)b * p.H + h) * p.Lq;
         auto drain_dq = [&](int qr) {            // TMEM dQ tile -> fp32 accumulator (vector red.global), or straight to bf16 dQ
-            float* dqrow = p.dq_direct ? nullptr : p.dq_acc + (stat_base + qr) * p.dq_ld + p.col0;
+            // fp32 accumulator layout [B, H, d/4, Lq, 4]: for a fixed 4-column group the 32 rows of a warp are 32 consecutive
+            // 16-byte slots, so one red.v4 instruction covers 16 full sectors instead of 32 half-used ones
+            float* dqcol = p.dq_direct ? nullptr
+                                       : p.dq_acc + ((((int64_t)b * p.H + h) * (p.dq_ld / 4) + p.col0 / 4) * p.Lq + qr) * 4;
             __nv_bfloat16* drow = p.dq_direct ? p.dq_direct + ((int64_t)b * p.Lq + qr) * p.lddq + (int64_t)h * p.d + p.col0 : nullptr;
             for (int c = part; c < p.ncols_out / 16; c += kBwdParts) {
                 uint32_t o[16];
@@ -789,7 +792,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                         for (int g = 0; g < 4; ++g) {
                             const int col = p.col0 + c * 16 + g * 4;
                             if (col < p.d)
-                                red_add_v4(dqrow + c * 16 + g * 4, __uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]),
+                                red_add_v4(dqcol + (int64_t)(c * 4 + g) * p.Lq * 4, __uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]),
                                            __uint_as_float(o[g * 4 + 2]), __uint_as_float(o[g * 4 + 3]));
                         }
                     }
@@ -1042,7 +1045,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16*
     delta[((int64_t)b * H + h) * Lq + q] = acc;
 }
 
-// dQ bf16 [B, Lq, lddq] <- fp32 accumulator [B,H,Lq,dq_ld]
+// dQ bf16 [B, Lq, lddq] <- fp32 accumulator [B,H,dq_ld/4,Lq,4]
 __global__ void attn_bwd_post_kernel(const float* __restrict__ dq_acc, int dq_ld, int B, int H, int Lq, int d,
                                      __nv_bfloat16* __restrict__ dQ, int64_t lddq) {
     pdl_trigger();
@@ -1057,7 +1060,7 @@ __global__ void attn_bwd_post_kernel(const float* __restrict__ dq_acc, int dq_ld
     const int64_t bq = r / H;
     const int q = (int)(bq % Lq);
     const int b = (int)(bq / Lq);
-    const float4 v = *reinterpret_cast<const float4*>(dq_acc + (((int64_t)b * H + h) * Lq + q) * dq_ld + e);
+    const float4 v = *reinterpret_cast<const float4*>(dq_acc + ((((int64_t)b * H + h) * (dq_ld / 4) + e / 4) * Lq + q) * 4);   // [B,H,d/4,Lq,4]
     uint2 o;
     o.x = pack_bf16x2(v.x, v.y);
     o.y = pack_bf16x2(v.z, v.w);

@@ -65,6 +65,7 @@ struct alignas(64) GemmKParams {
     int64_t ldo;
     // split-K: CTA (x, y) reduces the k-blocks [y*kb_per_split, (y+1)*kb_per_split) and stores raw fp32 partials
     int32_t splits, kb_per_split;
+    int32_t epi_batch;                 // epilogue schedule (see the epilogue)
     float* ws;                         // [splits, M, N] fp32
 };
 
@@ -315,21 +316,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             if (sub == 0) mbar_wait(&tmem_full_bar[as], fph);
             tc_fence_after();
             const uint32_t trow = tmem_base + acc_idx * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
-            // all TMEM chunks of this thread are pulled into registers with ONE wait, and the accumulator is handed back to the MMA
-            // warp before any of the epilogue arithmetic / staging stores (it used to be held until the last chunk was written)
+            // Two epilogue schedules (GemmKParams::epi_batch): 1 = all TMEM chunks of this thread are pulled into registers with ONE
+            // wait and the accumulator is handed back to the MMA warp before any arithmetic / staging store; 0 = chunk by chunk
+            // (load, wait, convert, store), the accumulator is released after the last chunk.
             constexpr int NCH = (CH16 + 1) / 2;
-            uint32_t vv[NCH][16];
-#pragma unroll
-            for (int cl = 0; cl < NCH; ++cl)
-                if (half * NCH + cl < CH16) tmem_ld16(trow + (half * NCH + cl) * 16, vv[cl]);
-            tmem_wait_ld();
-            tc_fence_before();
-            if (sub == MSUB - 1) mbar_arrive(&tmem_empty_bar[as]); // accumulator(s) free: the MMA warp may go on
-#pragma unroll
-            for (int cl = 0; cl < NCH; ++cl) {
-                const int c = half * NCH + cl;
-                const uint32_t (&v)[16] = vv[cl];
-                if (c < CH16 && row_ok) {
+            auto chunk = [&](int c, const uint32_t (&v)[16]) {
+                if (row_ok) {
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
                         const int col = n0 + c * 16 + g * 8;
@@ -374,6 +366,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                         }
                     }
                 }
+            };
+            if (p.epi_batch) {
+                uint32_t vv[NCH][16];
+#pragma unroll
+                for (int cl = 0; cl < NCH; ++cl)
+                    if (half * NCH + cl < CH16) tmem_ld16(trow + (half * NCH + cl) * 16, vv[cl]);
+                tmem_wait_ld();
+                tc_fence_before();
+                if (sub == MSUB - 1) mbar_arrive(&tmem_empty_bar[as]); // accumulator(s) free: the MMA warp may go on
+#pragma unroll
+                for (int cl = 0; cl < NCH; ++cl)
+                    if (half * NCH + cl < CH16) chunk(half * NCH + cl, vv[cl]);
+            } else {
+#pragma unroll 1
+                for (int c = half * NCH; c < min(CH16, (half + 1) * NCH); ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(trow + c * 16, v);
+                    tmem_wait_ld();
+                    chunk(c, v);
+                }
+                tc_fence_before();
+                if (sub == MSUB - 1) mbar_arrive(&tmem_empty_bar[as]);
             }
             if (staged) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -647,8 +661,23 @@ static int pick_bn(int64_t N) {
     return 128;
 }
 
+// Plain GEMMs with a short reduction whose 128x160 tiling would leave half of the SMs idle (24..73 tiles: the M = 1024 level of
+// the UNet) take 128x80 tiles instead: every k-block is bound by what ONE SM can pull through the crossbar (~46 B/clk), so twice
+// the CTAs halve the main loop.  Long reductions keep 160 columns and split K (plan_splits); the range is chosen so that neither
+// tiling splits, i.e. hcp_splitk_workspace_bytes (which does not know the caller) stays consistent.
+static int pick_bn_gemm(int64_t N, int64_t m_tiles, int64_t total_kb) {
+    const int bn = pick_bn(N);
+    if (bn == 160 && total_kb < 40) {
+        const int64_t t160 = m_tiles * (N / 160);
+        if (t160 >= 24 && t160 < 74 && getenv("HCP_GEMM_BN80") != nullptr) return 80;      // opt-in: no gain measured in the full step
+    }
+    return bn;
+}
+
 static int dispatch_gemm(int bn, GemmKParams& kp, int m_tiles, cudaStream_t stream) {
     kp.tiles_m = m_tiles;
+    static const int epi_batch = [] { const char* e = getenv("HCP_GEMM_EPI_BATCH"); return e ? atoi(e) : 1; }();
+    kp.epi_batch = epi_batch;
     // two M tiles per work item when the reduction is long (operand-stream bound) and there are plenty of tiles
     int64_t total_kb = 0;
     for (int s = 0; s < kp.nseg; ++s) total_kb += (int64_t)kp.nkb[s] * ((kp.conv && s == 0) ? kp.ntaps : 1);
@@ -659,6 +688,7 @@ static int dispatch_gemm(int bn, GemmKParams& kp, int m_tiles, cudaStream_t stre
     switch (bn) {
         case 32: return launch_gemm<32, 1>(kp, stream);
         case 64: return launch_gemm<64, 1>(kp, stream);
+        case 80: return launch_gemm<80, 1>(kp, stream);
         case 128: return launch_gemm<128, 1>(kp, stream);
         case 160: return launch_gemm<160, 1>(kp, stream);
         default: return set_error(HCP_ERR_INVALID, "unsupported BLOCK_N");
@@ -711,7 +741,9 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     if (a->residual && (a->ldr % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: ldr");
     GemmKParams kp;
     memset(&kp, 0, sizeof(kp));
-    const int bn = pick_bn(a->N);
+    int64_t kb_all = 0;
+    for (int s = 0; s < a->nseg; ++s) kb_all += (a->k[s] + BLOCK_K - 1) / BLOCK_K;
+    const int bn = pick_bn_gemm(a->N, (a->M + BLOCK_M - 1) / BLOCK_M, kb_all);
     for (int s = 0; s < a->nseg; ++s) {
         if (a->k[s] <= 0) return set_error(HCP_ERR_INVALID, "gemm: k must be positive");
         if ((a->lda[s] % 8) != 0 || (a->ldb[s] % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: lda/ldb");
