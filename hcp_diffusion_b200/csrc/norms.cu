@@ -740,13 +740,31 @@ template <bool BWD, int NVPL>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                         const __nv_bfloat16* __restrict__ add, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int64_t M, int C,
-                                                        float* __restrict__ stats, __nv_bfloat16* __restrict__ out) {
+                                                        float* __restrict__ stats, __nv_bfloat16* __restrict__ out, int rows_per_warp) {
     pdl_trigger();
     pdl_wait();
-    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t warp_g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (row >= M) return;
     const int nv = C / 8;
+    // a warp walks `rows_per_warp` consecutive rows: the affine parameters of its columns are loaded once and stay in registers
+    float gm[NVPL][8], bt[NVPL][8];
+#pragma unroll
+    for (int k = 0; k < NVPL; ++k) {
+        const int i = lane + 32 * k;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { gm[k][e] = 0.f; bt[k][e] = 0.f; }
+        if (i < nv) {
+            const float4 g0 = *reinterpret_cast<const float4*>(gamma + i * 8), g1 = *reinterpret_cast<const float4*>(gamma + i * 8 + 4);
+            gm[k][0] = g0.x; gm[k][1] = g0.y; gm[k][2] = g0.z; gm[k][3] = g0.w; gm[k][4] = g1.x; gm[k][5] = g1.y; gm[k][6] = g1.z; gm[k][7] = g1.w;
+            if (!BWD) {
+                const float4 b0 = *reinterpret_cast<const float4*>(beta + i * 8), b1 = *reinterpret_cast<const float4*>(beta + i * 8 + 4);
+                bt[k][0] = b0.x; bt[k][1] = b0.y; bt[k][2] = b0.z; bt[k][3] = b0.w; bt[k][4] = b1.x; bt[k][5] = b1.y; bt[k][6] = b1.z; bt[k][7] = b1.w;
+            }
+        }
+    }
+    for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const int64_t row = warp_g * rows_per_warp + rr;
+    if (row >= M) return;
     const __nv_bfloat16* xr = x + row * C;
     float v[NVPL][8];
     float s = 0.f;
@@ -777,29 +795,30 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
         for (int k = 0; k < NVPL; ++k) {
             const int i = lane + 32 * k;
             if (i < nv) {
-                const int c = i * 8;
                 float o[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = (v[k][e] - mean) * rstd * gamma[c + e] + beta[c + e];
-                *reinterpret_cast<uint4*>(out + row * C + c) = pack8(o);
+                for (int e = 0; e < 8; ++e) o[e] = (v[k][e] - mean) * rstd * gm[k][e] + bt[k][e];
+                *reinterpret_cast<uint4*>(out + row * C + i * 8) = pack8(o);
             }
         }
     } else {
         const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
         float g[NVPL][8];
         float s1 = 0.f, s2 = 0.f;
+        uint4 av[NVPL];                                   // residual-gradient loads issued together with the dy loads
 #pragma unroll
         for (int k = 0; k < NVPL; ++k) {
             const int i = lane + 32 * k;
+            av[k] = make_uint4(0u, 0u, 0u, 0u);
             if (i < nv) {
-                const int c = i * 8;
                 float d[8];
-                unpack8(*reinterpret_cast<const uint4*>(dy + row * C + c), d);
+                unpack8(*reinterpret_cast<const uint4*>(dy + row * C + i * 8), d);
+                if (add) av[k] = *reinterpret_cast<const uint4*>(add + row * C + i * 8);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float xh = (v[k][e] - mean) * rstd;
                     v[k][e] = xh;
-                    g[k][e] = d[e] * gamma[c + e];
+                    g[k][e] = d[e] * gm[k][e];
                     s1 += g[k][e];
                     s2 += g[k][e] * xh;
                 }
@@ -807,34 +826,32 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
         }
         s1 = warp_sum(s1) / C;
         s2 = warp_sum(s2) / C;
-        uint4 av[NVPL];                                   // all residual-gradient loads in flight before the first store
-#pragma unroll
-        for (int k = 0; k < NVPL; ++k) {
-            const int i = lane + 32 * k;
-            av[k] = make_uint4(0u, 0u, 0u, 0u);
-            if (add && i < nv) av[k] = *reinterpret_cast<const uint4*>(add + row * C + i * 8);
-        }
 #pragma unroll
         for (int k = 0; k < NVPL; ++k) {
             const int i = lane + 32 * k;
             if (i < nv) {
-                const int c = i * 8;
                 float o[8], a[8];
                 unpack8(av[k], a);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = rstd * (g[k][e] - s1 - v[k][e] * s2) + a[e];
-                *reinterpret_cast<uint4*>(out + row * C + c) = pack8(o);
+                *reinterpret_cast<uint4*>(out + row * C + i * 8) = pack8(o);
             }
         }
     }
+    }   // rows of this warp
 }
 
 template <bool BWD>
 static void launch_layernorm(const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* add, const float* gamma,
                              const float* beta, float eps, int64_t M, int C, float* stats, __nv_bfloat16* out, cudaStream_t st) {
-    const unsigned blocks = (unsigned)((M * 32 + 255) / 256);
+    // one wave of CTAs: 148 SMs x 2 resident CTAs (the register-resident rows + affine parameters cost 75-190 registers) x 8 warps
+    int rpw = (int)((M + 2367) / 2368);
+    if (rpw < 1) rpw = 1;
+    if (rpw > 32) rpw = 32;
+    const int64_t warps = (M + rpw - 1) / rpw;
+    const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
     const int nvpl = (C / 8 + 31) / 32;
-#define LN_CASE(N) case N: launch_k(layernorm_kernel<BWD, N>, dim3(blocks), dim3(256), 0, st, x, dy, add, gamma, beta, eps, M, C, stats, out); break;
+#define LN_CASE(N) case N: launch_k(layernorm_kernel<BWD, N>, dim3(blocks), dim3(256), 0, st, x, dy, add, gamma, beta, eps, M, C, stats, out, rpw); break;
     switch (nvpl) {
         LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
     }
