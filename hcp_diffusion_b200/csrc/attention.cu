@@ -344,25 +344,31 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
                     tma_load_4d(sV + st * tile_bytes + bx * TILE_BYTES, &p.tmV, &kv_full[st], bx * 64, h, j * 128, b);
                 }
             };
+            // One thread issues every MMA of the CTA: descriptor bases are built once per call and advanced by constants, the
+            // k-loops are unrolled with predicates (see attn_bwd_kernel).
+            const int nks = p.dn / 16;
+            const uint32_t idesc_pv = make_idesc_bf16(128, p.dn, 0, 1);
+            auto koff = [](int ks) -> uint64_t { return (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4); };
             auto issue_s = [&](int t, int j) {        // S_t = Q_t K_j^T
                 const int st = j % S;
                 const int ncols = min(128, p.Lkv - j * 128);
                 const uint32_t idesc = make_idesc_bf16(128, (ncols + 15) & ~15, 0, 0);
-                const uint32_t qb = smem_u32(sQ + t * tile_bytes), kb = smem_u32(sK + st * tile_bytes);
-                for (int ks = 0; ks < p.dn / 16; ++ks) {
-                    const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
-                    umma_ss(tmem + t * 256, make_smem_desc(qb + off, 16, 1024), make_smem_desc(kb + off, 16, 1024), idesc, ks > 0);
-                }
+                const uint64_t qd = make_smem_desc(smem_u32(sQ + t * tile_bytes), 16, 1024);
+                const uint64_t kd = make_smem_desc(smem_u32(sK + st * tile_bytes), 16, 1024);
+                const uint32_t ts = tmem + t * 256;
+#pragma unroll
+                for (int ks = 0; ks < 12; ++ks)
+                    if (ks < nks) umma_ss(ts, qd + koff(ks), kd + koff(ks), idesc, ks > 0);
                 umma_commit(&s_full[t]);
             };
             auto issue_pv = [&](int t, int j) {       // O_t += P_t V_j  (P from TMEM, V MN-major)
                 const int st = j % S;
-                const int ncols = min(128, p.Lkv - j * 128);
-                const uint32_t idesc = make_idesc_bf16(128, p.dn, 0, 1);
-                const uint32_t vb = smem_u32(sV + st * tile_bytes);
-                for (int ks = 0; ks < ((ncols + 15) >> 4); ++ks)
-                    umma_ts(tmem + t * 256 + 192, tmem + t * 256 + 128 + ks * 8, make_smem_desc(vb + ks * 2048, TILE_BYTES, 1024), idesc,
-                            (j > 0 || ks > 0) ? 1u : 0u);
+                const int nst = (min(128, p.Lkv - j * 128) + 15) >> 4;
+                const uint64_t vd = make_smem_desc(smem_u32(sV + st * tile_bytes), TILE_BYTES, 1024);
+                const uint32_t to = tmem + t * 256 + 192, tp = tmem + t * 256 + 128;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    if (ks < nst) umma_ts(to, tp + ks * 8, vd + (uint64_t)(ks * 128), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
                 umma_commit(&pv_done[t]);
             };
             mbar_arrive_expect_tx(q_full, p.nq * tile_bytes);
@@ -653,41 +659,49 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             const uint32_t box0 = (p.col0 / 64) * TILE_BYTES;                     // first box of the output slice
             const uint32_t kb = smem_u32(sK), vb = smem_u32(sV);
             const uint32_t pb = smem_u32(sP), dsb = smem_u32(sdS);
+            // The issuing thread is ONE thread: every instruction it spends building descriptors delays the next MMA.  Descriptor
+            // bases are built once; inside a 1024-byte swizzle atom / between 64-column boxes the start-address field advances by a
+            // constant (>> 4), so each MMA costs one 64-bit add per operand (ncu: the softmax warps of the forward kernel spent a
+            // third of their samples waiting for S while this thread was assembling descriptors).
+            const int nks = p.dn / 16;                                   // k-steps of the d contraction (<= 12)
+            const uint64_t kdesc_k = make_smem_desc(kb, 16, 1024);           // K as K-major operand (S = Q K^T)
+            const uint64_t vdesc_k = make_smem_desc(vb, 16, 1024);           // V as K-major operand (dP = dO V^T)
+            const uint64_t pdesc_mn = make_smem_desc(pb, TILE_BYTES, 1024);  // P^T  (MN-major A of dV)
+            const uint64_t dsdesc_mn = make_smem_desc(dsb, TILE_BYTES, 1024);// dS^T (MN-major A of dK)
+            const uint64_t dsdesc_k = make_smem_desc(dsb, 16, 1024);         // dS   (K-major A of dQ)
+            const uint64_t kdesc_mn = make_smem_desc(kb + box0, TILE_BYTES, 1024);   // K (MN-major B of dQ)
+            auto koff = [](int ks) -> uint64_t { return (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4); };
             auto issue_s = [&](int st) {            // S = Q K^T  (contraction over d)
-                const uint32_t qb = smem_u32(sQ + st * tile_bytes);
-                for (int ks = 0; ks < p.dn / 16; ++ks) {
-                    const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
-                    umma_ss(tS, make_smem_desc(qb + off, 16, 1024), make_smem_desc(kb + off, 16, 1024), idesc_s, ks > 0);
-                }
+                const uint64_t qd = make_smem_desc(smem_u32(sQ + st * tile_bytes), 16, 1024);
+#pragma unroll
+                for (int ks = 0; ks < 12; ++ks)
+                    if (ks < nks) umma_ss(tS, qd + koff(ks), kdesc_k + koff(ks), idesc_s, ks > 0);
             };
             auto issue_dp = [&](int st) {           // dP = dO V^T, then signal "S and dP ready"
-                const uint32_t dob = smem_u32(sdO + st * tile_bytes);
-                for (int ks = 0; ks < p.dn / 16; ++ks) {
-                    const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
-                    umma_ss(tdP, make_smem_desc(dob + off, 16, 1024), make_smem_desc(vb + off, 16, 1024), idesc_s, ks > 0);
-                }
+                const uint64_t dod = make_smem_desc(smem_u32(sdO + st * tile_bytes), 16, 1024);
+#pragma unroll
+                for (int ks = 0; ks < 12; ++ks)
+                    if (ks < nks) umma_ss(tdP, dod + koff(ks), vdesc_k + koff(ks), idesc_s, ks > 0);
                 umma_commit(sdp_full);
             };
             auto issue_sdp = [&](int st) { issue_s(st); issue_dp(st); };
             auto issue_dv = [&](int st, bool acc) {  // dV += P^T dO   (M = kv, K = q rows: both operands MN-major, 2048 B per k-step)
-                const uint32_t dob = smem_u32(sdO + st * tile_bytes);
+                const uint64_t dod = make_smem_desc(smem_u32(sdO + st * tile_bytes) + box0, TILE_BYTES, 1024);
+#pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    umma_ss(tdV, make_smem_desc(pb + ks * 2048, TILE_BYTES, 1024), make_smem_desc(dob + box0 + ks * 2048, TILE_BYTES, 1024),
-                            idesc_acc, (acc || ks > 0) ? 1u : 0u);
+                    umma_ss(tdV, pdesc_mn + (uint64_t)(ks * 128), dod + (uint64_t)(ks * 128), idesc_acc, (acc || ks > 0) ? 1u : 0u);
                 umma_commit(dv_done);
             };
             auto issue_dk = [&](int st, bool acc) {  // dK += dS^T Q
-                const uint32_t qb = smem_u32(sQ + st * tile_bytes);
+                const uint64_t qd = make_smem_desc(smem_u32(sQ + st * tile_bytes) + box0, TILE_BYTES, 1024);
+#pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    umma_ss(tdK, make_smem_desc(dsb + ks * 2048, TILE_BYTES, 1024), make_smem_desc(qb + box0 + ks * 2048, TILE_BYTES, 1024),
-                            idesc_acc, (acc || ks > 0) ? 1u : 0u);
+                    umma_ss(tdK, dsdesc_mn + (uint64_t)(ks * 128), qd + (uint64_t)(ks * 128), idesc_acc, (acc || ks > 0) ? 1u : 0u);
             };
             auto issue_dq = [&]() {                  // dQ_i = dS K: dS K-major (two 64-wide boxes), K_j MN-major
-                for (int ks = 0; ks < 8; ++ks) {
-                    const uint32_t aoff = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
-                    umma_ss(tdQ, make_smem_desc(dsb + aoff, 16, 1024), make_smem_desc(kb + box0 + ks * 2048, TILE_BYTES, 1024), idesc_dq,
-                            ks > 0);
-                }
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_ss(tdQ, dsdesc_k + koff(ks), kdesc_mn + (uint64_t)(ks * 128), idesc_dq, ks > 0);
                 umma_commit(dq_full);
             };
             if (p.early_sdp) {
