@@ -31,7 +31,7 @@ constexpr int kBwdParts = 4;               // bwd: softmax warps per TMEM lane q
                                            // the TMEM-load / MUFU latencies that 8 warps (2 per scheduler) left exposed (ncu: 2.25 active warps,
                                            // issue slot used every 3.1 cycles); 16-column register chunks keep them under the 120-register cap
 constexpr int kBwdSoftmaxThreads = 4 * kBwdParts * 32;
-constexpr int kAttnBwdThreads = kBwdSoftmaxThreads + 32;   // + one control warp (the last)
+constexpr int kAttnBwdThreads = kBwdSoftmaxThreads + 3 * 32;   // + three single-thread warps: S/dP issue (+ TMA), dV/dK/dQ issue, Q/dO refill
 constexpr int TILE_BYTES = 128 * 128;      // one [128 rows x 64 cols] bf16 box
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -260,13 +260,44 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_fwd_kernel(const __grid_
     if (warp == 4) tmem_dealloc(tmem, p.tmem_cols);
 }
 
+// ---- MMA issue helpers for the single issuing threads -------------------------------------------------------------------------
+// A thread that issues tcgen05.mma runs a chain of dependent uniform-datapath instructions at ~0.15 IPC (ncu: 596 instructions
+// per kv step in the first forward kernel = the whole step time), so its instruction count IS the critical path.  Descriptors are
+// built once and advanced on the low word only (the 14-bit start-address field never carries out for shared-memory addresses),
+// and the k-loops are fully unrolled for the head sizes of the UNets (d 40 / 64 / 80 / 160 -> 3 / 4 / 5 / 10 steps of 16).
+__device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t off16) {
+    return (d & 0xffffffff00000000ull) | (uint64_t)((uint32_t)d + off16);
+}
+// offset (in 16-byte units) of k-step ks inside a K-major operand tile made of 64-column SWIZZLE_128B boxes
+__device__ __forceinline__ constexpr uint32_t kmajor_off(int ks) { return (uint32_t)((ks >> 2) * (TILE_BYTES >> 4) + (ks & 3) * 2); }
+template <int N>
+__device__ __forceinline__ void umma_ss_kmajor(uint32_t tacc, uint64_t a, uint64_t b, uint32_t idesc) {
+#pragma unroll
+    for (int ks = 0; ks < N; ++ks) umma_ss(tacc, desc_adv(a, kmajor_off(ks)), desc_adv(b, kmajor_off(ks)), idesc, ks > 0 ? 1u : 0u);
+}
+__device__ __forceinline__ void umma_ss_kmajor_n(int nks, uint32_t tacc, uint64_t a, uint64_t b, uint32_t idesc) {
+    switch (nks) {
+        case 3: umma_ss_kmajor<3>(tacc, a, b, idesc); break;
+        case 4: umma_ss_kmajor<4>(tacc, a, b, idesc); break;
+        case 5: umma_ss_kmajor<5>(tacc, a, b, idesc); break;
+        case 10: umma_ss_kmajor<10>(tacc, a, b, idesc); break;
+        default:
+#pragma unroll 1
+            for (int ks = 0; ks < nks; ++ks)
+                umma_ss(tacc, desc_adv(a, kmajor_off(ks)), desc_adv(b, kmajor_off(ks)), idesc, ks > 0 ? 1u : 0u);
+    }
+}
+
 // =============================================================================================
 // forward, version 2: two 128-row query tiles per CTA (they share every K/V tile that TMA brings in), 16 softmax warps
 // (per query tile: 4 TMEM lane quarters x 2 column halves) and one control warp that ping-pongs the tensor pipe between the
 // two tiles: while the softmax warps of tile A exponentiate tile j, the pipe runs S_B(j), PV_B(j-1)...  Each softmax thread
 // reads its 64 logits from TMEM ONCE, the row maximum of the two column halves is combined through shared memory.
+// Warp 16 is the TMA producer (Q once, K/V stages), warps 17 and 18 each issue the MMAs of one query tile: three short
+// instruction streams instead of one long one (the single control thread of the first version was busy 90 % of the time and the
+// softmax warps spent a third of theirs waiting for logits it had not issued yet).
 // =============================================================================================
-constexpr int kFwd2Threads = 17 * 32;
+constexpr int kFwd2Threads = 19 * 32;
 
 struct alignas(64) AttnFwd2Params {
     CUtensorMap tmQ, tmK, tmV;
@@ -312,12 +343,12 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
-        for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_done[i], 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_done[i], p.nq); }   // one commit per MMA warp
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 256);
             mbar_init(&s_free[i], 256); mbar_init(&pv_done[i], 1);
         }
-        mbar_init(o_full, 1);
+        mbar_init(o_full, p.nq);
         fence_mbar_init();
     }
     if (warp == 16) {
@@ -335,86 +366,84 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
     // registers: QK^T(j+1) runs on the tensor pipe while the exponentials of tile j are computed.
 
     if (warp == 16) {
+        // ------------------------------ TMA producer ------------------------------
         if (elect_one()) {
-            auto load_kv = [&](int j) {
-                const int st = j % S;
+            mbar_arrive_expect_tx(q_full, p.nq * tile_bytes);
+            for (int t = 0; t < p.nq; ++t)
+                for (int bx = 0; bx < p.nbox; ++bx)
+                    tma_load_4d(sQ + t * tile_bytes + bx * TILE_BYTES, &p.tmQ, q_full, bx * 64, h, q0 + t * 128, b);
+            int st = 0, round = 0;                                       // stage / use count of the stage for kv tile j
+            for (int j = 0; j < nkv; ++j) {
+                if (round > 0) mbar_wait(&kv_done[st], (round - 1) & 1);  // both query tiles have retired P V of the tile that was here
                 mbar_arrive_expect_tx(&kv_full[st], 2 * tile_bytes);
                 for (int bx = 0; bx < p.nbox; ++bx) {
                     tma_load_4d(sK + st * tile_bytes + bx * TILE_BYTES, &p.tmK, &kv_full[st], bx * 64, h, j * 128, b);
                     tma_load_4d(sV + st * tile_bytes + bx * TILE_BYTES, &p.tmV, &kv_full[st], bx * 64, h, j * 128, b);
                 }
-            };
-            // One thread issues every MMA of the CTA: descriptor bases are built once per call and advanced by constants, the
-            // k-loops are unrolled with predicates (see attn_bwd_kernel).
+                if (++st == S) { st = 0; ++round; }
+            }
+        }
+    } else if (warp >= 17) {
+        // ------------------------------ MMA issue, one warp per query tile ------------------------------
+        const int t = warp - 17;
+        if (t < p.nq && elect_one()) {
             const int nks = p.dn / 16;
             const uint32_t idesc_pv = make_idesc_bf16(128, p.dn, 0, 1);
-            auto koff = [](int ks) -> uint64_t { return (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4); };
-            auto issue_s = [&](int t, int j) {        // S_t = Q_t K_j^T
-                const int st = j % S;
-                const int ncols = min(128, p.Lkv - j * 128);
-                const uint32_t idesc = make_idesc_bf16(128, (ncols + 15) & ~15, 0, 0);
-                const uint64_t qd = make_smem_desc(smem_u32(sQ + t * tile_bytes), 16, 1024);
-                const uint64_t kd = make_smem_desc(smem_u32(sK + st * tile_bytes), 16, 1024);
-                const uint32_t ts = tmem + t * 256;
-#pragma unroll
-                for (int ks = 0; ks < 12; ++ks)
-                    if (ks < nks) umma_ss(ts, qd + koff(ks), kd + koff(ks), idesc, ks > 0);
+            const uint32_t idesc_s_full = make_idesc_bf16(128, 128, 0, 0);
+            const int ncols_last = p.Lkv - (nkv - 1) * 128;
+            const uint32_t idesc_s_last = make_idesc_bf16(128, (ncols_last + 15) & ~15, 0, 0);
+            const int nst_last = (ncols_last + 15) >> 4;
+            const uint64_t qd = make_smem_desc(smem_u32(sQ + t * tile_bytes), 16, 1024);
+            const uint64_t kd0 = make_smem_desc(smem_u32(sK), 16, 1024);
+            const uint64_t vd0 = make_smem_desc(smem_u32(sV), TILE_BYTES, 1024);
+            const uint32_t stage16 = (uint32_t)tile_bytes >> 4;
+            const uint32_t ts = tmem + t * 256, tp = ts + 128, to = ts + 192;
+            auto issue_s = [&](int j, int st) {        // S_t = Q_t K_j^T
+                umma_ss_kmajor_n(nks, ts, qd, desc_adv(kd0, st * stage16), j == nkv - 1 ? idesc_s_last : idesc_s_full);
                 umma_commit(&s_full[t]);
             };
-            auto issue_pv = [&](int t, int j) {       // O_t += P_t V_j  (P from TMEM, V MN-major)
-                const int st = j % S;
-                const int nst = (min(128, p.Lkv - j * 128) + 15) >> 4;
-                const uint64_t vd = make_smem_desc(smem_u32(sV + st * tile_bytes), TILE_BYTES, 1024);
-                const uint32_t to = tmem + t * 256 + 192, tp = tmem + t * 256 + 128;
+            auto issue_pv = [&](int j, int st) {       // O_t += P_t V_j  (P from TMEM, V MN-major: 2048 B per k-step)
+                const uint64_t vd = desc_adv(vd0, st * stage16);
+                if (j < nkv - 1 || nst_last == 8) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    if (ks < nst) umma_ts(to, tp + ks * 8, vd + (uint64_t)(ks * 128), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_ts(to, tp + ks * 8, desc_adv(vd, ks * 128), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+                } else {
+#pragma unroll 1
+                    for (int ks = 0; ks < nst_last; ++ks)
+                        umma_ts(to, tp + ks * 8, desc_adv(vd, ks * 128), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+                }
                 umma_commit(&pv_done[t]);
+                umma_commit(&kv_done[st]);             // K_j / V_j are free once both tiles' commits have arrived
             };
-            mbar_arrive_expect_tx(q_full, p.nq * tile_bytes);
-            for (int t = 0; t < p.nq; ++t)
-                for (int bx = 0; bx < p.nbox; ++bx)
-                    tma_load_4d(sQ + t * tile_bytes + bx * TILE_BYTES, &p.tmQ, q_full, bx * 64, h, q0 + t * 128, b);
-            for (int j = 0; j < min(S, nkv); ++j) load_kv(j);
             mbar_wait(q_full, 0);
             mbar_wait(&kv_full[0], 0);
-            tc_fence_after();
             // The two query tiles are started half an iteration apart: tile 1 gets its first logits only when tile 0 has pulled
             // its own into registers and enters the exponential phase.  Each tile's chain (logits -> max -> exp -> P) is strictly
             // sequential, so the offset persists and the MUFU pipe serves one tile's exponentials while the other tile loads /
             // reduces / stores (ncu, in-phase start: XU pipe 49 % busy, both tiles contending in the same window).
+            if (t == 1) mbar_wait(&s_free[0], 0);
+            tc_fence_after();
             issue_s(0, 0);
-            if (p.nq == 2) {
-                mbar_wait(&s_free[0], 0);
-                tc_fence_after();
-                issue_s(1, 0);
-            }
+            int st = 0, round = 0;
             for (int j = 0; j < nkv; ++j) {
-                const int st = j % S;
+                int st1 = st + 1, round1 = round;
+                if (st1 == S) { st1 = 0; ++round1; }
                 if (S > 1 && j + 1 < nkv) {                             // next K tile is resident: issue S(j+1) early
-                    mbar_wait(&kv_full[(j + 1) % S], ((j + 1) / S) & 1);
+                    mbar_wait(&kv_full[st1], round1 & 1);
+                    mbar_wait(&s_free[t], j & 1);                       // logits of tile j are in registers
                     tc_fence_after();
-                    for (int t = 0; t < p.nq; ++t) {
-                        mbar_wait(&s_free[t], j & 1);                   // logits of tile j are in registers
-                        tc_fence_after();
-                        issue_s(t, j + 1);
-                    }
+                    issue_s(j + 1, st1);
                 }
-                for (int t = 0; t < p.nq; ++t) {
-                    mbar_wait(&p_ready[t], j & 1);
-                    tc_fence_after();
-                    issue_pv(t, j);
-                    if (t == p.nq - 1) umma_commit(&kv_done[st]);      // K_j / V_j no longer needed once these retire
-                }
-                if (j + S < nkv) {                                      // refill the stage tile j used
-                    mbar_wait(&kv_done[st], (j / S) & 1);
-                    load_kv(j + S);
-                }
-                if (S == 1 && j + 1 < nkv) {                            // single stage (d > 128): load, then issue
+                mbar_wait(&p_ready[t], j & 1);
+                tc_fence_after();
+                issue_pv(j, st);
+                if (S == 1 && j + 1 < nkv) {                            // single stage (d > 128): the producer reloads, then issue
                     mbar_wait(&kv_full[0], (j + 1) & 1);
                     tc_fence_after();
-                    for (int t = 0; t < p.nq; ++t) issue_s(t, j + 1);
+                    issue_s(j + 1, 0);
                 }
+                st = st1; round = round1;
             }
             umma_commit(o_full);
         }
@@ -439,17 +468,24 @@ __global__ void __launch_bounds__(kFwd2Threads, 1) attn_fwd2_kernel(const __grid
             tmem_ld32(tS + lb + c0 + 32, v1);
             tmem_wait_ld();
             float sc = p.scale_log2;
-            if (special) {                 // masked / biased tile: move to the scaled domain in place, then sc = 1
+            if (bias) {                    // additive key bias: move to the scaled domain in place, then sc = 1
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                     float a = __uint_as_float(v0[e]) * p.scale_log2, c = __uint_as_float(v1[e]) * p.scale_log2;
                     const int ca = c0 + e, cb = c0 + 32 + e;
-                    if (bias && ca < ncols) a += bias[kv0 + ca] * kLog2e;
-                    if (bias && cb < ncols) c += bias[kv0 + cb] * kLog2e;
+                    if (ca < ncols) a += __ldg(bias + kv0 + ca) * kLog2e;
+                    if (cb < ncols) c += __ldg(bias + kv0 + cb) * kLog2e;
                     v0[e] = __float_as_uint(ca < ncols ? a : -INFINITY);
                     v1[e] = __float_as_uint(cb < ncols ? c : -INFINITY);
+                    if ((e & 7) == 7) asm volatile("" ::: "memory");   // keep at most 16 bias loads in flight (register pressure)
                 }
                 sc = 1.f;
+            } else if (special) {          // ragged last tile: columns past Lkv become -inf (the positive scale keeps them there)
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    if (c0 + e >= ncols) v0[e] = 0xff800000u;
+                    if (c0 + 32 + e >= ncols) v1[e] = 0xff800000u;
+                }
             }
             float mx = fmaxf(__uint_as_float(v0[0]), __uint_as_float(v1[0]));
 #pragma unroll
@@ -635,8 +671,12 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
     const uint32_t tdK = p.early_sdp ? tmem + 256 + p.ncols_out : tmem + 384;
     const uint32_t tdQ = p.early_sdp ? tmem + 256 + 2 * p.ncols_out : tmem;
 
-    if (warp == 4 * kBwdParts) {
-        if (elect_one()) {
+    if (warp >= 4 * kBwdParts) {
+        // role 0: TMA prologue + S / dP issue (and the whole schedule when !early_sdp); role 1: dV / dK / dQ issue; role 2: Q/dO
+        // refills.  Three short instruction streams: one thread issuing all ~30 MMAs and the TMA of an iteration was busy 70 %
+        // of the time (ncu) and sat on the critical path (see the forward kernel).
+        const int role = warp - 4 * kBwdParts;
+        if ((role == 0 || p.early_sdp) && elect_one()) {
             auto qbar = [&](int st) { return st == 2 ? q_full2 : &q_full[st]; };
             auto load_q = [&](int i) {
                 const int st = i % p.q_stages;
@@ -646,12 +686,18 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                     tma_load_4d(sdO + st * tile_bytes + bx * TILE_BYTES, &p.tmdO, qbar(st), bx * 64, h, (i0 + i) * 128, b);
                 }
             };
-            mbar_arrive_expect_tx(kv_full, 2 * tile_bytes);
-            for (int bx = 0; bx < p.nbox; ++bx) {
-                tma_load_4d(sK + bx * TILE_BYTES, &p.tmK, kv_full, bx * 64, h, kv0, b);
-                tma_load_4d(sV + bx * TILE_BYTES, &p.tmV, kv_full, bx * 64, h, kv0, b);
+            if (role == 0) {
+                mbar_arrive_expect_tx(kv_full, 2 * tile_bytes);
+                for (int bx = 0; bx < p.nbox; ++bx) {
+                    tma_load_4d(sK + bx * TILE_BYTES, &p.tmK, kv_full, bx * 64, h, kv0, b);
+                    tma_load_4d(sV + bx * TILE_BYTES, &p.tmV, kv_full, bx * 64, h, kv0, b);
+                }
+                load_q(0);
+                if (p.early_sdp) {
+                    if (nq > 1) load_q(1);
+                    if (nq > 2) load_q(2);
+                }
             }
-            load_q(0);
             mbar_wait(kv_full, 0);
             const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
             const uint32_t idesc_acc = make_idesc_bf16(128, p.ncols_out, 1, 1);   // dV, dK: A and B MN-major
@@ -659,10 +705,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             const uint32_t box0 = (p.col0 / 64) * TILE_BYTES;                     // first box of the output slice
             const uint32_t kb = smem_u32(sK), vb = smem_u32(sV);
             const uint32_t pb = smem_u32(sP), dsb = smem_u32(sdS);
-            // The issuing thread is ONE thread: every instruction it spends building descriptors delays the next MMA.  Descriptor
-            // bases are built once; inside a 1024-byte swizzle atom / between 64-column boxes the start-address field advances by a
-            // constant (>> 4), so each MMA costs one 64-bit add per operand (ncu: the softmax warps of the forward kernel spent a
-            // third of their samples waiting for S while this thread was assembling descriptors).
+            // The issuing thread is ONE thread: descriptor bases are built once and advanced by constants (see umma_ss_kmajor_n).
             const int nks = p.dn / 16;                                   // k-steps of the d contraction (<= 12)
             const uint64_t kdesc_k = make_smem_desc(kb, 16, 1024);           // K as K-major operand (S = Q K^T)
             const uint64_t vdesc_k = make_smem_desc(vb, 16, 1024);           // V as K-major operand (dP = dO V^T)
@@ -670,18 +713,11 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             const uint64_t dsdesc_mn = make_smem_desc(dsb, TILE_BYTES, 1024);// dS^T (MN-major A of dK)
             const uint64_t dsdesc_k = make_smem_desc(dsb, 16, 1024);         // dS   (K-major A of dQ)
             const uint64_t kdesc_mn = make_smem_desc(kb + box0, TILE_BYTES, 1024);   // K (MN-major B of dQ)
-            auto koff = [](int ks) -> uint64_t { return (uint64_t)(((ks >> 2) * TILE_BYTES + (ks & 3) * 32) >> 4); };
             auto issue_s = [&](int st) {            // S = Q K^T  (contraction over d)
-                const uint64_t qd = make_smem_desc(smem_u32(sQ + st * tile_bytes), 16, 1024);
-#pragma unroll
-                for (int ks = 0; ks < 12; ++ks)
-                    if (ks < nks) umma_ss(tS, qd + koff(ks), kdesc_k + koff(ks), idesc_s, ks > 0);
+                umma_ss_kmajor_n(nks, tS, make_smem_desc(smem_u32(sQ + st * tile_bytes), 16, 1024), kdesc_k, idesc_s);
             };
             auto issue_dp = [&](int st) {           // dP = dO V^T, then signal "S and dP ready"
-                const uint64_t dod = make_smem_desc(smem_u32(sdO + st * tile_bytes), 16, 1024);
-#pragma unroll
-                for (int ks = 0; ks < 12; ++ks)
-                    if (ks < nks) umma_ss(tdP, dod + koff(ks), vdesc_k + koff(ks), idesc_s, ks > 0);
+                umma_ss_kmajor_n(nks, tdP, make_smem_desc(smem_u32(sdO + st * tile_bytes), 16, 1024), vdesc_k, idesc_s);
                 umma_commit(sdp_full);
             };
             auto issue_sdp = [&](int st) { issue_s(st); issue_dp(st); };
@@ -689,57 +725,62 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                 const uint64_t dod = make_smem_desc(smem_u32(sdO + st * tile_bytes) + box0, TILE_BYTES, 1024);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    umma_ss(tdV, pdesc_mn + (uint64_t)(ks * 128), dod + (uint64_t)(ks * 128), idesc_acc, (acc || ks > 0) ? 1u : 0u);
+                    umma_ss(tdV, desc_adv(pdesc_mn, ks * 128), desc_adv(dod, ks * 128), idesc_acc, (acc || ks > 0) ? 1u : 0u);
                 umma_commit(dv_done);
             };
             auto issue_dk = [&](int st, bool acc) {  // dK += dS^T Q
                 const uint64_t qd = make_smem_desc(smem_u32(sQ + st * tile_bytes) + box0, TILE_BYTES, 1024);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    umma_ss(tdK, dsdesc_mn + (uint64_t)(ks * 128), qd + (uint64_t)(ks * 128), idesc_acc, (acc || ks > 0) ? 1u : 0u);
+                    umma_ss(tdK, desc_adv(dsdesc_mn, ks * 128), desc_adv(qd, ks * 128), idesc_acc, (acc || ks > 0) ? 1u : 0u);
             };
             auto issue_dq = [&]() {                  // dQ_i = dS K: dS K-major (two 64-wide boxes), K_j MN-major
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    umma_ss(tdQ, dsdesc_k + koff(ks), kdesc_mn + (uint64_t)(ks * 128), idesc_dq, ks > 0);
+                    umma_ss(tdQ, desc_adv(dsdesc_k, kmajor_off(ks)), desc_adv(kdesc_mn, ks * 128), idesc_dq, ks > 0 ? 1u : 0u);
                 umma_commit(dq_full);
             };
             if (p.early_sdp) {
                 // dQ has its own TMEM columns and Q/dO have three stages.  The softmax threads pull their S / dP values of tile i
-                // into registers first (sdp_free), so S/dP of tile i+1 are issued while the exponentials of tile i are computed;
-                // dV_i, dK_i, dQ_i follow as their operands appear.  The tensor pipe and the softmax warps never wait for each
-                // other except for true data dependencies.
-                if (nq > 1) load_q(1);
-                if (nq > 2) load_q(2);
-                mbar_wait(&q_full[0], 0);
-                tc_fence_after();
-                issue_sdp(0);
-                for (int i = 0; i < nq; ++i) {
-                    const int st = i % 3;
-                    if (i + 1 < nq) {
-                        mbar_wait(sdp_free, i & 1);          // S_i is in registers: S_{i+1} may overwrite the columns
-                        mbar_wait(qbar((i + 1) % 3), ((i + 1) / 3) & 1);
-                        tc_fence_after();
-                        issue_s((i + 1) % 3);
-                    }
-                    mbar_wait(p_ready, i & 1);
+                // into registers first (sdp_free / dp_free), so S/dP of tile i+1 are issued while the exponentials of tile i are
+                // computed; dV_i, dK_i, dQ_i follow as their operands appear.  The tensor pipe and the softmax warps never wait
+                // for each other except for true data dependencies.
+                if (role == 0) {
+                    mbar_wait(&q_full[0], 0);
                     tc_fence_after();
-                    issue_dv(st, i > 0);
-                    if (i + 1 < nq) {
-                        mbar_wait(dp_free, i & 1);           // dP_i is in registers
+                    issue_sdp(0);
+                    int st1 = 1, ph1 = 0;                        // stage / parity of tile i+1
+                    for (int i = 0; i + 1 < nq; ++i) {
+                        mbar_wait(sdp_free, i & 1);              // S_i is in registers: S_{i+1} may overwrite the columns
+                        mbar_wait(qbar(st1), ph1);
                         tc_fence_after();
-                        issue_dp((i + 1) % 3);
-                    }
-                    mbar_wait(ds_ready, i & 1);
-                    tc_fence_after();
-                    issue_dk(st, i > 0);
-                    if (i > 0) {
-                        mbar_wait(dq_read, (i - 1) & 1);     // dQ_{i-1} drained from TMEM
+                        issue_s(st1);
+                        mbar_wait(dp_free, i & 1);               // dP_i is in registers
                         tc_fence_after();
+                        issue_dp(st1);
+                        if (++st1 == 3) { st1 = 0; ph1 ^= 1; }
                     }
-                    issue_dq();
-                    if (i + 3 < nq) {
-                        mbar_wait(dq_full, i & 1);           // every MMA reading Q_i / dO_i has retired: the stage is free
+                } else if (role == 1) {
+                    int st = 0, ph = 0;
+                    for (int i = 0; i < nq; ++i) {
+                        mbar_wait(qbar(st), ph);                 // (complete long ago: S_i came from this stage) smem visibility
+                        mbar_wait(p_ready, i & 1);
+                        tc_fence_after();
+                        issue_dv(st, i > 0);
+                        mbar_wait(ds_ready, i & 1);
+                        tc_fence_after();
+                        issue_dk(st, i > 0);
+                        if (i > 0) {
+                            mbar_wait(dq_read, (i - 1) & 1);     // dQ_{i-1} drained from TMEM
+                            tc_fence_after();
+                        }
+                        issue_dq();
+                        if (++st == 3) { st = 0; ph ^= 1; }
+                    }
+                    umma_commit(acc_full);
+                } else {
+                    for (int i = 0; i + 3 < nq; ++i) {
+                        mbar_wait(dq_full, i & 1);               // every MMA reading Q_i / dO_i has retired: the stage is free
                         load_q(i + 3);
                     }
                 }
@@ -765,8 +806,8 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                     mbar_wait(dq_read, i & 1);          // S/dP/dQ columns free again
                     tc_fence_after();
                 }
+                umma_commit(acc_full);
             }
-            umma_commit(acc_full);
         }
     } else {
         // ------------------------------ thread == query row (S, dP) / kv row (dK, dV) --------------
@@ -819,7 +860,8 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             const int qrow = (i0 + i) * 128 + row;
             const bool qok = qrow < p.Lq;
             const int64_t stat_idx = stat_base + qrow;
-            const float neg_lse2 = -lse_nx * kLog2e;
+            // rows past Lq: Q / dO rows are TMA zero fill, so S = dP = 0 there and a -inf offset makes every P (and dS) exactly 0
+            const float neg_lse2 = qok ? -lse_nx * kLog2e : -INFINITY;
             const float neg_dlt_s = -dlt_nx * p.scale;
             if (i + 1 < nq) {
                 const int qn = qrow + 128;
@@ -896,7 +938,6 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                             q2 = (col + 16 < ncols) ? q2 : -INFINITY;
                             q3 = (col + 17 < ncols) ? q3 : -INFINITY;
                         }
-                        if (!qok) q0 = q1 = q2 = q3 = -INFINITY;           // exp2(-inf) == 0
                         pk[e >> 1] = pack_bf16x2(fast_exp2(q0), fast_exp2(q1));
                         pk[8 + (e >> 1)] = pack_bf16x2(fast_exp2(q2), fast_exp2(q3));
                     }
