@@ -178,6 +178,24 @@ def time_kernel(fn, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
+def ncu_dram_traffic(summary="profiles/r01_ncu_attn_bwd_v23.summary.csv"):
+    """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed `ncu --set full` summary of the same
+    kernel at the same shape (attention backward, B=4 H=8 L=4096 d=40).  None when the file is absent."""
+    import csv
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), summary)
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, unit, val = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            tot += float(val[i]) * scale[unit[i]]
+        return {"bytes_per_launch": tot, "kernel": "attn_bwd_kernel B4 H8 L4096 d40", "source": summary}
+    except (OSError, ValueError, KeyError, IndexError):
+        return None
+
+
 def dominant_kernel_roofline(peak_tflops):
     """Live CUDA-event timing of the kernels that dominate the step, at their benchmark shapes (B=4)."""
     from hcp_diffusion_b200 import ops
@@ -292,7 +310,7 @@ def run_product_arm(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": step.launches_per_step * args.steps,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-                     "traffic": None, "peak_source": f"{peak_src} bf16_tflops_sustained (step-level); kernels vs burst {burst}",
+                     "traffic": ncu_dram_traffic(), "peak_source": f"{peak_src} bf16_tflops_sustained (step-level); kernels vs burst {burst}",
                      "flop_per_image": F_STEP, "kernels": kern},
         "final_loss": losses[-1],
     }
