@@ -962,11 +962,12 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                     // dS = P (dP - delta) scale, with the bf16-rounded P the tensor pipe sees in dV
 #pragma unroll
                     for (int e = 0; e < 16; e += 2) {
-                        const float2 pa = unpack_bf16x2(pk[e >> 1]), pb2 = unpack_bf16x2(pk[8 + (e >> 1)]);
-                        pk[e >> 1] = pack_bf16x2(pa.x * fmaf(__uint_as_float(w0[e]), p.scale, neg_dlt_s),
-                                                 pa.y * fmaf(__uint_as_float(w0[e + 1]), p.scale, neg_dlt_s));
-                        pk[8 + (e >> 1)] = pack_bf16x2(pb2.x * fmaf(__uint_as_float(w1[e]), p.scale, neg_dlt_s),
-                                                       pb2.y * fmaf(__uint_as_float(w1[e + 1]), p.scale, neg_dlt_s));
+                        // packed product: (dP - delta) scale is rounded to bf16 like P and multiplied two at a time -- no
+                        // re-expansion of the packed P (2 unpack + 2 FMUL per pair -> 1 HMUL2)
+                        pk[e >> 1] = mul_bf16x2(pk[e >> 1], pack_bf16x2(fmaf(__uint_as_float(w0[e]), p.scale, neg_dlt_s),
+                                                                        fmaf(__uint_as_float(w0[e + 1]), p.scale, neg_dlt_s)));
+                        pk[8 + (e >> 1)] = mul_bf16x2(pk[8 + (e >> 1)], pack_bf16x2(fmaf(__uint_as_float(w1[e]), p.scale, neg_dlt_s),
+                                                                                    fmaf(__uint_as_float(w1[e + 1]), p.scale, neg_dlt_s)));
                     }
                 }
 #pragma unroll
