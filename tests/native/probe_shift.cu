@@ -1,6 +1,6 @@
 // SPDX-License-Identifier: Apache-2.0
-// Row-shifted A operand probe (test infrastructure, NOT part of the product path; written without GPU access at the end of round 1
-// and compile-checked only).
+// Row-shifted A operand probe (test infrastructure, NOT part of the product path).  Result on B200 (profiles/r01_native_probe_shift.log):
+// every shift is exact with the base-offset field LEFT AT 0 and wrong with it set -- the swizzle depends on the absolute address only.
 //
 // Question: can ONE shared-memory copy of an activation halo serve all nine taps of a 3x3 convolution?  The implicit-GEMM kernel
 // loads the A tile (128 pixels x 64 channels, K-major, SWIZZLE_128B) nine times per 64-channel block, once per tap, and is bound by
