@@ -50,6 +50,9 @@ struct alignas(64) HaloParams {
     __nv_bfloat16* out;     // [B, H, W, Cout]
 };
 
+// MSUB = 2: two virtually adjacent 128-pixel tiles per work item share every B (weight) tile -- the product kernel's answer to the
+// operand-stream bound, and the configuration the halo has to beat (A 59 KB per 256 pixels instead of 2 x 9 x 16 KB).
+template <int MSUB>
 __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             uint32_t pa = 0, pb = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const int m = w / p.tiles_n, n0 = (w % p.tiles_n) * BN;
-                const int b = m / p.tiles_m_img, v0 = (m % p.tiles_m_img) * BM;
+                const int b = m / p.tiles_m_img, v0 = (m % p.tiles_m_img) * BM * MSUB;
                 const int r0 = v0 / p.P;                                   // first padded image row of the halo (image row r0 - 1)
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&a_empty[sa], pa ^ 1);
@@ -113,10 +116,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             int sa = 0, sb = 0, item = 0;
             uint32_t pa = 0, pb = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
-                const int v0 = ((w / p.tiles_n) % p.tiles_m_img) * BM;
+                const int v0 = ((w / p.tiles_n) % p.tiles_m_img) * BM * MSUB;
                 const uint32_t off = (uint32_t)(v0 % p.P);                  // row of output pixel v0 inside the halo box, tap (0, 0)
-                const int as = item & 1;
-                mbar_wait(&tmem_empty[as], ((item >> 1) & 1) ^ 1);          // epilogue drained this accumulator
+                // MSUB == 1: two accumulators alternate between items; MSUB == 2: one item owns both
+                const int as = (MSUB == 1) ? (item & 1) : 0;
+                const uint32_t eph = (MSUB == 1) ? ((item >> 1) & 1) : (item & 1);
+                mbar_wait(&tmem_empty[as], eph ^ 1);                        // epilogue drained the accumulator(s)
                 tc_fence_after();
                 const uint32_t acc = tmem + as * ACC_STRIDE;
                 uint32_t accum = 0;
@@ -133,7 +138,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                         const uint32_t b16 = (uint32_t)(sb * B_STAGE_BYTES) >> 4;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
-                            umma_ss(acc, adesc0 + a16 + 2 * k, bdesc0 + b16 + 2 * k, idesc, accum);
+#pragma unroll
+                            for (int sub = 0; sub < MSUB; ++sub)            // the M sub-tiles are 128 rows (1024 units) apart in the halo
+                                umma_ss(acc + sub * ACC_STRIDE, adesc0 + a16 + sub * 1024 + 2 * k, bdesc0 + b16 + 2 * k, idesc, accum);
                             accum = 1;
                         }
                         umma_commit(&b_empty[sb]);
@@ -153,30 +160,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         int item = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
             const int m = w / p.tiles_n, n0 = (w % p.tiles_n) * BN;
-            const int b = m / p.tiles_m_img, v = (m % p.tiles_m_img) * BM + row;
-            const int h = v / p.P, wq = v % p.P;
-            const bool valid = (h < p.H) && (wq < p.W);
-            __nv_bfloat16* orow = p.out + ((static_cast<int64_t>(b) * p.H + h) * p.W + wq) * p.Cout + n0;
-            const int as = item & 1;
-            mbar_wait(&tmem_full[as], (item >> 1) & 1);
+            const int b = m / p.tiles_m_img;
+            const int as = (MSUB == 1) ? (item & 1) : 0;
+            mbar_wait(&tmem_full[as], (MSUB == 1) ? ((item >> 1) & 1) : (item & 1));
             tc_fence_after();
-            const uint32_t acc = tmem + as * ACC_STRIDE + lb;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t r[32];
-                tmem_ld32(acc + c, r);
-                tmem_wait_ld();
-                if (valid) {
+            for (int sub = 0; sub < MSUB; ++sub) {
+                const int v = (m % p.tiles_m_img) * BM * MSUB + sub * BM + row;
+                const int h = v / p.P, wq = v % p.P;
+                const bool valid = (h < p.H) && (wq < p.W);
+                __nv_bfloat16* orow = p.out + ((static_cast<int64_t>(b) * p.H + h) * p.W + wq) * p.Cout + n0;
+                const uint32_t acc = tmem + (as + sub) * ACC_STRIDE + lb;
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(acc + c, r);
+                    tmem_wait_ld();
+                    if (valid) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float f[8];
+                        for (int g = 0; g < 4; ++g) {
+                            float f[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            f[e] = __uint_as_float(r[g * 8 + e]) + (p.bias ? __ldg(p.bias + n0 + c + g * 8 + e) : 0.f);
-                        uint4 o;
-                        o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-                        o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-                        *reinterpret_cast<uint4*>(orow + c + g * 8) = o;
+                            for (int e = 0; e < 8; ++e)
+                                f[e] = __uint_as_float(r[g * 8 + e]) + (p.bias ? __ldg(p.bias + n0 + c + g * 8 + e) : 0.f);
+                            uint4 o;
+                            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(orow + c + g * 8) = o;
+                        }
                     }
                 }
             }
@@ -210,6 +221,7 @@ __global__ void conv_ref_kernel(const __nv_bfloat16* x, const __nv_bfloat16* wt,
     out_sample[idx] = acc;
 }
 
+template <int MSUB>
 bool run_case(int B, int H, int W, int Cin, int Cout, int stride, int iters) {
     const int64_t nx = (int64_t)B * H * W * Cin, nw = (int64_t)Cout * 9 * Cin, ny = (int64_t)B * H * W * Cout;
     std::vector<__nv_bfloat16> hx(nx), hw(nw);
@@ -230,8 +242,8 @@ bool run_case(int B, int H, int W, int Cin, int Cout, int stride, int iters) {
     memset(&p, 0, sizeof(p));
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
     p.P = W + 2;
-    p.R = 3 + 128 / p.P + 1;
-    p.tiles_m_img = ((H - 1) * p.P + W + BM - 1) / BM;
+    p.R = 3 + (BM * MSUB) / p.P + 1;
+    p.tiles_m_img = ((H - 1) * p.P + W + BM * MSUB - 1) / (BM * MSUB);
     p.tiles_n = Cout / BN;
     p.a_stage_bytes = (p.R * p.P * 128 + 1023) / 1024 * 1024;
     p.bias = db; p.out = dy;
@@ -245,12 +257,12 @@ bool run_case(int B, int H, int W, int Cin, int Cout, int stride, int iters) {
     }
     const int smem = A_STAGES * p.a_stage_bytes + B_STAGES * B_STAGE_BYTES + 256 + 1024;
     if (smem > 227 * 1024) { printf("[SKIP] shared memory %d\n", smem); return true; }
-    cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(conv_halo_kernel<MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const int work = B * p.tiles_m_img * p.tiles_n;
     const int grid = work < sms ? work : sms;
-    conv_halo_kernel<<<grid, kThreads, smem>>>(p);
+    conv_halo_kernel<MSUB><<<grid, kThreads, smem>>>(p);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("[FAIL] conv_halo: kernel error %s\n", cudaGetErrorString(e)); exit(3); }
 
@@ -273,15 +285,15 @@ bool run_case(int B, int H, int W, int Cin, int Cout, int stride, int iters) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    for (int i = 0; i < iters; ++i) conv_halo_kernel<<<grid, kThreads, smem>>>(p);
+    for (int i = 0; i < iters; ++i) conv_halo_kernel<MSUB><<<grid, kThreads, smem>>>(p);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     const double us = 1e3 * ms / iters, tf = 2.0 * B * H * W * Cout * 9.0 * Cin / (us * 1e-6) * 1e-12;
     const bool ok = rel < 1e-2;                                        // bf16 output rounding: ~2e-3
-    printf("[%s] conv_halo B%d %dx%d %4d->%4d  relL2=%.3e  %8.2f us  %7.1f TF/s  (tiles %d x %d, R=%d, A stage %d B)\n", ok ? "PASS" : "FAIL", B,
-           H, W, Cin, Cout, rel, us, tf, B * p.tiles_m_img, p.tiles_n, p.R, p.a_stage_bytes);
+    printf("[%s] conv_halo MSUB%d B%d %dx%d %4d->%4d  relL2=%.3e  %8.2f us  %7.1f TF/s  (tiles %d x %d, R=%d, A stage %d B)\n", ok ? "PASS" : "FAIL", MSUB,
+           B, H, W, Cin, Cout, rel, us, tf, B * p.tiles_m_img, p.tiles_n, p.R, p.a_stage_bytes);
     fflush(stdout);
     cudaFree(dx); cudaFree(dw); cudaFree(dy); cudaFree(db); cudaFree(dref);
     return ok;
@@ -292,11 +304,16 @@ bool run_case(int B, int H, int W, int Cin, int Cout, int stride, int iters) {
 int main() {
     if (hcp_device_check() != 0) { printf("no sm_100 device: %s\n", hcp_last_error_string()); return 2; }
     int fail = 0;
-    fail += !run_case(1, 16, 16, 64, 160, 1, 3);          // small, every pixel checked
-    fail += !run_case(2, 32, 32, 128, 320, 1, 3);
-    fail += !run_case(4, 64, 64, 320, 320, 13, 20);       // product shapes (bench_ops: 34.7 us / 870 TF/s with nine A loads per block)
-    fail += !run_case(4, 64, 64, 640, 320, 13, 20);       //   55.8 us / 1082 TF/s
-    fail += !run_case(4, 32, 32, 640, 640, 13, 20);       //   35.7 us / 846 TF/s
-    fail += !run_case(4, 32, 32, 1280, 640, 13, 20);      //   63.2 us / 956 TF/s
+    fail += !run_case<1>(1, 16, 16, 64, 160, 1, 3);          // small, every pixel checked
+    fail += !run_case<2>(1, 16, 16, 64, 160, 1, 3);
+    fail += !run_case<1>(2, 32, 32, 128, 320, 1, 3);
+    fail += !run_case<2>(2, 32, 32, 128, 320, 1, 3);
+    // product shapes; bench_ops (nine A loads per block, MSUB 2 for the long reductions): 34.7 us / 870 TF/s, 55.8 / 1082, 35.7 / 846, 63.2 / 956
+    fail += !run_case<1>(4, 64, 64, 320, 320, 13, 20);
+    fail += !run_case<2>(4, 64, 64, 320, 320, 13, 20);
+    fail += !run_case<2>(4, 64, 64, 640, 320, 13, 20);
+    fail += !run_case<1>(4, 32, 32, 640, 640, 13, 20);
+    fail += !run_case<2>(4, 32, 32, 640, 640, 13, 20);
+    fail += !run_case<2>(4, 32, 32, 1280, 640, 13, 20);
     return fail ? 1 : 0;
 }
