@@ -34,14 +34,27 @@ class CkptManagerPKL:
         return {k: v for k, v in state.items() if key not in k}
 
     def save_model_with_lora(self, model: Optional[nn.Module], lora_blocks: Optional[PluginGroup], name: str, step: int,
-                             model_ema=None, exclude_key=None):
+                             model_ema=None, exclude_key=None, ema_state: Optional[Dict[nn.Parameter, torch.Tensor]] = None):
+        """Reference ckpt_pkl.py:55-71.  The EMA parts ('base_ema' / 'lora_ema', same keys as 'base' / 'lora') come from
+        `ema_state` = {parameter: EMA tensor} (`LoraTrainStep.ema_state()`: the EMA lives in the engine's flat buffer, not in a
+        ModelEMA object); buffers (LoRA `alpha`) are copied as they are, like ModelEMA.update does (utils/ema.py:29-31)."""
         sd_model: Dict[str, Dict[str, torch.Tensor]] = {}
         if model is not None:
             sd_model["base"] = self.exclude_state(BasePluginBlock.extract_state_without_plugin(model, trainable=True), exclude_key)
         if lora_blocks is not None and not lora_blocks.empty():
             sd_model["lora"] = lora_blocks.state_dict(model if self.plugin_from_raw else None)
         if model_ema is not None:
-            raise NotImplementedError("EMA checkpoints are outside the hot path")
+            raise NotImplementedError("pass the engine's `ema_state()` instead of a ModelEMA object")
+        if ema_state is not None:
+            def ema_of(t):
+                for p, e in ema_state.items():
+                    if p.data_ptr() == t.data_ptr() and p.shape == t.shape:
+                        return e
+                return t
+            if "base" in sd_model:
+                sd_model["base_ema"] = {k: ema_of(v) for k, v in sd_model["base"].items()}
+            if "lora" in sd_model:
+                sd_model["lora_ema"] = {k: ema_of(v) for k, v in sd_model["lora"].items()}
         return self._save_ckpt(sd_model, name, step)
 
     def _save_ckpt(self, sd_model, name=None, step=None, save_path=None):

@@ -69,19 +69,34 @@ struct alignas(64) GemmKParams {
     float* ws;                         // [splits, M, N] fp32
 };
 
-// MSUB = number of 128-row M tiles one work item covers.  MSUB = 2 halves the B (weight) traffic per FLOP -- the long-K
+// MSUB = number of 128-row M tiles (per CTA) one work item covers.  MSUB = 2 halves the B (weight) traffic per FLOP -- the long-K
 // convolutions are bound by the L2 -> SM operand stream, not by the tensor pipe -- at the price of using both TMEM accumulators
 // for one item (no epilogue / main-loop overlap, irrelevant when K is thousands).
-template <int BN, int MSUB = 1>
+// PAIR = the work item is computed by a CTA PAIR (cluster of two CTAs on one TPC, tcgen05 cta_group::2): one MMA of M = 256 whose
+// B operand (BN rows) is split between the two CTAs' shared memories -- each CTA streams 128 rows of A and only BN/2 rows of B per
+// k-block, i.e. 128x320 of output per CTA for 36 KB of operands (71 MAC/B) where the single-CTA 128x160 tile needs the same 36 KB
+// for half the work (35 MAC/B).  The L2 -> SM stream (~44 B/clk/SM whatever the tiling) is what bounds these kernels.
+template <int BN, int MSUB = 1, bool PAIR = false>
 struct GemmCfg {
-    static constexpr int STAGES = (MSUB == 2) ? 3 : (BN > 64) ? 5 : 8;     // one CTA per SM: the ring must cover the TMA latency alone
+    static constexpr int B_ROWS = PAIR ? BN / 2 : BN;             // rows of B this CTA loads per k-block
     static constexpr int A_BYTES = MSUB * A_STAGE_BYTES;
-    static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+    static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int ACC_STRIDE = 256;                         // TMEM columns between the two accumulators
-    static constexpr int STG_PITCH = BN * 2 + 16;                  // staging row pitch in bytes: odd number of 16-byte units
+    static constexpr bool DOUBLE_ACC = (MSUB == 1 && BN <= 256);   // two accumulators alternate between work items
+    // the epilogue walks the accumulator in column parts of EBN (<= 160) columns through one staging buffer
+    static constexpr int EBN = (BN <= 160) ? BN : (BN % 160 == 0 ? 160 : 128);
+    static constexpr int NPART = BN / EBN;
+    static constexpr int STG_PITCH = EBN * 2 + 16;                 // staging row pitch in bytes: odd number of 16-byte units
     static constexpr int STG_BYTES = BLOCK_M * STG_PITCH;
     static constexpr int BIAS_BYTES = ((BN * 4 + 127) / 128) * 128;  // bias slice of the tile's columns, staged once per work item
-    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_STAGE_BYTES) + STG_BYTES + BIAS_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+    static constexpr int FIXED_BYTES = STG_BYTES + BIAS_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+    static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+    static constexpr int MAX_STAGES = (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
+    // one CTA per SM: the ring must cover the TMA latency alone
+    static constexpr int STAGES = PAIR ? (MAX_STAGES > 6 ? 6 : MAX_STAGES) : (MSUB == 2) ? 3 : (BN > 64) ? 5 : 8;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
+    static_assert(BN % EBN == 0 && (MSUB - 1) * ACC_STRIDE + BN <= 512, "accumulators must fit the 512 TMEM columns");
+    static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
 struct TileOrigin {
@@ -119,15 +134,19 @@ __device__ __forceinline__ int64_t tile_row(const GemmKParams& p, const TileOrig
     return g;
 }
 
-// Persistent kernel: grid = min(#work items, #SMs); a work item is (split, m_tile, n_tile) with n fastest so that the CTAs
-// running concurrently share A tiles in L2.  Two TMEM accumulators: the epilogue of item i overlaps the main loop of i+1.
+// Persistent kernel: grid = min(#work items, #SMs) CTAs (PAIR: CTA pairs); a work item is (split, m_tile, n_tile) with n fastest so
+// that the CTAs running concurrently share A tiles in L2.  Two TMEM accumulators: the epilogue of item i overlaps the main loop of i+1.
 // Epilogue: the residual tile is prefetched into a padded smem staging buffer with coalesced loads, each thread (== row) adds
 // bias / per-image bias / residual to its TMEM row and writes bf16 back into the staging buffer, then the tile leaves with
 // coalesced 16-byte stores (full 32-byte sectors instead of one 16-byte fragment per row and instruction).
-template <int BN, int MSUB>
+// PAIR: both CTAs run the TMA producer (own A rows, own half of B; all bytes credited to the LEADER's full barrier), the leader's
+// elected thread issues the M = 256 MMAs and multicasts the commits to both CTAs' empty / tmem_full barriers; each CTA drains its own
+// 128 accumulator rows and tells the leader's tmem_empty barrier (one elected lane per epilogue warp, remote arrive for the peer).
+template <int BN, int MSUB, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
-    using Cfg = GemmCfg<BN, MSUB>;
+    using Cfg = GemmCfg<BN, MSUB, PAIR>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int NCTA = PAIR ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -142,8 +161,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tiles_mn = p.tiles_n * ((p.tiles_m + MSUB - 1) / MSUB);      // work items per split
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // index of this CTA (pair) among the persistent workers
+    const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int tiles_mn = p.tiles_n * ((p.tiles_m + MSUB * NCTA - 1) / (MSUB * NCTA));      // work items per split
     const int total_work = tiles_mn * p.splits;
+    // m tile of (work item row mi, sub-tile sub) for this CTA
+    auto m_tile_of = [&](int mi, int sub) { return (mi * MSUB + sub) * NCTA + (int)rank; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -152,7 +176,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], kGemmEpiThreads);
+            mbar_init(&tmem_empty_bar[i], PAIR ? 2 * (kGemmEpiThreads / 32) : kGemmEpiThreads);
         }
         fence_mbar_init();
         for (int s = 0; s < p.nseg; ++s) {
@@ -160,9 +184,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             tma_prefetch_desc(&p.tmB[s]);
         }
     }
+    if constexpr (PAIR) {            // the peer's barriers must be initialised before anything signals them
+        cluster_arrive();
+        cluster_wait();
+    }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
+        if constexpr (PAIR) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
@@ -176,12 +204,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            for (int w = worker; w < total_work; w += nworkers) {
                 const int split = w / tiles_mn, mn = w % tiles_mn;
-                const int n0 = (mn % p.tiles_n) * BN;
+                const int n0 = (mn % p.tiles_n) * BN + (int)rank * Cfg::B_ROWS;      // PAIR: this CTA's half of the B rows
                 TileOrigin o[MSUB];
 #pragma unroll
-                for (int sub = 0; sub < MSUB; ++sub) o[sub] = tile_origin(p, (mn / p.tiles_n) * MSUB + sub);
+                for (int sub = 0; sub < MSUB; ++sub) o[sub] = tile_origin(p, m_tile_of(mn / p.tiles_n, sub));
                 const int kb_lo = split * p.kb_per_split, kb_hi = kb_lo + p.kb_per_split;
                 int it = 0;
                 for (int s = 0; s < p.nseg; ++s) {
@@ -190,25 +218,48 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                         for (int kb = 0; kb < p.nkb[s]; ++kb, ++it) {
                             if (it < kb_lo || it >= kb_hi) continue;
                             mbar_wait(&empty_bar[stage], phase ^ 1);
-                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_STAGE_BYTES);
                             void* dB = sB + stage * Cfg::B_STAGE_BYTES;
+                            if constexpr (!PAIR) {
+                                mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_STAGE_BYTES);
 #pragma unroll
-                            for (int sub = 0; sub < MSUB; ++sub) {
-                                void* dA = sA + stage * Cfg::A_BYTES + sub * A_STAGE_BYTES;
-                                if (p.conv && s == 0) {
-                                    const TapEntry& te = p.taps[t];
-                                    if (p.conv == 4)
-                                        tma_load_4d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw,
-                                                    o[sub].h0 + te.dh, o[sub].img0);
-                                    else
-                                        tma_load_5d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw, te.c2,
-                                                    o[sub].h0 + te.dh, o[sub].img0);
-                                } else {
-                                    tma_load_2d(dA, &p.tmA[s], &full_bar[stage], kb * BLOCK_K, o[sub].m0);
+                                for (int sub = 0; sub < MSUB; ++sub) {
+                                    void* dA = sA + stage * Cfg::A_BYTES + sub * A_STAGE_BYTES;
+                                    if (p.conv && s == 0) {
+                                        const TapEntry& te = p.taps[t];
+                                        if (p.conv == 4)
+                                            tma_load_4d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw,
+                                                        o[sub].h0 + te.dh, o[sub].img0);
+                                        else
+                                            tma_load_5d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw, te.c2,
+                                                        o[sub].h0 + te.dh, o[sub].img0);
+                                    } else {
+                                        tma_load_2d(dA, &p.tmA[s], &full_bar[stage], kb * BLOCK_K, o[sub].m0);
+                                    }
                                 }
+                                if (p.conv && s == 0) tma_load_2d(dB, &p.tmB[0], &full_bar[stage], p.taps[t].wk_off + kb * BLOCK_K, n0);
+                                else tma_load_2d(dB, &p.tmB[s], &full_bar[stage], kb * BLOCK_K, n0);
+                            } else {
+                                // every byte of the pair lands on the LEADER's barrier: its one arrival names the bytes of both CTAs
+                                const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_STAGE_BYTES));
+#pragma unroll
+                                for (int sub = 0; sub < MSUB; ++sub) {
+                                    void* dA = sA + stage * Cfg::A_BYTES + sub * A_STAGE_BYTES;
+                                    if (p.conv && s == 0) {
+                                        const TapEntry& te = p.taps[t];
+                                        if (p.conv == 4)
+                                            tma_load_4d_pair(dA, &p.tmA[0], lfull, te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw, o[sub].h0 + te.dh,
+                                                             o[sub].img0);
+                                        else
+                                            tma_load_5d_pair(dA, &p.tmA[0], lfull, te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw, te.c2,
+                                                             o[sub].h0 + te.dh, o[sub].img0);
+                                    } else {
+                                        tma_load_2d_pair(dA, &p.tmA[s], lfull, kb * BLOCK_K, o[sub].m0);
+                                    }
+                                }
+                                if (p.conv && s == 0) tma_load_2d_pair(dB, &p.tmB[0], lfull, p.taps[t].wk_off + kb * BLOCK_K, n0);
+                                else tma_load_2d_pair(dB, &p.tmB[s], lfull, kb * BLOCK_K, n0);
                             }
-                            if (p.conv && s == 0) tma_load_2d(dB, &p.tmB[0], &full_bar[stage], p.taps[t].wk_off + kb * BLOCK_K, n0);
-                            else tma_load_2d(dB, &p.tmB[s], &full_bar[stage], kb * BLOCK_K, n0);
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -216,19 +267,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        // ===================================== MMA issuer ========================================
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0, 0);
+        // ===================================== MMA issuer (PAIR: the leader CTA only) ========================================
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * NCTA, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int item = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
+            for (int w = worker; w < total_work; w += nworkers, ++item) {
                 const int split = w / tiles_mn;
                 const int kb_lo = split * p.kb_per_split, kb_hi = kb_lo + p.kb_per_split;
-                // MSUB == 1: two accumulators alternate between items; MSUB == 2: one item owns both
-                const int as = (MSUB == 1) ? (item & 1) : 0;
-                const uint32_t eph = (MSUB == 1) ? ((item >> 1) & 1) : (item & 1);
-                mbar_wait(&tmem_empty_bar[as], eph ^ 1);                     // epilogue drained this accumulator
+                // DOUBLE_ACC: two accumulators alternate between items; otherwise one item owns all the columns in use
+                const int as = Cfg::DOUBLE_ACC ? (item & 1) : 0;
+                const uint32_t eph = Cfg::DOUBLE_ACC ? ((item >> 1) & 1) : (item & 1);
+                mbar_wait(&tmem_empty_bar[as], eph ^ 1);                     // epilogue(s) drained this accumulator
                 tc_fence_after();
                 const uint32_t acc = tmem_base + as * Cfg::ACC_STRIDE;
                 uint32_t accum = 0;
@@ -246,32 +297,40 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                             for (int k = 0; k < ksteps; ++k) {
                                 // +32 bytes (= 2 in descriptor units) per 16-element k-step inside the swizzle atom
 #pragma unroll
-                                for (int sub = 0; sub < MSUB; ++sub)   // the M sub-tiles share the B operand of this k-step
-                                    umma_ss(acc + sub * Cfg::ACC_STRIDE, adesc + sub * (A_STAGE_BYTES >> 4) + 2 * k, bdesc + 2 * k, idesc, accum);
+                                for (int sub = 0; sub < MSUB; ++sub) {   // the M sub-tiles share the B operand of this k-step
+                                    if constexpr (PAIR)
+                                        umma_ss_pair(acc + sub * Cfg::ACC_STRIDE, adesc + sub * (A_STAGE_BYTES >> 4) + 2 * k, bdesc + 2 * k, idesc, accum);
+                                    else
+                                        umma_ss(acc + sub * Cfg::ACC_STRIDE, adesc + sub * (A_STAGE_BYTES >> 4) + 2 * k, bdesc + 2 * k, idesc, accum);
+                                }
                                 accum = 1;
                             }
-                            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                            if constexpr (PAIR) umma_commit_pair(&empty_bar[stage], 0b11);
+                            else umma_commit(&empty_bar[stage]);
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
                 }
-                umma_commit(&tmem_full_bar[as]);
+                if constexpr (PAIR) umma_commit_pair(&tmem_full_bar[as], 0b11);
+                else umma_commit(&tmem_full_bar[as]);
             }
         }
     } else {
         // ===================================== epilogue ==========================================
+        constexpr int EBN = Cfg::EBN;
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;             // which half of the tile's columns this warp converts
+        const int half = (warp - 2) >> 2;             // which half of the part's columns this warp converts
         const int r = quarter * 32 + lane;            // row inside the tile
         const int et = threadIdx.x - 64;              // 0..255 among the epilogue threads
-        constexpr int UNITS = BN / 8;                 // 16-byte units per tile row
-        constexpr int CH16 = BN / 16;                 // 16-column TMEM chunks per row
+        constexpr int UNITS = EBN / 8;                // 16-byte units per staged row
+        constexpr int CH16 = EBN / 16;                // 16-column TMEM chunks per part
         int item = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
+        for (int w = worker; w < total_work; w += nworkers, ++item) {
             const int split = w / tiles_mn, mn = w % tiles_mn;
             const int n0 = (mn % p.tiles_n) * BN;
-            const int as = (MSUB == 1) ? (item & 1) : 0;
-            const uint32_t fph = (MSUB == 1) ? ((item >> 1) & 1) : (item & 1);
+            const int as = Cfg::DOUBLE_ACC ? (item & 1) : 0;
+            const uint32_t fph = Cfg::DOUBLE_ACC ? ((item >> 1) & 1) : (item & 1);
             const bool staged = (p.splits == 1);
             if (staged && p.bias) {
                 // the bias slice of this item's columns goes to shared memory once (ncu: the per-chunk global bias loads were the
@@ -283,9 +342,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
 #pragma unroll 1
-            for (int sub = 0; sub < MSUB; ++sub) {
-            const TileOrigin o = tile_origin(p, (mn / p.tiles_n) * MSUB + sub);
-            const int acc_idx = (MSUB == 1) ? as : sub;
+            for (int part = 0; part < MSUB * Cfg::NPART; ++part) {
+            const int sub = part / Cfg::NPART;
+            const int nc0 = (part % Cfg::NPART) * EBN;          // first column of this part inside the item's BN columns
+            const bool last_part = (part == MSUB * Cfg::NPART - 1);
+            const TileOrigin o = tile_origin(p, m_tile_of(mn / p.tiles_n, sub));
+            const int acc_idx = Cfg::DOUBLE_ACC ? as : sub;
             if (staged && p.residual) {
                 // coalesced prefetch of the residual tile into the staging buffer (overlaps the main loop).  All loads of a thread
                 // are issued before the first store: one L2 round trip per tile instead of one per 16-byte unit.
@@ -299,7 +361,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                     if (u < BLOCK_M * UNITS) {
                         int grp;
                         const int64_t g = tile_row(p, o, rr, grp);
-                        const int col = n0 + cu * 8;
+                        const int col = n0 + nc0 + cu * 8;
                         if (g < (int64_t)p.M && col < p.N) rbuf[it] = *reinterpret_cast<const uint4*>(p.residual + g * p.ldr + col);
                     }
                 }
@@ -313,9 +375,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             int group;
             const int64_t grow = tile_row(p, o, r, group);
             const bool row_ok = grow < (int64_t)p.M;
-            if (sub == 0) mbar_wait(&tmem_full_bar[as], fph);
+            if (part == 0) mbar_wait(&tmem_full_bar[as], fph);
             tc_fence_after();
-            const uint32_t trow = tmem_base + acc_idx * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
+            const uint32_t trow = tmem_base + acc_idx * Cfg::ACC_STRIDE + nc0 + (static_cast<uint32_t>(quarter * 32) << 16);
+            // the accumulator goes back to the MMA warp as soon as its last part sits in registers (PAIR: one elected lane per warp
+            // tells the LEADER's barrier -- a remote arrive for the peer CTA)
+            auto release_acc = [&]() {
+                tc_fence_before();
+                if constexpr (PAIR) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
+                } else {
+                    mbar_arrive(&tmem_empty_bar[as]);
+                }
+            };
             // Two epilogue schedules (GemmKParams::epi_batch): 1 = all TMEM chunks of this thread are pulled into registers with ONE
             // wait and the accumulator is handed back to the MMA warp before any arithmetic / staging store; 0 = chunk by chunk
             // (load, wait, convert, store), the accumulator is released after the last chunk.
@@ -324,7 +397,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                 if (row_ok) {
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
-                        const int col = n0 + c * 16 + g * 8;
+                        const int col = n0 + nc0 + c * 16 + g * 8;
                         if (col < p.N) {
                             float f[8];
 #pragma unroll
@@ -336,8 +409,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                                 continue;
                             }
                             if (p.bias) {
-                                const float4 b0 = *reinterpret_cast<const float4*>(sBias + c * 16 + g * 8);
-                                const float4 b1 = *reinterpret_cast<const float4*>(sBias + c * 16 + g * 8 + 4);
+                                const float4 b0 = *reinterpret_cast<const float4*>(sBias + nc0 + c * 16 + g * 8);
+                                const float4 b1 = *reinterpret_cast<const float4*>(sBias + nc0 + c * 16 + g * 8 + 4);
                                 f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                                 f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                             }
@@ -373,8 +446,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                 for (int cl = 0; cl < NCH; ++cl)
                     if (half * NCH + cl < CH16) tmem_ld16(trow + (half * NCH + cl) * 16, vv[cl]);
                 tmem_wait_ld();
-                tc_fence_before();
-                if (sub == MSUB - 1) mbar_arrive(&tmem_empty_bar[as]); // accumulator(s) free: the MMA warp may go on
+                if (last_part) release_acc();
 #pragma unroll
                 for (int cl = 0; cl < NCH; ++cl)
                     if (half * NCH + cl < CH16) chunk(half * NCH + cl, vv[cl]);
@@ -386,8 +458,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                     tmem_wait_ld();
                     chunk(c, v);
                 }
-                tc_fence_before();
-                if (sub == MSUB - 1) mbar_arrive(&tmem_empty_bar[as]);
+                if (last_part) release_acc();
             }
             if (staged) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -395,19 +466,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                     const int rr = u / UNITS, cu = u % UNITS;
                     int grp;
                     const int64_t g = tile_row(p, o, rr, grp);
-                    const int col = n0 + cu * 8;
+                    const int col = n0 + nc0 + cu * 8;
                     if (g < (int64_t)p.M && col < p.N)
                         *reinterpret_cast<uint4*>(p.out + g * p.ldo + col) = *reinterpret_cast<const uint4*>(sStg + rr * Cfg::STG_PITCH + cu * 16);
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");     // staging buffer reusable
             }
-            }   // sub
+            }   // part
         }
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) {            // neither CTA frees TMEM / exits while the peer may still touch the pair's state
+        cluster_arrive();
+        cluster_wait();
+    } else {
+        __syncthreads();
+    }
+    if (warp == 1) {
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // out = sum_s ws[s] + bias + rowbias + residual  (bf16), 8 columns per thread
@@ -631,22 +710,25 @@ __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __gri
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN, int MSUB>
+template <int BN, int MSUB, bool PAIR>
 static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, MSUB>;
+    using Cfg = GemmCfg<BN, MSUB, PAIR>;
     static bool configured = false;
     static int num_sms = 148;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MSUB, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
         int dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         configured = true;
     }
-    const int total = kp.tiles_n * ((kp.tiles_m + MSUB - 1) / MSUB) * kp.splits;
-    dim3 grid(total < num_sms ? total : num_sms);
-    launch_k(gemm_tc_kernel<BN, MSUB>, dim3(grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, stream, kp);
+    constexpr int NCTA = PAIR ? 2 : 1;
+    const int total = kp.tiles_n * ((kp.tiles_m + MSUB * NCTA - 1) / (MSUB * NCTA)) * kp.splits;
+    const int workers = num_sms / NCTA;
+    dim3 grid((total < workers ? total : workers) * NCTA);
+    if (PAIR) launch_k_cluster(gemm_tc_kernel<BN, MSUB, PAIR>, dim3(grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, stream, 2u, kp);
+    else launch_k(gemm_tc_kernel<BN, MSUB, PAIR>, dim3(grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, stream, kp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "gemm launch");
     return HCP_OK;
@@ -659,6 +741,22 @@ static int pick_bn(int64_t N) {
     if (N % 128 == 0) return 128;
     if (N % 64 == 0 && N < 256) return 64;
     return 128;
+}
+
+// CTA-pair tiling (256 x BN per pair, BN in {320, 256}): 0 = keep the single-CTA kernel.  Chosen when the launch has enough 256-row
+// work items for the 74 pairs (whole waves: a part-filled last wave costs a full main loop) and the reduction is long enough
+// for the operand stream to matter (>= HCP_PAIR_MIN_KB k-blocks; the K = 320 linears are epilogue-bound either way).
+static int pick_pair(int64_t N, int64_t m_tiles, int64_t total_kb) {
+    static const int mode = [] { const char* e = getenv("HCP_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+    static const int min_kb = [] { const char* e = getenv("HCP_PAIR_MIN_KB"); return e ? atoi(e) : 10; }();
+    if (mode == 0 || total_kb < min_kb || N < 256) return 0;
+    const int bn = (N % 320 == 0) ? 320 : (N % 256 == 0) ? 256 : 0;
+    if (!bn) return 0;
+    const int64_t items = ((m_tiles + 1) / 2) * (N / bn);
+    if (mode == 2) return bn;                                   // forced (bring-up / A-B runs)
+    const int64_t waves = (items + 73) / 74;
+    const double fill = (double)items / (double)(waves * 74);
+    return (items >= 56 && fill >= 0.75) ? bn : 0;
 }
 
 // Plain GEMMs with a short reduction whose 128x160 tiling would leave half of the SMs idle (24..73 tiles: the M = 1024 level of
@@ -674,31 +772,36 @@ static int pick_bn_gemm(int64_t N, int64_t m_tiles, int64_t total_kb) {
     return bn;
 }
 
-static int dispatch_gemm(int bn, GemmKParams& kp, int m_tiles, cudaStream_t stream) {
+static int dispatch_gemm(int bn, bool cta_pair, GemmKParams& kp, int m_tiles, cudaStream_t stream) {
     kp.tiles_m = m_tiles;
     static const int epi_batch = [] { const char* e = getenv("HCP_GEMM_EPI_BATCH"); return e ? atoi(e) : 1; }();
     kp.epi_batch = epi_batch;
+    if (cta_pair) {
+        if (bn == 320) return launch_gemm<320, 1, true>(kp, stream);
+        if (bn == 256) return launch_gemm<256, 1, true>(kp, stream);
+        return set_error(HCP_ERR_INVALID, "unsupported CTA-pair BLOCK_N");
+    }
     // two M tiles per work item when the reduction is long (operand-stream bound) and there are plenty of tiles
     int64_t total_kb = 0;
     for (int s = 0; s < kp.nseg; ++s) total_kb += (int64_t)kp.nkb[s] * ((kp.conv && s == 0) ? kp.ntaps : 1);
     static const int msub2_min_kb = [] { const char* e = getenv("HCP_MSUB2_MIN_KB"); return e ? atoi(e) : 40; }();
-    const bool pair = bn == 160 && kp.splits == 1 && total_kb >= msub2_min_kb && (int64_t)kp.tiles_n * m_tiles >= 200 &&
-                      getenv("HCP_GEMM_NO_MSUB2") == nullptr;
-    if (pair) return launch_gemm<160, 2>(kp, stream);
+    const bool msub2 = bn == 160 && kp.splits == 1 && total_kb >= msub2_min_kb && (int64_t)kp.tiles_n * m_tiles >= 200 &&
+                       getenv("HCP_GEMM_NO_MSUB2") == nullptr;
+    if (msub2) return launch_gemm<160, 2, false>(kp, stream);
     switch (bn) {
-        case 32: return launch_gemm<32, 1>(kp, stream);
-        case 64: return launch_gemm<64, 1>(kp, stream);
-        case 80: return launch_gemm<80, 1>(kp, stream);
-        case 128: return launch_gemm<128, 1>(kp, stream);
-        case 160: return launch_gemm<160, 1>(kp, stream);
+        case 32: return launch_gemm<32, 1, false>(kp, stream);
+        case 64: return launch_gemm<64, 1, false>(kp, stream);
+        case 80: return launch_gemm<80, 1, false>(kp, stream);
+        case 128: return launch_gemm<128, 1, false>(kp, stream);
+        case 160: return launch_gemm<160, 1, false>(kp, stream);
         default: return set_error(HCP_ERR_INVALID, "unsupported BLOCK_N");
     }
 }
 
-// plain or split-K launch (+ finalize).  `ws` may be NULL / too small: then the launch is not split.
-static int run_gemm(int bn, GemmKParams& kp, int m_tiles, int64_t total_kb, float* ws, size_t ws_bytes, bool allow_split,
+// plain or split-K launch (+ finalize).  `ws` may be NULL / too small: then the launch is not split.  CTA-pair launches never split.
+static int run_gemm(int bn, bool cta_pair, GemmKParams& kp, int m_tiles, int64_t total_kb, float* ws, size_t ws_bytes, bool allow_split,
                     cudaStream_t stream) {
-    int splits = allow_split ? plan_splits((int64_t)m_tiles * kp.tiles_n, total_kb, kp.N) : 1;
+    int splits = (allow_split && !cta_pair) ? plan_splits((int64_t)m_tiles * kp.tiles_n, total_kb, kp.N) : 1;
     if (splits > 1 && (!ws || ws_bytes < (size_t)splits * kp.M * kp.N * sizeof(float))) splits = 1;
     if (splits > 1) {
         kp.kb_per_split = (int)((total_kb + splits - 1) / splits);
@@ -708,11 +811,11 @@ static int run_gemm(int bn, GemmKParams& kp, int m_tiles, int64_t total_kb, floa
         kp.splits = 1;
         kp.kb_per_split = 1 << 30;
         kp.ws = nullptr;
-        return dispatch_gemm(bn, kp, m_tiles, stream);
+        return dispatch_gemm(bn, cta_pair, kp, m_tiles, stream);
     }
     kp.splits = splits;
     kp.ws = ws;
-    int rc = dispatch_gemm(bn, kp, m_tiles, stream);
+    int rc = dispatch_gemm(bn, cta_pair, kp, m_tiles, stream);
     if (rc) return rc;
     const int64_t n = (int64_t)kp.M * (kp.N / 8);
     launch_k(splitk_finalize_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, ws, splits, kp.M, kp.N, kp.bias, kp.rowbias,
@@ -729,7 +832,9 @@ using namespace hcp;
 
 extern "C" size_t hcp_splitk_workspace_bytes(int64_t M, int64_t N, int64_t total_k) {
     const int bn = pick_bn(N);
-    const int64_t ctas = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
+    const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    if (pick_pair(N, m_tiles, (total_k + BLOCK_K - 1) / BLOCK_K)) return 0;        // CTA-pair launches never split
+    const int64_t ctas = m_tiles * ((N + bn - 1) / bn);
     const int splits = plan_splits(ctas, (total_k + BLOCK_K - 1) / BLOCK_K, N);
     return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
 }
@@ -743,14 +848,16 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     memset(&kp, 0, sizeof(kp));
     int64_t kb_all = 0;
     for (int s = 0; s < a->nseg; ++s) kb_all += (a->k[s] + BLOCK_K - 1) / BLOCK_K;
-    const int bn = pick_bn_gemm(a->N, (a->M + BLOCK_M - 1) / BLOCK_M, kb_all);
+    const int pair_bn = pick_pair(a->N, (a->M + BLOCK_M - 1) / BLOCK_M, kb_all);
+    const int bn = pair_bn ? pair_bn : pick_bn_gemm(a->N, (a->M + BLOCK_M - 1) / BLOCK_M, kb_all);
+    const int b_box_rows = pair_bn ? pair_bn / 2 : bn;       // a CTA of a pair loads half of the tile's B rows
     for (int s = 0; s < a->nseg; ++s) {
         if (a->k[s] <= 0) return set_error(HCP_ERR_INVALID, "gemm: k must be positive");
         if ((a->lda[s] % 8) != 0 || (a->ldb[s] % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: lda/ldb");
         const int64_t nrb = a->n_rows_b[s] > 0 ? a->n_rows_b[s] : a->N;
         int rc = make_tmap_2d(&kp.tmA[s], a->a[s], (uint64_t)a->k[s], (uint64_t)a->M, (uint64_t)a->lda[s], BLOCK_K, BLOCK_M);
         if (rc) return rc;
-        rc = make_tmap_2d(&kp.tmB[s], a->b[s], (uint64_t)a->k[s], (uint64_t)nrb, (uint64_t)a->ldb[s], BLOCK_K, bn);
+        rc = make_tmap_2d(&kp.tmB[s], a->b[s], (uint64_t)a->k[s], (uint64_t)nrb, (uint64_t)a->ldb[s], BLOCK_K, b_box_rows);
         if (rc) return rc;
         kp.nkb[s] = (int)((a->k[s] + BLOCK_K - 1) / BLOCK_K);
         const int64_t rem = a->k[s] - (int64_t)(kp.nkb[s] - 1) * BLOCK_K;
@@ -772,17 +879,17 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     const int m_tiles = (int)((a->M + BLOCK_M - 1) / BLOCK_M);
     int64_t total_kb = 0;
     for (int s = 0; s < a->nseg; ++s) total_kb += kp.nkb[s];
-    return run_gemm(bn, kp, m_tiles, total_kb, a->workspace, a->workspace_bytes, true, (cudaStream_t)stream_);
+    return run_gemm(bn, pair_bn != 0, kp, m_tiles, total_kb, a->workspace, a->workspace_bytes, true, (cudaStream_t)stream_);
 }
 
 // Conv2d LoRA: out += T . Bl^T as K-segment 1 (plain 2D operands; the rows of an M tile of the convolution are contiguous pixels)
-static int conv_lora_segment(const hcp_conv3x3_args* a, GemmKParams& kp, int bn) {
+static int conv_lora_segment(const hcp_conv3x3_args* a, GemmKParams& kp, int b_box_rows) {
     if (!a->lora_t) return HCP_OK;
     if (!a->lora_b || a->lora_r <= 0 || a->lora_r > a->lora_ld || (a->lora_ld % 8) != 0)
         return set_error(HCP_ERR_INVALID, "conv3x3: LoRA segment (lora_b / lora_r / lora_ld)");
     int rc = make_tmap_2d(&kp.tmA[1], a->lora_t, (uint64_t)a->lora_r, (uint64_t)kp.M, (uint64_t)a->lora_ld, BLOCK_K, BLOCK_M);
     if (rc) return rc;
-    rc = make_tmap_2d(&kp.tmB[1], a->lora_b, (uint64_t)a->lora_r, (uint64_t)a->Cout, (uint64_t)a->lora_ld, BLOCK_K, bn);
+    rc = make_tmap_2d(&kp.tmB[1], a->lora_b, (uint64_t)a->lora_r, (uint64_t)a->Cout, (uint64_t)a->lora_ld, BLOCK_K, b_box_rows);
     if (rc) return rc;
     kp.nseg = 2;
     kp.nkb[1] = (int)((a->lora_r + BLOCK_K - 1) / BLOCK_K);
@@ -797,7 +904,7 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
     if (a->mode != 0 && !(a->mode == 1)) return set_error(HCP_ERR_INVALID, "conv3x3: mode");
     GemmKParams kp;
     memset(&kp, 0, sizeof(kp));
-    const int bn = pick_bn(a->Cout);
+    int bn = pick_bn(a->Cout);
     const int64_t Cin = a->Cin;
 
     // geometry of the "tile grid" (the grid the 128-pixel M tiles walk over) and of the output map
@@ -839,9 +946,16 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
     kp.ldr = a->Cout;
     kp.out = (__nv_bfloat16*)a->out;
     kp.ldo = a->Cout;
-    int rc = make_tmap_2d(&kp.tmB[0], a->w, (uint64_t)(9 * Cin), (uint64_t)a->Cout, (uint64_t)(9 * Cin), BLOCK_K, bn);
-    if (rc) return rc;
     const int m_tiles = (bnimg == 1) ? (int)(a->B * kp.tiles_w * kp.tiles_h) : (int)((a->B + bnimg - 1) / bnimg);
+    // CTA pairs for the forward-mode launches (mode 1 = four short phase launches of the stride-2 dgrad: single CTAs)
+    const int pair_bn = (a->mode == 0) ? pick_pair(a->Cout, m_tiles, 9 * (Cin / BLOCK_K) + (a->lora_t ? (a->lora_ld + BLOCK_K - 1) / BLOCK_K : 0)) : 0;
+    if (pair_bn) {
+        bn = pair_bn;
+        kp.tiles_n = (int)((a->Cout + bn - 1) / bn);
+    }
+    const int b_box_rows = pair_bn ? pair_bn / 2 : bn;
+    int rc = make_tmap_2d(&kp.tmB[0], a->w, (uint64_t)(9 * Cin), (uint64_t)a->Cout, (uint64_t)(9 * Cin), BLOCK_K, b_box_rows);
+    if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
 
     if (a->mode == 0 && a->stride == 1) {
@@ -859,8 +973,8 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
                 t.wk_off = (int)((kh * 3 + kw) * Cin);
             }
         kp.sh = kp.sw = 1; kp.oh0 = kp.ow0 = 0;
-        if ((rc = conv_lora_segment(a, kp, bn))) return rc;
-        return run_gemm(bn, kp, m_tiles, (int64_t)9 * kp.nkb[0] + (kp.nseg > 1 ? kp.nkb[1] : 0), a->workspace, a->workspace_bytes, true, stream);
+        if ((rc = conv_lora_segment(a, kp, b_box_rows))) return rc;
+        return run_gemm(bn, pair_bn != 0, kp, m_tiles, (int64_t)9 * kp.nkb[0] + (kp.nseg > 1 ? kp.nkb[1] : 0), a->workspace, a->workspace_bytes, true, stream);
     }
     if (a->mode == 0 && a->stride == 2) {
         // view x as [B][Hin/2][2][Win/2][2*Cin]: input row ih = 2*oh + kh - 1 -> (phase, index)
@@ -883,8 +997,8 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
                 t.wk_off = (int)((kh * 3 + kw) * Cin);
             }
         kp.sh = kp.sw = 1; kp.oh0 = kp.ow0 = 0;
-        if ((rc = conv_lora_segment(a, kp, bn))) return rc;
-        return run_gemm(bn, kp, m_tiles, (int64_t)9 * kp.nkb[0] + (kp.nseg > 1 ? kp.nkb[1] : 0), a->workspace, a->workspace_bytes, true, stream);
+        if ((rc = conv_lora_segment(a, kp, b_box_rows))) return rc;
+        return run_gemm(bn, pair_bn != 0, kp, m_tiles, (int64_t)9 * kp.nkb[0] + (kp.nseg > 1 ? kp.nkb[1] : 0), a->workspace, a->workspace_bytes, true, stream);
     }
     if (a->lora_t) return set_error(HCP_ERR_INVALID, "conv3x3: the LoRA segment is only available in mode 0");
     // mode 1: dgrad of the stride-2 conv.  x = dY [B, Hin, Win, Cin] (Cin = Cout of the fwd conv),
@@ -916,7 +1030,7 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
             }
             kp.ntaps = nt;
             kp.oh0 = ph; kp.ow0 = pw;
-            rc = run_gemm(bn, kp, m_tiles, 0, nullptr, 0, false, stream);
+            rc = run_gemm(bn, false, kp, m_tiles, 0, nullptr, 0, false, stream);
             if (rc) return rc;
         }
     return HCP_OK;

@@ -340,6 +340,34 @@ __global__ void adamw_flat_kernel(float* __restrict__ p, const float* __restrict
     w -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
     p[i] = w;
 }
+// same update with every hyper-parameter read from device memory: hyper = {lr, beta1, beta2, eps, weight_decay}.  LR schedulers
+// (OneCycleLR also cycles beta1) then only write five floats; the captured CUDA graph stays valid.
+__global__ void adamw_flat_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                      int64_t n, const float* __restrict__ hyper, float gscale, const float* __restrict__ sumsq,
+                                      float max_norm, const int* __restrict__ step_ptr) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float clip = 1.f;
+    if (sumsq && max_norm > 0.f) {
+        const float norm = sqrtf(*sumsq) * gscale;
+        clip = fminf(1.f, max_norm / (norm + 1e-6f));
+    }
+    const float lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3], wd = hyper[4];
+    const int step = *step_ptr;
+    const float grad = g[i] * gscale * clip;
+    const float mi = beta1 * m[i] + (1.f - beta1) * grad;
+    const float vi = beta2 * v[i] + (1.f - beta2) * grad * grad;
+    m[i] = mi;
+    v[i] = vi;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2 = 1.f - powf(beta2, (float)step);
+    float w = p[i];
+    w -= lr * wd * w;
+    w -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    p[i] = w;
+}
 __global__ void incr_step_kernel(int* step) {
     pdl_trigger();
     pdl_wait(); *step += 1; }
@@ -474,5 +502,15 @@ extern "C" int hcp_adamw_flat(float* p, const float* g, float* m, float* v, int6
     launch_k(adamw_flat_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)st, p, g, m, v, n, lr_device, beta1, beta2, eps, weight_decay,
                                                                                grad_scale, sumsq_device, max_norm, step_device);
     LAUNCH_CHECK("adamw launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_adamw_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper_device, float grad_scale,
+                                  const float* sumsq_device, float max_norm, int* step_device, hcp_stream_t st) {
+    if (!p || !g || !m || !v || !hyper_device || !step_device) return set_error(HCP_ERR_INVALID, "adamw_dev: null pointer");
+    launch_k(incr_step_kernel, dim3(1), dim3(1), 0, (cudaStream_t)st, step_device);
+    launch_k(adamw_flat_dev_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)st, p, g, m, v, n, hyper_device, grad_scale,
+             sumsq_device, max_norm, step_device);
+    LAUNCH_CHECK("adamw_dev launch");
     return HCP_OK;
 }

@@ -98,6 +98,11 @@ class PatchPluginContainer(nn.Module):
         setattr(parent_block, host_name, self)
 
     def add_plugin(self, name: str, plugin: "PatchPluginBlock"):
+        if name in self.plugin_names:
+            # the reference silently overwrites the attribute and lists the name twice (plugin.py:236-238): the first block is
+            # orphaned but its delta is applied twice.  Loading a checkpoint INTO existing blocks is `load_lora_state` / resume.
+            raise ValueError(f"plugin {name!r} is already patched onto this layer: use another lora_id (lora_id_offset) or load the "
+                             "checkpoint into the existing blocks")
         setattr(self, name, plugin)
         self.plugin_names.append(name)
 

@@ -81,14 +81,14 @@ class ResnetBlock2D(nn.Module):
         n1 = self.norm1
         outs = ops.group_norm(n1.weight, n1.bias, n1.num_groups, n1.eps, True, xs[0], x2)
         y1, aliases = outs[0], outs[1:]
-        h = ops.conv3x3(g.conv1.prepare(), y1, geom, rowbias=temb)
+        h = g.conv1(y1, geom, rowbias=temb)
         n2 = self.norm2
         y2 = ops.group_norm(n2.weight, n2.bias, n2.num_groups, n2.eps, True, h, None)[0]
         if g.shortcut is not None:
             res = g.shortcut(list(aliases))
         else:
             res = aliases[0]
-        return ops.conv3x3(g.conv2.prepare(), y2, geom, residual=res)
+        return g.conv2(y2, geom, residual=res)
 
 
 class Attention(nn.Module):
@@ -261,7 +261,7 @@ class Downsample2D(nn.Module):
         return g
 
     def run(self, x, geom):
-        return ops.conv3x3(self._group().prepare(), x, geom)
+        return self._group()(x, geom)
 
 
 class Upsample2D(nn.Module):
@@ -280,7 +280,7 @@ class Upsample2D(nn.Module):
     def run(self, x, geom):
         B, H, W = geom
         up = ops.Upsample2xFn.apply(geom, x)
-        return ops.conv3x3(self._group().prepare(), up, (B, 2 * H, 2 * W))
+        return self._group()(up, (B, 2 * H, 2 * W))
 
 
 class DownBlock(nn.Module):

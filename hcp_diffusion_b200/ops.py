@@ -61,6 +61,85 @@ def join_side() -> None:
     _Side.keep.clear()
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# dropout (reference: nn.Dropout on the whole output of a patched layer, hcpdiff/models/lora_base_patch.py:74).  The mask is a
+# function of a device-resident (seed, draw) pair and a per-call `site` number: the backward pass regenerates it, CUDA-graph
+# replays read the advanced `draw` and get fresh masks.
+# ----------------------------------------------------------------------------------------------------------------------
+class _Drop:
+    state: Optional[torch.Tensor] = None     # int64 [2] on the device: (seed, draw)
+    site = 0                                 # call sites of the current forward pass
+    used = False
+
+
+def set_dropout_seed(seed: int) -> None:
+    dev = torch.device("cuda", torch.cuda.current_device())
+    _Drop.state = torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev)
+
+
+def _dropout_state() -> torch.Tensor:
+    if _Drop.state is None:
+        set_dropout_seed(torch.initial_seed())
+    return _Drop.state
+
+
+def advance_dropout() -> None:
+    """End of one forward/backward: the next one draws new masks (one tiny kernel, only when a dropout site ran)."""
+    if _Drop.used and _Drop.state is not None:
+        call("hcp_counter_add_u64", _Drop.state.data_ptr() + 8, 1, stream_ptr())
+    _Drop.site = 0
+
+
+def dropout_state_snapshot():
+    return None if _Drop.state is None else _Drop.state.clone()
+
+
+def dropout_state_restore(saved) -> None:
+    if saved is not None and _Drop.state is not None:
+        _Drop.state.copy_(saved)
+
+
+class DropoutFn(torch.autograd.Function):
+    """out[:, c0:c0+n] = dropout_p(y[:, c0:c0+n]) for every (c0, n, p) range (p = 0: copy), + residual + per-image row bias.
+    y bf16 [..., N]; the ranges must tile [0, N)."""
+
+    @staticmethod
+    def forward(ctx, ranges, residual: Optional[torch.Tensor], rowbias: Optional[torch.Tensor], rows_per_group: int, y: torch.Tensor):
+        y = _chk(y, "dropout input")
+        N = y.shape[-1]
+        M = y.numel() // N
+        res = None if residual is None else _chk(residual, "dropout residual")
+        out = torch.empty_like(y)
+        st = _dropout_state()
+        sites = []
+        rb_ld = 0 if rowbias is None else rowbias.stride(0)
+        for (c0, n, p) in ranges:
+            _Drop.site += 1
+            _Drop.used = True
+            sites.append(_Drop.site)
+            call("hcp_dropout_bf16", y.data_ptr() + 2 * c0, N, None if res is None else res.data_ptr() + 2 * c0, N,
+                 None if rowbias is None else rowbias.data_ptr() + 4 * c0, rb_ld, max(rows_per_group, 1), M, n, float(p), st.data_ptr(),
+                 sites[-1], out.data_ptr() + 2 * c0, N, stream_ptr())
+        ctx.ranges, ctx.sites, ctx.has_res = list(ranges), sites, residual is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _chk(dout, "dropout grad")
+        N = dout.shape[-1]
+        M = dout.numel() // N
+        dy = torch.empty_like(dout)
+        st = _dropout_state()
+        for (c0, n, p), site in zip(ctx.ranges, ctx.sites):
+            call("hcp_dropout_bf16", dout.data_ptr() + 2 * c0, N, None, 0, None, 0, 1, M, n, float(p), st.data_ptr(), site,
+                 dy.data_ptr() + 2 * c0, N, stream_ptr())
+        return None, (dout if (ctx.has_res and ctx.needs_input_grad[1]) else None), None, None, dy
+
+
+def dropout_cols(y, ranges, residual=None, rowbias=None, rows_per_group=0):
+    return DropoutFn.apply(tuple(ranges), residual, rowbias, rows_per_group, y)
+
+
 def _chk(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.dtype != BF16 or not t.is_cuda:
         raise _lib.HcpError(f"{name}: expected a CUDA bf16 tensor, got {t.dtype} on {t.device}")
@@ -219,12 +298,13 @@ class LinearPack:
 class ConvLoraRef:
     """One LoRA block on a 3x3 convolution (reference LoraLayer.Conv2dLayer, lora_layers_patch.py:64-100):
     W_down fp32 [r, Cin, 3, 3], W_up fp32 [Cout, r, 1, 1], alpha."""
-    __slots__ = ("w_down", "w_up", "alpha", "rank", "c0")
+    __slots__ = ("w_down", "w_up", "alpha", "rank", "c0", "branch")
 
-    def __init__(self, w_down, w_up, alpha):
+    def __init__(self, w_down, w_up, alpha, branch=None):
         self.w_down, self.w_up, self.alpha = w_down, w_up, float(alpha)
         self.rank = w_down.shape[0]
         self.c0 = 0
+        self.branch = branch       # None, or 'p' / 'n' (DreamArtist++: batch = [negative half | positive half])
 
 
 class ConvPack:
@@ -244,7 +324,9 @@ class ConvPack:
         self.bias = None if bias is None else bias.detach().float().contiguous()
         self.lora: List[ConvLoraRef] = []
         self.r_tot = self.R = 0
+        self.dapp = False
         self.Wt = self.Wdl = self.Bl = self.BlT = None
+        self.Wt_br = self.BlT_br = None      # DAPP: {'n': ..., 'p': ...} row-masked variants of Wt / BlT
 
     def attach_lora(self, blocks: List[ConvLoraRef]) -> None:
         self.lora = blocks
@@ -259,10 +341,17 @@ class ConvPack:
         self.r_tot, self.R = c, (c + 63) // 64 * 64
         dev = self.W.device
         z = lambda *shape: torch.zeros(shape, dtype=BF16, device=dev)   # noqa: E731
-        self.Wt = z(self.R, 3, 3, self.Cin)          # forward weights of T = conv3x3(x, W_down)
-        self.Wdl = z(self.Cin, 3, 3, self.R)         # dgrad arrangement of the same taps
+        self.dapp = any(b.branch is not None for b in blocks)
+        self.Wdl = z(self.Cin, 3, 3, self.R)         # dgrad arrangement of the taps of W_down
         self.Bl = z(self.Cout, self.R)
-        self.BlT = z(self.R, self.Cout)
+        if self.dapp:
+            # every block writes the rows of ITS branch's buffers only: T / U of a batch half come out with zeros in the columns of
+            # the other branch, so the main convolution's LoRA segment, the dgrad through W_down and both gradient kernels stay unmasked
+            self.Wt_br = {"n": z(self.R, 3, 3, self.Cin), "p": z(self.R, 3, 3, self.Cin)}
+            self.BlT_br = {"n": z(self.R, self.Cout), "p": z(self.R, self.Cout)}
+        else:
+            self.Wt = z(self.R, 3, 3, self.Cin)      # forward weights of T = conv3x3(x, W_down)
+            self.BlT = z(self.R, self.Cout)
 
     def jobs(self) -> List[_lib.LoraJob]:
         out = []
@@ -271,7 +360,8 @@ class ConvPack:
             j.w_down, j.w_up, j.alpha = b.w_up.data_ptr(), b.w_up.data_ptr(), b.alpha
             j.rank, j.in_dim, j.out_dim = b.rank, 0, self.Cout
             j.c0, j.o0, j.out_tot, j.ld_r = b.c0, 0, self.Cout, self.R
-            j.A, j.AT, j.Bl, j.BlT = self.Bl.data_ptr(), self.Bl.data_ptr(), self.Bl.data_ptr(), self.BlT.data_ptr()
+            blt = self.BlT_br[b.branch] if self.dapp else self.BlT
+            j.A, j.AT, j.Bl, j.BlT = self.Bl.data_ptr(), self.Bl.data_ptr(), self.Bl.data_ptr(), blt.data_ptr()
             out.append(j)
         return out
 
@@ -281,7 +371,7 @@ class ConvPack:
             j = _lib.LoraConvJob()
             j.w_down, j.rank, j.cin, j.c0, j.ld_r = b.w_down.data_ptr(), b.rank, self.Cin, b.c0, self.R
             j.flip = 1 if self.stride == 1 else 0
-            j.wt, j.wd = self.Wt.data_ptr(), self.Wdl.data_ptr()
+            j.wt, j.wd = (self.Wt_br[b.branch] if self.dapp else self.Wt).data_ptr(), self.Wdl.data_ptr()
             out.append(j)
         return out
 
@@ -482,7 +572,15 @@ class Conv3x3Fn(torch.autograd.Function):
         T, lora = None, None
         if pack.lora:
             T = torch.empty((B, Ho * Wo, pack.R), dtype=BF16, device=x.device)
-            conv3x3_raw(x, pack.Wt, B, H, W, pack.Cin, pack.R, s, 0, T)                   # T = conv3x3(x, W_down)
+            if not pack.dapp:
+                conv3x3_raw(x, pack.Wt, B, H, W, pack.Cin, pack.R, s, 0, T)               # T = conv3x3(x, W_down)
+            else:                                    # DreamArtist++: one launch per batch half against that half's branch rows
+                if B % 2:
+                    raise _lib.HcpError("DreamArtist++ (dapp) layers need an even batch: [negative half | positive half]")
+                Bh = B // 2
+                for half, br in ((0, "n"), (1, "p")):
+                    conv3x3_raw(_RowView(x, half * Bh * H * W * pack.Cin), pack.Wt_br[br], Bh, H, W, pack.Cin, pack.R, s, 0,
+                                _RowView(T, half * Bh * Ho * Wo * pack.R))
             lora = (T, pack.Bl, pack.r_tot, pack.R)
         conv3x3_raw(x, pack.W, B, H, W, pack.Cin, pack.Cout, s, 0, out, bias=pack.bias, rowbias=rowbias, residual=res, rowbias_ld=rb_ld,
                     lora=lora)
@@ -505,7 +603,12 @@ class Conv3x3Fn(torch.autograd.Function):
             x, T = ctx.saved_tensors
             R, N = pack.R, pack.Cout
             U = torch.empty((M, R), dtype=BF16, device=dy.device)
-            gemm_raw([(dy, N, N)], [(pack.BlT, N, R, 0)], M, R, U, R)                       # U = dY . (alpha W_up)
+            if not pack.dapp:
+                gemm_raw([(dy, N, N)], [(pack.BlT, N, R, 0)], M, R, U, R)                   # U = dY . (alpha W_up)
+            else:
+                Mh = M // 2
+                for half, br in ((0, "n"), (1, "p")):
+                    gemm_raw([(_RowView(dy, half * Mh * N), N, N)], [(pack.BlT_br[br], N, R, 0)], Mh, R, _RowView(U, half * Mh * R), R)
             for q, pieces in pack.slabs():
                 for p0 in range(0, len(pieces), 8):
                     chunk = pieces[p0:p0 + 8]

@@ -25,12 +25,26 @@ def host_and_blocks(child: nn.Module) -> Tuple[nn.Module, List[LoraBlock]]:
         for b in blocks:
             if not isinstance(b, LoraBlock):
                 raise NotImplementedError(f"plugin {type(b).__name__} on a hot-path layer is not supported")
-            if b.dropout.p > 0 and b.training:
-                raise NotImplementedError("LoRA dropout > 0 is not supported on the B200 hot path (set dropout: 0)")
         return child._host, blocks
     if isinstance(child, (nn.Linear, nn.Conv2d)):
         return child, []
     raise NotImplementedError(f"layer type {type(child).__name__} on the UNet hot path is not supported by hcp_diffusion_b200")
+
+
+def dropout_p(blocks: Sequence[LoraBlock]) -> float:
+    """nn.Dropout probability applied to the patched layer's output: the reference container calls `self[name].post_forward` with
+    the LAST plugin name of its loop (lora_base_patch.py:35,74; lora_layers_patch.py:128-131), i.e. the last block's dropout."""
+    if not blocks:
+        return 0.0
+    d = blocks[-1].dropout
+    return float(d.p) if (d.training and d.p > 0) else 0.0
+
+
+def _versions(host: nn.Module, blocks: Sequence[LoraBlock]):
+    """In-place edits that must invalidate a pack: base weight / bias, each block's alpha buffer, the dropout setting."""
+    bias = getattr(host, "bias", None)
+    return (host.weight._version, host.weight.data_ptr(), None if bias is None else (bias._version, bias.data_ptr()),
+            tuple((id(b), b.alpha._version, getattr(b, "branch", None)) for b in blocks), dropout_p(blocks))
 
 
 def _weight_2d(host: nn.Module) -> torch.Tensor:
@@ -48,12 +62,13 @@ class LinearGroup:
         self.pack: Optional[LinearPack] = None
         self._sig = None
         self._k_splits = None
+        self.drops = None
 
     def _signature(self, k_splits):
         sig = [tuple(k_splits) if k_splits else None]
         for ch in self.children:
             host, blocks = host_and_blocks(ch)
-            sig.append((id(ch), id(host), host.weight._version, host.weight.data_ptr(), tuple(id(b) for b in blocks)))
+            sig.append((id(ch), id(host), _versions(host, blocks)))
         return tuple(sig)
 
     def prepare(self, k_splits: Optional[Sequence[int]] = None) -> LinearPack:
@@ -85,12 +100,21 @@ class LinearGroup:
             o0 += host.weight.shape[0]
         if refs:
             pack.attach_lora(refs)
+        # nn.Dropout of the patched children: column ranges of the fused output, None when nothing is dropped
+        ranges, c0 = [], 0
+        for host, blocks in hosts:
+            ranges.append((c0, host.weight.shape[0], dropout_p(blocks)))
+            c0 += host.weight.shape[0]
+        self.drops = ranges if any(p > 0 for _, _, p in ranges) else None
         self.pack, self._sig, self._k_splits = pack, sig, k_splits
         return pack
 
     def __call__(self, xs: Sequence[torch.Tensor], residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         pack = self.prepare([x.shape[-1] for x in xs] if len(xs) > 1 else None)
-        return ops.fused_linear(pack, xs, residual)
+        if self.drops is None:
+            return ops.fused_linear(pack, xs, residual)
+        # y = dropout(layer(x)) + residual: the residual leaves the GEMM epilogue and rides the dropout kernel instead
+        return ops.dropout_cols(ops.fused_linear(pack, xs, None), self.drops, residual=residual)
 
     def run_standalone(self, x: torch.Tensor) -> torch.Tensor:
         """Used by LoraPatchContainer.forward: any float dtype in, same dtype out.  Linear hosts take [..., in]; 1x1 Conv2d hosts
@@ -105,9 +129,9 @@ class LinearGroup:
         if isinstance(host, nn.Conv2d):
             B, C_, H, W = x.shape
             t = x.permute(0, 2, 3, 1).reshape(B, H * W, C_).to(BF16).contiguous()
-            y = ops.fused_linear(pack, [t], None)
+            y = self([t])
             return y.view(B, H, W, -1).permute(0, 3, 1, 2).to(x.dtype)
-        y = ops.fused_linear(pack, [x.to(BF16)], None)
+        y = self([x.to(BF16)])
         return y.to(x.dtype)
 
 
@@ -155,15 +179,15 @@ class ConvGroup:
         self.conv = conv
         self.pack: Optional[ConvPack] = None
         self._sig = None
+        self.drop_p = 0.0
 
     def prepare(self) -> ConvPack:
         child = self.conv
-        if isinstance(child, DAPPPatchContainer):
-            raise NotImplementedError("DreamArtist++ (dapp) blocks on 3x3 convolutions are not supported on the B200 hot path")
+        dapp = isinstance(child, DAPPPatchContainer)
         conv, blocks = host_and_blocks(child)
         if not isinstance(conv, nn.Conv2d):
             raise NotImplementedError(f"{type(conv).__name__} on a 3x3 convolution of the hot path is not supported")
-        sig = (id(child), id(conv), conv.weight._version, conv.weight.data_ptr(), tuple(id(b) for b in blocks))
+        sig = (id(child), id(conv), _versions(conv, blocks))
         if self.pack is None or sig != self._sig:
             if conv.weight.requires_grad:
                 raise NotImplementedError("training base convolution weights needs the wgrad kernels, which are not built yet")
@@ -172,10 +196,28 @@ class ConvGroup:
             if conv.kernel_size != (3, 3) or conv.padding != (1, 1) or conv.stride[0] not in (1, 2):
                 raise NotImplementedError("only 3x3 / pad 1 / stride 1|2 convolutions are supported")
             pack = ConvPack(conv.weight, conv.bias, conv.stride[0])
-            if blocks:
-                pack.attach_lora([ConvLoraRef(b.layer.W_down, b.layer.W_up, float(b.alpha)) for b in blocks])
+            refs = []
+            for b in blocks:
+                branch = getattr(b, "branch", None) if dapp else None
+                if dapp and branch not in ("p", "n"):
+                    continue                       # DAPPPatchContainer.forward only reads 'p' / 'n' blocks (lora_layers_patch.py:108-126)
+                refs.append(ConvLoraRef(b.layer.W_down, b.layer.W_up, float(b.alpha), branch))
+            if refs:
+                pack.attach_lora(refs)
+            self.drop_p = dropout_p(blocks)
             self.pack, self._sig = pack, sig
         return self.pack
+
+    def __call__(self, x: torch.Tensor, geom, rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """conv(x) [+ per-image row bias] [+ residual]; with nn.Dropout on the patched layer (reference lora_base_patch.py:74) the
+        two additions leave the convolution epilogue and ride the dropout kernel: dropout(conv(x) + b) + rowbias + residual."""
+        pack = self.prepare()
+        if self.drop_p <= 0:
+            return ops.conv3x3(pack, x, geom, rowbias=rowbias, residual=residual)
+        y = ops.conv3x3(pack, x, geom)
+        B, H, W = geom
+        s = pack.stride
+        return ops.dropout_cols(y, [(0, pack.Cout, self.drop_p)], residual=residual, rowbias=rowbias, rows_per_group=(H // s) * (W // s))
 
     def run_standalone(self, x: torch.Tensor) -> torch.Tensor:
         """LoraPatchContainer.forward on a 3x3 host: NCHW in / out like the reference layer."""
@@ -186,6 +228,6 @@ class ConvGroup:
             pack_lora([self])
         B, C_, H, W = x.shape
         t = x.permute(0, 2, 3, 1).reshape(B, H * W, C_).to(BF16).contiguous()
-        y = ops.conv3x3(pack, t, (B, H, W))
+        y = self(t, (B, H, W))
         s = pack.stride
         return y.view(B, H // s, W // s, -1).permute(0, 3, 1, 2).to(x.dtype)

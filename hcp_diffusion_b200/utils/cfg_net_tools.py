@@ -58,8 +58,8 @@ def get_match_layers(layers, all_layers: Dict[str, nn.Module], return_metas: boo
 def get_lora_rank_and_cls(lora_state: Dict[str, torch.Tensor]):
     if "layer.W_down" in lora_state:
         return lora_layer_map["lora"], lora_state["layer.W_down"].shape[0], False
-    if "layer.lora_down.weight" in lora_state:
-        raise ValueError("old-format LoRA checkpoints (layer.lora_down.weight) must be converted first")
+    if "layer.lora_down.weight" in lora_state:      # old format (reference cfg_net_tools.py:78-82, tools/convert_old_lora.py)
+        return lora_layer_map["lora"], lora_state["layer.lora_down.weight"].shape[0], True
     raise ValueError("Unknown lora format.")
 
 
@@ -114,36 +114,66 @@ class HCPModelLoader:
         self.named_modules = dict(host.named_modules())
 
     @torch.no_grad()
-    def load_lora(self, cfg, mask=None, state_dict: Dict[str, torch.Tensor] = None, lora_id_offset: int = 0) -> List[LoraGroup]:
-        """cfg: list of {path | state_dict, alpha, layers?}.  Every checkpoint becomes one more stacked LoraBlock per layer."""
+    def load_lora(self, cfg, base_model_alpha: float = 1.0, load_ema: bool = False, lora_id_offset: int = 0) -> LoraGroup:
+        """cfg: list of {path | state_dict, alpha, alpha_auto_scale, dropout, layers}.  Every checkpoint becomes one more stacked
+        LoraBlock per layer, exactly like the reference (cfg_net_tools.py:249-292): the `alpha` STORED in the checkpoint is dropped and
+        the block is rebuilt with `item.alpha` (default 1.0) and `alpha_auto_scale` (default True, i.e. alpha / rank); `dropout` comes
+        from the item; old-format (`.lora_block.`) keys and `lora_ema` parts are accepted.  `lora_id_offset` (not in the reference)
+        shifts the block ids when the model already carries blocks from `make_hcpdiff` -- the reference would collide on
+        `lora_block_0`."""
         from ..ckpt_manager import auto_manager
-        groups = []
+        all_blocks: Dict[str, LoraBlock] = {}
         for ck_id, item in enumerate(cfg or []):
             sd = _get(item, "state_dict")
             if sd is None:
                 path = _get(item, "path")
                 sd = auto_manager(path).load_ckpt(path, map_location="cpu")
-            sd = sd.get("lora", sd)
+            part = "lora_ema" if load_ema else "lora"
+            sd = sd.get(part, sd)
             per_layer: Dict[str, Dict[str, torch.Tensor]] = {}
             for k, v in sd.items():
-                layer, key = k.split(".___.")
+                layer, key = k.split(".___." if k.rfind("lora_block.") == -1 else ".lora_block.", 1)
                 per_layer.setdefault(layer, {})[key] = v
             only = _get(item, "layers", "all")
             if only != "all":
-                keep = set(get_match_layers(only, self.named_modules))
-                per_layer = {k: v for k, v in per_layer.items() if any(k == p or k.startswith(p + ".") for p in keep)}
-            alpha_scale = _get(item, "alpha", 1.0)
-            blocks = {}
+                keep = get_match_layers(only, self.named_modules)
+                per_layer = {k: v for k, v in per_layer.items() if any(k.startswith(p) for p in keep)}
             for layer_name, state in per_layer.items():
-                cls, rank, _ = get_lora_rank_and_cls(state)
+                cls, rank, old_format = get_lora_rank_and_cls(state)
+                state = {k: v for k, v in state.items() if k != "alpha"}
+                if old_format:
+                    state = {"layer.W_down": state["layer.lora_down.weight"], "layer.W_up": state["layer.lora_up.weight"]}
                 parent_name, host_name = split_module_name(layer_name)
                 modules = dict(self.host.named_modules())
-                blk = cls.wrap_layer(lora_id_offset + ck_id, modules[layer_name], rank=rank, dropout=0.0, alpha=1.0, bias=False,
-                                     alpha_auto_scale=False, parent_block=modules[parent_name], host_name=host_name)
+                blk = cls.wrap_layer(lora_id_offset + ck_id, modules[layer_name], rank=rank, dropout=_get(item, "dropout", 0.0),
+                                     alpha=_get(item, "alpha", 1.0), bias="layer.bias" in state,
+                                     alpha_auto_scale=_get(item, "alpha_auto_scale", True), parent_block=modules[parent_name],
+                                     host_name=host_name)
                 dev = blk.layer.W_down.device
                 blk.layer.W_down.copy_(state["layer.W_down"].to(dev, torch.float32))
                 blk.layer.W_up.copy_(state["layer.W_up"].to(dev, torch.float32))
-                blk.alpha.copy_(state["alpha"].to(blk.alpha.device, torch.float32) * alpha_scale)
-                blocks[layer_name] = blk
-            groups.append(LoraGroup(blocks))
-        return groups
+                all_blocks[f"{layer_name}.{blk.name}"] = blk
+        return LoraGroup(all_blocks)
+
+
+@torch.no_grad()
+def load_lora_state(group: LoraGroup, state: Dict[str, torch.Tensor], strict: bool = True) -> int:
+    """Copy a `{'<layer>.___.<key>': tensor}` checkpoint part INTO the existing blocks of `group` (training resume).  The reference
+    resumes with `model.load_state_dict(sd['lora'], strict=False)` (train_ac.py:281-288, ckpt_pkl.py:81-88), which only matches
+    checkpoints written with `plugin_from_raw` keys; here both key styles land in the blocks that are being trained."""
+    n = 0
+    for k, v in state.items():
+        if ".___." not in k:
+            continue
+        layer, key = k.split(".___.", 1)
+        if layer not in group.plugin_dict:
+            if strict:
+                raise KeyError(f"checkpoint layer {layer!r} has no LoRA block in the model being resumed")
+            continue
+        blk = group[layer]
+        target = blk
+        for part in key.split("."):
+            target = getattr(target, part)
+        target.copy_(v.to(target.device, target.dtype).reshape(target.shape))
+        n += 1
+    return n

@@ -1,9 +1,10 @@
 """Minimal loader for hcpdiff-style yaml configs (omegaconf / hydra are not available offline).
 
 Implements the subset the training entrypoint needs, with the reference's semantics:
-  * `_base_: [file, ...]` recursive inheritance, later files and the file itself override earlier ones
-    (reference hcpdiff/utils/utils.py:56-64);
-  * the `'---'` sentinel deletes an inherited key (utils.py:43-54);
+  * `_base_: [file, ...]` recursive inheritance: the reference folds `cfg = merge(load(base), cfg)` over the list
+    (hcpdiff/utils/utils.py:56-64), so the file itself overrides every base and an EARLIER base overrides a LATER one;
+  * the `'---'` sentinel travels through the merges like any value and the keys still holding it are deleted once, after
+    the command-line overrides (utils.py:43-54, 66-72);
   * `key.sub=value` dot-list overrides from the command line (utils.py:66-72);
   * `${hcp.eval:...}`, `${hcp.time:}`, `${hcp.dtype:...}` resolvers (hcpdiff/utils/cfg_resolvers.py:11-16) and plain
     `${a.b}` interpolation;
@@ -57,32 +58,39 @@ def _wrap(x):
 
 
 def _merge(base, new):
-    """Recursive dict merge; '---' deletes."""
+    """OmegaConf.merge(base, new) for plain containers: dicts merge recursively, everything else (lists, scalars, the '---'
+    sentinel) is replaced by `new`."""
     if isinstance(base, dict) and isinstance(new, dict):
         out = dict(base)
         for k, v in new.items():
-            if isinstance(v, str) and v == "---":
-                out.pop(k, None)
-            elif k in out:
-                out[k] = _merge(out[k], v)
-            else:
-                out[k] = v
+            out[k] = _merge(out[k], v) if k in out else v
         return out
     return new
 
 
+def _remove_undefined(node):
+    """Delete every key / list item whose value is the '---' sentinel (reference remove_config_undefined, utils.py:43-54)."""
+    if isinstance(node, dict):
+        return {k: _remove_undefined(v) for k, v in node.items() if not (isinstance(v, str) and v == "---")}
+    if isinstance(node, list):
+        return [_remove_undefined(v) for v in node if not (isinstance(v, str) and v == "---")]
+    return node
+
+
 def _load_with_base(path: str) -> Dict[str, Any]:
+    """reference load_config(path, remove_undefined=False), utils.py:56-64."""
     with open(path) as f:
         cfg = yaml.safe_load(f) or {}
-    bases = cfg.pop("_base_", [])
-    merged: Dict[str, Any] = {}
-    for b in bases:
+    for b in cfg.get("_base_", None) or []:
         bp = b if os.path.isabs(b) or os.path.exists(b) else os.path.join(os.path.dirname(path), b)
-        merged = _merge(merged, _load_with_base(bp))
-    return _merge(merged, cfg)
+        cfg = _merge(_load_with_base(bp), cfg)          # what is already in cfg (the file, earlier bases) wins
+    cfg.pop("_base_", None)
+    return cfg
 
 
 def _parse_scalar(s: str):
+    if s.strip() == "---":          # the undefined sentinel, not a yaml document marker
+        return "---"
     try:
         return yaml.safe_load(s)
     except yaml.YAMLError:
@@ -148,7 +156,7 @@ def load_config_with_cli(path: str, args_list: List[str] = None) -> Cfg:
     for item in args_list or []:
         key, _, val = item.partition("=")
         _set_path(cfg, key, _parse_scalar(val))
-    root = _wrap(cfg)
+    root = _wrap(_remove_undefined(cfg))
     return _resolve(root, root)
 
 

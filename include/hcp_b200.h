@@ -296,6 +296,37 @@ int hcp_sumsq(const float* g, int64_t n, float* out /* += */, hcp_stream_t strea
 int hcp_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_device, float beta1, float beta2,
                    float eps, float weight_decay, float grad_scale, const float* sumsq_device, float max_norm,
                    int* step_device, hcp_stream_t stream);
+/* The same step with the hyper-parameters in device memory: hyper_device = {lr, beta1, beta2, eps, weight_decay} (fp32 [5]); an LR
+ * scheduler (OneCycleLR cycles lr AND beta1) rewrites them between CUDA-graph replays. */
+int hcp_adamw_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper_device, float grad_scale,
+                       const float* sumsq_device, float max_norm, int* step_device, hcp_stream_t stream);
+
+/* SNR-weighted eps loss (reference hcpdiff/loss/min_snr_loss.py:5-52): loss_sum += mean_i(w(t_b) (pred_i - target_i)^2),
+ * dpred_i = 2 w d grad_scale / n;  snr = acp/(1-acp);  mode 0 MinSNRLoss w = min(gamma/snr, 1), 1 SoftMinSNRLoss, 2 KDiffMinSNRLoss,
+ * 3 EDMLoss.  t int64 [n / per_image]. */
+int hcp_snr_mse_loss(const float* pred, const float* target, const int64_t* t, const float* alphas_cumprod, float gamma, int32_t mode,
+                     int64_t per_image, int64_t n, float grad_scale, float* loss_sum /* += */, float* dpred /* may be NULL */,
+                     hcp_stream_t stream);
+/* ModelEMA.update on a flat fp32 buffer (reference hcpdiff/utils/ema.py:18-27): decay = clip(1 - (1 + step/inv_gamma)^-power, 0,
+ * decay_max), ema = lerp(ema, p, 1 - decay); `step_device` is the optimizer's device-side step counter (already incremented). */
+int hcp_ema_flat(float* ema, const float* p, int64_t n, const int* step_device, float decay_max, float inv_gamma, float power,
+                 hcp_stream_t stream);
+/* nn.Dropout on a patched layer's output (reference hcpdiff/models/lora_base_patch.py:74), optionally followed by the residual
+ * add the GEMM epilogue would otherwise fuse: out[r, c] = keep * x[r, c] / (1 - p) (+ residual[r, c]), c < ncols (% 8 == 0),
+ * row pitches ldx / ldr / ldo in elements.  keep = f(state_device[0] seed, state_device[1] draw, site, r, c) (Philox4x32-10):
+ * the backward pass calls the same function on the gradient with the same (state, site); hcp_counter_add_u64 on
+ * &state_device[1] once per step makes CUDA-graph replays draw fresh masks. */
+int hcp_dropout_bf16(const void* x, int64_t ldx, const void* residual /* may be NULL */, int64_t ldr,
+                     const float* rowbias /* fp32 [rows / rows_per_group, rowbias_ld], may be NULL: added after the dropout */,
+                     int64_t rowbias_ld, int64_t rows_per_group, int64_t rows, int64_t ncols, float p, const uint64_t* state_device,
+                     uint32_t site, void* out, int64_t ldo, hcp_stream_t stream);
+int hcp_counter_add_u64(uint64_t* counter_device, uint64_t inc, hcp_stream_t stream);
+/* DreamArtistPTContext.post (reference hcpdiff/models/cfg_context.py:23-39) on fp32 NCHW predictions of the doubled batch
+ * eps2 = [uncond (B) | cond (B)]: out[b] = e_u + s(t_b) (e_c - e_u), s = (hi - lo) rate(t_b) + lo, rate = t/(T-1) shaped by
+ * mode (0 'ln', 1 'cos', 2 'cos2'); lo == hi: constant scale.  Forward: eps2 given, dout NULL, out [B*per_image].
+ * Backward: dout given (eps2 ignored), out = d eps2 [2*B*per_image] = [(1-s) dout | s dout]. */
+int hcp_cfg_mix_f32(const float* eps2, const float* dout, const int64_t* t, int64_t B, int64_t per_image, float scale_lo,
+                    float scale_hi, int32_t mode, int32_t num_train_timesteps, float* out, hcp_stream_t stream);
 
 #ifdef __cplusplus
 }

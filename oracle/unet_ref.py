@@ -286,10 +286,17 @@ def _linear(sd: Dict[str, Tensor], lora: Optional[LoraDict], name: str, x: Tenso
 def _conv(sd: Dict[str, Tensor], lora: Optional[LoraDict], name: str, x: Tensor, stride: int = 1, padding: int = 0) -> Tensor:
     """F.conv2d(x, W_host + delta, b) -- LoraLayer.Conv2dLayer.forward (lora_layers_patch.py:97-98) for patched convolutions."""
     w = sd[name + ".weight"]
+    b = sd.get(name + ".bias")
     entries = lora.get(name) if lora is not None else None
+    if entries and any(e.branch is not None for e in entries):
+        # DAPPPatchContainer.forward on a Conv2d host (lora_layers_patch.py:102-133): x = [negative half | positive half]
+        B = x.shape[0] // 2
+        y_p = F.conv2d(x[B:], w + lora_delta(entries, "p"), b, stride=stride, padding=padding)
+        y_n = F.conv2d(x[:B], w + lora_delta(entries, "n"), b, stride=stride, padding=padding)
+        return torch.cat([y_n, y_p], dim=0)
     if entries:
         w = w + lora_delta(entries)
-    return F.conv2d(x, w, sd.get(name + ".bias"), stride=stride, padding=padding)
+    return F.conv2d(x, w, b, stride=stride, padding=padding)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -9,6 +9,10 @@ Outputs (small, committed):
                           checkpoint key names (the operator the CUDA kernels sit behind)
   ref_lora_dapp_conv.pt   the same for the DreamArtist++ pair (DAPPLayer / DAPPPatchContainer: batch = [negative | positive]) and
                           for LoraLayer on Conv2d hosts (3x3 stride 1 / stride 2 and 1x1)
+  ref_step.pt             the step either side of the UNet, from the REAL reference code: MinSNRLoss / SoftMinSNRLoss / KDiffMinSNRLoss /
+                          EDMLoss (hcpdiff/loss/min_snr_loss.py), a ModelEMA trajectory (hcpdiff/utils/ema.py), DreamArtistPTContext
+                          pre/post (hcpdiff/models/cfg_context.py), get_cfg_range (hcpdiff/utils/utils.py), and DAPPLayer on a 3x3
+                          Conv2d host (batch = [negative | positive])
   lora_webui_keys.json    hcpdiff <-> webui key maps of the REAL reference LoraConverter for the 160 SD1.5 attention/ff LoRA layers
 """
 import importlib
@@ -244,8 +248,117 @@ def make_webui_keys():
     print("lora_webui_keys.json:", len(fx["to_webui"]), "keys; sample", list(fx["to_webui"].items())[0])
 
 
+def _load_by_path(name, rel):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_step():
+    """Loss / EMA / CFG-context / cfg-range vectors of the real reference, plus DAPP on a 3x3 convolution."""
+    sys.dont_write_bytecode = True
+    if "diffusers" not in sys.modules:                       # min_snr_loss.py only needs the name for a type annotation
+        d = types.ModuleType("diffusers")
+        d.SchedulerMixin = type("SchedulerMixin", (), {})
+        sys.modules["diffusers"] = d
+    if "omegaconf" not in sys.modules:                       # utils.py imports the names at module level; get_cfg_range does not use them
+        o = types.ModuleType("omegaconf")
+        o.OmegaConf = type("OmegaConf", (), {})
+        o.ListConfig = type("ListConfig", (), {})
+        sys.modules["omegaconf"] = o
+    loss_mod = _load_by_path("_ref_min_snr_loss", "hcpdiff/loss/min_snr_loss.py")
+    ema_mod = _load_by_path("_ref_ema", "hcpdiff/utils/ema.py")
+    ctx_mod = _load_by_path("_ref_cfg_context", "hcpdiff/models/cfg_context.py")
+    utils_mod = _load_by_path("_ref_utils", "hcpdiff/utils/utils.py")
+    g = torch.Generator().manual_seed(11)
+    fx = {}
+    # --- losses: scheduler stand-in carrying the SD1.5 scaled-linear alphas_cumprod (what DDPMScheduler holds)
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2
+    sched = types.SimpleNamespace(alphas_cumprod=torch.cumprod(1.0 - betas, dim=0))
+    pred = torch.randn(6, 4, 8, 8, generator=g)
+    target = torch.randn(6, 4, 8, 8, generator=g)
+    t = torch.tensor([0, 17, 250, 499, 873, 999])
+    fx["loss"] = {"pred": pred, "target": target, "t": t, "out": {}}
+    for cls, gamma in (("MinSNRLoss", 5.0), ("MinSNRLoss", 1.0), ("SoftMinSNRLoss", 2.0), ("KDiffMinSNRLoss", 1.0), ("EDMLoss", 1.0)):
+        crit = getattr(loss_mod, cls)(gamma=gamma, noise_scheduler=sched, device="cpu")
+        p = pred.clone().requires_grad_(True)
+        per_elem = crit(p.float(), target.float(), t)           # reduction 'none' (train_base.yaml:29), then .mean() in get_loss
+        loss = per_elem.mean()
+        loss.backward()
+        fx["loss"]["out"][f"{cls}:{gamma}"] = {"loss": loss.detach().clone(), "dpred": p.grad.clone()}
+    # --- ModelEMA: 6 updates of a 2-parameter module (+ a buffer) with the ema.yaml hyper-parameters and the defaults
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Parameter(torch.randn(5, 3, generator=g))
+            self.b = nn.Parameter(torch.randn(7, generator=g))
+            self.frozen = nn.Parameter(torch.randn(2, generator=g), requires_grad=False)
+            self.register_buffer("alpha", torch.tensor(0.125))
+    fx["ema"] = []
+    for kw in ({"decay_max": 0.9997, "power": 0.85}, {}, {"decay_max": 0.5, "inv_gamma": 2.0, "power": 0.75}):
+        m = M()
+        ema = ema_mod.ModelEMA(m, **kw)
+        # ModelEMA keeps `p.data.to(device)`: with model and EMA on the same device that is an ALIAS of the live parameter (in
+        # training the model is on the GPU and the EMA on the CPU, a real copy) -- give the EMA its own storage like there
+        ema.train_params = {k: v.clone() for k, v in ema.train_params.items()}
+        traj = {"kw": kw, "init": {k: v.detach().clone() for k, v in m.named_parameters()}, "params": [], "ema": []}
+        for _ in range(6):
+            with torch.no_grad():
+                m.a.add_(torch.randn(m.a.shape, generator=g) * 0.1)
+                m.b.add_(torch.randn(m.b.shape, generator=g) * 0.1)
+            ema.update(m)
+            traj["params"].append({"a": m.a.detach().clone(), "b": m.b.detach().clone()})
+            traj["ema"].append({k: v.clone() for k, v in ema.state_dict().items()})
+        fx["ema"].append(traj)
+    # --- DreamArtistPTContext
+    fx["cfg"] = []
+    for text in ("3.0", "1.0-3.0:cos", "1.5-4.0:cos2", "2.0-5.0:ln", "1.0-3.0"):
+        rng = utils_mod.get_cfg_range(text)
+        ctx = ctx_mod.DreamArtistPTContext(rng, 1000)
+        lat = torch.randn(3, 4, 8, 8, generator=g)
+        ts = torch.tensor([5, 500, 999])
+        lat2, ts2 = ctx.pre(lat, ts)
+        eps2 = torch.randn(6, 4, 8, 8, generator=g, requires_grad=True)
+        out = ctx.post(eps2)
+        dout = torch.randn(out.shape, generator=g)
+        out.backward(dout)
+        fx["cfg"].append({"text": text, "range": rng, "lat": lat, "t": ts, "lat2": lat2.clone(), "t2": ts2.clone(), "eps2": eps2.detach().clone(),
+                          "out": out.detach().clone(), "dout": dout, "deps2": eps2.grad.clone()})
+    # --- DAPP on a 3x3 convolution
+    plugin, base, layers = import_reference_lora()
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.Conv2d(8, 16, 3, padding=1)
+            self.conv_s2 = nn.Conv2d(8, 8, 3, stride=2, padding=1)
+    torch.manual_seed(3)
+    net = Net().float()
+    blocks = {}
+    for lname in ("conv", "conv_s2"):
+        for lora_id, (branch, rank) in enumerate((("p", 4), ("n", 2))):
+            blk = layers.DAPPLayer.wrap_layer(lora_id, getattr(net, lname), rank=rank, dropout=0.0, alpha=1.0, branch=branch, parent_block=net,
+                                              host_name=lname)
+            with torch.no_grad():
+                blk.layer.W_up.copy_(torch.randn(blk.layer.W_up.shape, generator=g) * 0.2)
+            blocks[f"{lname}.{branch}"] = blk
+    x = torch.randn(4, 8, 8, 8, generator=g, requires_grad=True)             # [2 negative | 2 positive]
+    outs = {"conv": net.conv(x), "conv_s2": net.conv_s2(x)}
+    sum((o ** 2).sum() for o in outs.values()).backward()
+    fx["dapp_conv"] = {"state": {k: v.detach().clone() for k, v in net.state_dict().items()}, "x": x.detach().clone(),
+                       "outs": {k: v.detach().clone() for k, v in outs.items()}, "dx": x.grad.clone(),
+                       "grads": {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None and "lora_block" in n},
+                       "container_types": {n: type(m).__name__ for n, m in net.named_children()}}
+    torch.save(fx, os.path.join(HERE, "ref_step.pt"))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "step":
+        make_step()
+        sys.exit(0)
     make_struct()
     make_lora()
     make_dapp_conv()
+    make_step()
     make_webui_keys()

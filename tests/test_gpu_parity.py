@@ -49,7 +49,10 @@ def bf(x):
 # ----------------------------------------------------------------------------------------------------------------------
 # per-op parity against fp32 torch
 # ----------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("M,K,N,ranks", [(256, 320, 320, (8,)), (77, 768, 640, (8, 8)), (1024, 320, 960, (8, 8, 8)), (64, 1280, 1280, ())])
+# last rows: the benchmark's dominant GEMM shapes (config 2, batch 4): ff.net.0.proj at 64x64 (M 16384, K 320, N 2560), the fused QKV with
+# three rank-8 blocks at 64x64, and the K = 10240 split-K linear of the 16x16 level
+@pytest.mark.parametrize("M,K,N,ranks", [(256, 320, 320, (8,)), (77, 768, 640, (8, 8)), (1024, 320, 960, (8, 8, 8)), (64, 1280, 1280, ()),
+                                         (16384, 320, 2560, ()), (16384, 320, 960, (8, 8, 8)), (1024, 10240, 1280, ()), (256, 1280, 1280, (8,))])
 def test_linear_lora_fwd_bwd(M, K, N, ranks):
     x = rnd(M, K, seed=1).to(BF).requires_grad_(True)
     W = rnd(N, K, scale=1 / math.sqrt(K), seed=2)
@@ -143,7 +146,11 @@ def test_reference_lora_golden_through_product_container(golden_dir):
     assert sum(1 for n, _ in model.named_parameters() if n in fx["grads"]) == len(fx["grads"])
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 16, 16, 64, 128, 1), (2, 32, 32, 320, 320, 2), (3, 8, 8, 128, 64, 1), (1, 64, 64, 64, 64, 1)])
+# last rows: the benchmark's dominant convolutions (config 2, batch 4): 960->320 at 64x64 (two M tiles per work item), 1280->1280 at 16x16
+# and 8x8 (split-K), 320->320 at 64x64 and the stride-2 downsampler
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 16, 16, 64, 128, 1), (2, 32, 32, 320, 320, 2), (3, 8, 8, 128, 64, 1), (1, 64, 64, 64, 64, 1),
+                                                   (4, 64, 64, 960, 320, 1), (4, 16, 16, 1280, 1280, 1), (4, 8, 8, 1280, 1280, 1),
+                                                   (4, 64, 64, 320, 320, 1), (4, 64, 64, 320, 320, 2), (4, 8, 8, 2560, 1280, 1)])
 def test_conv3x3_fwd_bwd(B, H, W, Cin, Cout, stride):
     x = rnd(B, H * W, Cin, seed=1).to(BF).requires_grad_(True)
     w = rnd(Cout, Cin, 3, 3, scale=1 / math.sqrt(9 * Cin), seed=2)
@@ -223,7 +230,10 @@ def test_geglu_and_upsample():
     assert rel_l2(x.grad, xr.grad.permute(0, 2, 3, 1).reshape(2, 64, 64)) < 1e-2
 
 
-@pytest.mark.parametrize("B,H,L,Lkv,d,mask", [(2, 8, 256, 256, 40, False), (2, 8, 200, 77, 40, True), (1, 8, 1024, 1024, 80, False), (2, 8, 64, 64, 160, False), (2, 8, 256, 77, 160, True)])
+# last rows: the benchmark's attention shapes (config 2, batch 4): self-attention L = 4096, d = 40 (87 % of the attention FLOPs) and its
+# cross-attention twin against 77 text tokens
+@pytest.mark.parametrize("B,H,L,Lkv,d,mask", [(2, 8, 256, 256, 40, False), (2, 8, 200, 77, 40, True), (1, 8, 1024, 1024, 80, False), (2, 8, 64, 64, 160, False), (2, 8, 256, 77, 160, True),
+                                              (4, 8, 4096, 4096, 40, False), (4, 8, 4096, 77, 40, False), (4, 8, 1024, 1024, 80, False)])
 def test_attention_fwd_bwd(B, H, L, Lkv, d, mask):
     C = H * d
     self_attn = (L == Lkv) and not mask

@@ -110,10 +110,28 @@ def test_checkpoint_roundtrip_and_loader(tmp_path):
             assert all(k.startswith("lora:") and ".___." in k for k in f.keys())   # reference unfold_dict key scheme
     # load into a fresh model
     unet2 = UNet2DConditionModel(**TINY_KW)
-    groups = HCPModelLoader(unet2).load_lora([{"path": os.path.join(tmp_path, "unet-7.safetensors"), "alpha": 1.0}])
-    got = groups[0].state_dict()
+    group = HCPModelLoader(unet2).load_lora([{"path": os.path.join(tmp_path, "unet-7.safetensors"), "alpha": 1.0}])
+    got = group.state_dict()                      # reference key: '<layer>.<block name>' (cfg_net_tools.py:289)
     for k, v in lora.state_dict().items():
-        torch.testing.assert_close(got[k], v.detach(), msg=k)
+        layer, key = k.split(".___.")
+        torch.testing.assert_close(got[f"{layer}.lora_block_0.___.{key}"], v.detach(), msg=k)   # alpha 1.0, auto-scaled by the same rank
+    # reference semantics of `alpha`: the stored alpha is dropped, the block gets item.alpha / rank (alpha_auto_scale default True)
+    unet3 = UNet2DConditionModel(**TINY_KW)
+    g3 = HCPModelLoader(unet3).load_lora([{"path": os.path.join(tmp_path, "unet-7.safetensors"), "alpha": 0.5}])
+    assert all(abs(float(b.alpha) - 0.5 / 4) < 1e-7 for b in g3.plugin_dict.values())
+    g4 = HCPModelLoader(unet3).load_lora([{"path": os.path.join(tmp_path, "unet-7.ckpt"), "alpha": 2.0, "alpha_auto_scale": False}], lora_id_offset=1)
+    assert all(float(b.alpha) == 2.0 and b.name == "lora_block_1" for b in g4.plugin_dict.values())
+    with pytest.raises(ValueError, match="already patched"):      # the reference would silently orphan block 0 here
+        HCPModelLoader(unet3).load_lora([{"path": os.path.join(tmp_path, "unet-7.ckpt")}])
+    # resume: the checkpoint goes INTO the blocks being trained
+    from hcp_diffusion_b200.utils.cfg_net_tools import load_lora_state
+    unet5 = UNet2DConditionModel(**TINY_KW)
+    _, lora5 = make_hcpdiff(unet5, None, [{"rank": 4, "layers": [r"re:.*\.attn1$"]}])
+    n = load_lora_state(lora5, CkptManagerSafe().load_ckpt(os.path.join(tmp_path, "unet-7.safetensors"))["lora"])
+    assert n == len(lora.state_dict())
+    for k, v in lora.state_dict().items():
+        torch.testing.assert_close(lora5.state_dict()[k], v.detach(), msg=k)
+    assert all(c.plugin_names == ["lora_block_0"] for c in unet5.modules() if hasattr(c, "plugin_names"))
 
 
 def test_flat_params_keep_names_and_alias_storage():
