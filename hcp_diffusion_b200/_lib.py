@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libhcpb200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["gemm.cu", "host_util.cu", "attention.cu", "norms.cu", "misc.cu", "step.cu"]
+SOURCES = ["gemm.cu", "host_util.cu", "attention.cu", "norms.cu", "misc.cu", "step.cu", "wgrad.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared", "-Xcompiler", "-fPIC"]
 
 MAX_SEG = 3
@@ -114,6 +114,13 @@ class LoraConvJob(C.Structure):
     ]
 
 
+class RepackJob(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("dst0", C.c_void_p), ("dst1", C.c_void_p),
+        ("kind", C.c_int32), ("rows", C.c_int32), ("K", C.c_int32), ("o0", C.c_int32), ("n_tot", C.c_int32), ("flip", C.c_int32),
+    ]
+
+
 class LoraGradBlock(C.Structure):
     _fields_ = [
         ("n_lo", C.c_int64), ("n_hi", C.c_int64), ("c0", C.c_int32), ("rank", C.c_int32), ("scale", C.c_float),
@@ -134,6 +141,8 @@ EXPORTS = [
     "hcp_sinusoid_f32", "hcp_conv_in_f32", "hcp_conv_out_f32", "hcp_conv_out_dgrad_f32", "hcp_skinny_linear", "hcp_cast_f32_to_bf16",
     "hcp_lora_pack", "hcp_lora_pack_conv", "hcp_lora_grad", "hcp_lora_grad_pair", "hcp_lora_grad_conv3x3", "hcp_add_noise", "hcp_mse_loss", "hcp_sumsq", "hcp_adamw_flat",
     "hcp_adamw_flat_dev", "hcp_snr_mse_loss", "hcp_ema_flat", "hcp_dropout_bf16", "hcp_counter_add_u64", "hcp_cfg_mix_f32",
+    "hcp_wgrad_bf16", "hcp_wgrad_conv3x3_bf16", "hcp_colsum_bf16", "hcp_norm_affine_grad_bf16", "hcp_small_linear_bwd_f32", "hcp_silu_f32",
+    "hcp_conv_in_wgrad_f32", "hcp_conv_out_wgrad_f32", "hcp_repack_weights",
 ]
 
 
@@ -192,6 +201,15 @@ def lib() -> C.CDLL:
             l.hcp_ema_flat.argtypes = [vp, vp, i64, vp, f32, f32, f32, vp]
             l.hcp_dropout_bf16.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i64, f32, vp, C.c_uint32, vp, i64, vp]
             l.hcp_counter_add_u64.argtypes = [vp, C.c_uint64, vp]
+            l.hcp_wgrad_bf16.argtypes = [vp, i64, i64, vp, i64, i64, i64, f32, vp, i64, i64, vp]
+            l.hcp_wgrad_conv3x3_bf16.argtypes = [vp, i64, vp, i64, i64, i64, i64, C.c_int32, f32, vp, vp]
+            l.hcp_colsum_bf16.argtypes = [vp, i64, i64, i64, i64, f32, vp, i64, vp]
+            l.hcp_norm_affine_grad_bf16.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, i64, i64, i64, C.c_int32, vp, vp, vp]
+            l.hcp_small_linear_bwd_f32.argtypes = [vp, i64, vp, vp, i64, i64, i64, vp, vp, vp, vp]
+            l.hcp_silu_f32.argtypes = [vp, vp, i64, vp, vp]
+            l.hcp_conv_in_wgrad_f32.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
+            l.hcp_conv_out_wgrad_f32.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
+            l.hcp_repack_weights.argtypes = [vp, i64, vp]
             l.hcp_cfg_mix_f32.argtypes = [vp, vp, vp, i64, i64, f32, f32, C.c_int32, C.c_int32, vp, vp]
             _lib = l
     return _lib

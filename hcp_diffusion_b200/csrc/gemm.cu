@@ -79,6 +79,12 @@ struct alignas(64) GemmKParams {
 template <int BN, int MSUB = 1, bool PAIR = false>
 struct GemmCfg {
     static constexpr int B_ROWS = PAIR ? BN / 2 : BN;             // rows of B this CTA loads per k-block
+    // one tcgen05.mma covers at most N = 256 columns: wider tiles issue NSPLIT instructions per k-step, each on MMA_N columns.
+    // A CTA of a pair holds MMA_N / 2 rows of B per instruction (rows [h * MMA_N + rank * MMA_N / 2, + MMA_N / 2) of the tile for
+    // instruction h), so the accumulator columns stay in the natural order of the tile.
+    static constexpr int NSPLIT = (BN > 256) ? 2 : 1;
+    static constexpr int MMA_N = BN / NSPLIT;
+    static constexpr int B_BOX_ROWS = B_ROWS / NSPLIT;            // rows per TMA box of B
     static constexpr int A_BYTES = MSUB * A_STAGE_BYTES;
     static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int ACC_STRIDE = 256;                         // TMEM columns between the two accumulators
@@ -96,6 +102,7 @@ struct GemmCfg {
     static constexpr int STAGES = PAIR ? (MAX_STAGES > 6 ? 6 : MAX_STAGES) : (MSUB == 2) ? 3 : (BN > 64) ? 5 : 8;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
     static_assert(BN % EBN == 0 && (MSUB - 1) * ACC_STRIDE + BN <= 512, "accumulators must fit the 512 TMEM columns");
+    static_assert(MMA_N <= 256 && MMA_N % 16 == 0 && (PAIR || NSPLIT == 1) && (B_BOX_ROWS % 8) == 0, "tcgen05.mma shape");
     static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             uint32_t phase = 0;
             for (int w = worker; w < total_work; w += nworkers) {
                 const int split = w / tiles_mn, mn = w % tiles_mn;
-                const int n0 = (mn % p.tiles_n) * BN + (int)rank * Cfg::B_ROWS;      // PAIR: this CTA's half of the B rows
+                const int n0 = (mn % p.tiles_n) * BN + (int)rank * Cfg::B_BOX_ROWS;  // PAIR: this CTA's part of every instruction's B rows
                 TileOrigin o[MSUB];
 #pragma unroll
                 for (int sub = 0; sub < MSUB; ++sub) o[sub] = tile_origin(p, m_tile_of(mn / p.tiles_n, sub));
@@ -257,8 +264,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                                         tma_load_2d_pair(dA, &p.tmA[s], lfull, kb * BLOCK_K, o[sub].m0);
                                     }
                                 }
-                                if (p.conv && s == 0) tma_load_2d_pair(dB, &p.tmB[0], lfull, p.taps[t].wk_off + kb * BLOCK_K, n0);
-                                else tma_load_2d_pair(dB, &p.tmB[s], lfull, kb * BLOCK_K, n0);
+#pragma unroll
+                                for (int h = 0; h < Cfg::NSPLIT; ++h) {
+                                    void* dBh = (uint8_t*)dB + h * Cfg::B_BOX_ROWS * 128;
+                                    if (p.conv && s == 0) tma_load_2d_pair(dBh, &p.tmB[0], lfull, p.taps[t].wk_off + kb * BLOCK_K, n0 + h * Cfg::MMA_N);
+                                    else tma_load_2d_pair(dBh, &p.tmB[s], lfull, kb * BLOCK_K, n0 + h * Cfg::MMA_N);
+                                }
                             }
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
@@ -269,7 +280,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     } else if (warp == 1) {
         // ===================================== MMA issuer (PAIR: the leader CTA only) ========================================
         if (rank == 0 && elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * NCTA, BN, 0, 0);
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * NCTA, Cfg::MMA_N, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int item = 0;
@@ -298,10 +309,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                                 // +32 bytes (= 2 in descriptor units) per 16-element k-step inside the swizzle atom
 #pragma unroll
                                 for (int sub = 0; sub < MSUB; ++sub) {   // the M sub-tiles share the B operand of this k-step
-                                    if constexpr (PAIR)
-                                        umma_ss_pair(acc + sub * Cfg::ACC_STRIDE, adesc + sub * (A_STAGE_BYTES >> 4) + 2 * k, bdesc + 2 * k, idesc, accum);
-                                    else
+                                    if constexpr (PAIR) {
+#pragma unroll
+                                        for (int h = 0; h < Cfg::NSPLIT; ++h)
+                                            umma_ss_pair(acc + sub * Cfg::ACC_STRIDE + h * Cfg::MMA_N, adesc + sub * (A_STAGE_BYTES >> 4) + 2 * k,
+                                                         bdesc + h * ((Cfg::B_BOX_ROWS * 128) >> 4) + 2 * k, idesc, accum);
+                                    } else {
                                         umma_ss(acc + sub * Cfg::ACC_STRIDE, adesc + sub * (A_STAGE_BYTES >> 4) + 2 * k, bdesc + 2 * k, idesc, accum);
+                                    }
                                 }
                                 accum = 1;
                             }
@@ -743,20 +758,35 @@ static int pick_bn(int64_t N) {
     return 128;
 }
 
-// CTA-pair tiling (256 x BN per pair, BN in {320, 256}): 0 = keep the single-CTA kernel.  Chosen when the launch has enough 256-row
-// work items for the 74 pairs (whole waves: a part-filled last wave costs a full main loop) and the reduction is long enough
-// for the operand stream to matter (>= HCP_PAIR_MIN_KB k-blocks; the K = 320 linears are epilogue-bound either way).
-static int pick_pair(int64_t N, int64_t m_tiles, int64_t total_kb) {
+// CTA-pair tiling (256 x BN per pair, BN in {256, 320}) and its K-split.  bn == 0: keep the single-CTA kernel.
+//   * plenty of 256-row work items for the 74 pairs (whole waves: a part-filled last wave costs a full main loop): no split;
+//   * FEW items but a long reduction (the 16x16 / 8x8 levels: M = 1024 / 256 rows against 1280..2560-channel weights -- pure weight
+//     streaming): the reduction is cut so that items x splits fill one wave of pairs.  A pair streams every weight byte ONCE for its
+//     256 rows where two single CTAs each stream all of it, which halves the L2 -> SM traffic these launches are bound by.
+// BN = 256 (two accumulators: epilogue of item i under the main loop of i + 1) when it divides N, else 320 (one accumulator).
+struct PairPlan {
+    int bn, splits;
+};
+static PairPlan plan_pair(int64_t N, int64_t m_tiles, int64_t total_kb, bool allow_split) {
     static const int mode = [] { const char* e = getenv("HCP_GEMM_PAIR"); return e ? atoi(e) : 1; }();
     static const int min_kb = [] { const char* e = getenv("HCP_PAIR_MIN_KB"); return e ? atoi(e) : 10; }();
-    if (mode == 0 || total_kb < min_kb || N < 256) return 0;
-    const int bn = (N % 320 == 0) ? 320 : (N % 256 == 0) ? 256 : 0;
-    if (!bn) return 0;
+    static const int split_min_kb = [] { const char* e = getenv("HCP_PAIR_SPLIT_MIN_KB"); return e ? atoi(e) : 40; }();
+    PairPlan none{0, 1};
+    if (mode == 0 || total_kb < min_kb || N < 256) return none;
+    const int bn = (N % 256 == 0 && getenv("HCP_PAIR_NO256") == nullptr) ? 256 : (N % 320 == 0) ? 320 : 0;
+    if (!bn) return none;
     const int64_t items = ((m_tiles + 1) / 2) * (N / bn);
-    if (mode == 2) return bn;                                   // forced (bring-up / A-B runs)
+    if (mode == 2) return PairPlan{bn, 1};                      // forced (bring-up / A-B runs)
     const int64_t waves = (items + 73) / 74;
     const double fill = (double)items / (double)(waves * 74);
-    return (items >= 56 && fill >= 0.75) ? bn : 0;
+    if (items >= 56 && fill >= 0.75) return PairPlan{bn, 1};
+    if (allow_split && mode != 3 && items <= 37 && total_kb >= split_min_kb) {
+        int64_t s = 74 / items;
+        if (s > total_kb / 8) s = total_kb / 8;                 // at least 8 k-blocks per item
+        if (s > 16) s = 16;
+        if (s >= 2) return PairPlan{bn, (int)s};
+    }
+    return none;
 }
 
 // Plain GEMMs with a short reduction whose 128x160 tiling would leave half of the SMs idle (24..73 tiles: the M = 1024 level of
@@ -798,10 +828,10 @@ static int dispatch_gemm(int bn, bool cta_pair, GemmKParams& kp, int m_tiles, cu
     }
 }
 
-// plain or split-K launch (+ finalize).  `ws` may be NULL / too small: then the launch is not split.  CTA-pair launches never split.
-static int run_gemm(int bn, bool cta_pair, GemmKParams& kp, int m_tiles, int64_t total_kb, float* ws, size_t ws_bytes, bool allow_split,
-                    cudaStream_t stream) {
-    int splits = (allow_split && !cta_pair) ? plan_splits((int64_t)m_tiles * kp.tiles_n, total_kb, kp.N) : 1;
+// plain or split-K launch (+ finalize).  `ws` may be NULL / too small: then the launch is not split.
+static int run_gemm(int bn, bool cta_pair, int pair_splits, GemmKParams& kp, int m_tiles, int64_t total_kb, float* ws, size_t ws_bytes,
+                    bool allow_split, cudaStream_t stream) {
+    int splits = !allow_split ? 1 : cta_pair ? pair_splits : plan_splits((int64_t)m_tiles * kp.tiles_n, total_kb, kp.N);
     if (splits > 1 && (!ws || ws_bytes < (size_t)splits * kp.M * kp.N * sizeof(float))) splits = 1;
     if (splits > 1) {
         kp.kb_per_split = (int)((total_kb + splits - 1) / splits);
@@ -833,7 +863,8 @@ using namespace hcp;
 extern "C" size_t hcp_splitk_workspace_bytes(int64_t M, int64_t N, int64_t total_k) {
     const int bn = pick_bn(N);
     const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-    if (pick_pair(N, m_tiles, (total_k + BLOCK_K - 1) / BLOCK_K)) return 0;        // CTA-pair launches never split
+    const PairPlan pp = plan_pair(N, m_tiles, (total_k + BLOCK_K - 1) / BLOCK_K, true);
+    if (pp.bn) return pp.splits > 1 ? (size_t)pp.splits * M * N * sizeof(float) : 0;
     const int64_t ctas = m_tiles * ((N + bn - 1) / bn);
     const int splits = plan_splits(ctas, (total_k + BLOCK_K - 1) / BLOCK_K, N);
     return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
@@ -848,9 +879,10 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     memset(&kp, 0, sizeof(kp));
     int64_t kb_all = 0;
     for (int s = 0; s < a->nseg; ++s) kb_all += (a->k[s] + BLOCK_K - 1) / BLOCK_K;
-    const int pair_bn = pick_pair(a->N, (a->M + BLOCK_M - 1) / BLOCK_M, kb_all);
+    const PairPlan pp = plan_pair(a->N, (a->M + BLOCK_M - 1) / BLOCK_M, kb_all, a->workspace != nullptr);
+    const int pair_bn = pp.bn;
     const int bn = pair_bn ? pair_bn : pick_bn_gemm(a->N, (a->M + BLOCK_M - 1) / BLOCK_M, kb_all);
-    const int b_box_rows = pair_bn ? pair_bn / 2 : bn;       // a CTA of a pair loads half of the tile's B rows
+    const int b_box_rows = pair_bn ? (pair_bn > 256 ? pair_bn / 4 : pair_bn / 2) : bn;       // rows of one TMA box of B (see GemmCfg::B_BOX_ROWS)
     for (int s = 0; s < a->nseg; ++s) {
         if (a->k[s] <= 0) return set_error(HCP_ERR_INVALID, "gemm: k must be positive");
         if ((a->lda[s] % 8) != 0 || (a->ldb[s] % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: lda/ldb");
@@ -879,7 +911,7 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     const int m_tiles = (int)((a->M + BLOCK_M - 1) / BLOCK_M);
     int64_t total_kb = 0;
     for (int s = 0; s < a->nseg; ++s) total_kb += kp.nkb[s];
-    return run_gemm(bn, pair_bn != 0, kp, m_tiles, total_kb, a->workspace, a->workspace_bytes, true, (cudaStream_t)stream_);
+    return run_gemm(bn, pair_bn != 0, pp.splits, kp, m_tiles, total_kb, a->workspace, a->workspace_bytes, true, (cudaStream_t)stream_);
 }
 
 // Conv2d LoRA: out += T . Bl^T as K-segment 1 (plain 2D operands; the rows of an M tile of the convolution are contiguous pixels)
@@ -948,12 +980,15 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
     kp.ldo = a->Cout;
     const int m_tiles = (bnimg == 1) ? (int)(a->B * kp.tiles_w * kp.tiles_h) : (int)((a->B + bnimg - 1) / bnimg);
     // CTA pairs for the forward-mode launches (mode 1 = four short phase launches of the stride-2 dgrad: single CTAs)
-    const int pair_bn = (a->mode == 0) ? pick_pair(a->Cout, m_tiles, 9 * (Cin / BLOCK_K) + (a->lora_t ? (a->lora_ld + BLOCK_K - 1) / BLOCK_K : 0)) : 0;
+    const PairPlan pp = (a->mode == 0) ? plan_pair(a->Cout, m_tiles, 9 * (Cin / BLOCK_K) + (a->lora_t ? (a->lora_ld + BLOCK_K - 1) / BLOCK_K : 0),
+                                                   a->workspace != nullptr)
+                                       : PairPlan{0, 1};
+    const int pair_bn = pp.bn;
     if (pair_bn) {
         bn = pair_bn;
         kp.tiles_n = (int)((a->Cout + bn - 1) / bn);
     }
-    const int b_box_rows = pair_bn ? pair_bn / 2 : bn;
+    const int b_box_rows = pair_bn ? (pair_bn > 256 ? pair_bn / 4 : pair_bn / 2) : bn;
     int rc = make_tmap_2d(&kp.tmB[0], a->w, (uint64_t)(9 * Cin), (uint64_t)a->Cout, (uint64_t)(9 * Cin), BLOCK_K, b_box_rows);
     if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -974,7 +1009,7 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
             }
         kp.sh = kp.sw = 1; kp.oh0 = kp.ow0 = 0;
         if ((rc = conv_lora_segment(a, kp, b_box_rows))) return rc;
-        return run_gemm(bn, pair_bn != 0, kp, m_tiles, (int64_t)9 * kp.nkb[0] + (kp.nseg > 1 ? kp.nkb[1] : 0), a->workspace, a->workspace_bytes, true, stream);
+        return run_gemm(bn, pair_bn != 0, pp.splits, kp, m_tiles, (int64_t)9 * kp.nkb[0] + (kp.nseg > 1 ? kp.nkb[1] : 0), a->workspace, a->workspace_bytes, true, stream);
     }
     if (a->mode == 0 && a->stride == 2) {
         // view x as [B][Hin/2][2][Win/2][2*Cin]: input row ih = 2*oh + kh - 1 -> (phase, index)
@@ -998,7 +1033,7 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
             }
         kp.sh = kp.sw = 1; kp.oh0 = kp.ow0 = 0;
         if ((rc = conv_lora_segment(a, kp, b_box_rows))) return rc;
-        return run_gemm(bn, pair_bn != 0, kp, m_tiles, (int64_t)9 * kp.nkb[0] + (kp.nseg > 1 ? kp.nkb[1] : 0), a->workspace, a->workspace_bytes, true, stream);
+        return run_gemm(bn, pair_bn != 0, pp.splits, kp, m_tiles, (int64_t)9 * kp.nkb[0] + (kp.nseg > 1 ? kp.nkb[1] : 0), a->workspace, a->workspace_bytes, true, stream);
     }
     if (a->lora_t) return set_error(HCP_ERR_INVALID, "conv3x3: the LoRA segment is only available in mode 0");
     // mode 1: dgrad of the stride-2 conv.  x = dY [B, Hin, Win, Cin] (Cin = Cout of the fwd conv),
@@ -1030,7 +1065,7 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
             }
             kp.ntaps = nt;
             kp.oh0 = ph; kp.ow0 = pw;
-            rc = run_gemm(bn, false, kp, m_tiles, 0, nullptr, 0, false, stream);
+            rc = run_gemm(bn, false, 1, kp, m_tiles, 0, nullptr, 0, false, stream);
             if (rc) return rc;
         }
     return HCP_OK;

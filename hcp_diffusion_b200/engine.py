@@ -80,6 +80,63 @@ class FlatParams:
         return self.offsets[i + 1] if i + 1 < len(self.offsets) else self.numel
 
 
+class GradBuckets:
+    """Bucketed all-reduce of the flat gradient buffer, overlapped with the backward pass (the reference: DistributedDataParallel's
+    reducer, 25 MB buckets launched from autograd hooks).  The flat buffer is cut into contiguous ranges of about `bucket_bytes`; the
+    weight-gradient kernels report the parameters they have just produced (ops.notify_grad), and when the last parameter of a range
+    has been reported the range is all-reduced over NCCL on a communication stream ordered after the producing kernels.  The
+    optimizer waits for the communication stream.  Parameters nobody reported (frozen / unused) are flushed by `finish()`."""
+
+    def __init__(self, flat: FlatParams, pg, bucket_bytes: int = 256 << 20):
+        self.flat, self.pg = flat, pg
+        self.comm = torch.cuda.Stream()
+        per = max(bucket_bytes // 4, 1)
+        self.ranges, self.bucket_of = [], {}
+        lo, k = 0, 0
+        for i, p in enumerate(flat.params):
+            self.bucket_of[id(p)] = k
+            hi = flat.end_of(i)
+            if hi - lo >= per or i == len(flat.params) - 1:
+                self.ranges.append((lo, hi))
+                lo, k = hi, k + 1
+        self.count = [0] * len(self.ranges)
+        for p in flat.params:
+            self.count[self.bucket_of[id(p)]] += 1
+        self.reset()
+
+    def reset(self):
+        self.remaining = list(self.count)
+        self.seen = set()
+        self.launched = [False] * len(self.ranges)
+
+    def on_grad(self, params):
+        for p in params:
+            k = self.bucket_of.get(id(p))
+            if k is None or id(p) in self.seen:
+                continue
+            self.seen.add(id(p))
+            self.remaining[k] -= 1
+            if self.remaining[k] == 0:
+                self._launch(k)
+
+    def _launch(self, k):
+        if self.launched[k]:
+            return
+        self.launched[k] = True
+        lo, hi = self.ranges[k]
+        ev = torch.cuda.Event()
+        ev.record()                                       # after the kernels that produced the bucket's last gradient
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ev)
+            dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def finish(self):
+        for k in range(len(self.ranges)):
+            self._launch(k)
+        torch.cuda.current_stream().wait_stream(self.comm)
+        self.reset()
+
+
 class _CfgMixFn(torch.autograd.Function):
     """DreamArtistPTContext.post (cfg_context.py:23-39) on the doubled-batch prediction [uncond | cond]."""
 
@@ -177,6 +234,11 @@ class LoraTrainStep:
         self._static = None
         self._graph_fb = None
         self._graph_opt = None
+        # data parallel + eager launches + a large gradient (full fine-tune: 3.4 GB): bucketed all-reduce overlapped with backward;
+        # otherwise (LoRA: 6 MB; or CUDA graphs) one all-reduce between the two graphs
+        self.buckets = None
+        if self.world > 1 and not use_cuda_graph and self.flat.numel * 4 >= (64 << 20):
+            self.buckets = GradBuckets(self.flat, process_group)
         # work off the critical path (LoRA-gradient kernels, text-embedding k/v projections) goes to a side stream inside
         # _forward_backward and is joined there, before anything reads the gradients (HCP_SIDE_STREAM=0 keeps a single stream)
         self.side_stream = side_stream
@@ -211,9 +273,13 @@ class LoraTrainStep:
         """x_t = add_noise, pred = unet(x_t, t, ehs), loss, backward (gradients ACCUMULATE into the flat buffer)."""
         self.loss.zero_()
         ops.set_side_stream(self.side_stream)
+        overlap = self.buckets is not None and self._micro == self.accum - 1      # DDP no_sync on all but the last micro-step
+        if overlap:
+            ops.set_grad_ready_callback(self.buckets.on_grad)
         try:
             self._fb_body(latents, noise, t, ehs, added)
         finally:
+            ops.set_grad_ready_callback(None)
             ops.join_side()
             ops.set_side_stream(False)
         ops.advance_dropout()
@@ -256,7 +322,10 @@ class LoraTrainStep:
 
     def _all_reduce(self):
         if self.world > 1:
-            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)   # averaged by grad_scale = 1/world in AdamW
+            if self.buckets is not None:
+                self.buckets.finish()                      # buckets were launched from the backward pass; flush the rest and join
+            else:
+                dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)   # averaged by grad_scale = 1/world in AdamW
 
     def _finish_micro(self, run_opt):
         self._micro += 1

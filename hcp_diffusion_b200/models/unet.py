@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from .. import _lib, ops
-from ..runtime import ConvGroup, LinearGroup, _JobTable, pack_lora
+from ..runtime import ConvGroup, LinearGroup, _JobTable, pack_lora, repack_trained
 
 
 @dataclass
@@ -435,19 +435,43 @@ class UNet2DConditionModel(nn.Module):
         return out
 
     # ---- time embedding: three skinny-linear launches for the whole network --------------------------------------------
+    @staticmethod
+    def _temb_host(r) -> nn.Linear:
+        """`time_emb_proj` of a resnet, or the host below a LoraPatchContainer patched onto it (`layers: ['re:.*\\.resnets$']`
+        wraps every nn.Linear / nn.Conv2d of a ResnetBlock2D, reference cfgs/train/examples/locon.yaml)."""
+        m = r.time_emb_proj
+        return m._host if hasattr(m, "_host") else m
+
     def _time_runtime(self):
         rt = self.__dict__["_rt"]
         resnets = self.resnets_in_order()
         te = self.time_embedding
         sig = (te.linear_1.weight._version, te.linear_2.weight._version, te.linear_1.weight.data_ptr(),
-               tuple((r.time_emb_proj.weight._version, r.time_emb_proj.weight.data_ptr()) for r in resnets))
+               tuple((self._temb_host(r).weight._version, self._temb_host(r).weight.data_ptr(), self._temb_host(r).weight.requires_grad,
+                      id(r.time_emb_proj), tuple(getattr(r.time_emb_proj, "plugin_names", ()))) for r in resnets),
+               te.linear_1.weight.requires_grad, te.linear_2.weight.requires_grad, self.conv_in.weight.requires_grad,
+               self.conv_out.weight.requires_grad, self.conv_in.weight.data_ptr(), self.conv_out.weight.data_ptr())
         if rt is None or rt.sig != sig:
-            for p in (te.linear_1, te.linear_2, *[r.time_emb_proj for r in resnets]):
+            from .lora import DAPPPatchContainer, LoraPatchContainer
+            for p in (te.linear_1, te.linear_2):
                 if not isinstance(p, nn.Linear):
-                    raise NotImplementedError("plugins on the time-embedding layers are not supported on the B200 hot path")
-                if p.weight.requires_grad:
-                    raise NotImplementedError("training the time-embedding layers needs wgrad kernels, which are not built yet")
+                    raise NotImplementedError("plugins on time_embedding.linear_1 / linear_2 are not supported on the B200 hot path")
+            for r in resnets:
+                m = r.time_emb_proj
+                if isinstance(m, DAPPPatchContainer) or not isinstance(m, (nn.Linear, LoraPatchContainer)):
+                    raise NotImplementedError(f"{type(m).__name__} on time_emb_proj is not supported on the B200 hot path")
             rt = SimpleNamespace(sig=sig)
+            # LoRA on time_emb_proj: per patched resnet the stacked blocks; their rank-r products are two small fp32 linears each
+            rt.temb_lora = [[m[name] for name in m.plugin_names] if isinstance(m, LoraPatchContainer) else []
+                            for m in (r.time_emb_proj for r in resnets)]
+            for blocks in rt.temb_lora:
+                for b in blocks:
+                    if b.rank % 2 or (b.dropout.p > 0 and b.dropout.training):
+                        raise NotImplementedError("LoRA on time_emb_proj needs an even rank and dropout 0")
+            # full fine-tune: the time-embedding MLP, the time_emb_proj layers and the boundary convolutions are trained -> their
+            # operands are refreshed every step and the path records autograd nodes (ops.SmallLinearFn / ConvInFn / ConvOutFn)
+            rt.train_time = any(p.weight.requires_grad for p in (te.linear_1, te.linear_2, *[self._temb_host(r) for r in resnets]))
+            rt.train_in, rt.train_out = self.conv_in.weight.requires_grad, self.conv_out.weight.requires_grad
             rt.w1 = te.linear_1.weight.detach().to(torch.bfloat16).contiguous()
             rt.b1 = te.linear_1.bias.detach().float().contiguous()
             rt.w2 = te.linear_2.weight.detach().to(torch.bfloat16).contiguous()
@@ -460,17 +484,40 @@ class UNet2DConditionModel(nn.Module):
                 for p in (ae.linear_1, ae.linear_2):
                     if not isinstance(p, nn.Linear) or p.weight.requires_grad:
                         raise NotImplementedError("plugins / training on the additional-embedding layers are not supported on the B200 hot path")
+                if rt.train_time:
+                    raise NotImplementedError("training the time embedding of a UNet with an additional (text_time) embedding is not supported")
                 rt.add = SimpleNamespace(
                     w1=ae.linear_1.weight.detach().to(torch.bfloat16).contiguous(), b1=ae.linear_1.bias.detach().float().contiguous(),
                     w2cat=torch.cat([te.linear_2.weight.detach(), ae.linear_2.weight.detach()], 1).to(torch.bfloat16).contiguous(),
                     b2sum=(te.linear_2.bias.detach() + ae.linear_2.bias.detach()).float().contiguous())
-            rt.wp = torch.cat([r.time_emb_proj.weight.detach() for r in resnets], 0).to(torch.bfloat16).contiguous()
-            rt.bp = torch.cat([r.time_emb_proj.bias.detach() for r in resnets], 0).float().contiguous()
+            rt.wp = torch.cat([self._temb_host(r).weight.detach() for r in resnets], 0).to(torch.bfloat16).contiguous()
+            rt.bp = torch.cat([self._temb_host(r).bias.detach() for r in resnets], 0).float().contiguous()
             offs, o = [], 0
             for r in resnets:
                 offs.append((o, o + r.out_channels))
                 o += r.out_channels
             rt.offs = offs
+            rt.repack = _JobTable()
+            rt.time_jobs = []
+            if rt.train_time:
+                def job(kind, src, dst, rows, K, o0):
+                    j = _lib.RepackJob()
+                    j.src, j.dst0, j.dst1 = src.data_ptr(), dst.data_ptr(), None
+                    j.kind, j.rows, j.K, j.o0, j.n_tot, j.flip = kind, rows, K, o0, 0, 0
+                    return j
+                for lin, wdst, bdst in ((te.linear_1, rt.w1, rt.b1), (te.linear_2, rt.w2, rt.b2)):
+                    rt.time_jobs += [job(3, lin.weight, wdst, lin.weight.shape[0], lin.weight.shape[1], 0),
+                                     job(2, lin.bias, bdst, lin.bias.shape[0], 1, 0)]
+                for r, (a, b) in zip(resnets, offs):
+                    tp = self._temb_host(r)
+                    rt.time_jobs += [job(3, tp.weight, rt.wp, b - a, tp.weight.shape[1], a), job(2, tp.bias, rt.bp, b - a, 1, a)]
+                # b1 / b2 must be own buffers (a .float() of an fp32 parameter is the parameter itself)
+                rt.b1, rt.b2 = rt.b1.clone(), rt.b2.clone()
+                rt.time_jobs[1].dst0, rt.time_jobs[3].dst0 = rt.b1.data_ptr(), rt.b2.data_ptr()
+                rt.train_lists = SimpleNamespace(
+                    l1=[(te.linear_1.weight, te.linear_1.bias, 0, te.linear_1.weight.shape[0])],
+                    l2=[(te.linear_2.weight, te.linear_2.bias, 0, te.linear_2.weight.shape[0])],
+                    proj=[(self._temb_host(r).weight, self._temb_host(r).bias, a, b - a) for r, (a, b) in zip(resnets, offs)])
             rt.w_in = self.conv_in.weight.detach().float().permute(1, 2, 3, 0).contiguous()       # tap-major [Cin,3,3,Cout]
             rt.b_in = self.conv_in.bias.detach().float().contiguous()
             rt.w_out = self.conv_out.weight.detach().float().permute(2, 3, 0, 1).contiguous()     # tap-major [3,3,Cout,Cin]
@@ -508,16 +555,30 @@ class UNet2DConditionModel(nn.Module):
         for g in cgroups:
             g.prepare()
         pack_lora(groups + cgroups, rt.jobs)
+        # full fine-tune: one launch re-casts every trained fp32 master into the kernels' bf16 operand layouts
+        repack_trained(groups + cgroups, rt.repack, rt.time_jobs)
+        if rt.train_in:
+            rt.w_in = self.conv_in.weight.detach().float().permute(1, 2, 3, 0).contiguous()
+            rt.b_in = self.conv_in.bias.detach().float().contiguous()
+        if rt.train_out:
+            rt.w_out = self.conv_out.weight.detach().float().permute(2, 3, 0, 1).contiguous()
+            rt.b_out = self.conv_out.bias.detach().float().contiguous()
 
         # time embedding -> per-resnet bias rows [B, sum(C)] fp32
         t = torch.as_tensor(timestep, device=dev)
         if t.dim() == 0:
             t = t[None]
         t = t.expand(B).to(torch.float32).contiguous()
-        e1 = ops.skinny_linear(t, rt.w1, rt.b1, 2, True)                 # silu(linear_1(sinusoid(t)))
-        if rt.add is None:
+        if rt.train_time:
+            x0 = torch.empty((B, self.time_proj.num_channels), dtype=torch.float32, device=dev)
+            ops.sinusoid(t, self.time_proj.num_channels, 1, x0, 0)
+            e1 = ops.small_linear(x0, rt.w1, rt.b1, True, rt.train_lists.l1)
+            emb = ops.small_linear(e1, rt.w2, rt.b2, True, rt.train_lists.l2)
+        elif rt.add is None:
+            e1 = ops.skinny_linear(t, rt.w1, rt.b1, 2, True)             # silu(linear_1(sinusoid(t)))
             emb = ops.skinny_linear(e1, rt.w2, rt.b2, 0, True)           # silu(linear_2(.)): every consumer applies SiLU first
         else:
+            e1 = ops.skinny_linear(t, rt.w1, rt.b1, 2, True)
             te_, ids = added["text_embeds"], added["time_ids"]
             cfg = self.config
             P_, D_ = cfg.projection_class_embeddings_input_dim, cfg.addition_time_embed_dim
@@ -529,8 +590,18 @@ class UNet2DConditionModel(nn.Module):
             ops.sinusoid(ids.to(dev, torch.float32).reshape(-1).contiguous(), D_, n_ids, addin, te_.shape[-1])
             a1 = ops.skinny_linear(addin, rt.add.w1, rt.add.b1, 0, True)  # silu(add_embedding.linear_1(.))
             emb = ops.skinny_linear(torch.cat([e1, a1], 1), rt.add.w2cat, rt.add.b2sum, 0, True)   # silu(linear_2(e1) + add.linear_2(a1))
-        temb_all = ops.skinny_linear(emb, rt.wp, rt.bp, 0, False)        # all 22 time_emb_proj layers at once
-        tembs = iter([temb_all[:, a:b] for a, b in rt.offs])
+        if rt.train_time:
+            temb_all = ops.small_linear(emb, rt.wp, rt.bp, False, rt.train_lists.proj)
+        else:
+            temb_all = ops.skinny_linear(emb, rt.wp, rt.bp, 0, False)    # all 22 time_emb_proj layers at once
+        temb_list = [temb_all[:, a:b] for a, b in rt.offs]
+        for i, blocks in enumerate(rt.temb_lora):
+            # y = x (W + sum alpha B A)^T + b on the M = batch rows of the time embedding: T = emb A^T, delta = alpha T B^T
+            for b in blocks:
+                T = ops.small_linear(emb, b.layer.W_down.detach().to(torch.bfloat16), None, False, [(b.layer.W_down, None, 0, b.rank)])
+                d = ops.small_linear(T, b.layer.W_up.detach().to(torch.bfloat16), None, False, [(b.layer.W_up, None, 0, b.layer.W_up.shape[0])])
+                temb_list[i] = temb_list[i] + d * b.alpha
+        tembs = iter(temb_list)
 
         ctx = ops.cast_bf16(encoder_hidden_states)
         kv_bias = None
@@ -540,7 +611,8 @@ class UNet2DConditionModel(nn.Module):
         if ops.side_enabled():
             ctx = _HoistedKV(ctx, [m.attn2 for m in self.modules() if isinstance(m, BasicTransformerBlock)])
 
-        h = ops.conv_in(sample, rt.w_in, rt.b_in)                        # bf16 [B, H*W, C0]
+        h = ops.conv_in(sample, rt.w_in, rt.b_in,                        # bf16 [B, H*W, C0]
+                        train=(self.conv_in.weight, self.conv_in.bias) if rt.train_in else None)
         geom = (B, H, W)
         skips: List[Tuple[torch.Tensor, tuple]] = []
 
@@ -573,7 +645,7 @@ class UNet2DConditionModel(nn.Module):
                 geom = (B, geom[1] * 2, geom[2] * 2)
         n = self.conv_norm_out
         y = ops.group_norm(n.weight, n.bias, n.num_groups, n.eps, True, h, None)[0]
-        out = ops.ConvOutFn.apply(rt.w_out, rt.b_out, geom, y)
+        out = ops.ConvOutFn.apply(rt.w_out, rt.b_out, geom, (self.conv_out.weight, self.conv_out.bias) if rt.train_out else None, y)
         if out.dtype != sample.dtype and sample.dtype.is_floating_point:
             out = out.to(sample.dtype)
         if not return_dict:

@@ -140,6 +140,23 @@ def dropout_cols(y, ranges, residual=None, rowbias=None, rows_per_group=0):
     return DropoutFn.apply(tuple(ranges), residual, rowbias, rows_per_group, y)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# gradient-ready notifications (full fine-tune, data parallel): the engine buckets the flat gradient buffer and all-reduces a bucket
+# as soon as the kernels producing its last parameter gradient have been enqueued (the reference's DDP reducer hooks).
+# ----------------------------------------------------------------------------------------------------------------------
+class _GradHook:
+    cb = None
+
+
+def set_grad_ready_callback(cb) -> None:
+    _GradHook.cb = cb
+
+
+def notify_grad(*params) -> None:
+    if _GradHook.cb is not None:
+        _GradHook.cb([p for p in params if p is not None])
+
+
 def _chk(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.dtype != BF16 or not t.is_cuda:
         raise _lib.HcpError(f"{name}: expected a CUDA bf16 tensor, got {t.dtype} on {t.device}")
@@ -238,6 +255,23 @@ class LinearPack:
         self.dapp = False
         self.A = self.AT = self.Bl = self.BlT = None
         self.A_br = self.BlT_br = None      # DAPP: {'n': ..., 'p': ...} row-masked variants of A / BlT
+        # full fine-tune: [(weight Parameter [n, K] (or [n, K, 1, 1]), bias Parameter or None, first output row o0, n)] of the hosts
+        # whose parameters are trained; their bf16 operands are refreshed from the fp32 masters every step (repack_jobs)
+        self.train: List[Tuple[torch.Tensor, Optional[torch.Tensor], int, int]] = []
+
+    def repack_jobs(self) -> List[_lib.RepackJob]:
+        out = []
+        for w, b, o0, n in self.train:
+            j = _lib.RepackJob()
+            j.src, j.dst0, j.dst1 = w.data_ptr(), self.W.data_ptr(), self.WT.data_ptr()
+            j.kind, j.rows, j.K, j.o0, j.n_tot, j.flip = 0, n, self.K, o0, self.N, 0
+            out.append(j)
+            if b is not None and self.bias is not None and b.requires_grad:
+                j = _lib.RepackJob()
+                j.src, j.dst0, j.dst1 = b.data_ptr(), self.bias.data_ptr(), None
+                j.kind, j.rows, j.K, j.o0, j.n_tot, j.flip = 2, n, 1, o0, 0, 0
+                out.append(j)
+        return out
 
     def attach_lora(self, blocks: List[LoraBlockRef]) -> None:
         self.lora = blocks
@@ -325,8 +359,24 @@ class ConvPack:
         self.lora: List[ConvLoraRef] = []
         self.r_tot = self.R = 0
         self.dapp = False
+        self.train: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None     # (weight, bias) Parameters when the layer is trained
         self.Wt = self.Wdl = self.Bl = self.BlT = None
         self.Wt_br = self.BlT_br = None      # DAPP: {'n': ..., 'p': ...} row-masked variants of Wt / BlT
+
+    def repack_jobs(self) -> List[_lib.RepackJob]:
+        if self.train is None:
+            return []
+        w, b = self.train
+        j = _lib.RepackJob()
+        j.src, j.dst0, j.dst1 = w.data_ptr(), self.W.data_ptr(), self.Wd.data_ptr()
+        j.kind, j.rows, j.K, j.o0, j.n_tot, j.flip = 1, self.Cout, self.Cin, 0, 0, 1 if self.stride == 1 else 0
+        out = [j]
+        if b is not None and self.bias is not None and b.requires_grad and b.data_ptr() != self.bias.data_ptr():
+            j = _lib.RepackJob()
+            j.src, j.dst0, j.dst1 = b.data_ptr(), self.bias.data_ptr(), None
+            j.kind, j.rows, j.K, j.o0, j.n_tot, j.flip = 2, self.Cout, 1, 0, 0, 0
+            out.append(j)
+        return out
 
     def attach_lora(self, blocks: List[ConvLoraRef]) -> None:
         self.lora = blocks
@@ -466,7 +516,7 @@ class FusedLinearFn(torch.autograd.Function):
         ctx.pack, ctx.n_x, ctx.M, ctx.ks = pack, n_x, M, ks
         ctx.batch = xs[0].shape[0]
         ctx.has_res = residual is not None
-        saved = list(xs) if pack.lora else []
+        saved = list(xs) if (pack.lora or pack.train) else []
         if T is not None:
             saved.append(T)
         ctx.save_for_backward(*saved)
@@ -505,6 +555,18 @@ class FusedLinearFn(torch.autograd.Function):
         dy = _chk(dy, "linear grad")
         N, R = pack.N, pack.R
         U = None
+        if pack.train:
+            # full fine-tune: dW[o, k] += sum_m dY[m, o] x[m, k] per trained host (tcgen05 TN GEMM), db[o] += colsum(dY)
+            xs_t = ctx.saved_tensors[:len(ks)]
+            for w, b, o0, n in pack.train:
+                gw = _acc_grad(w)
+                koff = 0
+                for x, k in zip(xs_t, ks):
+                    call("hcp_wgrad_bf16", dy.data_ptr() + 2 * o0, N, n, x.data_ptr(), k, k, M, 1.0, gw.data_ptr() + 4 * koff, pack.K, 1, stream_ptr())
+                    koff += k
+                if b is not None and b.requires_grad:
+                    call("hcp_colsum_bf16", dy.data_ptr() + 2 * o0, N, M, n, 0, 1.0, _acc_grad(b).data_ptr(), n, stream_ptr())
+                notify_grad(w, b)
         if pack.lora:
             *xs, T = ctx.saved_tensors
             U = torch.empty((M, R), dtype=BF16, device=dy.device)
@@ -548,6 +610,8 @@ def fused_linear(pack: LinearPack, xs: Sequence[torch.Tensor], residual: Optiona
     extra = []
     for b in pack.lora:
         extra += [b.w_down, b.w_up]
+    for w, _, _, _ in pack.train:
+        extra.append(w)
     return FusedLinearFn.apply(pack, residual, len(xs), *xs, *extra)
 
 
@@ -589,6 +653,8 @@ class Conv3x3Fn(torch.autograd.Function):
         ctx.n_extra = len(lora_params)
         if pack.lora:
             ctx.save_for_backward(x, T)
+        elif pack.train is not None:
+            ctx.save_for_backward(x)
         return out
 
     @staticmethod
@@ -599,6 +665,19 @@ class Conv3x3Fn(torch.autograd.Function):
         s = pack.stride
         M = B * (H // s) * (W // s)
         U = None
+        if pack.train is not None:
+            # full fine-tune: dW [Cout, Cin, 3, 3] += dY^T x_shifted (nine TN GEMMs over the shifted NHWC boxes), db += colsum(dY)
+            w, b = pack.train
+            call("hcp_wgrad_conv3x3_bf16", dy.data_ptr(), pack.Cout, ctx.saved_tensors[0].data_ptr(), B, H, W, pack.Cin, s, 1.0,
+                 _acc_grad(w).data_ptr(), stream_ptr())
+            if b is not None and b.requires_grad:
+                call("hcp_colsum_bf16", dy.data_ptr(), pack.Cout, M, pack.Cout, 0, 1.0, _acc_grad(b).data_ptr(), pack.Cout, stream_ptr())
+            notify_grad(w, b)
+        d_rowbias = None
+        if ctx.needs_input_grad[2]:
+            # the per-image row bias is the time-embedding projection: d temb[b, c] = sum over the image's pixels of dY
+            d_rowbias = torch.zeros((B, pack.Cout), dtype=torch.float32, device=dy.device)
+            call("hcp_colsum_bf16", dy.data_ptr(), pack.Cout, M, pack.Cout, M // B, 1.0, d_rowbias.data_ptr(), pack.Cout, stream_ptr())
         if pack.lora:
             x, T = ctx.saved_tensors
             R, N = pack.R, pack.Cout
@@ -636,13 +715,15 @@ class Conv3x3Fn(torch.autograd.Function):
                 if U is not None:
                     conv3x3_raw(U, pack.Wdl, B, H // 2, W // 2, pack.R, pack.Cin, 2, 1, dx, residual=dx)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None
-        return (None, None, None, dres, dx, *([None] * ctx.n_extra))
+        return (None, None, d_rowbias, dres, dx, *([None] * ctx.n_extra))
 
 
 def conv3x3(pack: ConvPack, x: torch.Tensor, geom, rowbias=None, residual=None) -> torch.Tensor:
     extra = []
     for b in pack.lora:          # autograd inputs so the node exists even when x carries no gradient
         extra += [b.w_down, b.w_up]
+    if pack.train is not None:
+        extra.append(pack.train[0])
     return Conv3x3Fn.apply(pack, geom, rowbias, residual, x, *extra)
 
 
@@ -688,11 +769,15 @@ class GroupNormFn(torch.autograd.Function):
         C2 = 0 if x2 is None else x2.shape[-1]
         need1 = ctx.needs_input_grad[5]
         need2 = x2 is not None and ctx.needs_input_grad[6]
-        if not (need1 or need2):
+        if not (need1 or need2 or gamma.requires_grad):
             return (None,) * 7
         if dy is None:
             return None, None, None, None, None, d1, d2
         dy = _chk(dy, "groupnorm grad")
+        if gamma.requires_grad:       # full fine-tune: dgamma / dbeta accumulate straight into the parameters' fp32 gradients
+            call("hcp_norm_affine_grad_bf16", x1.data_ptr(), ptr(x2), C1, C2, dy.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                 B * HW, HW, groups, int(silu), _acc_grad(gamma).data_ptr(), _acc_grad(beta).data_ptr(), stream_ptr())
+            notify_grad(gamma, beta)
         dx1 = torch.empty_like(x1)
         dx2 = None if x2 is None else torch.empty_like(x2)
         wsb = _lib.lib().hcp_groupnorm_workspace_bytes(B, HW, groups)
@@ -725,19 +810,23 @@ class LayerNormFn(torch.autograd.Function):
         call("hcp_layernorm_fwd_bf16", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, M, C_, stats.data_ptr(), y.data_ptr(),
              stream_ptr())
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(x, stats, gamma)
+        ctx.save_for_backward(x, stats, gamma, beta)
         return y, x
 
     @staticmethod
     def backward(ctx, dy, dalias):
-        x, stats, gamma = ctx.saved_tensors
-        if not ctx.needs_input_grad[3]:
+        x, stats, gamma, beta = ctx.saved_tensors
+        if not ctx.needs_input_grad[3] and not gamma.requires_grad:
             return None, None, None, None
         if dy is None:
             return None, None, None, dalias
         dy = _chk(dy, "layernorm grad")
         C_ = x.shape[-1]
         M = x.numel() // C_
+        if gamma.requires_grad:
+            call("hcp_norm_affine_grad_bf16", x.data_ptr(), None, C_, 0, dy.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                 M, 0, 0, 0, _acc_grad(gamma).data_ptr(), _acc_grad(beta).data_ptr(), stream_ptr())
+            notify_grad(gamma, beta)
         dx = torch.empty_like(x)
         add = None if dalias is None else _chk(dalias, "layernorm alias grad")
         call("hcp_layernorm_bwd_bf16", x.data_ptr(), dy.data_ptr(), ptr(add), gamma.data_ptr(), stats.data_ptr(), M, C_, dx.data_ptr(),
@@ -881,35 +970,118 @@ class Fork2Fn(torch.autograd.Function):
 
 
 class ConvOutFn(torch.autograd.Function):
-    """bf16 NHWC [B,HW,Cin] -> fp32 NCHW [B,4,H,W] 3x3 convolution at the module boundary."""
+    """bf16 NHWC [B,HW,Cin] -> fp32 NCHW [B,4,H,W] 3x3 convolution at the module boundary.  `train` = (weight, bias) Parameters of the
+    nn.Conv2d when conv_out is trained (full fine-tune): their gradients are accumulated in place."""
 
     @staticmethod
-    def forward(ctx, w: torch.Tensor, bias: Optional[torch.Tensor], geom, x):
+    def forward(ctx, w: torch.Tensor, bias: Optional[torch.Tensor], geom, train, x):
         B, H, W = geom
         x = _chk(x, "conv_out input")
         Cin, Cout = x.shape[-1], w.shape[2]            # w: tap-major [3,3,Cout,Cin]
         y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device)
         call("hcp_conv_out_f32", x.data_ptr(), w.data_ptr(), ptr(bias), B, H, W, Cin, Cout, y.data_ptr(), stream_ptr())
-        ctx.w, ctx.geom, ctx.Cin = w, geom, Cin
+        ctx.w, ctx.geom, ctx.Cin, ctx.train = w, geom, Cin, train
+        if train is not None:
+            ctx.save_for_backward(x)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         B, H, W = ctx.geom
         dy = dy.float().contiguous()
+        Cout = ctx.w.shape[2]
+        if ctx.train is not None:
+            (x,) = ctx.saved_tensors
+            wp, bp = ctx.train
+            call("hcp_conv_out_wgrad_f32", dy.data_ptr(), x.data_ptr(), B, H, W, ctx.Cin, Cout, _acc_grad(wp).data_ptr(),
+                 None if bp is None else _acc_grad(bp).data_ptr(), stream_ptr())
+            notify_grad(wp, bp)
         dx = torch.empty((B, H * W, ctx.Cin), dtype=BF16, device=dy.device)
-        call("hcp_conv_out_dgrad_f32", dy.data_ptr(), ctx.w.data_ptr(), B, H, W, ctx.Cin, ctx.w.shape[2], dx.data_ptr(), stream_ptr())
-        return None, None, None, dx
+        call("hcp_conv_out_dgrad_f32", dy.data_ptr(), ctx.w.data_ptr(), B, H, W, ctx.Cin, Cout, dx.data_ptr(), stream_ptr())
+        return None, None, None, None, dx
 
 
-def conv_in(x_nchw: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
-    """fp32 NCHW latent -> bf16 NHWC [B, H*W, Cout] (no gradient: the latent is data, conv_in is frozen)."""
+class ConvInFn(torch.autograd.Function):
+    """fp32 NCHW latent -> bf16 NHWC [B, H*W, Cout].  The latent is data (no input gradient); with `train` = (weight, bias) Parameters
+    the backward accumulates the nn.Conv2d-layout weight / bias gradients (full fine-tune)."""
+
+    @staticmethod
+    def forward(ctx, w: torch.Tensor, bias: Optional[torch.Tensor], train, wparam, x):
+        B, Cin, H, W = x.shape
+        Cout = w.shape[3]                              # w: tap-major [Cin,3,3,Cout]
+        y = torch.empty((B, H * W, Cout), dtype=BF16, device=x.device)
+        call("hcp_conv_in_f32", x.data_ptr(), w.data_ptr(), ptr(bias), B, Cin, H, W, Cout, y.data_ptr(), stream_ptr())
+        ctx.train, ctx.dims = train, (B, Cin, H, W, Cout)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dh):
+        (x,) = ctx.saved_tensors
+        B, Cin, H, W, Cout = ctx.dims
+        dh = _chk(dh, "conv_in grad")
+        wp, bp = ctx.train
+        call("hcp_conv_in_wgrad_f32", dh.data_ptr(), x.data_ptr(), B, Cin, H, W, Cout, _acc_grad(wp).data_ptr(),
+             None if bp is None else _acc_grad(bp).data_ptr(), stream_ptr())
+        notify_grad(wp, bp)
+        return None, None, None, None, None
+
+
+def conv_in(x_nchw: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], train=None) -> torch.Tensor:
+    """fp32 NCHW latent -> bf16 NHWC [B, H*W, Cout] (no input gradient: the latent is data)."""
     x = x_nchw.float().contiguous()
+    if train is not None:
+        return ConvInFn.apply(w, bias, train, train[0], x)       # the weight Parameter is an autograd input so that the node exists
     B, Cin, H, W = x.shape
     Cout = w.shape[3]                                  # w: tap-major [Cin,3,3,Cout]
     y = torch.empty((B, H * W, Cout), dtype=BF16, device=x.device)
     call("hcp_conv_in_f32", x.data_ptr(), w.data_ptr(), ptr(bias), B, Cin, H, W, Cout, y.data_ptr(), stream_ptr())
     return y
+
+
+class SmallLinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) on fp32 rows (M = batch): the time-embedding MLP and the 22 time_emb_proj layers when they are trained or
+    carry a gradient (full fine-tune).  `w_bf16` is the operand the forward kernel reads (repacked from the fp32 master every step);
+    `train` = [(weight Parameter, bias Parameter or None, first row, rows)] -- one entry per nn.Linear stacked into `w_bf16`."""
+
+    @staticmethod
+    def forward(ctx, w_bf16: torch.Tensor, bias: Optional[torch.Tensor], silu: bool, train, anchor, x: torch.Tensor):
+        x = x.float().contiguous()
+        N, K = w_bf16.shape
+        M = x.shape[0]
+        z = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        call("hcp_skinny_linear", x.data_ptr(), w_bf16.data_ptr(), ptr(bias), M, K, N, 0, 0, z.data_ptr(), stream_ptr())
+        y = z
+        if silu:
+            y = torch.empty_like(z)
+            call("hcp_silu_f32", z.data_ptr(), None, z.numel(), y.data_ptr(), stream_ptr())
+        ctx.save_for_backward(x, z, w_bf16)
+        ctx.silu, ctx.train = silu, train
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, z, w_bf16 = ctx.saved_tensors
+        N, K = w_bf16.shape
+        M = x.shape[0]
+        dy = dy.float().contiguous()
+        if ctx.silu:
+            dz = torch.empty_like(dy)
+            call("hcp_silu_f32", z.data_ptr(), dy.data_ptr(), z.numel(), dz.data_ptr(), stream_ptr())
+        else:
+            dz = dy
+        dx = torch.empty_like(x) if ctx.needs_input_grad[5] else None
+        call("hcp_small_linear_bwd_f32", dz.data_ptr(), N, None, w_bf16.data_ptr(), M, N, K, ptr(dx), None, None, stream_ptr()) if dx is not None else None
+        for wp, bp, o0, n in ctx.train or []:
+            call("hcp_small_linear_bwd_f32", dz.data_ptr() + 4 * o0, N, x.data_ptr(), None, M, n, K, None, _acc_grad(wp).data_ptr(),
+                 None if bp is None else _acc_grad(bp).data_ptr(), stream_ptr())
+            notify_grad(wp, bp)
+        return None, None, None, None, None, dx
+
+
+def small_linear(x, w_bf16, bias, silu, train=None):
+    anchor = train[0][0] if train else None
+    return SmallLinearFn.apply(w_bf16, bias, silu, train, anchor, x)
 
 
 def skinny_linear(x: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[torch.Tensor], in_mode: int, out_silu: bool) -> torch.Tensor:

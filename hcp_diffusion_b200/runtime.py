@@ -78,9 +78,6 @@ class LinearGroup:
             return self.pack
         hosts = [host_and_blocks(ch) for ch in self.children]
         for host, _ in hosts:
-            if host.weight.requires_grad:
-                raise NotImplementedError("training base weights (full fine-tune) needs the wgrad kernels, which are not built yet; "
-                                          "freeze the base model and train LoRA blocks")
             if not host.weight.is_cuda:
                 raise _lib.HcpError("hcp_diffusion_b200 runs on CUDA only: move the model to a B200 device (there is no CPU path)")
         w = torch.cat([_weight_2d(h) for h, _ in hosts], dim=0)
@@ -89,6 +86,14 @@ class LinearGroup:
         if any(b is not None for b in biases):
             bias = torch.cat([b if b is not None else torch.zeros(h.weight.shape[0], device=w.device) for (h, _), b in zip(hosts, biases)])
         pack = LinearPack(w, bias, k_splits)
+        o0 = 0
+        for host, _ in hosts:                                    # full fine-tune (`unet:` config items): trained base layers
+            n = host.weight.shape[0]
+            if host.weight.requires_grad or (host.bias is not None and host.bias.requires_grad):
+                if not host.weight.requires_grad:
+                    raise NotImplementedError("training a bias without its weight is not supported")
+                pack.train.append((host.weight, host.bias, o0, n))
+            o0 += n
         refs, o0 = [], 0
         for ch, (host, blocks) in zip(self.children, hosts):
             dapp = isinstance(ch, DAPPPatchContainer)
@@ -171,6 +176,24 @@ def pack_lora(groups: Sequence, table: Optional[_JobTable] = None) -> None:
         _lib.call("hcp_lora_pack_conv", table.cdev.data_ptr(), table.cn, _lib.stream_ptr())
 
 
+def repack_trained(groups: Sequence, table: Optional[_JobTable] = None, extra_jobs: Sequence = ()) -> None:
+    """Full fine-tune: ONE launch refreshes the bf16 operands (W, W^T / the two 3x3 arrangements, fused biases) of every trained layer
+    from the fp32 master parameters the optimizer just updated (the reference's autocast re-casts the fp32 weights every forward)."""
+    jobs = list(extra_jobs)
+    for g in groups:
+        if g.pack is not None:
+            jobs += g.pack.repack_jobs()
+    if not jobs:
+        return
+    table = table or _JobTable()
+    key = tuple((j.src, j.dst0, j.dst1, j.kind, j.o0) for j in jobs)
+    if table.key != key:
+        arr = (_lib.RepackJob * len(jobs))(*jobs)
+        table.dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).cuda()
+        table.key, table.n = key, len(jobs)
+    _lib.call("hcp_repack_weights", table.dev.data_ptr(), table.n, _lib.stream_ptr())
+
+
 class ConvGroup:
     """Packed operands of one 3x3 convolution layer: a frozen nn.Conv2d, or a LoraPatchContainer around one (LoCon: LoraLayer
     blocks with W_down [r,Cin,3,3] / W_up [Cout,r,1,1], reference lora_layers_patch.py:64-100)."""
@@ -189,13 +212,13 @@ class ConvGroup:
             raise NotImplementedError(f"{type(conv).__name__} on a 3x3 convolution of the hot path is not supported")
         sig = (id(child), id(conv), _versions(conv, blocks))
         if self.pack is None or sig != self._sig:
-            if conv.weight.requires_grad:
-                raise NotImplementedError("training base convolution weights needs the wgrad kernels, which are not built yet")
             if not conv.weight.is_cuda:
                 raise _lib.HcpError("hcp_diffusion_b200 runs on CUDA only (there is no CPU path)")
             if conv.kernel_size != (3, 3) or conv.padding != (1, 1) or conv.stride[0] not in (1, 2):
                 raise NotImplementedError("only 3x3 / pad 1 / stride 1|2 convolutions are supported")
             pack = ConvPack(conv.weight, conv.bias, conv.stride[0])
+            if conv.weight.requires_grad:                        # full fine-tune
+                pack.train = (conv.weight, conv.bias)
             refs = []
             for b in blocks:
                 branch = getattr(b, "branch", None) if dapp else None

@@ -328,6 +328,56 @@ int hcp_counter_add_u64(uint64_t* counter_device, uint64_t inc, hcp_stream_t str
 int hcp_cfg_mix_f32(const float* eps2, const float* dout, const int64_t* t, int64_t B, int64_t per_image, float scale_lo,
                     float scale_hi, int32_t mode, int32_t num_train_timesteps, float* out, hcp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Full fine-tune (reference `unet:` config items, hcpdiff/utils/cfg_net_tools.py:96-106; cfgs/train/examples/DreamBooth.yaml:6-10):
+ * gradients of the base model's own parameters and the per-step repack of the trained fp32 masters.  Every gradient is ACCUMULATED
+ * (fp32, atomics / read-modify-write) into caller-owned buffers -- the flat gradient buffer of the engine -- so that
+ * gradient accumulation over micro-batches needs nothing extra.
+ * ---------------------------------------------------------------------------------------------- */
+/* dst[j * ld_j + n * ld_n] += scale * sum_m S[m, j] X[m, n],  j < j_cols, n < n_cols   (tcgen05 TN GEMM; S, X bf16 row-major [M, *])
+ * nn.Linear weight gradient dW[out, in] = dY^T x:  S = dY (lds = N), X = x (ldx = K), ld_j = K, ld_n = 1. */
+int hcp_wgrad_bf16(const void* S, int64_t lds, int64_t j_cols, const void* X, int64_t ldx, int64_t n_cols, int64_t M, float scale,
+                   float* dst, int64_t ld_j, int64_t ld_n, hcp_stream_t stream);
+/* nn.Conv2d(3x3, pad 1, stride 1|2) weight gradient dw[Cout, Cin, 3, 3] += scale * dY^T x_shifted(tap); dy bf16 [B*Hout*Wout, Cout],
+ * x bf16 NHWC [B, Hin, Win, Cin] (Cin % 64 == 0).  Nine launches (one per tap) with the shifted TMA box of the forward kernel. */
+int hcp_wgrad_conv3x3_bf16(const void* dy, int64_t Cout, const void* x, int64_t B, int64_t Hin, int64_t Win, int64_t Cin, int32_t stride,
+                           float scale, float* dw, hcp_stream_t stream);
+/* out[r / rows_per_group, c] += scale * x[r, c]  (x bf16 [M, ld]; bias gradients: one group; per-image time-embedding gradient of a
+ * ResnetBlock2D: rows_per_group = H*W).  rows_per_group <= 0 means M. */
+int hcp_colsum_bf16(const void* x, int64_t ld, int64_t M, int64_t N, int64_t rows_per_group, float scale, float* out, int64_t ldo,
+                    hcp_stream_t stream);
+/* GroupNorm (groups > 0: stats fp32 [B, groups, 2] = (mean, rstd), rows_per_image = H*W) / LayerNorm (groups == 0: stats [rows, 2])
+ * affine gradients: dgamma[c] += sum dz xhat, dbeta[c] += sum dz with dz = dy or dy * silu'(gamma xhat + beta) (silu != 0: the fused
+ * GroupNorm+SiLU of ResnetBlock2D).  The input is the channel concatenation [x1 | x2] (x2 may be NULL, C2 = 0). */
+int hcp_norm_affine_grad_bf16(const void* x1, const void* x2, int64_t C1, int64_t C2, const void* dy, const float* stats,
+                              const float* gamma, const float* beta, int64_t rows, int64_t rows_per_image, int64_t groups, int32_t silu,
+                              float* dgamma, float* dbeta, hcp_stream_t stream);
+/* Backward of the small fp32 linears of the time-embedding path (y = x W^T + b, M = batch rows): dx[M,K] = dy W (W bf16 [N,K], the
+ * operand the forward used; dx may be NULL), dw[N,K] += dy^T x, db[N] += colsum(dy) (fp32 masters; dw / db may be NULL).
+ * dy fp32 [M, N] with row pitch ldy (a column slice of a wider matrix: the 22 time_emb_proj layers share one input). */
+int hcp_small_linear_bwd_f32(const float* dy, int64_t ldy, const float* x, const void* w_bf16, int64_t M, int64_t N, int64_t K, float* dx,
+                             float* dw, float* db, hcp_stream_t stream);
+/* out = silu(x) (dy NULL) or dy * silu'(x), fp32 vectors */
+int hcp_silu_f32(const float* x, const float* dy, int64_t n, float* out, hcp_stream_t stream);
+/* Weight / bias gradients of the 4-channel boundary convolutions in the nn.Conv2d layout [Cout, Cin, 3, 3] (fp32, accumulated):
+ * conv_in: dh bf16 NHWC [B,H,W,Cout] (gradient of its output), x fp32 NCHW latent; conv_out: dy fp32 NCHW [B,Cout,H,W], x bf16 NHWC. */
+int hcp_conv_in_wgrad_f32(const void* dh_nhwc_bf16, const float* x_nchw, int64_t B, int64_t Cin, int64_t H, int64_t W, int64_t Cout,
+                          float* dw, float* db /* may be NULL */, hcp_stream_t stream);
+int hcp_conv_out_wgrad_f32(const float* dy_nchw, const void* x_nhwc_bf16, int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                           float* dw, float* db /* may be NULL */, hcp_stream_t stream);
+/* Per-step repack of trained fp32 master weights into the bf16 operand layouts (one launch for every trained layer):
+ *   kind 0  W [rows, K] -> dst0 bf16 rows [o0, o0+rows) of [*, K]  and  dst1 bf16 [K, n_tot] columns [o0, o0+rows)   (linear, 1x1 conv)
+ *   kind 1  W [rows = Cout, K = Cin, 3, 3] -> dst0 [Cout, 3, 3, Cin]  and  dst1 [Cin, 3, 3, Cout] (taps flipped when flip != 0)
+ *   kind 2  fp32 vector of `rows` elements (K = 1) -> dst0 fp32 at element offset o0
+ *   kind 3  W [rows, K] -> dst0 bf16 rows [o0, o0+rows) of [*, K] */
+typedef struct hcp_repack_job {
+    const float* src;
+    void* dst0;
+    void* dst1;
+    int32_t kind, rows, K, o0, n_tot, flip;
+} hcp_repack_job;
+int hcp_repack_weights(const hcp_repack_job* jobs_device, int64_t njobs, hcp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

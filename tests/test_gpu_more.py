@@ -12,6 +12,10 @@ from torch import nn
 
 pytestmark = pytest.mark.gpu
 
+if torch.cuda.is_available():          # fp32 torch references must be real fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
 from hcp_diffusion_b200 import ops  # noqa: E402
 from hcp_diffusion_b200.models import UNet2DConditionModel  # noqa: E402
 from hcp_diffusion_b200.models.lora import DAPPLayer, LoraLayer  # noqa: E402
@@ -271,3 +275,42 @@ def test_two_rank_nccl_step_equals_single_rank_on_concatenated_batch(tmp_path):
     cos = float((du_dp.double() @ du_1.double()) / (du_dp.double().norm() * du_1.double().norm()))
     assert cos > 0.98 and torch.equal(r0["init"], r1["init"])
     assert abs(0.5 * (r0["loss"][0] + r1["loss"][0]) - single["loss"][0]) < 1e-3 * abs(single["loss"][0])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the shipped locon.yaml placement, unmodified: attention + ff Linear (item 0) and everything under `resnets` -- conv1, conv2,
+# conv_shortcut AND time_emb_proj -- plus proj_in / proj_out / the sampler convs (item 1)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_tiny_unet_shipped_locon_yaml_items_match_oracle():
+    spec = U.TINY
+    sd = U.init_params(spec)
+    unet = tiny_unet(sd)
+    items = [{"lr": 1e-4, "rank": 8, "layers": [r"re:.*\.attn.?$", r"re:.*\.ff$"]},                                       # locon.yaml:3-9
+             {"lr": 1e-4, "rank": 8, "layers": [r"re:.*\.resnets$", r"re:.*\.proj_in$", r"re:.*\.proj_out$", r"re:.*\.conv$"]}]  # :10-17
+    _, group = make_hcpdiff(unet, None, items)
+    pat = r".*\.attn.?$|.*\.ff$|.*\.resnets$|.*\.proj_in$|.*\.proj_out$|.*\.conv$"
+    lora = U.init_lora(spec, rank=8, alpha=1.0, seed=9, up_std=0.05, pattern=pat, include_conv=True)
+    assert set(lora) == set(group.plugin_dict), set(lora) ^ set(group.plugin_dict)
+    assert any(k.endswith("time_emb_proj") for k in lora) and any(k.endswith("conv_shortcut") for k in lora)
+    with torch.no_grad():
+        for layer, entries in lora.items():
+            group[layer].layer.W_down.copy_(entries[0].W_down)
+            group[layer].layer.W_up.copy_(entries[0].W_up)
+    lat, noise, t, ehs = U.synthetic_batch(2, spec)
+    loss_ref, pred_ref, grads_ref = U.lora_step_loss_and_grads(sd, lora, lat, noise, t, ehs, spec)
+    x_t = U.add_noise(lat, noise, t, U.ddpm_alphas_cumprod())
+    pred = unet(x_t.to(DEV), t.to(DEV), ehs.to(DEV)).sample
+    assert rel_l2(pred, pred_ref) < 2e-2
+    F.mse_loss(pred, noise.to(DEV), reduction="none").mean().backward()
+    num = den = 0.0
+    tnum = tden = 0.0
+    for layer, blocks in grads_ref.items():
+        blk = group[layer]
+        for got, ref in ((blk.layer.W_down.grad, blocks[0][0]), (blk.layer.W_up.grad, blocks[0][1])):
+            assert got is not None, layer
+            e, n = float((got.cpu().double() - ref.double()).pow(2).sum()), float(ref.double().pow(2).sum())
+            num, den = num + e, den + n
+            if layer.endswith("time_emb_proj"):
+                tnum, tden = tnum + e, tden + n
+    assert math.sqrt(num / den) < 5e-2
+    assert math.sqrt(tnum / tden) < 5e-2          # the time-embedding adapters on their own

@@ -20,6 +20,10 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+if torch.cuda.is_available():          # fp32 torch references must be real fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
 from hcp_diffusion_b200 import _lib, ops  # noqa: E402
 from hcp_diffusion_b200._lib import call, stream_ptr  # noqa: E402
 from hcp_diffusion_b200.engine import LoraTrainStep  # noqa: E402
@@ -168,11 +172,12 @@ def run_side_by_side(spec, batch, rank, steps, lr, use_graph, accum=1, loss=None
             # first optimizer step: gradients are gone (zero_grad) but the first moments are (1 - beta1) * clip * grad
             num = den = 0.0
             moms = ref.moments()
+            offset_of = {id(p): o for p, o in zip(step.flat.params, step.flat.offsets)}
             i = 0
             for layer, blocks in lora.items():
                 for e in blocks:
                     for prod_param, _ in ((group[layer].layer.W_down, 0), (group[layer].layer.W_up, 1)):
-                        off = step.flat.offsets[step.flat.params.index(prod_param)]
+                        off = offset_of[id(prod_param)]
                         got = step.m[off:off + prod_param.numel()].view_as(prod_param)
                         num += float((got.cpu().double() - moms[i][0].double()).pow(2).sum())
                         den += float(moms[i][0].double().pow(2).sum())
