@@ -64,7 +64,7 @@ class ConvArgs(C.Structure):
         ("stride", C.c_int32), ("mode", C.c_int32),
         ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_ld", C.c_int64), ("residual", C.c_void_p), ("out", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-        ("lora_t", C.c_void_p), ("lora_b", C.c_void_p), ("lora_r", C.c_int64), ("lora_ld", C.c_int64),
+        ("lora_t", C.c_void_p), ("lora_b", C.c_void_p), ("lora_r", C.c_int64), ("lora_ld", C.c_int64), ("w_tiled", C.c_int32),
     ]
 
 
@@ -107,6 +107,14 @@ class LoraJob(C.Structure):
     ]
 
 
+class LoraMergeJob(C.Structure):
+    _fields_ = [
+        ("w_host", C.c_void_p), ("w_down", C.c_void_p * 4), ("w_up", C.c_void_p * 4), ("alpha", C.c_float * 4), ("rank", C.c_int32 * 4),
+        ("nblocks", C.c_int32), ("in_dim", C.c_int32), ("out_dim", C.c_int32), ("o0", C.c_int32), ("out_tot", C.c_int32), ("tile0", C.c_int32),
+        ("tiled", C.c_int32), ("pad_", C.c_int32), ("W", C.c_void_p), ("WT", C.c_void_p),
+    ]
+
+
 class LoraConvJob(C.Structure):
     _fields_ = [
         ("w_down", C.c_void_p), ("rank", C.c_int32), ("cin", C.c_int32), ("c0", C.c_int32), ("ld_r", C.c_int32), ("flip", C.c_int32),
@@ -139,7 +147,7 @@ EXPORTS = [
     "hcp_layernorm_fwd_bf16", "hcp_layernorm_bwd_bf16", "hcp_geglu_fwd_bf16", "hcp_geglu_bwd_bf16",
     "hcp_upsample2x_fwd_bf16", "hcp_upsample2x_bwd_bf16", "hcp_add_bf16",
     "hcp_sinusoid_f32", "hcp_conv_in_f32", "hcp_conv_out_f32", "hcp_conv_out_dgrad_f32", "hcp_skinny_linear", "hcp_cast_f32_to_bf16",
-    "hcp_lora_pack", "hcp_lora_pack_conv", "hcp_lora_grad", "hcp_lora_grad_pair", "hcp_lora_grad_conv3x3", "hcp_add_noise", "hcp_mse_loss", "hcp_sumsq", "hcp_adamw_flat",
+    "hcp_lora_pack", "hcp_lora_merge", "hcp_lora_pack_conv", "hcp_lora_grad", "hcp_lora_grad_pair", "hcp_lora_grad_conv3x3", "hcp_add_noise", "hcp_mse_loss", "hcp_sumsq", "hcp_adamw_flat",
     "hcp_adamw_flat_dev", "hcp_snr_mse_loss", "hcp_ema_flat", "hcp_dropout_bf16", "hcp_counter_add_u64", "hcp_cfg_mix_f32",
     "hcp_wgrad_bf16", "hcp_wgrad_conv3x3_bf16", "hcp_colsum_bf16", "hcp_norm_affine_grad_bf16", "hcp_small_linear_bwd_f32", "hcp_silu_f32",
     "hcp_conv_in_wgrad_f32", "hcp_conv_out_wgrad_f32", "hcp_repack_weights",
@@ -188,6 +196,7 @@ def lib() -> C.CDLL:
             l.hcp_sinusoid_f32.argtypes = [vp, i64, i64, i64, vp, i64, vp]
             l.hcp_lora_pack.argtypes = [vp, i64, vp]
             l.hcp_lora_pack_conv.argtypes = [vp, i64, vp]
+            l.hcp_lora_merge.argtypes = [vp, i64, i64, vp]
             l.hcp_lora_grad_conv3x3.argtypes = [vp, i64, vp, i64, i64, i64, i64, C.c_int32, C.POINTER(LoraGradBlock), C.c_int32, vp]
             l.hcp_lora_grad.argtypes = [vp, i64, vp, i64, i64, i64, i64, C.POINTER(LoraGradBlock), C.c_int32, vp]
             l.hcp_lora_grad_pair.argtypes = [vp, vp, i64, i64, C.POINTER(LoraGradBlock), vp, vp, i64, i64, C.POINTER(LoraGradBlock),

@@ -44,6 +44,7 @@ struct alignas(64) GemmKParams {
     int32_t nkb[HCP_GEMM_MAX_SEG];     // 64-wide k-blocks per segment (conv: per tap)
     int32_t klast[HCP_GEMM_MAX_SEG];   // 16-wide k-steps issued in the last k-block of the segment (1..4)
     int32_t nseg;
+    int32_t btile;                     // bit s: B of segment s is k-block-major [K/64][rows][64] (3D tensor map, coordinate 2 = k-block)
     int32_t M, N;
     int32_t tiles_n, tiles_m;
     // convolution geometry (conv == 0: plain GEMM)
@@ -243,8 +244,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                                         tma_load_2d(dA, &p.tmA[s], &full_bar[stage], kb * BLOCK_K, o[sub].m0);
                                     }
                                 }
-                                if (p.conv && s == 0) tma_load_2d(dB, &p.tmB[0], &full_bar[stage], p.taps[t].wk_off + kb * BLOCK_K, n0);
-                                else tma_load_2d(dB, &p.tmB[s], &full_bar[stage], kb * BLOCK_K, n0);
+                                const int kcol = ((p.conv && s == 0) ? p.taps[t].wk_off : 0) + kb * BLOCK_K;
+                                if ((p.btile >> s) & 1) tma_load_3d(dB, &p.tmB[s], &full_bar[stage], 0, n0, kcol / BLOCK_K);
+                                else tma_load_2d(dB, &p.tmB[s], &full_bar[stage], kcol, n0);
                             } else {
                                 // every byte of the pair lands on the LEADER's barrier: its one arrival names the bytes of both CTAs
                                 const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
@@ -267,8 +269,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                                 for (int h = 0; h < Cfg::NSPLIT; ++h) {
                                     void* dBh = (uint8_t*)dB + h * Cfg::B_BOX_ROWS * 128;
-                                    if (p.conv && s == 0) tma_load_2d_pair(dBh, &p.tmB[0], lfull, p.taps[t].wk_off + kb * BLOCK_K, n0 + h * Cfg::MMA_N);
-                                    else tma_load_2d_pair(dBh, &p.tmB[s], lfull, kb * BLOCK_K, n0 + h * Cfg::MMA_N);
+                                    const int kcol = ((p.conv && s == 0) ? p.taps[t].wk_off : 0) + kb * BLOCK_K;
+                                    if ((p.btile >> s) & 1) tma_load_3d_pair(dBh, &p.tmB[s], lfull, 0, n0 + h * Cfg::MMA_N, kcol / BLOCK_K);
+                                    else tma_load_2d_pair(dBh, &p.tmB[s], lfull, kcol, n0 + h * Cfg::MMA_N);
                                 }
                             }
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -885,11 +888,21 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     const int b_box_rows = pair_bn ? (pair_bn > 256 ? pair_bn / 4 : pair_bn / 2) : bn;       // rows of one TMA box of B (see GemmCfg::B_BOX_ROWS)
     for (int s = 0; s < a->nseg; ++s) {
         if (a->k[s] <= 0) return set_error(HCP_ERR_INVALID, "gemm: k must be positive");
-        if ((a->lda[s] % 8) != 0 || (a->ldb[s] % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: lda/ldb");
+        if ((a->lda[s] % 8) != 0 || (((a->flags >> s) & 1) == 0 && (a->ldb[s] % 8) != 0)) return set_error(HCP_ERR_INVALID, "gemm: lda/ldb");
         const int64_t nrb = a->n_rows_b[s] > 0 ? a->n_rows_b[s] : a->N;
         int rc = make_tmap_2d(&kp.tmA[s], a->a[s], (uint64_t)a->k[s], (uint64_t)a->M, (uint64_t)a->lda[s], BLOCK_K, BLOCK_M);
         if (rc) return rc;
-        rc = make_tmap_2d(&kp.tmB[s], a->b[s], (uint64_t)a->k[s], (uint64_t)nrb, (uint64_t)a->ldb[s], BLOCK_K, b_box_rows);
+        if ((a->flags >> s) & 1) {
+            // k-block-major B: element (n, k) at b + ((k / 64) * ldb + n) * 64 + k % 64 -- every TMA box is ONE contiguous run of memory
+            if (a->k[s] % BLOCK_K) return set_error(HCP_ERR_INVALID, "gemm: a k-block-major B operand needs k % 64 == 0");
+            uint64_t dims[3] = {BLOCK_K, (uint64_t)nrb, (uint64_t)(a->k[s] / BLOCK_K)};
+            uint64_t strides[2] = {BLOCK_K * 2, (uint64_t)a->ldb[s] * BLOCK_K * 2};
+            uint32_t box[3] = {BLOCK_K, (uint32_t)b_box_rows, 1};
+            rc = make_tmap_nd(&kp.tmB[s], a->b[s], 3, dims, strides, box);
+            kp.btile |= 1 << s;
+        } else {
+            rc = make_tmap_2d(&kp.tmB[s], a->b[s], (uint64_t)a->k[s], (uint64_t)nrb, (uint64_t)a->ldb[s], BLOCK_K, b_box_rows);
+        }
         if (rc) return rc;
         kp.nkb[s] = (int)((a->k[s] + BLOCK_K - 1) / BLOCK_K);
         const int64_t rem = a->k[s] - (int64_t)(kp.nkb[s] - 1) * BLOCK_K;
@@ -989,7 +1002,16 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
         kp.tiles_n = (int)((a->Cout + bn - 1) / bn);
     }
     const int b_box_rows = pair_bn ? (pair_bn > 256 ? pair_bn / 4 : pair_bn / 2) : bn;
-    int rc = make_tmap_2d(&kp.tmB[0], a->w, (uint64_t)(9 * Cin), (uint64_t)a->Cout, (uint64_t)(9 * Cin), BLOCK_K, b_box_rows);
+    int rc;
+    if (a->w_tiled) {          // k-block-major weights [9*Cin/64][Cout][64]
+        uint64_t dims[3] = {BLOCK_K, (uint64_t)a->Cout, (uint64_t)(9 * Cin / BLOCK_K)};
+        uint64_t strides[2] = {BLOCK_K * 2, (uint64_t)a->Cout * BLOCK_K * 2};
+        uint32_t box[3] = {BLOCK_K, (uint32_t)b_box_rows, 1};
+        rc = make_tmap_nd(&kp.tmB[0], a->w, 3, dims, strides, box);
+        kp.btile = 1;
+    } else {
+        rc = make_tmap_2d(&kp.tmB[0], a->w, (uint64_t)(9 * Cin), (uint64_t)a->Cout, (uint64_t)(9 * Cin), BLOCK_K, b_box_rows);
+    }
     if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
 

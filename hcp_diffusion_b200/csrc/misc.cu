@@ -261,6 +261,91 @@ __global__ void lora_pack_conv_kernel(const hcp_lora_conv_job* __restrict__ jobs
 }
 
 // ---------------------------------------------------------------------------------------------
+// LoRA weight merge: W_eff = bf16(W_host + sum_b alpha_b * W_up_b . W_down_b), written as the forward operand W [out_tot, in]
+// (rows o0 .. o0+out of a fused group) and as the dgrad operand WT [in, out_tot].  This is what the reference layer computes every
+// forward -- LoraBlock.get_weight (alpha * mm(W_up, W_down), lora_layers_patch.py:44-45) summed over the stacked blocks by
+// LoraPatchContainer.forward (lora_base_patch.py:21-35) and added to the host weight in LinearLayer.forward (:47-57) -- with the
+// sum formed in fp32 from the fp32 masters and rounded to bf16 ONCE (autocast's cast of the summed weight).  One launch per step
+// covers every patched Linear of the model: a flat grid over the 64x64 tiles of all jobs (tile0 = running tile count, ascending).
+// ---------------------------------------------------------------------------------------------
+constexpr int MG_T = 64;          // tile edge
+constexpr int MG_RMAX = 64;       // sum of the ranks stacked on one host
+__global__ void __launch_bounds__(256) lora_merge_kernel(const hcp_lora_merge_job* __restrict__ jobs, int njobs) {
+    __shared__ float s_dn[MG_RMAX][MG_T + 4];          // W_down rows (all stacked blocks) over the tile's k range
+    __shared__ float s_up[MG_T][MG_RMAX + 1];          // alpha * W_up rows of the tile's o range
+    __shared__ __nv_bfloat16 s_t[MG_T][MG_T + 8];      // the merged tile, for the transposed store
+    pdl_trigger();
+    pdl_wait();
+    // job of this tile: last job with tile0 <= blockIdx.x
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].tile0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const hcp_lora_merge_job& jb = jobs[lo];
+    const int in = jb.in_dim, out = jb.out_dim;
+    const int tiles_k = (in + MG_T - 1) / MG_T;
+    const int t = (int)blockIdx.x - jb.tile0;
+    const int o_base = (t / tiles_k) * MG_T, k_base = (t % tiles_k) * MG_T;
+    if (o_base >= out) return;
+    const int tid = threadIdx.x;
+    int rtot = 0;
+    for (int b = 0; b < jb.nblocks; ++b) {
+        const int r = jb.rank[b];
+        const float* dn = jb.w_down[b];
+        const float* up = jb.w_up[b];
+        const float alpha = jb.alpha[b];
+        for (int i = tid; i < r * MG_T; i += 256) {
+            const int rr = i / MG_T, k = k_base + i % MG_T;
+            s_dn[rtot + rr][i % MG_T] = (k < in) ? dn[(int64_t)rr * in + k] : 0.f;
+        }
+        for (int i = tid; i < MG_T * r; i += 256) {
+            const int o = o_base + i / r, rr = i % r;
+            s_up[i / r][rtot + rr] = (o < out) ? alpha * up[(int64_t)o * r + rr] : 0.f;
+        }
+        rtot += r;
+    }
+    __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;            // 4 consecutive k per thread, rows ty + 16 i
+    __nv_bfloat16* W = (__nv_bfloat16*)jb.W;
+    __nv_bfloat16* WT = (__nv_bfloat16*)jb.WT;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ol = ty + 16 * i, o = o_base + ol, k = k_base + tx * 4;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < out && k < in) w = *reinterpret_cast<const float4*>(jb.w_host + (int64_t)o * in + k);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        for (int r = 0; r < rtot; ++r) {
+            const float u = s_up[ol][r];
+            const float4 dn = *reinterpret_cast<const float4*>(&s_dn[r][tx * 4]);
+            d0 = fmaf(u, dn.x, d0); d1 = fmaf(u, dn.y, d1); d2 = fmaf(u, dn.z, d2); d3 = fmaf(u, dn.w, d3);
+        }
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(w.x + d0, w.y + d1), p1 = __floats2bfloat162_rn(w.z + d2, w.w + d3);
+        if (o < out && k < in) {
+            uint2 v;
+            v.x = *reinterpret_cast<const uint32_t*>(&p0);
+            v.y = *reinterpret_cast<const uint32_t*>(&p1);
+            // k-block-major: ((k / 64) * out_tot + row) * 64 + k % 64 (the 4 consecutive k of a thread never straddle a 64-block)
+            __nv_bfloat16* dst = jb.tiled ? W + ((int64_t)(k >> 6) * jb.out_tot + jb.o0 + o) * 64 + (k & 63) : W + (int64_t)(jb.o0 + o) * in + k;
+            *reinterpret_cast<uint2*>(dst) = v;
+        }
+        s_t[tx * 4 + 0][ol] = p0.x; s_t[tx * 4 + 1][ol] = p0.y; s_t[tx * 4 + 2][ol] = p1.x; s_t[tx * 4 + 3][ol] = p1.y;
+    }
+    __syncthreads();
+    if (WT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int kl = ty + 16 * i, k = k_base + kl, o = o_base + tx * 4;
+            if (k < in && o < out) {
+                const int oo = jb.o0 + o;
+                __nv_bfloat16* dst = jb.tiled ? WT + ((int64_t)(oo >> 6) * in + k) * 64 + (oo & 63) : WT + (int64_t)k * jb.out_tot + oo;
+                *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(&s_t[kl][tx * 4]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // loss = mean((pred - target)^2) (fp32, reference train_ac.py:506-515 with loss.type == 'eps'), dpred = 2(pred-target)/n
 // ---------------------------------------------------------------------------------------------
 __global__ void mse_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n, float grad_scale,
@@ -447,6 +532,13 @@ extern "C" int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp
     dim3 grid(16, (unsigned)njobs);
     launch_k(lora_pack_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)st, jobs_device, (int)njobs);
     LAUNCH_CHECK("lora_pack launch");
+    return HCP_OK;
+}
+
+extern "C" int hcp_lora_merge(const hcp_lora_merge_job* jobs_device, int64_t njobs, int64_t total_tiles, hcp_stream_t st) {
+    if (!jobs_device || njobs <= 0 || total_tiles <= 0) return set_error(HCP_ERR_INVALID, "lora_merge: jobs");
+    launch_k(lora_merge_kernel, dim3((unsigned)total_tiles), dim3(256), 0, (cudaStream_t)st, jobs_device, (int)njobs);
+    LAUNCH_CHECK("lora_merge launch");
     return HCP_OK;
 }
 

@@ -22,6 +22,23 @@ from ._lib import AttnArgs, AttnBwdArgs, ConvArgs, GemmArgs, GroupNormArgs, call
 
 BF16 = torch.bfloat16
 
+# LoRA on Linear / 1x1 hosts whose adapters apply to every row: the adapters are MERGED into the bf16 weight operands once per step
+# (W + sum alpha W_up W_down -- literally what the reference layer computes, lora_layers_patch.py:44-57), so the forward and the
+# input gradient are plain GEMMs; the rank-r products T = x A^T / U = dY (alpha B) only feed the factor gradients, off the critical
+# path.  HCP_LORA_MERGE=0 (or `ops.LORA_MERGE = False` before the packs are built) keeps the K-segment formulation, which DreamArtist++
+# (per-branch adapters) always uses.
+LORA_MERGE = os.environ.get("HCP_LORA_MERGE", "1") != "0"
+# Frozen (and merged-LoRA) weight operands are stored K-BLOCK-MAJOR, [K/64][rows][64]: a TMA box of the B operand is then one
+# contiguous run of 128 B x rows instead of `rows` 128-byte pieces at a 2K-byte pitch.  The small-M layers (16x16 / 8x8 levels) stream
+# every weight byte from HBM exactly once per pass; whole-page reads are what lets them approach the HBM roofline.
+WEIGHT_TILED = os.environ.get("HCP_WEIGHT_TILED", "0") != "0"
+
+
+def tile_kmajor(w2d: torch.Tensor) -> torch.Tensor:
+    """[rows, K] (K % 64 == 0) -> k-block-major [K/64, rows, 64], contiguous."""
+    rows, K = w2d.shape
+    return w2d.reshape(rows, K // 64, 64).permute(1, 0, 2).contiguous()
+
 
 # ----------------------------------------------------------------------------------------------------------------------
 # side stream: work that is OFF the critical path of the step (LoRA-gradient kernels, the cross-attention k/v projections of the
@@ -170,16 +187,20 @@ def gemm_raw(a_list: Sequence[Tuple[torch.Tensor, int, int]], b_list: Sequence[T
              out: torch.Tensor, ldo: int, bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
              rows_per_group: int = 0, residual: Optional[torch.Tensor] = None, ldr: int = 0) -> None:
     """out[M,N] = sum_s A_s . B_s^T (+bias +rowbias +residual).
-    a_list: (tensor_or_ptr_holder, lda, k);  b_list: (tensor, ldb, n_rows_b, elem_offset)."""
+    a_list: (tensor_or_ptr_holder, lda, k);  b_list: (tensor, ldb, n_rows_b, elem_offset[, k_block_major]) -- for a k-block-major
+    operand ldb is the row count of one k-block slab (see hcp_gemm_args.flags)."""
     g = GemmArgs()
     g.nseg = len(a_list)
-    for s, ((a, lda, k), (b, ldb, nrb, boff)) in enumerate(zip(a_list, b_list)):
+    for s, ((a, lda, k), bent) in enumerate(zip(a_list, b_list)):
+        b, ldb, nrb, boff = bent[:4]
         g.a[s] = a.data_ptr()
         g.lda[s] = lda
         g.k[s] = k
         g.b[s] = b.data_ptr() + 2 * boff
         g.ldb[s] = ldb
         g.n_rows_b[s] = nrb
+        if len(bent) > 4 and bent[4]:
+            g.flags |= 1 << s
     g.M, g.N = M, N
     g.bias = ptr(bias)
     g.rowbias = ptr(rowbias)
@@ -196,12 +217,13 @@ def gemm_raw(a_list: Sequence[Tuple[torch.Tensor, int, int]], b_list: Sequence[T
 
 
 def conv3x3_raw(x: torch.Tensor, w: torch.Tensor, B: int, Hin: int, Win: int, Cin: int, Cout: int, stride: int, mode: int,
-                out: torch.Tensor, bias=None, rowbias=None, residual=None, rowbias_ld: int = 0, lora=None) -> None:
+                out: torch.Tensor, bias=None, rowbias=None, residual=None, rowbias_ld: int = 0, lora=None, w_tiled: bool = False) -> None:
     """`lora`: (T [M,R] bf16, Bl [Cout,R] bf16, r_used, R) -- the Conv2d-LoRA K-segment of a forward convolution."""
     a = ConvArgs()
     a.x, a.w = x.data_ptr(), w.data_ptr()
     a.B, a.Hin, a.Win, a.Cin, a.Cout = B, Hin, Win, Cin, Cout
     a.stride, a.mode = stride, mode
+    a.w_tiled = int(w_tiled)
     a.bias, a.rowbias, a.residual = ptr(bias), ptr(rowbias), ptr(residual)
     a.rowbias_ld = rowbias_ld
     a.out = out.data_ptr()
@@ -247,6 +269,8 @@ class LinearPack:
         self.N, self.K = weight.shape
         self.W = weight.detach().to(BF16).contiguous()
         self.WT = self.W.t().contiguous()
+        # k-block-major operand layout (set by `tile_weights`, once the pack is known to hold frozen / merged weights only)
+        self.tiled = False
         self.bias = None if bias is None else bias.detach().float().contiguous()
         self.k_splits = list(k_splits) if k_splits else [self.K]
         self.lora: List[LoraBlockRef] = []
@@ -255,9 +279,31 @@ class LinearPack:
         self.dapp = False
         self.A = self.AT = self.Bl = self.BlT = None
         self.A_br = self.BlT_br = None      # DAPP: {'n': ..., 'p': ...} row-masked variants of A / BlT
+        # merged mode: [(fp32 host weight [n, K], first output row o0, n, [LoraBlockRef, ...])]; W / WT are then rewritten every step
+        # by hcp_lora_merge (runtime.pack_lora) and the GEMMs carry no LoRA segment
+        self.merged: List[Tuple[torch.Tensor, int, int, list]] = []
         # full fine-tune: [(weight Parameter [n, K] (or [n, K, 1, 1]), bias Parameter or None, first output row o0, n)] of the hosts
         # whose parameters are trained; their bf16 operands are refreshed from the fp32 masters every step (repack_jobs)
         self.train: List[Tuple[torch.Tensor, Optional[torch.Tensor], int, int]] = []
+
+    def tile_weights(self) -> None:
+        """W [N,K] -> [K/64][N][64], WT [K,N] -> [N/64][K][64] (frozen or merged weights only: hcp_repack_weights writes row-major)."""
+        if self.tiled or self.train or self.K % 64 or self.N % 64 or any(k % 64 for k in self.k_splits):
+            return
+        self.W, self.WT = tile_kmajor(self.W), tile_kmajor(self.WT)
+        self.tiled = True
+
+    def b_fwd(self, off: int):
+        """b_list entry of the forward operand for the input segment starting at column `off`."""
+        if self.tiled:
+            return (self.W, self.N, self.N, (off // 64) * self.N * 64, True)
+        return (self.W, self.K, self.N, off)
+
+    def b_dgrad(self, off: int, k: int):
+        """b_list entry of W^T rows [off, off + k) (the dX GEMM of the input segment at column `off`)."""
+        if self.tiled:
+            return (self.WT, self.K, k, off * 64, True)
+        return (self.WT, self.N, k, off * self.N)
 
     def repack_jobs(self) -> List[_lib.RepackJob]:
         out = []
@@ -299,6 +345,29 @@ class LinearPack:
         else:
             self.A = z(self.R, self.K)
             self.BlT = z(self.R, self.N)
+
+    def enable_merge(self, hosts: Sequence[Tuple[torch.Tensor, int, int, list]]) -> bool:
+        """Switch the pack to merged weights if every patched host qualifies (fp32 master weight, <= 4 stacked blocks, ranks summing
+        to <= 64, 4-element alignment); returns whether it did."""
+        if self.dapp or self.train or not self.lora or self.K % 4 or self.N % 4:
+            return False
+        for w, o0, n, blocks in hosts:
+            if w.dtype != torch.float32 or not w.is_contiguous() or len(blocks) > 4 or sum(b.rank for b in blocks) > 64 or o0 % 4 or n % 4:
+                return False
+        self.merged = [h for h in hosts if h[3]]
+        return True
+
+    def merge_jobs(self) -> List[_lib.LoraMergeJob]:
+        out = []
+        for w, o0, n, blocks in self.merged:
+            j = _lib.LoraMergeJob()
+            j.w_host = w.data_ptr()
+            for i, b in enumerate(blocks):
+                j.w_down[i], j.w_up[i], j.alpha[i], j.rank[i] = b.w_down.data_ptr(), b.w_up.data_ptr(), b.alpha, b.rank
+            j.nblocks, j.in_dim, j.out_dim, j.o0, j.out_tot = len(blocks), self.K, n, o0, self.N
+            j.W, j.WT, j.tiled = self.W.data_ptr(), self.WT.data_ptr(), int(self.tiled)
+            out.append(j)
+        return out
 
     def jobs(self) -> List[_lib.LoraJob]:
         out = []
@@ -362,6 +431,15 @@ class ConvPack:
         self.train: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None     # (weight, bias) Parameters when the layer is trained
         self.Wt = self.Wdl = self.Bl = self.BlT = None
         self.Wt_br = self.BlT_br = None      # DAPP: {'n': ..., 'p': ...} row-masked variants of Wt / BlT
+        self.tiled = False
+
+    def tile_weights(self) -> None:
+        """W [Cout, 9*Cin] / Wd [Cin, 9*Cout] -> k-block-major [9*C/64][rows][64] (frozen layers only)."""
+        if self.tiled or self.train is not None or self.Cout % 64:
+            return
+        self.W = tile_kmajor(self.W.reshape(self.Cout, 9 * self.Cin))
+        self.Wd = tile_kmajor(self.Wd.reshape(self.Cin, 9 * self.Cout))
+        self.tiled = True
 
     def repack_jobs(self) -> List[_lib.RepackJob]:
         if self.train is None:
@@ -499,10 +577,10 @@ class FusedLinearFn(torch.autograd.Function):
         a_list = [(x, k, k) for x, k in zip(xs, ks)]
         b_list, off = [], 0
         for k in ks:
-            b_list.append((pack.W, pack.K, N, off))
+            b_list.append(pack.b_fwd(off))
             off += k
         T = None
-        if pack.lora:
+        if pack.lora and not pack.merged:
             if len(a_list) + 1 > _lib.MAX_SEG:
                 raise _lib.HcpError("LoRA on a linear with more than two concatenated inputs is not supported")
             T = torch.empty((M, pack.R), dtype=BF16, device=xs[0].device)
@@ -567,7 +645,27 @@ class FusedLinearFn(torch.autograd.Function):
                 if b is not None and b.requires_grad:
                     call("hcp_colsum_bf16", dy.data_ptr() + 2 * o0, N, M, n, 0, 1.0, _acc_grad(b).data_ptr(), n, stream_ptr())
                 notify_grad(w, b)
-        if pack.lora:
+        if pack.merged:
+            # merged weights: dX below is a plain GEMM against W_eff^T; T = x A^T and U = dY (alpha B) exist only for the factor
+            # gradients dW_down = U^T x, dW_up = alpha dY^T T -- the whole LoRA backward of the layer is off the critical path
+            xs = ctx.saved_tensors
+
+            def lora_side():
+                T = torch.empty((M, R), dtype=BF16, device=dy.device)
+                Um = torch.empty((M, R), dtype=BF16, device=dy.device)
+                _skinny_rows(pack, [(x, k, k) for x, k in zip(xs, ks)], "A", M, ctx.batch, T, R)
+                _skinny_rows(pack, [(dy, N, N)], "BlT", M, ctx.batch, Um, R)
+                FusedLinearFn._lora_grads(pack, xs, ks, T, Um, dy, M, N, R)
+                return T, Um
+
+            if side_enabled():
+                side = fork_side(dy, *xs)
+                with torch.cuda.stream(side):
+                    tu = lora_side()
+                _Side.keep.extend(tu)
+            else:
+                lora_side()
+        elif pack.lora:
             *xs, T = ctx.saved_tensors
             U = torch.empty((M, R), dtype=BF16, device=dy.device)
             _skinny_rows(pack, [(dy, N, N)], "BlT", M, ctx.batch, U, R)
@@ -584,7 +682,7 @@ class FusedLinearFn(torch.autograd.Function):
             if ctx.needs_input_grad[3 + i]:
                 dx = torch.empty(ctx.x_shapes[i], dtype=BF16, device=dy.device)
                 a_list = [(dy, N, N)]
-                b_list = [(pack.WT, N, k, off * N)]
+                b_list = [pack.b_dgrad(off, k)]
                 if U is not None:
                     a_list.append((U, R, pack.r_tot))
                     b_list.append((pack.AT, R, k, off * R))
@@ -647,7 +745,7 @@ class Conv3x3Fn(torch.autograd.Function):
                                 _RowView(T, half * Bh * Ho * Wo * pack.R))
             lora = (T, pack.Bl, pack.r_tot, pack.R)
         conv3x3_raw(x, pack.W, B, H, W, pack.Cin, pack.Cout, s, 0, out, bias=pack.bias, rowbias=rowbias, residual=res, rowbias_ld=rb_ld,
-                    lora=lora)
+                    lora=lora, w_tiled=pack.tiled)
         ctx.pack, ctx.geom = pack, geom
         ctx.has_res = residual is not None
         ctx.n_extra = len(lora_params)
@@ -707,11 +805,11 @@ class Conv3x3Fn(torch.autograd.Function):
         if ctx.needs_input_grad[4]:
             dx = torch.empty((B, H * W, pack.Cin), dtype=BF16, device=dy.device)
             if s == 1:
-                conv3x3_raw(dy, pack.Wd, B, H, W, pack.Cout, pack.Cin, 1, 0, dx)
+                conv3x3_raw(dy, pack.Wd, B, H, W, pack.Cout, pack.Cin, 1, 0, dx, w_tiled=pack.tiled)
                 if U is not None:                                                           # + dgrad through W_down
                     conv3x3_raw(U, pack.Wdl, B, H, W, pack.R, pack.Cin, 1, 0, dx, residual=dx)
             else:
-                conv3x3_raw(dy, pack.Wd, B, H // 2, W // 2, pack.Cout, pack.Cin, 2, 1, dx)
+                conv3x3_raw(dy, pack.Wd, B, H // 2, W // 2, pack.Cout, pack.Cin, 2, 1, dx, w_tiled=pack.tiled)
                 if U is not None:
                     conv3x3_raw(U, pack.Wdl, B, H // 2, W // 2, pack.R, pack.Cin, 2, 1, dx, residual=dx)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None

@@ -65,7 +65,7 @@ class LinearGroup:
         self.drops = None
 
     def _signature(self, k_splits):
-        sig = [tuple(k_splits) if k_splits else None]
+        sig = [tuple(k_splits) if k_splits else None, ops.LORA_MERGE, ops.WEIGHT_TILED]
         for ch in self.children:
             host, blocks = host_and_blocks(ch)
             sig.append((id(ch), id(host), _versions(host, blocks)))
@@ -105,6 +105,15 @@ class LinearGroup:
             o0 += host.weight.shape[0]
         if refs:
             pack.attach_lora(refs)
+            if ops.LORA_MERGE:
+                per_host, o0 = [], 0
+                for host, _ in hosts:
+                    n = host.weight.shape[0]
+                    per_host.append((_weight_2d(host).detach(), o0, n, [r for r in refs if o0 <= r.o0 < o0 + n]))
+                    o0 += n
+                pack.enable_merge(per_host)
+        if ops.WEIGHT_TILED:
+            pack.tile_weights()
         # nn.Dropout of the patched children: column ranges of the fused output, None when nothing is dropped
         ranges, c0 = [], 0
         for host, blocks in hosts:
@@ -143,8 +152,8 @@ class LinearGroup:
 class _JobTable:
     def __init__(self):
         self.key = None
-        self.dev = self.cdev = None
-        self.n = self.cn = 0
+        self.dev = self.cdev = self.mdev = None
+        self.n = self.cn = self.mn = self.mtiles = 0
 
 
 _job_table = _JobTable()
@@ -154,16 +163,28 @@ def pack_lora(groups: Sequence, table: Optional[_JobTable] = None) -> None:
     """One kernel launch that refreshes the packed low-rank operands of every LoRA-carrying group (LinearGroup / ConvGroup) from
     the fp32 parameters, plus one for the 3x3 down-projections of Conv2d LoRA blocks."""
     table = table or _JobTable()
-    jobs, cjobs = [], []
+    jobs, cjobs, mjobs = [], [], []
     for g in groups:
         if g.pack is not None and g.pack.lora:
             jobs += g.pack.jobs()
             if isinstance(g.pack, ConvPack):
                 cjobs += g.pack.conv_jobs()
+            elif g.pack.merged:
+                mjobs += g.pack.merge_jobs()
     if not jobs:
         return
-    key = tuple((j.w_down, j.w_up, j.A, j.BlT, j.alpha) for j in jobs) + tuple((j.w_down, j.wt) for j in cjobs)
+    key = (tuple((j.w_down, j.w_up, j.A, j.BlT, j.alpha) for j in jobs) + tuple((j.w_down, j.wt) for j in cjobs)
+           + tuple((j.w_host, j.W, j.o0, j.nblocks, tuple(j.w_down), tuple(j.alpha)) for j in mjobs))
     if table.key != key:
+        table.mdev, table.mn, table.mtiles = None, 0, 0
+        if mjobs:
+            tiles = 0
+            for j in mjobs:
+                j.tile0 = tiles
+                tiles += ((j.out_dim + 63) // 64) * ((j.in_dim + 63) // 64)
+            marr = (_lib.LoraMergeJob * len(mjobs))(*mjobs)
+            table.mdev = torch.frombuffer(bytearray(bytes(marr)), dtype=torch.uint8).cuda()
+            table.mn, table.mtiles = len(mjobs), tiles
         arr = (_lib.LoraJob * len(jobs))(*jobs)
         table.dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).cuda()
         table.cdev = None
@@ -172,6 +193,8 @@ def pack_lora(groups: Sequence, table: Optional[_JobTable] = None) -> None:
             table.cdev = torch.frombuffer(bytearray(bytes(carr)), dtype=torch.uint8).cuda()
         table.key, table.n, table.cn = key, len(jobs), len(cjobs)
     _lib.call("hcp_lora_pack", table.dev.data_ptr(), table.n, _lib.stream_ptr())
+    if table.mdev is not None:
+        _lib.call("hcp_lora_merge", table.mdev.data_ptr(), table.mn, table.mtiles, _lib.stream_ptr())
     if table.cdev is not None:
         _lib.call("hcp_lora_pack_conv", table.cdev.data_ptr(), table.cn, _lib.stream_ptr())
 
@@ -210,7 +233,7 @@ class ConvGroup:
         conv, blocks = host_and_blocks(child)
         if not isinstance(conv, nn.Conv2d):
             raise NotImplementedError(f"{type(conv).__name__} on a 3x3 convolution of the hot path is not supported")
-        sig = (id(child), id(conv), _versions(conv, blocks))
+        sig = (id(child), id(conv), _versions(conv, blocks), ops.WEIGHT_TILED)
         if self.pack is None or sig != self._sig:
             if not conv.weight.is_cuda:
                 raise _lib.HcpError("hcp_diffusion_b200 runs on CUDA only (there is no CPU path)")
@@ -227,6 +250,8 @@ class ConvGroup:
                 refs.append(ConvLoraRef(b.layer.W_down, b.layer.W_up, float(b.alpha), branch))
             if refs:
                 pack.attach_lora(refs)
+            if ops.WEIGHT_TILED:
+                pack.tile_weights()
             self.drop_p = dropout_p(blocks)
             self.pack, self._sig = pack, sig
         return self.pack

@@ -70,7 +70,9 @@ typedef struct hcp_gemm_args {
     int64_t ldr;
     void* out;                             /* bf16 [M,N] pitch ldo */
     int64_t ldo;
-    int32_t flags;                         /* reserved, 0 */
+    int32_t flags;                         /* bit s: b[s] is K-BLOCK-MAJOR -- element (n, k) at b + ((k/64)*ldb[s] + n)*64 + k%64, i.e.
+                                            * [k[s]/64][ldb[s] rows][64]: every 64-wide TMA box of B is one contiguous run of memory
+                                            * (weight streaming at small M reads whole DRAM pages); needs k[s] % 64 == 0 */
     float* workspace;                      /* optional split-K scratch (see hcp_splitk_workspace_bytes); NULL = never split */
     size_t workspace_bytes;
 } hcp_gemm_args;
@@ -110,6 +112,7 @@ typedef struct hcp_conv3x3_args {
     const void* lora_b;  /* bf16 */
     int64_t lora_r;      /* rank columns in use (<= lora_ld) */
     int64_t lora_ld;     /* row pitch of lora_t / lora_b: the 64-padded rank */
+    int32_t w_tiled;     /* 1: w is K-BLOCK-MAJOR [9*Cin/64][Cout][64] (k = (kh*3+kw)*Cin + ci): every weight box is one contiguous 128*rows-byte run */
 } hcp_conv3x3_args;
 
 int hcp_conv3x3_bf16(const hcp_conv3x3_args* args, hcp_stream_t stream);
@@ -247,6 +250,26 @@ typedef struct hcp_lora_job {
 } hcp_lora_job;
 
 int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp_stream_t stream);
+/* LoRA weight merge, one launch per step for every patched Linear / 1x1 Conv2d whose adapters apply to all rows (no DreamArtist++
+ * branches): W_eff = bf16(W_host + sum_b alpha_b * W_up_b . W_down_b) -- LoraBlock.get_weight + LoraPatchContainer.forward +
+ * LinearLayer.forward (reference lora_base_patch.py:21-35,61-62, lora_layers_patch.py:44-57), summed in fp32 and rounded once.
+ * Written as W [out_tot, in_dim] rows [o0, o0+out_dim) (forward B operand) and WT [in_dim, out_tot] (dgrad B operand; may be NULL).
+ * The forward and the input gradient of the layer are then plain GEMMs.  Requirements: in_dim, out_dim, o0, out_tot multiples of
+ * 4; at most 4 stacked blocks whose ranks sum to <= 64.  tile0 = number of 64x64 tiles of the jobs before this one
+ * (ceil(out_dim/64) * ceil(in_dim/64) each); total_tiles = their sum. */
+typedef struct hcp_lora_merge_job {
+    const float* w_host;     /* fp32 [out_dim, in_dim] */
+    const float* w_down[4];  /* fp32 [rank_b, in_dim] */
+    const float* w_up[4];    /* fp32 [out_dim, rank_b] */
+    float alpha[4];
+    int32_t rank[4];
+    int32_t nblocks, in_dim, out_dim, o0, out_tot, tile0;
+    int32_t tiled;           /* 1: W / WT are k-block-major ([in_dim/64][out_tot][64] / [out_tot/64][in_dim][64], see hcp_gemm_args.flags) */
+    int32_t pad_;
+    void* W;
+    void* WT;
+} hcp_lora_merge_job;
+int hcp_lora_merge(const hcp_lora_merge_job* jobs_device, int64_t njobs, int64_t total_tiles, hcp_stream_t stream);
 /* Conv2d LoRA down-projection W_down fp32 [rank, Cin, 3, 3] -> the two bf16 operands the 3x3 kernels take:
  *   wt [R, 3, 3, Cin]  forward weights of T = conv3x3(x, W_down) (rows c0 .. c0+rank of the group's R-row matrix)
  *   wd [Cin, 3, 3, R]  dgrad arrangement of the same taps (flipped for stride 1, as-is for the stride-2 phase kernels)

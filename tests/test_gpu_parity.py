@@ -53,12 +53,22 @@ def bf(x):
 # three rank-8 blocks at 64x64, and the K = 10240 split-K linear of the 16x16 level
 @pytest.mark.parametrize("M,K,N,ranks", [(256, 320, 320, (8,)), (77, 768, 640, (8, 8)), (1024, 320, 960, (8, 8, 8)), (64, 1280, 1280, ()),
                                          (16384, 320, 2560, ()), (16384, 320, 960, (8, 8, 8)), (1024, 10240, 1280, ()), (256, 1280, 1280, (8,))])
-def test_linear_lora_fwd_bwd(M, K, N, ranks):
+@pytest.mark.parametrize("merge,tiled", [(False, False), (True, False), (True, True), (False, True)])
+def test_linear_lora_fwd_bwd(M, K, N, ranks, merge, tiled):
+    """merge=False: the LoRA delta as an extra K-segment of the GEMM; merge=True: adapters merged into the bf16 operands per step
+    (hcp_lora_merge), plain GEMMs forward / dgrad, T and U only for the factor gradients."""
+    if merge and not ranks:
+        pytest.skip("nothing to merge")
+    if tiled and (K % 64 or N % 64):
+        pytest.skip("k-block-major operands need 64-element multiples")
     x = rnd(M, K, seed=1).to(BF).requires_grad_(True)
     W = rnd(N, K, scale=1 / math.sqrt(K), seed=2)
     b = rnd(N, scale=0.1, seed=3)
     res = rnd(M, N, seed=4).to(BF).requires_grad_(True)
     pack = LinearPack(W, b)
+    if tiled:
+        pack.tile_weights()
+        assert pack.tiled
     blocks, refs, c0 = [], [], 0
     n_per = N // max(len(ranks), 1)
     for i, r in enumerate(ranks):          # block i patches output rows [i*n_per, (i+1)*n_per): the fused-QKV arrangement
@@ -69,6 +79,8 @@ def test_linear_lora_fwd_bwd(M, K, N, ranks):
         c0 += r
     if refs:
         pack.attach_lora(refs)
+        if merge:
+            assert pack.enable_merge([(W[i * n_per:(i + 1) * n_per], i * n_per, n_per, [ref]) for i, ref in enumerate(refs)])
 
         class G:
             pass
@@ -151,7 +163,11 @@ def test_reference_lora_golden_through_product_container(golden_dir):
 @pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 16, 16, 64, 128, 1), (2, 32, 32, 320, 320, 2), (3, 8, 8, 128, 64, 1), (1, 64, 64, 64, 64, 1),
                                                    (4, 64, 64, 960, 320, 1), (4, 16, 16, 1280, 1280, 1), (4, 8, 8, 1280, 1280, 1),
                                                    (4, 64, 64, 320, 320, 1), (4, 64, 64, 320, 320, 2), (4, 8, 8, 2560, 1280, 1)])
-def test_conv3x3_fwd_bwd(B, H, W, Cin, Cout, stride):
+@pytest.mark.parametrize("tiled", [False, True])
+def test_conv3x3_fwd_bwd(B, H, W, Cin, Cout, stride, tiled):
+    """tiled: k-block-major weight operands ([9*C/64][rows][64], hcp_conv3x3_args.w_tiled) for the forward and the dgrad."""
+    if tiled and (Cin % 64 or Cout % 64):
+        pytest.skip("k-block-major operands need 64-channel multiples")
     x = rnd(B, H * W, Cin, seed=1).to(BF).requires_grad_(True)
     w = rnd(Cout, Cin, 3, 3, scale=1 / math.sqrt(9 * Cin), seed=2)
     b = rnd(Cout, scale=0.1, seed=3)
@@ -159,6 +175,9 @@ def test_conv3x3_fwd_bwd(B, H, W, Cin, Cout, stride):
     Ho, Wo = H // stride, W // stride
     res = rnd(B, Ho * Wo, Cout, seed=5).to(BF).requires_grad_(True)
     pack = ConvPack(w, b, stride)
+    if tiled:
+        pack.tile_weights()
+        assert pack.tiled
     y = ops.conv3x3(pack, x, (B, H, W), rowbias=rb, residual=res)
     xr = x.detach().float().view(B, H, W, Cin).permute(0, 3, 1, 2).requires_grad_(True)
     yr = F.conv2d(xr, bf(w), b, stride=stride, padding=1) + rb[:, :, None, None] + res.detach().float().view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)
@@ -331,7 +350,9 @@ def test_tiny_unet_forward_no_lora():
     check_end_to_end(U.TINY, batch=2, rank=0, ctx_len=77)
 
 
-def test_tiny_unet_lora_forward_backward():
+@pytest.mark.parametrize("merge", [True, False])
+def test_tiny_unet_lora_forward_backward(merge, monkeypatch):
+    monkeypatch.setattr(ops, "LORA_MERGE", merge)
     check_end_to_end(U.TINY, batch=3, rank=4, ctx_len=77)
 
 
