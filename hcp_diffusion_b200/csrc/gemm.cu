@@ -68,6 +68,7 @@ struct alignas(64) GemmKParams {
     int32_t splits, kb_per_split;
     int32_t epi_batch;                 // epilogue schedule (see the epilogue)
     float* ws;                         // [splits, M, N] fp32
+    long long* trace;                  // bring-up only (hcp_gemm_set_trace): 16 int64 slots per CTA (clock64 stamps / wait sums), NULL in production
 };
 
 // MSUB = number of 128-row M tiles (per CTA) one work item covers.  MSUB = 2 halves the B (weight) traffic per FLOP -- the long-K
@@ -96,7 +97,8 @@ struct GemmCfg {
     static constexpr int STG_PITCH = EBN * 2 + 16;                 // staging row pitch in bytes: odd number of 16-byte units
     static constexpr int STG_BYTES = BLOCK_M * STG_PITCH;
     static constexpr int BIAS_BYTES = ((BN * 4 + 127) / 128) * 128;  // bias slice of the tile's columns, staged once per work item
-    static constexpr int FIXED_BYTES = STG_BYTES + BIAS_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+    static constexpr int ROW_BYTES = BLOCK_M * 16;                   // per tile row: row of `out` (or -1) and its row-bias group
+    static constexpr int FIXED_BYTES = STG_BYTES + BIAS_BYTES + ROW_BYTES + 256 /*barriers*/ + 1024 /*align*/;
     static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
     static constexpr int MAX_STAGES = (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
     // one CTA per SM: the ring must cover the TMA latency alone
@@ -142,6 +144,43 @@ __device__ __forceinline__ int64_t tile_row(const GemmKParams& p, const TileOrig
     return g;
 }
 
+// Position of a k-block inside a work item's reduction: (segment s, tap t of the convolution segment, k-block kb of nkb_s).
+struct KPos {
+    int s, t, kb, nkb_s;
+};
+// The reduction of a work item, held in REGISTERS of the single-thread control paths (TMA producer, MMA issuer).  Dynamically indexed
+// loads from the kernel-parameter block (p.nkb[s], p.klast[s], p.taps[t]...) cost about 200 cycles each on those threads: the r01
+// walk-and-skip loop over all k-blocks spent 215 cycles per SKIPPED k-block, i.e. 20 us per launch of the 14-way split 8x8
+// convolutions (profiles/r02_probe_trace_a.txt).  A split seeks its first k-block directly and advances incrementally.
+struct KPlan {
+    int nkb0, nkb1, nkb2, kl0, kl1, kl2, ntap0, seg0, total_kb, conv, btile, kb_per_split;
+    __device__ __forceinline__ explicit KPlan(const GemmKParams& p) {
+        nkb0 = p.nkb[0]; nkb1 = p.nkb[1]; nkb2 = p.nkb[2];
+        kl0 = p.klast[0]; kl1 = p.klast[1]; kl2 = p.klast[2];
+        conv = p.conv; btile = p.btile; kb_per_split = p.kb_per_split;
+        ntap0 = conv ? p.ntaps : 1;
+        seg0 = nkb0 * ntap0;
+        total_kb = seg0 + nkb1 + nkb2;
+    }
+    __device__ __forceinline__ int klast(int s) const { return s == 0 ? kl0 : (s == 1 ? kl1 : kl2); }
+    __device__ __forceinline__ KPos seek(int it) const {
+        KPos q;
+        if (it < seg0) { q.s = 0; q.nkb_s = nkb0; q.t = it / nkb0; q.kb = it - q.t * nkb0; }
+        else if (it < seg0 + nkb1) { q.s = 1; q.nkb_s = nkb1; q.t = 0; q.kb = it - seg0; }
+        else { q.s = 2; q.nkb_s = nkb2; q.t = 0; q.kb = it - seg0 - nkb1; }
+        return q;
+    }
+    // next k-block; true when a new tap of the convolution segment begins (the caller reloads its TapEntry)
+    __device__ __forceinline__ bool advance(KPos& q) const {
+        if (++q.kb < q.nkb_s) return false;
+        q.kb = 0;
+        if (q.s == 0 && q.t + 1 < ntap0) { ++q.t; return true; }
+        ++q.s; q.t = 0;
+        q.nkb_s = (q.s == 1) ? nkb1 : nkb2;
+        return false;
+    }
+};
+
 // Persistent kernel: grid = min(#work items, #SMs) CTAs (PAIR: CTA pairs); a work item is (split, m_tile, n_tile) with n fastest so
 // that the CTAs running concurrently share A tiles in L2.  Two TMEM accumulators: the epilogue of item i overlaps the main loop of i+1.
 // Epilogue: the residual tile is prefetched into a padded smem staging buffer with coalesced loads, each thread (== row) adds
@@ -161,7 +200,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
     uint8_t* sStg = sB + STAGES * Cfg::B_STAGE_BYTES;
     float* sBias = reinterpret_cast<float*>(sStg + Cfg::STG_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStg + Cfg::STG_BYTES + Cfg::BIAS_BYTES);
+    uint8_t* sRow = sStg + Cfg::STG_BYTES + Cfg::BIAS_BYTES;          // [128] x (int64 row of `out`, int64 row-bias group)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sRow + Cfg::ROW_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
@@ -206,79 +246,81 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
     pdl_wait();     // the set-up above overlapped the previous kernel's tail; its results are visible from here on
+    long long* trc = p.trace ? p.trace + (int64_t)blockIdx.x * 16 : nullptr;
+    if (trc && threadIdx.x == 0) { trc[0] = clock64(); unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); trc[7] = (long long)g; }
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            KPlan kq(p);
+            long long tr_first = 0, tr_last = 0, tr_wait = 0, tr_n = 0;      // bring-up trace, kept in registers until the role ends
             for (int w = worker; w < total_work; w += nworkers) {
                 const int split = w / tiles_mn, mn = w % tiles_mn;
                 const int n0 = (mn % p.tiles_n) * BN + (int)rank * Cfg::B_BOX_ROWS;  // PAIR: this CTA's part of every instruction's B rows
                 TileOrigin o[MSUB];
 #pragma unroll
                 for (int sub = 0; sub < MSUB; ++sub) o[sub] = tile_origin(p, m_tile_of(mn / p.tiles_n, sub));
-                const int kb_lo = split * p.kb_per_split, kb_hi = kb_lo + p.kb_per_split;
-                int it = 0;
-                for (int s = 0; s < p.nseg; ++s) {
-                    const int ntap = (p.conv && s == 0) ? p.ntaps : 1;
-                    for (int t = 0; t < ntap; ++t) {
-                        for (int kb = 0; kb < p.nkb[s]; ++kb, ++it) {
-                            if (it < kb_lo || it >= kb_hi) continue;
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
-                            void* dB = sB + stage * Cfg::B_STAGE_BYTES;
-                            if constexpr (!PAIR) {
-                                mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_STAGE_BYTES);
+                const int kb_lo = split * kq.kb_per_split, kb_hi = min(kb_lo + kq.kb_per_split, kq.total_kb);
+                KPos q = kq.seek(kb_lo);
+                TapEntry te = p.taps[q.t];
+                for (int it = kb_lo; it < kb_hi; ++it) {
+                    const int s = q.s, kb = q.kb;
+                    const bool tap_seg = kq.conv && s == 0;
+                    const long long tw0 = trc ? clock64() : 0;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (trc) { tr_wait += clock64() - tw0; tr_n += 1; }
+                    void* dB = sB + stage * Cfg::B_STAGE_BYTES;
+                    const int kcol = (tap_seg ? te.wk_off : 0) + kb * BLOCK_K;
+                    const bool btiled = (kq.btile >> s) & 1;
+                    if constexpr (!PAIR) {
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_STAGE_BYTES);
 #pragma unroll
-                                for (int sub = 0; sub < MSUB; ++sub) {
-                                    void* dA = sA + stage * Cfg::A_BYTES + sub * A_STAGE_BYTES;
-                                    if (p.conv && s == 0) {
-                                        const TapEntry& te = p.taps[t];
-                                        if (p.conv == 4)
-                                            tma_load_4d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw,
-                                                        o[sub].h0 + te.dh, o[sub].img0);
-                                        else
-                                            tma_load_5d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw, te.c2,
-                                                        o[sub].h0 + te.dh, o[sub].img0);
-                                    } else {
-                                        tma_load_2d(dA, &p.tmA[s], &full_bar[stage], kb * BLOCK_K, o[sub].m0);
-                                    }
-                                }
-                                const int kcol = ((p.conv && s == 0) ? p.taps[t].wk_off : 0) + kb * BLOCK_K;
-                                if ((p.btile >> s) & 1) tma_load_3d(dB, &p.tmB[s], &full_bar[stage], 0, n0, kcol / BLOCK_K);
-                                else tma_load_2d(dB, &p.tmB[s], &full_bar[stage], kcol, n0);
+                        for (int sub = 0; sub < MSUB; ++sub) {
+                            void* dA = sA + stage * Cfg::A_BYTES + sub * A_STAGE_BYTES;
+                            if (tap_seg) {
+                                if (kq.conv == 4)
+                                    tma_load_4d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw, o[sub].h0 + te.dh, o[sub].img0);
+                                else
+                                    tma_load_5d(dA, &p.tmA[0], &full_bar[stage], te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw, te.c2, o[sub].h0 + te.dh,
+                                                o[sub].img0);
                             } else {
-                                // every byte of the pair lands on the LEADER's barrier: its one arrival names the bytes of both CTAs
-                                const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_STAGE_BYTES));
-#pragma unroll
-                                for (int sub = 0; sub < MSUB; ++sub) {
-                                    void* dA = sA + stage * Cfg::A_BYTES + sub * A_STAGE_BYTES;
-                                    if (p.conv && s == 0) {
-                                        const TapEntry& te = p.taps[t];
-                                        if (p.conv == 4)
-                                            tma_load_4d_pair(dA, &p.tmA[0], lfull, te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw, o[sub].h0 + te.dh,
-                                                             o[sub].img0);
-                                        else
-                                            tma_load_5d_pair(dA, &p.tmA[0], lfull, te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw, te.c2,
-                                                             o[sub].h0 + te.dh, o[sub].img0);
-                                    } else {
-                                        tma_load_2d_pair(dA, &p.tmA[s], lfull, kb * BLOCK_K, o[sub].m0);
-                                    }
-                                }
-#pragma unroll
-                                for (int h = 0; h < Cfg::NSPLIT; ++h) {
-                                    void* dBh = (uint8_t*)dB + h * Cfg::B_BOX_ROWS * 128;
-                                    const int kcol = ((p.conv && s == 0) ? p.taps[t].wk_off : 0) + kb * BLOCK_K;
-                                    if ((p.btile >> s) & 1) tma_load_3d_pair(dBh, &p.tmB[s], lfull, 0, n0 + h * Cfg::MMA_N, kcol / BLOCK_K);
-                                    else tma_load_2d_pair(dBh, &p.tmB[s], lfull, kcol, n0 + h * Cfg::MMA_N);
-                                }
+                                tma_load_2d(dA, &p.tmA[s], &full_bar[stage], kb * BLOCK_K, o[sub].m0);
                             }
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                        if (btiled) tma_load_3d(dB, &p.tmB[s], &full_bar[stage], 0, n0, kcol / BLOCK_K);
+                        else tma_load_2d(dB, &p.tmB[s], &full_bar[stage], kcol, n0);
+                    } else {
+                        // every byte of the pair lands on the LEADER's barrier: its one arrival names the bytes of both CTAs
+                        const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_STAGE_BYTES));
+#pragma unroll
+                        for (int sub = 0; sub < MSUB; ++sub) {
+                            void* dA = sA + stage * Cfg::A_BYTES + sub * A_STAGE_BYTES;
+                            if (tap_seg) {
+                                if (kq.conv == 4)
+                                    tma_load_4d_pair(dA, &p.tmA[0], lfull, te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw, o[sub].h0 + te.dh, o[sub].img0);
+                                else
+                                    tma_load_5d_pair(dA, &p.tmA[0], lfull, te.c0_off + kb * BLOCK_K, o[sub].w0 + te.dw, te.c2, o[sub].h0 + te.dh,
+                                                     o[sub].img0);
+                            } else {
+                                tma_load_2d_pair(dA, &p.tmA[s], lfull, kb * BLOCK_K, o[sub].m0);
+                            }
+                        }
+#pragma unroll
+                        for (int h = 0; h < Cfg::NSPLIT; ++h) {
+                            void* dBh = (uint8_t*)dB + h * Cfg::B_BOX_ROWS * 128;
+                            if (btiled) tma_load_3d_pair(dBh, &p.tmB[s], lfull, 0, n0 + h * Cfg::MMA_N, kcol / BLOCK_K);
+                            else tma_load_2d_pair(dBh, &p.tmB[s], lfull, kcol, n0 + h * Cfg::MMA_N);
                         }
                     }
+                    if (trc) { tr_last = clock64(); if (tr_first == 0) tr_first = tr_last; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kq.advance(q)) te = p.taps[q.t];
                 }
             }
+            if (trc) { trc[1] = tr_first; trc[2] = tr_last; trc[9] = tr_wait; trc[11] = tr_n; }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer (PAIR: the leader CTA only) ========================================
@@ -287,55 +329,63 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             int item = 0;
+            KPlan kq(p);
+            long long tr_first = 0, tr_wait = 0, tr_acc = 0, tr_commit = 0;
             for (int w = worker; w < total_work; w += nworkers, ++item) {
                 const int split = w / tiles_mn;
-                const int kb_lo = split * p.kb_per_split, kb_hi = kb_lo + p.kb_per_split;
+                const int kb_lo = split * kq.kb_per_split, kb_hi = min(kb_lo + kq.kb_per_split, kq.total_kb);
                 // DOUBLE_ACC: two accumulators alternate between items; otherwise one item owns all the columns in use
                 const int as = Cfg::DOUBLE_ACC ? (item & 1) : 0;
                 const uint32_t eph = Cfg::DOUBLE_ACC ? ((item >> 1) & 1) : (item & 1);
+                const long long te0 = trc ? clock64() : 0;
                 mbar_wait(&tmem_empty_bar[as], eph ^ 1);                     // epilogue(s) drained this accumulator
                 tc_fence_after();
+                if (trc) tr_acc += clock64() - te0;
                 const uint32_t acc = tmem_base + as * Cfg::ACC_STRIDE;
                 uint32_t accum = 0;
-                int it = 0;
-                for (int s = 0; s < p.nseg; ++s) {
-                    const int ntap = (p.conv && s == 0) ? p.ntaps : 1;
-                    for (int t = 0; t < ntap; ++t) {
-                        for (int kb = 0; kb < p.nkb[s]; ++kb, ++it) {
-                            if (it < kb_lo || it >= kb_hi) continue;
-                            mbar_wait(&full_bar[stage], phase);
-                            tc_fence_after();
-                            const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * Cfg::A_BYTES), 16, 1024);
-                            const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * Cfg::B_STAGE_BYTES), 16, 1024);
-                            const int ksteps = (kb == p.nkb[s] - 1) ? p.klast[s] : (BLOCK_K / 16);
-                            for (int k = 0; k < ksteps; ++k) {
-                                // +32 bytes (= 2 in descriptor units) per 16-element k-step inside the swizzle atom
+                KPos q = kq.seek(kb_lo);
+                for (int it = kb_lo; it < kb_hi; ++it) {
+                    const long long tw0 = trc ? clock64() : 0;
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (trc) { const long long tn = clock64(); tr_wait += tn - tw0; if (tr_first == 0) tr_first = tn; }
+                    const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * Cfg::A_BYTES), 16, 1024);
+                    const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * Cfg::B_STAGE_BYTES), 16, 1024);
+                    const int ksteps = (q.kb == q.nkb_s - 1) ? kq.klast(q.s) : (BLOCK_K / 16);
+                    for (int k = 0; k < ksteps; ++k) {
+                        // +32 bytes (= 2 in descriptor units) per 16-element k-step inside the swizzle atom
 #pragma unroll
-                                for (int sub = 0; sub < MSUB; ++sub) {   // the M sub-tiles share the B operand of this k-step
-                                    if constexpr (PAIR) {
+                        for (int sub = 0; sub < MSUB; ++sub) {   // the M sub-tiles share the B operand of this k-step
+                            if constexpr (PAIR) {
 #pragma unroll
-                                        for (int h = 0; h < Cfg::NSPLIT; ++h)
-                                            umma_ss_pair(acc + sub * Cfg::ACC_STRIDE + h * Cfg::MMA_N, adesc + sub * (A_STAGE_BYTES >> 4) + 2 * k,
-                                                         bdesc + h * ((Cfg::B_BOX_ROWS * 128) >> 4) + 2 * k, idesc, accum);
-                                    } else {
-                                        umma_ss(acc + sub * Cfg::ACC_STRIDE, adesc + sub * (A_STAGE_BYTES >> 4) + 2 * k, bdesc + 2 * k, idesc, accum);
-                                    }
-                                }
-                                accum = 1;
+                                for (int h = 0; h < Cfg::NSPLIT; ++h)
+                                    umma_ss_pair(acc + sub * Cfg::ACC_STRIDE + h * Cfg::MMA_N, adesc + sub * (A_STAGE_BYTES >> 4) + 2 * k,
+                                                 bdesc + h * ((Cfg::B_BOX_ROWS * 128) >> 4) + 2 * k, idesc, accum);
+                            } else {
+                                umma_ss(acc + sub * Cfg::ACC_STRIDE, adesc + sub * (A_STAGE_BYTES >> 4) + 2 * k, bdesc + 2 * k, idesc, accum);
                             }
-                            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-                            if constexpr (PAIR) umma_commit_pair(&empty_bar[stage], 0b11);
-                            else umma_commit(&empty_bar[stage]);
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
+                        accum = 1;
                     }
+                    // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                    if constexpr (PAIR) umma_commit_pair(&empty_bar[stage], 0b11);
+                    else umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    kq.advance(q);
                 }
                 if constexpr (PAIR) umma_commit_pair(&tmem_full_bar[as], 0b11);
                 else umma_commit(&tmem_full_bar[as]);
+                if (trc) tr_commit = clock64();
             }
+            if (trc) { trc[3] = tr_first; trc[4] = tr_commit; trc[8] = tr_wait; trc[10] = tr_acc; }
         }
     } else {
         // ===================================== epilogue ==========================================
+        // Every shared-memory access below is an explicit ld.shared / st.shared on a 32-bit shared address: the staging pointers
+        // are derived from the aligned dynamic-smem base through integer arithmetic, which makes nvcc fall back to GENERIC loads
+        // and stores, and the r01 code had one branch per 8-column group -- together 2 600 cycles to convert one 128x160 part and
+        // 2 000 (GEMM) / 5 100 (convolution: four integer divisions per 16-byte unit) to store it (profiles/r02_probe_trace_c.txt):
+        // the K = 320 GEMMs of the 64x64 level were bound by this epilogue, not by their main loop.
         constexpr int EBN = Cfg::EBN;
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;             // which half of the part's columns this warp converts
@@ -343,157 +393,176 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         const int et = threadIdx.x - 64;              // 0..255 among the epilogue threads
         constexpr int UNITS = EBN / 8;                // 16-byte units per staged row
         constexpr int CH16 = EBN / 16;                // 16-column TMEM chunks per part
+        constexpr int NCH = (CH16 + 1) / 2;           // chunks per column half
+        const uint32_t stg = smem_u32(sStg), sbias = smem_u32(sBias), srow = smem_u32(sRow);
+        const uint32_t my_stg = stg + r * Cfg::STG_PITCH;
+        const int N = p.N;
+        const int64_t Mrows = p.M;
+        const bool staged = (p.splits == 1);
+        const bool has_bias = staged && p.bias != nullptr, has_res = staged && p.residual != nullptr;
+        const float* const rowbias = staged ? p.rowbias : nullptr;
+        const int64_t rowbias_ld = p.rowbias_ld;
         int item = 0;
         for (int w = worker; w < total_work; w += nworkers, ++item) {
             const int split = w / tiles_mn, mn = w % tiles_mn;
             const int n0 = (mn % p.tiles_n) * BN;
             const int as = Cfg::DOUBLE_ACC ? (item & 1) : 0;
             const uint32_t fph = Cfg::DOUBLE_ACC ? ((item >> 1) & 1) : (item & 1);
-            const bool staged = (p.splits == 1);
-            if (staged && p.bias) {
-                // the bias slice of this item's columns goes to shared memory once (ncu: the per-chunk global bias loads were the
-                // top stall of the epilogue, 25 % of the samples of the K=320 N=2560 GEMM); the previous item's trailing bar.sync
-                // guarantees nobody still reads the old slice
+            if (has_bias) {
+                // the bias slice of this item's columns goes to shared memory once; the previous item's trailing bar.sync guarantees
+                // nobody still reads the old slice.  Columns >= N read as zero.
                 for (int c = et; c < BN / 4; c += kGemmEpiThreads)
-                    reinterpret_cast<float4*>(sBias)[c] = (n0 + c * 4 < p.N) ? *reinterpret_cast<const float4*>(p.bias + n0 + c * 4)
-                                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                    sts_f4(sbias + c * 16, (n0 + c * 4 < N) ? *reinterpret_cast<const float4*>(p.bias + n0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f));
             }
 #pragma unroll 1
             for (int part = 0; part < MSUB * Cfg::NPART; ++part) {
-            const int sub = part / Cfg::NPART;
-            const int nc0 = (part % Cfg::NPART) * EBN;          // first column of this part inside the item's BN columns
-            const bool last_part = (part == MSUB * Cfg::NPART - 1);
-            const TileOrigin o = tile_origin(p, m_tile_of(mn / p.tiles_n, sub));
-            const int acc_idx = Cfg::DOUBLE_ACC ? as : sub;
-            if (staged && p.residual) {
-                // coalesced prefetch of the residual tile into the staging buffer (overlaps the main loop).  All loads of a thread
-                // are issued before the first store: one L2 round trip per tile instead of one per 16-byte unit.
-                constexpr int NRES = (BLOCK_M * UNITS + kGemmEpiThreads - 1) / kGemmEpiThreads;
-                uint4 rbuf[NRES];
-#pragma unroll
-                for (int it = 0; it < NRES; ++it) {
-                    const int u = et + it * kGemmEpiThreads;
-                    const int rr = u / UNITS, cu = u % UNITS;
-                    rbuf[it] = make_uint4(0u, 0u, 0u, 0u);
-                    if (u < BLOCK_M * UNITS) {
-                        int grp;
-                        const int64_t g = tile_row(p, o, rr, grp);
-                        const int col = n0 + nc0 + cu * 8;
-                        if (g < (int64_t)p.M && col < p.N) rbuf[it] = *reinterpret_cast<const uint4*>(p.residual + g * p.ldr + col);
-                    }
+                const int sub = part / Cfg::NPART;
+                const int nc0 = (part % Cfg::NPART) * EBN;          // first column of this part inside the item's BN columns
+                const bool last_part = (part == MSUB * Cfg::NPART - 1);
+                const bool dbg = trc && et == 0 && item == 0 && part == 0;
+                int group = 0;
+                int64_t grow = -1;
+                if (nc0 == 0) {
+                    // row of `out` behind every tile row, once per M sub-tile (the store loops below read it back instead of redoing the
+                    // integer divisions of the pixel <-> row mapping for every 16-byte unit); -1 = row beyond M
+                    const TileOrigin o = tile_origin(p, m_tile_of(mn / p.tiles_n, sub));
+                    grow = tile_row(p, o, r, group);
+                    if (grow >= Mrows) grow = -1;
+                    if (half == 0) { sts_b64(srow + r * 16, grow); sts_b64(srow + r * 16 + 8, (int64_t)group); }
                 }
+                if (has_res) {
+                    // coalesced prefetch of the residual tile into the staging buffer (overlaps the main loop).  All loads of a thread
+                    // are issued before the first store: one L2 round trip per tile instead of one per 16-byte unit.
+                    if (nc0 == 0) asm volatile("bar.sync 1, 256;" ::: "memory");          // row table visible
+                    constexpr int NRES = (BLOCK_M * UNITS + kGemmEpiThreads - 1) / kGemmEpiThreads;
+                    uint4 rbuf[NRES];
 #pragma unroll
-                for (int it = 0; it < NRES; ++it) {
-                    const int u = et + it * kGemmEpiThreads;
-                    if (u < BLOCK_M * UNITS) *reinterpret_cast<uint4*>(sStg + (u / UNITS) * Cfg::STG_PITCH + (u % UNITS) * 16) = rbuf[it];
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
-            int group;
-            const int64_t grow = tile_row(p, o, r, group);
-            const bool row_ok = grow < (int64_t)p.M;
-            if (part == 0) mbar_wait(&tmem_full_bar[as], fph);
-            tc_fence_after();
-            const uint32_t trow = tmem_base + acc_idx * Cfg::ACC_STRIDE + nc0 + (static_cast<uint32_t>(quarter * 32) << 16);
-            // the accumulator goes back to the MMA warp as soon as its last part sits in registers (PAIR: one elected lane per warp
-            // tells the LEADER's barrier -- a remote arrive for the peer CTA)
-            auto release_acc = [&]() {
-                tc_fence_before();
-                if constexpr (PAIR) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
-                } else {
-                    mbar_arrive(&tmem_empty_bar[as]);
-                }
-            };
-            // Two epilogue schedules (GemmKParams::epi_batch): 1 = all TMEM chunks of this thread are pulled into registers with ONE
-            // wait and the accumulator is handed back to the MMA warp before any arithmetic / staging store; 0 = chunk by chunk
-            // (load, wait, convert, store), the accumulator is released after the last chunk.
-            constexpr int NCH = (CH16 + 1) / 2;
-            auto chunk = [&](int c, const uint32_t (&v)[16]) {
-                if (row_ok) {
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const int col = n0 + nc0 + c * 16 + g * 8;
-                        if (col < p.N) {
-                            float f[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-                            if (!staged) {      // split-K: raw partial; bias / residual are applied by splitk_finalize_kernel
-                                float* dst = p.ws + ((int64_t)split * p.M + grow) * p.N + col;
-                                *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
-                                *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                                continue;
-                            }
-                            if (p.bias) {
-                                const float4 b0 = *reinterpret_cast<const float4*>(sBias + nc0 + c * 16 + g * 8);
-                                const float4 b1 = *reinterpret_cast<const float4*>(sBias + nc0 + c * 16 + g * 8 + 4);
-                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                            }
-                            if (p.rowbias) {
-                                const float* rb = p.rowbias + (int64_t)group * p.rowbias_ld + col;
-                                const float4 b0 = *reinterpret_cast<const float4*>(rb);
-                                const float4 b1 = *reinterpret_cast<const float4*>(rb + 4);
-                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                            }
-                            uint4* slot = reinterpret_cast<uint4*>(sStg + r * Cfg::STG_PITCH + (c * 2 + g) * 16);
-                            if (p.residual) {
-                                const uint4 rv = *slot;
-                                float2 t;
-                                t = unpack_bf16x2(rv.x); f[0] += t.x; f[1] += t.y;
-                                t = unpack_bf16x2(rv.y); f[2] += t.x; f[3] += t.y;
-                                t = unpack_bf16x2(rv.z); f[4] += t.x; f[5] += t.y;
-                                t = unpack_bf16x2(rv.w); f[6] += t.x; f[7] += t.y;
-                            }
-                            uint4 ov;
-                            ov.x = pack_bf16x2(f[0], f[1]);
-                            ov.y = pack_bf16x2(f[2], f[3]);
-                            ov.z = pack_bf16x2(f[4], f[5]);
-                            ov.w = pack_bf16x2(f[6], f[7]);
-                            *slot = ov;
+                    for (int it = 0; it < NRES; ++it) {
+                        const int u = et + it * kGemmEpiThreads;
+                        const int rr = u / UNITS, cu = u % UNITS;
+                        rbuf[it] = make_uint4(0u, 0u, 0u, 0u);
+                        if (u < BLOCK_M * UNITS) {
+                            const int64_t g = lds_b64(srow + rr * 16);
+                            const int col = n0 + nc0 + cu * 8;
+                            if (g >= 0 && col < N) rbuf[it] = *reinterpret_cast<const uint4*>(p.residual + g * p.ldr + col);
                         }
                     }
+#pragma unroll
+                    for (int it = 0; it < NRES; ++it) {
+                        const int u = et + it * kGemmEpiThreads;
+                        if (u < BLOCK_M * UNITS) sts128(stg + (u / UNITS) * Cfg::STG_PITCH + (u % UNITS) * 16, rbuf[it]);
+                    }
                 }
-            };
-            if (p.epi_batch) {
+                if (has_res || has_bias || nc0 == 0) asm volatile("bar.sync 1, 256;" ::: "memory");      // residual / bias / row table staged
+                if (nc0 != 0) {             // later column parts of the same rows: this thread's row comes back from the table
+                    grow = lds_b64(srow + r * 16);
+                    group = (int)lds_b64(srow + r * 16 + 8);
+                }
+                const bool row_ok = grow >= 0;
+                if (part == 0) mbar_wait(&tmem_full_bar[as], fph);
+                tc_fence_after();
+                if (trc && et == 0 && trc[5] == 0) trc[5] = clock64();
+                const int acc_idx = Cfg::DOUBLE_ACC ? as : sub;
+                const uint32_t trow = tmem_base + acc_idx * Cfg::ACC_STRIDE + nc0 + (static_cast<uint32_t>(quarter * 32) << 16);
+                // all TMEM chunks of this thread are pulled into registers with ONE wait and the accumulator goes back to the MMA warp
+                // before any arithmetic (PAIR: one elected lane per warp tells the LEADER's barrier -- a remote arrive for the peer CTA)
                 uint32_t vv[NCH][16];
 #pragma unroll
                 for (int cl = 0; cl < NCH; ++cl)
                     if (half * NCH + cl < CH16) tmem_ld16(trow + (half * NCH + cl) * 16, vv[cl]);
                 tmem_wait_ld();
-                if (last_part) release_acc();
+                if (dbg) trc[12] = clock64();
+                if (last_part) {
+                    tc_fence_before();
+                    if constexpr (PAIR) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
+                    } else {
+                        mbar_arrive(&tmem_empty_bar[as]);
+                    }
+                }
+                if (staged) {
+                    // bias + per-image row bias + residual -> bf16 -> this thread's row of the staging buffer; no branches: columns >= N
+                    // carry zeros (TMA zero fill, zeroed bias / residual slots) and are masked by the store loop
+                    const float* rb = (rowbias && row_ok) ? rowbias + (int64_t)group * rowbias_ld + n0 + nc0 : nullptr;
 #pragma unroll
-                for (int cl = 0; cl < NCH; ++cl)
-                    if (half * NCH + cl < CH16) chunk(half * NCH + cl, vv[cl]);
-            } else {
+                    for (int cl = 0; cl < NCH; ++cl) {
+                        const int c = half * NCH + cl;
+                        if (c < CH16) {
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+                                const int cc = c * 16 + g * 8;                 // first column of the group inside the part
+                                float f[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(vv[cl][g * 8 + j]);
+                                if (has_bias) {
+                                    const float4 b0 = lds_f4(sbias + (nc0 + cc) * 4), b1 = lds_f4(sbias + (nc0 + cc) * 4 + 16);
+                                    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                                    f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                                }
+                                if (rb && n0 + nc0 + cc < N) {
+                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb + cc)), b1 = __ldg(reinterpret_cast<const float4*>(rb + cc + 4));
+                                    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                                    f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                                }
+                                const uint32_t slot = my_stg + (c * 2 + g) * 16;
+                                if (has_res) {
+                                    const uint4 rv = lds128(slot);
+                                    float2 t;
+                                    t = unpack_bf16x2(rv.x); f[0] += t.x; f[1] += t.y;
+                                    t = unpack_bf16x2(rv.y); f[2] += t.x; f[3] += t.y;
+                                    t = unpack_bf16x2(rv.z); f[4] += t.x; f[5] += t.y;
+                                    t = unpack_bf16x2(rv.w); f[6] += t.x; f[7] += t.y;
+                                }
+                                sts128(slot, make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
+                            }
+                        }
+                    }
+                    if (dbg) trc[13] = clock64();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (dbg) trc[14] = clock64();
+                    for (int u = et; u < BLOCK_M * UNITS; u += kGemmEpiThreads) {     // coalesced 16-byte stores
+                        const int rr = u / UNITS, cu = u % UNITS;
+                        const int64_t g = lds_b64(srow + rr * 16);
+                        const int col = n0 + nc0 + cu * 8;
+                        if (g >= 0 && col < N) *reinterpret_cast<uint4*>(p.out + g * p.ldo + col) = lds128(stg + rr * Cfg::STG_PITCH + cu * 16);
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");     // staging buffer / row table reusable
+                    if (dbg) trc[15] = clock64();
+                } else {
+                    // split-K partials (raw fp32; bias / residual are applied by splitk_finalize_kernel).  The fp32 values of one column
+                    // HALF of the part fill the staging buffer exactly (NCH * 64 + 16 bytes per row = the bf16 pitch), so the two halves
+                    // take turns: park, then all 256 threads write whole 16-byte units of consecutive columns.
+                    static_assert(NCH * 64 + 16 <= Cfg::STG_PITCH, "fp32 half part must fit the staging row");
+                    constexpr int FU = NCH * 4;                       // float4 units per staged row
 #pragma unroll 1
-                for (int c = half * NCH; c < min(CH16, (half + 1) * NCH); ++c) {
-                    uint32_t v[16];
-                    tmem_ld16(trow + c * 16, v);
-                    tmem_wait_ld();
-                    chunk(c, v);
+                    for (int hp = 0; hp < 2; ++hp) {
+                        if (half == hp) {
+#pragma unroll
+                            for (int cl = 0; cl < NCH; ++cl)
+                                if (hp * NCH + cl < CH16) {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        sts128(my_stg + cl * 64 + j * 16, make_uint4(vv[cl][4 * j], vv[cl][4 * j + 1], vv[cl][4 * j + 2], vv[cl][4 * j + 3]));
+                                }
+                        }
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        const int ncols_h = min(CH16 - hp * NCH, NCH) * 16;           // columns this half holds
+                        for (int u = et; u < BLOCK_M * FU; u += kGemmEpiThreads) {
+                            const int rr = u / FU, cu = u % FU;
+                            const int64_t g = lds_b64(srow + rr * 16);
+                            const int col = n0 + nc0 + hp * NCH * 16 + cu * 4;
+                            if (cu * 4 < ncols_h && g >= 0 && col < N)
+                                *reinterpret_cast<uint4*>(p.ws + ((int64_t)split * Mrows + g) * N + col) = lds128(stg + rr * Cfg::STG_PITCH + cu * 16);
+                        }
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                    }
                 }
-                if (last_part) release_acc();
-            }
-            if (staged) {
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                for (int u = et; u < BLOCK_M * UNITS; u += kGemmEpiThreads) {     // coalesced 16-byte stores
-                    const int rr = u / UNITS, cu = u % UNITS;
-                    int grp;
-                    const int64_t g = tile_row(p, o, rr, grp);
-                    const int col = n0 + nc0 + cu * 8;
-                    if (g < (int64_t)p.M && col < p.N)
-                        *reinterpret_cast<uint4*>(p.out + g * p.ldo + col) = *reinterpret_cast<const uint4*>(sStg + rr * Cfg::STG_PITCH + cu * 16);
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");     // staging buffer reusable
-            }
             }   // part
         }
     }
 
+    if (trc && threadIdx.x == 64) trc[6] = clock64();
     tc_fence_before();
     if constexpr (PAIR) {            // neither CTA frees TMEM / exits while the peer may still touch the pair's state
         cluster_arrive();
@@ -792,21 +861,13 @@ static PairPlan plan_pair(int64_t N, int64_t m_tiles, int64_t total_kb, bool all
     return none;
 }
 
-// Plain GEMMs with a short reduction whose 128x160 tiling would leave half of the SMs idle (24..73 tiles: the M = 1024 level of
-// the UNet) take 128x80 tiles instead: every k-block is bound by what ONE SM can pull through the crossbar (~46 B/clk), so twice
-// the CTAs halve the main loop.  Long reductions keep 160 columns and split K (plan_splits); the range is chosen so that neither
-// tiling splits, i.e. hcp_splitk_workspace_bytes (which does not know the caller) stays consistent.
-static int pick_bn_gemm(int64_t N, int64_t m_tiles, int64_t total_kb) {
-    const int bn = pick_bn(N);
-    if (bn == 160 && total_kb < 40) {
-        const int64_t t160 = m_tiles * (N / 160);
-        if (t160 >= 24 && t160 < 74 && getenv("HCP_GEMM_BN80") != nullptr) return 80;      // opt-in: no gain measured in the full step
-    }
-    return bn;
-}
+static int pick_bn_gemm(int64_t N, int64_t, int64_t) { return pick_bn(N); }      // (the 128x80 tiling for half-filled grids measured neutral in r01 and is gone)
+
+static long long* g_gemm_trace = nullptr;
 
 static int dispatch_gemm(int bn, bool cta_pair, GemmKParams& kp, int m_tiles, cudaStream_t stream) {
     kp.tiles_m = m_tiles;
+    kp.trace = g_gemm_trace;
     static const int epi_batch = [] { const char* e = getenv("HCP_GEMM_EPI_BATCH"); return e ? atoi(e) : 1; }();
     kp.epi_batch = epi_batch;
     if (cta_pair) {
@@ -824,7 +885,6 @@ static int dispatch_gemm(int bn, bool cta_pair, GemmKParams& kp, int m_tiles, cu
     switch (bn) {
         case 32: return launch_gemm<32, 1, false>(kp, stream);
         case 64: return launch_gemm<64, 1, false>(kp, stream);
-        case 80: return launch_gemm<80, 1, false>(kp, stream);
         case 128: return launch_gemm<128, 1, false>(kp, stream);
         case 160: return launch_gemm<160, 1, false>(kp, stream);
         default: return set_error(HCP_ERR_INVALID, "unsupported BLOCK_N");
@@ -862,6 +922,10 @@ static int run_gemm(int bn, bool cta_pair, int pair_splits, GemmKParams& kp, int
 }  // namespace hcp
 
 using namespace hcp;
+
+// bring-up hook (not in include/hcp_b200.h): every GEMM / conv launched after this call records 16 int64 slots per CTA (stamps and wait-cycle sums, see gemm_tc_kernel) into
+// `buf` (device memory, zeroed by the caller, 16 x 8 bytes per CTA of the largest grid); NULL switches tracing off
+extern "C" int hcp_debug_gemm_trace(long long* buf) { g_gemm_trace = buf; return HCP_OK; }
 
 extern "C" size_t hcp_splitk_workspace_bytes(int64_t M, int64_t N, int64_t total_k) {
     const int bn = pick_bn(N);
