@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhcpb200.so")
+LIB_PATH = os.environ.get("HCP_LIB", os.path.join(_HERE, "lib", "libhcpb200.so"))     # HCP_LIB: an alternative build (A/B experiments)
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["gemm.cu", "host_util.cu", "attention.cu", "norms.cu", "misc.cu", "step.cu", "wgrad.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared", "-Xcompiler", "-fPIC"]
@@ -54,6 +54,7 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("flags", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("out2", C.c_void_p), ("ldo2", C.c_int64), ("n_main", C.c_int64),
     ]
 
 
@@ -196,7 +197,7 @@ def lib() -> C.CDLL:
             l.hcp_sinusoid_f32.argtypes = [vp, i64, i64, i64, vp, i64, vp]
             l.hcp_lora_pack.argtypes = [vp, i64, vp]
             l.hcp_lora_pack_conv.argtypes = [vp, i64, vp]
-            l.hcp_lora_merge.argtypes = [vp, i64, i64, vp]
+            l.hcp_lora_merge.argtypes = [vp, i64, i64, vp, vp]
             l.hcp_lora_grad_conv3x3.argtypes = [vp, i64, vp, i64, i64, i64, i64, C.c_int32, C.POINTER(LoraGradBlock), C.c_int32, vp]
             l.hcp_lora_grad.argtypes = [vp, i64, vp, i64, i64, i64, i64, C.POINTER(LoraGradBlock), C.c_int32, vp]
             l.hcp_lora_grad_pair.argtypes = [vp, vp, i64, i64, C.POINTER(LoraGradBlock), vp, vp, i64, i64, C.POINTER(LoraGradBlock),

@@ -64,6 +64,11 @@ struct alignas(64) GemmKParams {
     int64_t ldr;
     __nv_bfloat16* out;
     int64_t ldo;
+    // columns >= n_main of the result are a SECOND output (the rank-r LoRA products T = x A^T / U = dY (alpha B) riding the layer's own
+    // GEMM as extra rows of its weight operand): stored raw (no bias / residual) to out2[row, col - n_main]; out2 == NULL: n_main = N
+    __nv_bfloat16* out2;
+    int64_t ldo2;
+    int32_t n_main;
     // split-K: CTA (x, y) reduces the k-blocks [y*kb_per_split, (y+1)*kb_per_split) and stores raw fp32 partials
     int32_t splits, kb_per_split;
     int32_t epi_batch;                 // epilogue schedule (see the epilogue)
@@ -92,9 +97,11 @@ struct GemmCfg {
     static constexpr int ACC_STRIDE = 256;                         // TMEM columns between the two accumulators
     static constexpr bool DOUBLE_ACC = (MSUB == 1 && BN <= 256);   // two accumulators alternate between work items
     // the epilogue walks the accumulator in column parts of EBN (<= 160) columns through one staging buffer
-    static constexpr int EBN = (BN <= 160) ? BN : (BN % 160 == 0 ? 160 : 128);
+    static constexpr int EBN = (BN <= 176) ? BN : (BN % 160 == 0 ? 160 : 128);
     static constexpr int NPART = BN / EBN;
-    static constexpr int STG_PITCH = EBN * 2 + 16;                 // staging row pitch in bytes: odd number of 16-byte units
+    static constexpr int EPI_NCH = (EBN / 16 + 1) / 2;             // 16-column TMEM chunks per column half of a part
+    // staging row pitch in bytes, an odd number of 16-byte units: a bf16 row of the part, or the fp32 values of one column half (split-K)
+    static constexpr int STG_PITCH = (EBN * 2 > EPI_NCH * 64 ? EBN * 2 : EPI_NCH * 64) + 16;
     static constexpr int STG_BYTES = BLOCK_M * STG_PITCH;
     static constexpr int BIAS_BYTES = ((BN * 4 + 127) / 128) * 128;  // bias slice of the tile's columns, staged once per work item
     static constexpr int ROW_BYTES = BLOCK_M * 16;                   // per tile row: row of `out` (or -1) and its row-bias group
@@ -102,7 +109,7 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
     static constexpr int MAX_STAGES = (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
     // one CTA per SM: the ring must cover the TMA latency alone
-    static constexpr int STAGES = PAIR ? (MAX_STAGES > 6 ? 6 : MAX_STAGES) : (MSUB == 2) ? 3 : (BN > 64) ? 5 : 8;
+    static constexpr int STAGES = PAIR ? (MAX_STAGES > 6 ? 6 : MAX_STAGES) : (MSUB == 2) ? 3 : (BN > 160) ? 4 : (BN > 64) ? 5 : 8;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
     static_assert(BN % EBN == 0 && (MSUB - 1) * ACC_STRIDE + BN <= 512, "accumulators must fit the 512 TMEM columns");
     static_assert(MMA_N <= 256 && MMA_N % 16 == 0 && (PAIR || NSPLIT == 1) && (B_BOX_ROWS % 8) == 0, "tcgen05.mma shape");
@@ -113,7 +120,17 @@ struct TileOrigin {
     int m0, img0, h0, w0;
 };
 
-__device__ __forceinline__ TileOrigin tile_origin(const GemmKParams& p, int m_tile) {
+// The output geometry of a launch, copied out of the parameter block BEFORE griddepcontrol.wait: the first touch of every
+// constant-bank line of the 1.6 KB parameter block costs a few hundred cycles, which then overlap the previous kernel's tail
+// instead of delaying this kernel's first TMA / first store.
+struct TileGeom {
+    int conv, bw, bh, bn, tiles_w, tiles_h, oW, oH, sh, sw, oh0, ow0, rows_per_group;
+    __device__ __forceinline__ explicit TileGeom(const GemmKParams& p)
+        : conv(p.conv), bw(p.bw), bh(p.bh), bn(p.bn), tiles_w(p.tiles_w), tiles_h(p.tiles_h), oW(p.oW), oH(p.oH), sh(p.sh), sw(p.sw),
+          oh0(p.oh0), ow0(p.ow0), rows_per_group(p.rows_per_group) {}
+};
+
+__device__ __forceinline__ TileOrigin tile_origin(const TileGeom& p, int m_tile) {
     TileOrigin o{m_tile * BLOCK_M, 0, 0, 0};
     if (p.conv) {
         if (p.bn == 1) {
@@ -129,7 +146,7 @@ __device__ __forceinline__ TileOrigin tile_origin(const GemmKParams& p, int m_ti
     return o;
 }
 // row r of the tile -> row of `out` (and the per-image bias group)
-__device__ __forceinline__ int64_t tile_row(const GemmKParams& p, const TileOrigin& o, int r, int& group) {
+__device__ __forceinline__ int64_t tile_row(const TileGeom& p, const TileOrigin& o, int r, int& group) {
     if (p.conv) {
         const int per = p.bw * p.bh;
         const int im = o.img0 + r / per;
@@ -244,9 +261,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // parameter block -> registers while the previous kernel of the stream is still draining
+    const KPlan kq(p);
+    const TileGeom geo(p);
+    const int tiles_n = p.tiles_n;
+    const int pN = p.N;
+    const int64_t pM = p.M, pldo = p.ldo, pldr = p.ldr, prowbias_ld = p.rowbias_ld;
+    const bool staged = (p.splits == 1);
+    const float* const pbias = p.bias;
+    const float* const prowbias = p.rowbias;
+    const __nv_bfloat16* const pres = p.residual;
+    __nv_bfloat16* const pout = p.out;
+    __nv_bfloat16* const pout2 = p.out2;
+    const int64_t pldo2 = p.ldo2;
+    const int n_main = p.n_main;
+    float* const pws = p.ws;
+    long long* const ptrace = p.trace;
     pdl_trigger();
     pdl_wait();     // the set-up above overlapped the previous kernel's tail; its results are visible from here on
-    long long* trc = p.trace ? p.trace + (int64_t)blockIdx.x * 16 : nullptr;
+    long long* trc = ptrace ? ptrace + (int64_t)blockIdx.x * 16 : nullptr;
     if (trc && threadIdx.x == 0) { trc[0] = clock64(); unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); trc[7] = (long long)g; }
 
     if (warp == 0) {
@@ -254,14 +287,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            KPlan kq(p);
             long long tr_first = 0, tr_last = 0, tr_wait = 0, tr_n = 0;      // bring-up trace, kept in registers until the role ends
             for (int w = worker; w < total_work; w += nworkers) {
                 const int split = w / tiles_mn, mn = w % tiles_mn;
-                const int n0 = (mn % p.tiles_n) * BN + (int)rank * Cfg::B_BOX_ROWS;  // PAIR: this CTA's part of every instruction's B rows
+                const int n0 = (mn % tiles_n) * BN + (int)rank * Cfg::B_BOX_ROWS;  // PAIR: this CTA's part of every instruction's B rows
                 TileOrigin o[MSUB];
 #pragma unroll
-                for (int sub = 0; sub < MSUB; ++sub) o[sub] = tile_origin(p, m_tile_of(mn / p.tiles_n, sub));
+                for (int sub = 0; sub < MSUB; ++sub) o[sub] = tile_origin(geo, m_tile_of(mn / tiles_n, sub));
                 const int kb_lo = split * kq.kb_per_split, kb_hi = min(kb_lo + kq.kb_per_split, kq.total_kb);
                 KPos q = kq.seek(kb_lo);
                 TapEntry te = p.taps[q.t];
@@ -329,7 +361,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             int item = 0;
-            KPlan kq(p);
             long long tr_first = 0, tr_wait = 0, tr_acc = 0, tr_commit = 0;
             for (int w = worker; w < total_work; w += nworkers, ++item) {
                 const int split = w / tiles_mn;
@@ -393,26 +424,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         const int et = threadIdx.x - 64;              // 0..255 among the epilogue threads
         constexpr int UNITS = EBN / 8;                // 16-byte units per staged row
         constexpr int CH16 = EBN / 16;                // 16-column TMEM chunks per part
-        constexpr int NCH = (CH16 + 1) / 2;           // chunks per column half
+        constexpr int NCH = Cfg::EPI_NCH;             // chunks per column half
         const uint32_t stg = smem_u32(sStg), sbias = smem_u32(sBias), srow = smem_u32(sRow);
         const uint32_t my_stg = stg + r * Cfg::STG_PITCH;
-        const int N = p.N;
-        const int64_t Mrows = p.M;
-        const bool staged = (p.splits == 1);
-        const bool has_bias = staged && p.bias != nullptr, has_res = staged && p.residual != nullptr;
-        const float* const rowbias = staged ? p.rowbias : nullptr;
-        const int64_t rowbias_ld = p.rowbias_ld;
+        const int N = pN;
+        const int64_t Mrows = pM;
+        const bool has_bias = staged && pbias != nullptr, has_res = staged && pres != nullptr;
+        const float* const rowbias = staged ? prowbias : nullptr;
+        const int64_t rowbias_ld = prowbias_ld;
         int item = 0;
         for (int w = worker; w < total_work; w += nworkers, ++item) {
             const int split = w / tiles_mn, mn = w % tiles_mn;
-            const int n0 = (mn % p.tiles_n) * BN;
+            const int n0 = (mn % tiles_n) * BN;
             const int as = Cfg::DOUBLE_ACC ? (item & 1) : 0;
             const uint32_t fph = Cfg::DOUBLE_ACC ? ((item >> 1) & 1) : (item & 1);
             if (has_bias) {
                 // the bias slice of this item's columns goes to shared memory once; the previous item's trailing bar.sync guarantees
                 // nobody still reads the old slice.  Columns >= N read as zero.
                 for (int c = et; c < BN / 4; c += kGemmEpiThreads)
-                    sts_f4(sbias + c * 16, (n0 + c * 4 < N) ? *reinterpret_cast<const float4*>(p.bias + n0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f));
+                    sts_f4(sbias + c * 16, (n0 + c * 4 < n_main) ? *reinterpret_cast<const float4*>(pbias + n0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f));
             }
 #pragma unroll 1
             for (int part = 0; part < MSUB * Cfg::NPART; ++part) {
@@ -425,8 +455,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                 if (nc0 == 0) {
                     // row of `out` behind every tile row, once per M sub-tile (the store loops below read it back instead of redoing the
                     // integer divisions of the pixel <-> row mapping for every 16-byte unit); -1 = row beyond M
-                    const TileOrigin o = tile_origin(p, m_tile_of(mn / p.tiles_n, sub));
-                    grow = tile_row(p, o, r, group);
+                    const TileOrigin o = tile_origin(geo, m_tile_of(mn / tiles_n, sub));
+                    grow = tile_row(geo, o, r, group);
                     if (grow >= Mrows) grow = -1;
                     if (half == 0) { sts_b64(srow + r * 16, grow); sts_b64(srow + r * 16 + 8, (int64_t)group); }
                 }
@@ -444,7 +474,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                         if (u < BLOCK_M * UNITS) {
                             const int64_t g = lds_b64(srow + rr * 16);
                             const int col = n0 + nc0 + cu * 8;
-                            if (g >= 0 && col < N) rbuf[it] = *reinterpret_cast<const uint4*>(p.residual + g * p.ldr + col);
+                            if (g >= 0 && col < n_main) rbuf[it] = *reinterpret_cast<const uint4*>(pres + g * pldr + col);
                         }
                     }
 #pragma unroll
@@ -500,7 +530,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                                     f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                                     f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                                 }
-                                if (rb && n0 + nc0 + cc < N) {
+                                if (rb && n0 + nc0 + cc < n_main) {
                                     const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb + cc)), b1 = __ldg(reinterpret_cast<const float4*>(rb + cc + 4));
                                     f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                                     f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
@@ -521,11 +551,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                     if (dbg) trc[13] = clock64();
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     if (dbg) trc[14] = clock64();
-                    for (int u = et; u < BLOCK_M * UNITS; u += kGemmEpiThreads) {     // coalesced 16-byte stores
-                        const int rr = u / UNITS, cu = u % UNITS;
-                        const int64_t g = lds_b64(srow + rr * 16);
-                        const int col = n0 + nc0 + cu * 8;
-                        if (g >= 0 && col < N) *reinterpret_cast<uint4*>(p.out + g * p.ldo + col) = lds128(stg + rr * Cfg::STG_PITCH + cu * 16);
+                    if (n0 + nc0 + EBN <= n_main) {                                   // (uniform) the usual case: one output
+                        for (int u = et; u < BLOCK_M * UNITS; u += kGemmEpiThreads) {     // coalesced 16-byte stores
+                            const int rr = u / UNITS, cu = u % UNITS;
+                            const int64_t g = lds_b64(srow + rr * 16);
+                            if (g >= 0) *reinterpret_cast<uint4*>(pout + g * pldo + (n0 + nc0 + cu * 8)) = lds128(stg + rr * Cfg::STG_PITCH + cu * 16);
+                        }
+                    } else {                                                          // N tail and / or the second output
+                        for (int u = et; u < BLOCK_M * UNITS; u += kGemmEpiThreads) {
+                            const int rr = u / UNITS, cu = u % UNITS;
+                            const int64_t g = lds_b64(srow + rr * 16);
+                            const int col = n0 + nc0 + cu * 8;
+                            if (g >= 0 && col < N) {
+                                __nv_bfloat16* dst = (col < n_main) ? pout + g * pldo + col : pout2 + g * pldo2 + (col - n_main);
+                                *reinterpret_cast<uint4*>(dst) = lds128(stg + rr * Cfg::STG_PITCH + cu * 16);
+                            }
+                        }
                     }
                     asm volatile("bar.sync 1, 256;" ::: "memory");     // staging buffer / row table reusable
                     if (dbg) trc[15] = clock64();
@@ -553,7 +594,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                             const int64_t g = lds_b64(srow + rr * 16);
                             const int col = n0 + nc0 + hp * NCH * 16 + cu * 4;
                             if (cu * 4 < ncols_h && g >= 0 && col < N)
-                                *reinterpret_cast<uint4*>(p.ws + ((int64_t)split * Mrows + g) * N + col) = lds128(stg + rr * Cfg::STG_PITCH + cu * 16);
+                                *reinterpret_cast<uint4*>(pws + ((int64_t)split * Mrows + g) * N + col) = lds128(stg + rr * Cfg::STG_PITCH + cu * 16);
                         }
                         asm volatile("bar.sync 1, 256;" ::: "memory");
                     }
@@ -824,10 +865,17 @@ static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
 static int pick_bn(int64_t N) {
     if (N <= 32) return 32;
     if (N <= 64) return 64;
-    if (N % 160 == 0) return 160;
-    if (N % 128 == 0) return 128;
-    if (N % 64 == 0 && N < 256) return 64;
-    return 128;
+    if (N % 64 == 0 && N < 256 && N % 128 != 0) return 64;
+    // 160 divides every channel count of the UNet; 176 covers a layer whose weight operand carries its LoRA down-projection as extra
+    // rows (N + 8..16 per 160 columns) without an extra column tile; the least padded width wins, ties go to the fewer tiles
+    int best = 128;
+    int64_t best_w = (N + 127) / 128 * 128;
+    const int cand[2] = {160, 176};
+    for (int c : cand) {
+        const int64_t w = (N + c - 1) / c * c;
+        if (w < best_w || (w == best_w && c > best)) { best = c; best_w = w; }
+    }
+    return best;
 }
 
 // CTA-pair tiling (256 x BN per pair, BN in {256, 320}) and its K-split.  bn == 0: keep the single-CTA kernel.
@@ -887,6 +935,7 @@ static int dispatch_gemm(int bn, bool cta_pair, GemmKParams& kp, int m_tiles, cu
         case 64: return launch_gemm<64, 1, false>(kp, stream);
         case 128: return launch_gemm<128, 1, false>(kp, stream);
         case 160: return launch_gemm<160, 1, false>(kp, stream);
+        case 176: return launch_gemm<176, 1, false>(kp, stream);
         default: return set_error(HCP_ERR_INVALID, "unsupported BLOCK_N");
     }
 }
@@ -985,10 +1034,17 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     kp.ldr = a->ldr;
     kp.out = (__nv_bfloat16*)a->out;
     kp.ldo = a->ldo;
+    kp.n_main = kp.N;
+    if (a->out2) {
+        if (a->n_main <= 0 || a->n_main >= a->N || (a->n_main % 8) != 0 || (a->ldo2 % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: out2 / n_main / ldo2");
+        kp.out2 = (__nv_bfloat16*)a->out2;
+        kp.ldo2 = a->ldo2;
+        kp.n_main = (int)a->n_main;
+    }
     const int m_tiles = (int)((a->M + BLOCK_M - 1) / BLOCK_M);
     int64_t total_kb = 0;
     for (int s = 0; s < a->nseg; ++s) total_kb += kp.nkb[s];
-    return run_gemm(bn, pair_bn != 0, pp.splits, kp, m_tiles, total_kb, a->workspace, a->workspace_bytes, true, (cudaStream_t)stream_);
+    return run_gemm(bn, pair_bn != 0, pp.splits, kp, m_tiles, total_kb, a->workspace, a->workspace_bytes, a->out2 == nullptr, (cudaStream_t)stream_);
 }
 
 // Conv2d LoRA: out += T . Bl^T as K-segment 1 (plain 2D operands; the rows of an M tile of the convolution are contiguous pixels)
@@ -1055,6 +1111,7 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
     kp.ldr = a->Cout;
     kp.out = (__nv_bfloat16*)a->out;
     kp.ldo = a->Cout;
+    kp.n_main = (int)a->Cout;
     const int m_tiles = (bnimg == 1) ? (int)(a->B * kp.tiles_w * kp.tiles_h) : (int)((a->B + bnimg - 1) / bnimg);
     // CTA pairs for the forward-mode launches (mode 1 = four short phase launches of the stride-2 dgrad: single CTAs)
     const PairPlan pp = (a->mode == 0) ? plan_pair(a->Cout, m_tiles, 9 * (Cin / BLOCK_K) + (a->lora_t ? (a->lora_ld + BLOCK_K - 1) / BLOCK_K : 0),

@@ -270,17 +270,23 @@ __global__ void lora_pack_conv_kernel(const hcp_lora_conv_job* __restrict__ jobs
 // ---------------------------------------------------------------------------------------------
 constexpr int MG_T = 64;          // tile edge
 constexpr int MG_RMAX = 64;       // sum of the ranks stacked on one host
-__global__ void __launch_bounds__(256) lora_merge_kernel(const hcp_lora_merge_job* __restrict__ jobs, int njobs) {
+__global__ void __launch_bounds__(256) lora_merge_kernel(const hcp_lora_merge_job* __restrict__ jobs, int njobs, const int32_t* __restrict__ tile_job) {
     __shared__ float s_dn[MG_RMAX][MG_T + 4];          // W_down rows (all stacked blocks) over the tile's k range
     __shared__ float s_up[MG_T][MG_RMAX + 1];          // alpha * W_up rows of the tile's o range
-    __shared__ __nv_bfloat16 s_t[MG_T][MG_T + 8];      // the merged tile, for the transposed store
+    __shared__ __align__(16) __nv_bfloat16 s_t[MG_T][MG_T + 8];      // the merged tile, for the transposed store
     pdl_trigger();
     pdl_wait();
-    // job of this tile: last job with tile0 <= blockIdx.x
-    int lo = 0, hi = njobs - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (jobs[mid].tile0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    // job of this tile: one load from the caller's tile -> job table, or (no table) the last job with tile0 <= blockIdx.x by a
+    // binary search -- seven DEPENDENT global loads per CTA, which was most of the r02 first version's 320 us
+    int lo = 0;
+    if (tile_job) {
+        lo = tile_job[blockIdx.x];
+    } else {
+        int hi = njobs - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs[mid].tile0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+        }
     }
     const hcp_lora_merge_job& jb = jobs[lo];
     const int in = jb.in_dim, out = jb.out_dim;
@@ -289,6 +295,17 @@ __global__ void __launch_bounds__(256) lora_merge_kernel(const hcp_lora_merge_jo
     const int o_base = (t / tiles_k) * MG_T, k_base = (t % tiles_k) * MG_T;
     if (o_base >= out) return;
     const int tid = threadIdx.x;
+    // this thread's share of the host tile: 8 consecutive k of rows ty and ty + 32, requested before anything else (the fp32 masters
+    // are 2/3 of the kernel's traffic and nothing below depends on the low-rank factors until the FMAs)
+    const int tx = tid & 7, ty = tid >> 3;
+    float4 w[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int o = o_base + ty + 32 * i, k = k_base + tx * 8;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            w[i][h] = (o < out && k + 4 * h < in) ? __ldg(reinterpret_cast<const float4*>(jb.w_host + (int64_t)o * in + k + 4 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     int rtot = 0;
     for (int b = 0; b < jb.nblocks; ++b) {
         const int r = jb.rank[b];
@@ -306,40 +323,44 @@ __global__ void __launch_bounds__(256) lora_merge_kernel(const hcp_lora_merge_jo
         rtot += r;
     }
     __syncthreads();
-    const int tx = tid & 15, ty = tid >> 4;            // 4 consecutive k per thread, rows ty + 16 i
     __nv_bfloat16* W = (__nv_bfloat16*)jb.W;
     __nv_bfloat16* WT = (__nv_bfloat16*)jb.WT;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int ol = ty + 16 * i, o = o_base + ol, k = k_base + tx * 4;
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o < out && k < in) w = *reinterpret_cast<const float4*>(jb.w_host + (int64_t)o * in + k);
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    for (int i = 0; i < 2; ++i) {
+        const int ol = ty + 32 * i, o = o_base + ol, k = k_base + tx * 8;
+        float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int r = 0; r < rtot; ++r) {
             const float u = s_up[ol][r];
-            const float4 dn = *reinterpret_cast<const float4*>(&s_dn[r][tx * 4]);
-            d0 = fmaf(u, dn.x, d0); d1 = fmaf(u, dn.y, d1); d2 = fmaf(u, dn.z, d2); d3 = fmaf(u, dn.w, d3);
+            const float4 d0 = *reinterpret_cast<const float4*>(&s_dn[r][tx * 8]), d1 = *reinterpret_cast<const float4*>(&s_dn[r][tx * 8 + 4]);
+            d[0] = fmaf(u, d0.x, d[0]); d[1] = fmaf(u, d0.y, d[1]); d[2] = fmaf(u, d0.z, d[2]); d[3] = fmaf(u, d0.w, d[3]);
+            d[4] = fmaf(u, d1.x, d[4]); d[5] = fmaf(u, d1.y, d[5]); d[6] = fmaf(u, d1.z, d[6]); d[7] = fmaf(u, d1.w, d[7]);
         }
-        const __nv_bfloat162 p0 = __floats2bfloat162_rn(w.x + d0, w.y + d1), p1 = __floats2bfloat162_rn(w.z + d2, w.w + d3);
+        uint4 v;
+        v.x = pack_bf16x2(w[i][0].x + d[0], w[i][0].y + d[1]);
+        v.y = pack_bf16x2(w[i][0].z + d[2], w[i][0].w + d[3]);
+        v.z = pack_bf16x2(w[i][1].x + d[4], w[i][1].y + d[5]);
+        v.w = pack_bf16x2(w[i][1].z + d[6], w[i][1].w + d[7]);
         if (o < out && k < in) {
-            uint2 v;
-            v.x = *reinterpret_cast<const uint32_t*>(&p0);
-            v.y = *reinterpret_cast<const uint32_t*>(&p1);
-            // k-block-major: ((k / 64) * out_tot + row) * 64 + k % 64 (the 4 consecutive k of a thread never straddle a 64-block)
+            // k-block-major: ((k / 64) * out_tot + row) * 64 + k % 64 (the 8 consecutive k of a thread never straddle a 64-block)
             __nv_bfloat16* dst = jb.tiled ? W + ((int64_t)(k >> 6) * jb.out_tot + jb.o0 + o) * 64 + (k & 63) : W + (int64_t)(jb.o0 + o) * in + k;
-            *reinterpret_cast<uint2*>(dst) = v;
+            if (k + 8 <= in) *reinterpret_cast<uint4*>(dst) = v;
+            else *reinterpret_cast<uint2*>(dst) = make_uint2(v.x, v.y);            // in % 8 == 4 tail
         }
-        s_t[tx * 4 + 0][ol] = p0.x; s_t[tx * 4 + 1][ol] = p0.y; s_t[tx * 4 + 2][ol] = p1.x; s_t[tx * 4 + 3][ol] = p1.y;
+        const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_t[tx * 8 + j][ol] = e[j];
     }
     __syncthreads();
     if (WT) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int kl = ty + 16 * i, k = k_base + kl, o = o_base + tx * 4;
+        for (int i = 0; i < 2; ++i) {
+            const int kl = ty + 32 * i, k = k_base + kl, o = o_base + tx * 8;
             if (k < in && o < out) {
                 const int oo = jb.o0 + o;
                 __nv_bfloat16* dst = jb.tiled ? WT + ((int64_t)(oo >> 6) * in + k) * 64 + (oo & 63) : WT + (int64_t)k * jb.out_tot + oo;
-                *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(&s_t[kl][tx * 4]);
+                const uint4 v = *reinterpret_cast<const uint4*>(&s_t[kl][tx * 8]);
+                if (o + 8 <= out) *reinterpret_cast<uint4*>(dst) = v;
+                else *reinterpret_cast<uint2*>(dst) = make_uint2(v.x, v.y);
             }
         }
     }
@@ -535,9 +556,10 @@ extern "C" int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp
     return HCP_OK;
 }
 
-extern "C" int hcp_lora_merge(const hcp_lora_merge_job* jobs_device, int64_t njobs, int64_t total_tiles, hcp_stream_t st) {
+extern "C" int hcp_lora_merge(const hcp_lora_merge_job* jobs_device, int64_t njobs, int64_t total_tiles, const int32_t* tile_job_device,
+                              hcp_stream_t st) {
     if (!jobs_device || njobs <= 0 || total_tiles <= 0) return set_error(HCP_ERR_INVALID, "lora_merge: jobs");
-    launch_k(lora_merge_kernel, dim3((unsigned)total_tiles), dim3(256), 0, (cudaStream_t)st, jobs_device, (int)njobs);
+    launch_k(lora_merge_kernel, dim3((unsigned)total_tiles), dim3(256), 0, (cudaStream_t)st, jobs_device, (int)njobs, tile_job_device);
     LAUNCH_CHECK("lora_merge launch");
     return HCP_OK;
 }

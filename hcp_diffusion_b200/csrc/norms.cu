@@ -488,13 +488,15 @@ __global__ void __maxnreg__(96) gnf_kernel(const __grid_constant__ GNFParams p) 
         mean[0] = st[g_lo * 2]; rstd[0] = st[g_lo * 2 + 1];
         mean[1] = st[g_hi * 2]; rstd[1] = st[g_hi * 2 + 1];
     }
+    // explicit shared-space reads of the slab (the aligned-base pointer arithmetic would make them generic loads)
+    const uint32_t sx_addr = smem_u32(sX), sdy_addr = smem_u32(sDY);
     mbar_wait(bar, 0);
 
     // ---- pass 1: partial sums of this CTA's slab
     float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};
     for (int pp = rl; pp < p.P; pp += p.lanes) {
         float x[8];
-        unpack8(*reinterpret_cast<const uint4*>(sX + ((size_t)pp * p.CB + tv * 8) * 2), x);
+        unpack8(lds128(sx_addr + (uint32_t)(pp * p.CB + tv * 8) * 2u), x);
         if (!BWD) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -504,7 +506,7 @@ __global__ void __maxnreg__(96) gnf_kernel(const __grid_constant__ GNFParams p) 
             }
         } else {
             float d[8];
-            unpack8(*reinterpret_cast<const uint4*>(sDY + ((size_t)pp * p.CB + tv * 8) * 2), d);
+            unpack8(lds128(sdy_addr + (uint32_t)(pp * p.CB + tv * 8) * 2u), d);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const bool lo = e < nb;       // selects, not runtime-indexed arrays (those live in local memory)
@@ -589,7 +591,7 @@ __global__ void __maxnreg__(96) gnf_kernel(const __grid_constant__ GNFParams p) 
             if (pp >= p.P) break;
             const int64_t pix = row0 + pp;
             float x[8], o[8];
-            unpack8(*reinterpret_cast<const uint4*>(sX + ((size_t)pp * p.CB + tv * 8) * 2), x);
+            unpack8(lds128(sx_addr + (uint32_t)(pp * p.CB + tv * 8) * 2u), x);
             if (!BWD) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -601,7 +603,7 @@ __global__ void __maxnreg__(96) gnf_kernel(const __grid_constant__ GNFParams p) 
                 *reinterpret_cast<uint4*>(p.y + pix * p.C + ch) = pack8(o);
             } else {
                 float d[8], a[8];
-                unpack8(*reinterpret_cast<const uint4*>(sDY + ((size_t)pp * p.CB + tv * 8) * 2), d);
+                unpack8(lds128(sdy_addr + (uint32_t)(pp * p.CB + tv * 8) * 2u), d);
                 unpack8(av[j], a);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {

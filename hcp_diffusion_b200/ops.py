@@ -32,6 +32,9 @@ LORA_MERGE = os.environ.get("HCP_LORA_MERGE", "1") != "0"
 # contiguous run of 128 B x rows instead of `rows` 128-byte pieces at a 2K-byte pitch.  The small-M layers (16x16 / 8x8 levels) stream
 # every weight byte from HBM exactly once per pass; whole-page reads are what lets them approach the HBM roofline.
 WEIGHT_TILED = os.environ.get("HCP_WEIGHT_TILED", "0") != "0"
+# Merged-LoRA layers carry their rank-r factors as extra rows of the weight operands, so T = x W_down^T and U = dY (alpha W_up) come
+# out of the layer's own forward / dgrad GEMM as a second output (hcp_gemm_args.out2) instead of two skinny GEMM launches per layer.
+LORA_EXT = os.environ.get("HCP_LORA_EXT", "1") != "0"
 
 
 def tile_kmajor(w2d: torch.Tensor) -> torch.Tensor:
@@ -185,7 +188,8 @@ def _chk(t: torch.Tensor, name: str) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------------------
 def gemm_raw(a_list: Sequence[Tuple[torch.Tensor, int, int]], b_list: Sequence[Tuple[torch.Tensor, int, int, int]], M: int, N: int,
              out: torch.Tensor, ldo: int, bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
-             rows_per_group: int = 0, residual: Optional[torch.Tensor] = None, ldr: int = 0) -> None:
+             rows_per_group: int = 0, residual: Optional[torch.Tensor] = None, ldr: int = 0,
+             out2: Optional[torch.Tensor] = None, ldo2: int = 0, n_main: int = 0) -> None:
     """out[M,N] = sum_s A_s . B_s^T (+bias +rowbias +residual).
     a_list: (tensor_or_ptr_holder, lda, k);  b_list: (tensor, ldb, n_rows_b, elem_offset[, k_block_major]) -- for a k-block-major
     operand ldb is the row count of one k-block slab (see hcp_gemm_args.flags)."""
@@ -209,7 +213,9 @@ def gemm_raw(a_list: Sequence[Tuple[torch.Tensor, int, int]], b_list: Sequence[T
     g.ldr = ldr
     g.out = out.data_ptr()
     g.ldo = ldo
-    wsb = _lib.lib().hcp_splitk_workspace_bytes(M, N, sum(k for _, _, k in a_list))
+    if out2 is not None:          # columns [n_main, N) -> out2 (hcp_gemm_args.out2)
+        g.out2, g.ldo2, g.n_main = out2.data_ptr(), ldo2, n_main
+    wsb = 0 if out2 is not None else _lib.lib().hcp_splitk_workspace_bytes(M, N, sum(k for _, _, k in a_list))
     if wsb:
         ws = torch.empty((wsb // 4,), dtype=torch.float32, device=out.device)
         g.workspace, g.workspace_bytes = ws.data_ptr(), wsb
@@ -282,13 +288,16 @@ class LinearPack:
         # merged mode: [(fp32 host weight [n, K], first output row o0, n, [LoraBlockRef, ...])]; W / WT are then rewritten every step
         # by hcp_lora_merge (runtime.pack_lora) and the GEMMs carry no LoRA segment
         self.merged: List[Tuple[torch.Tensor, int, int, list]] = []
+        # merged mode with rank columns riding the layer's own GEMMs: W is [N + ext_rp, K] with W_down in the extra rows (the forward
+        # GEMM also emits T = x W_down^T), WT is [K + ext_rp, N] with alpha*W_up^T in the extra rows (the dgrad GEMM also emits U)
+        self.ext_rp = 0
         # full fine-tune: [(weight Parameter [n, K] (or [n, K, 1, 1]), bias Parameter or None, first output row o0, n)] of the hosts
         # whose parameters are trained; their bf16 operands are refreshed from the fp32 masters every step (repack_jobs)
         self.train: List[Tuple[torch.Tensor, Optional[torch.Tensor], int, int]] = []
 
     def tile_weights(self) -> None:
         """W [N,K] -> [K/64][N][64], WT [K,N] -> [N/64][K][64] (frozen or merged weights only: hcp_repack_weights writes row-major)."""
-        if self.tiled or self.train or self.K % 64 or self.N % 64 or any(k % 64 for k in self.k_splits):
+        if self.tiled or self.train or self.ext_rp or self.K % 64 or self.N % 64 or any(k % 64 for k in self.k_splits):
             return
         self.W, self.WT = tile_kmajor(self.W), tile_kmajor(self.WT)
         self.tiled = True
@@ -348,13 +357,22 @@ class LinearPack:
 
     def enable_merge(self, hosts: Sequence[Tuple[torch.Tensor, int, int, list]]) -> bool:
         """Switch the pack to merged weights if every patched host qualifies (fp32 master weight, <= 4 stacked blocks, ranks summing
-        to <= 64, 4-element alignment); returns whether it did."""
-        if self.dapp or self.train or not self.lora or self.K % 4 or self.N % 4:
+        to <= 64, 8-element alignment); returns whether it did."""
+        if self.dapp or self.train or not self.lora or self.K % 8 or self.N % 8:
             return False
         for w, o0, n, blocks in hosts:
-            if w.dtype != torch.float32 or not w.is_contiguous() or len(blocks) > 4 or sum(b.rank for b in blocks) > 64 or o0 % 4 or n % 4:
+            if w.dtype != torch.float32 or not w.is_contiguous() or len(blocks) > 4 or sum(b.rank for b in blocks) > 64 or o0 % 8 or n % 8:
                 return False
         self.merged = [h for h in hosts if h[3]]
+        if LORA_EXT and self.R == 64 and len(self.k_splits) == 1 and not self.tiled:
+            rp = (self.r_tot + 7) // 8 * 8
+            dev = self.W.device
+            W = torch.zeros((self.N + rp, self.K), dtype=BF16, device=dev)
+            WT = torch.zeros((self.K + rp, self.N), dtype=BF16, device=dev)
+            W[:self.N].copy_(self.W)
+            WT[:self.K].copy_(self.WT)
+            self.W, self.WT, self.ext_rp = W, WT, rp
+            self.A, self.BlT = W[self.N:], WT[self.K:]            # hcp_lora_pack writes the factors straight into the extra rows
         return True
 
     def merge_jobs(self) -> List[_lib.LoraMergeJob]:
@@ -527,13 +545,14 @@ def _skinny_rows(pack: LinearPack, a_list, b_key: str, M: int, batch: int, out: 
     R = pack.R
 
     def b_list_for(t):
+        rows = min(n_out, t.shape[0])      # rows beyond the operand read as zero (merged packs keep only the 8-padded rank rows)
         if b_key == "A":       # [R, K] against the (possibly multi-input) x: column offsets follow the k splits
             bl, off = [], 0
             for (_, _, k) in a_list:
-                bl.append((t, pack.K, n_out, off))
+                bl.append((t, pack.K, rows, off))
                 off += k
             return bl
-        return [(t, pack.N, n_out, 0)]
+        return [(t, pack.N, rows, 0)]
 
     if not pack.dapp:
         gemm_raw(a_list, b_list_for(pack.A if b_key == "A" else pack.BlT), M, R, out, R)
@@ -590,7 +609,15 @@ class FusedLinearFn(torch.autograd.Function):
         res = None
         if residual is not None:
             res = _chk(residual, "linear residual")
-        gemm_raw(a_list, b_list, M, N, out, N, bias=pack.bias, residual=res, ldr=N)
+        if pack.ext_rp and any(ctx.needs_input_grad[3 + n_x:]):
+            # the factor gradients will need T = x W_down^T: it rides this GEMM as ext_rp extra output columns
+            T = torch.empty((M, pack.R), dtype=BF16, device=xs[0].device)
+            gemm_raw(a_list, [(pack.W, pack.K, N + pack.ext_rp, 0)], M, N + pack.ext_rp, out, N, bias=pack.bias, residual=res, ldr=N,
+                     out2=T, ldo2=pack.R, n_main=N)
+        else:
+            if pack.ext_rp:
+                b_list = [(pack.W, pack.K, N, 0)]
+            gemm_raw(a_list, b_list, M, N, out, N, bias=pack.bias, residual=res, ldr=N)
         ctx.pack, ctx.n_x, ctx.M, ctx.ks = pack, n_x, M, ks
         ctx.batch = xs[0].shape[0]
         ctx.has_res = residual is not None
@@ -645,26 +672,38 @@ class FusedLinearFn(torch.autograd.Function):
                 if b is not None and b.requires_grad:
                     call("hcp_colsum_bf16", dy.data_ptr() + 2 * o0, N, M, n, 0, 1.0, _acc_grad(b).data_ptr(), n, stream_ptr())
                 notify_grad(w, b)
+        dx_done = None
         if pack.merged:
-            # merged weights: dX below is a plain GEMM against W_eff^T; T = x A^T and U = dY (alpha B) exist only for the factor
-            # gradients dW_down = U^T x, dW_up = alpha dY^T T -- the whole LoRA backward of the layer is off the critical path
-            xs = ctx.saved_tensors
-
-            def lora_side():
-                T = torch.empty((M, R), dtype=BF16, device=dy.device)
+            # merged weights: dX is a plain GEMM against W_eff^T; T = x A^T and U = dY (alpha B) exist only for the factor gradients
+            # dW_down = U^T x, dW_up = alpha dY^T T -- the whole LoRA backward of the layer is off the critical path.  With the rank
+            # rows riding the weight operands (ext_rp) T came out of the forward GEMM and U comes out of the dX GEMM.
+            saved = list(ctx.saved_tensors)
+            T_saved = saved.pop() if (pack.ext_rp and len(saved) > len(ks)) else None
+            xs = saved
+            Um = None
+            if T_saved is not None and ctx.needs_input_grad[3]:
+                dx_done = torch.empty(ctx.x_shapes[0], dtype=BF16, device=dy.device)
                 Um = torch.empty((M, R), dtype=BF16, device=dy.device)
-                _skinny_rows(pack, [(x, k, k) for x, k in zip(xs, ks)], "A", M, ctx.batch, T, R)
-                _skinny_rows(pack, [(dy, N, N)], "BlT", M, ctx.batch, Um, R)
-                FusedLinearFn._lora_grads(pack, xs, ks, T, Um, dy, M, N, R)
-                return T, Um
+                gemm_raw([(dy, N, N)], [(pack.WT, N, pack.K + pack.ext_rp, 0)], M, pack.K + pack.ext_rp, dx_done, pack.K,
+                         out2=Um, ldo2=R, n_main=pack.K)
+
+            def lora_side(Tm, Um):
+                if Tm is None:
+                    Tm = torch.empty((M, R), dtype=BF16, device=dy.device)
+                    _skinny_rows(pack, [(x, k, k) for x, k in zip(xs, ks)], "A", M, ctx.batch, Tm, R)
+                if Um is None:
+                    Um = torch.empty((M, R), dtype=BF16, device=dy.device)
+                    _skinny_rows(pack, [(dy, N, N)], "BlT", M, ctx.batch, Um, R)
+                FusedLinearFn._lora_grads(pack, xs, ks, Tm, Um, dy, M, N, R)
+                return Tm, Um
 
             if side_enabled():
-                side = fork_side(dy, *xs)
+                side = fork_side(dy, T_saved, Um, *xs)
                 with torch.cuda.stream(side):
-                    tu = lora_side()
+                    tu = lora_side(T_saved, Um)
                 _Side.keep.extend(tu)
             else:
-                lora_side()
+                lora_side(T_saved, Um)
         elif pack.lora:
             *xs, T = ctx.saved_tensors
             U = torch.empty((M, R), dtype=BF16, device=dy.device)
@@ -679,7 +718,9 @@ class FusedLinearFn(torch.autograd.Function):
         grads = []
         off = 0
         for i, k in enumerate(ks):
-            if ctx.needs_input_grad[3 + i]:
+            if dx_done is not None:
+                grads.append(dx_done)
+            elif ctx.needs_input_grad[3 + i]:
                 dx = torch.empty(ctx.x_shapes[i], dtype=BF16, device=dy.device)
                 a_list = [(dy, N, N)]
                 b_list = [pack.b_dgrad(off, k)]

@@ -65,7 +65,7 @@ class LinearGroup:
         self.drops = None
 
     def _signature(self, k_splits):
-        sig = [tuple(k_splits) if k_splits else None, ops.LORA_MERGE, ops.WEIGHT_TILED]
+        sig = [tuple(k_splits) if k_splits else None, ops.LORA_MERGE, ops.WEIGHT_TILED, ops.LORA_EXT]
         for ch in self.children:
             host, blocks = host_and_blocks(ch)
             sig.append((id(ch), id(host), _versions(host, blocks)))
@@ -152,7 +152,7 @@ class LinearGroup:
 class _JobTable:
     def __init__(self):
         self.key = None
-        self.dev = self.cdev = self.mdev = None
+        self.dev = self.cdev = self.mdev = self.mmap = None
         self.n = self.cn = self.mn = self.mtiles = 0
 
 
@@ -176,12 +176,15 @@ def pack_lora(groups: Sequence, table: Optional[_JobTable] = None) -> None:
     key = (tuple((j.w_down, j.w_up, j.A, j.BlT, j.alpha) for j in jobs) + tuple((j.w_down, j.wt) for j in cjobs)
            + tuple((j.w_host, j.W, j.o0, j.nblocks, tuple(j.w_down), tuple(j.alpha)) for j in mjobs))
     if table.key != key:
-        table.mdev, table.mn, table.mtiles = None, 0, 0
+        table.mdev, table.mn, table.mtiles, table.mmap = None, 0, 0, None
         if mjobs:
-            tiles = 0
-            for j in mjobs:
+            tiles, tmap = 0, []
+            for i, j in enumerate(mjobs):
                 j.tile0 = tiles
-                tiles += ((j.out_dim + 63) // 64) * ((j.in_dim + 63) // 64)
+                n = ((j.out_dim + 63) // 64) * ((j.in_dim + 63) // 64)
+                tmap += [i] * n
+                tiles += n
+            table.mmap = torch.tensor(tmap, dtype=torch.int32).cuda()
             marr = (_lib.LoraMergeJob * len(mjobs))(*mjobs)
             table.mdev = torch.frombuffer(bytearray(bytes(marr)), dtype=torch.uint8).cuda()
             table.mn, table.mtiles = len(mjobs), tiles
@@ -194,7 +197,7 @@ def pack_lora(groups: Sequence, table: Optional[_JobTable] = None) -> None:
         table.key, table.n, table.cn = key, len(jobs), len(cjobs)
     _lib.call("hcp_lora_pack", table.dev.data_ptr(), table.n, _lib.stream_ptr())
     if table.mdev is not None:
-        _lib.call("hcp_lora_merge", table.mdev.data_ptr(), table.mn, table.mtiles, _lib.stream_ptr())
+        _lib.call("hcp_lora_merge", table.mdev.data_ptr(), table.mn, table.mtiles, table.mmap.data_ptr(), _lib.stream_ptr())
     if table.cdev is not None:
         _lib.call("hcp_lora_pack_conv", table.cdev.data_ptr(), table.cn, _lib.stream_ptr())
 

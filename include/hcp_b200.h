@@ -75,6 +75,12 @@ typedef struct hcp_gemm_args {
                                             * (weight streaming at small M reads whole DRAM pages); needs k[s] % 64 == 0 */
     float* workspace;                      /* optional split-K scratch (see hcp_splitk_workspace_bytes); NULL = never split */
     size_t workspace_bytes;
+    /* Second output: columns [n_main, N) of the product go, raw (no bias / rowbias / residual), to out2[row*ldo2 + col - n_main].
+     * This is how the rank-r LoRA products ride the layer's own GEMM: the weight operand carries W_down (forward: T = x W_down^T) or
+     * alpha*W_up^T (dgrad: U = dY alpha W_up) as rows n_main.. of b[].  out2 == NULL: single output.  n_main, ldo2 multiples of 8. */
+    void* out2;
+    int64_t ldo2;
+    int64_t n_main;
 } hcp_gemm_args;
 
 int hcp_gemm_bf16(const hcp_gemm_args* args, hcp_stream_t stream);
@@ -255,7 +261,7 @@ int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp_stream_t s
  * LinearLayer.forward (reference lora_base_patch.py:21-35,61-62, lora_layers_patch.py:44-57), summed in fp32 and rounded once.
  * Written as W [out_tot, in_dim] rows [o0, o0+out_dim) (forward B operand) and WT [in_dim, out_tot] (dgrad B operand; may be NULL).
  * The forward and the input gradient of the layer are then plain GEMMs.  Requirements: in_dim, out_dim, o0, out_tot multiples of
- * 4; at most 4 stacked blocks whose ranks sum to <= 64.  tile0 = number of 64x64 tiles of the jobs before this one
+ * 8; at most 4 stacked blocks whose ranks sum to <= 64.  tile0 = number of 64x64 tiles of the jobs before this one
  * (ceil(out_dim/64) * ceil(in_dim/64) each); total_tiles = their sum. */
 typedef struct hcp_lora_merge_job {
     const float* w_host;     /* fp32 [out_dim, in_dim] */
@@ -269,7 +275,9 @@ typedef struct hcp_lora_merge_job {
     void* W;
     void* WT;
 } hcp_lora_merge_job;
-int hcp_lora_merge(const hcp_lora_merge_job* jobs_device, int64_t njobs, int64_t total_tiles, hcp_stream_t stream);
+/* tile_job_device: optional int32 [total_tiles] table, tile index -> job index (NULL: the kernel searches the job table itself). */
+int hcp_lora_merge(const hcp_lora_merge_job* jobs_device, int64_t njobs, int64_t total_tiles, const int32_t* tile_job_device,
+                   hcp_stream_t stream);
 /* Conv2d LoRA down-projection W_down fp32 [rank, Cin, 3, 3] -> the two bf16 operands the 3x3 kernels take:
  *   wt [R, 3, 3, Cin]  forward weights of T = conv3x3(x, W_down) (rows c0 .. c0+rank of the group's R-row matrix)
  *   wd [Cin, 3, 3, R]  dgrad arrangement of the same taps (flipped for stride 1, as-is for the stride-2 phase kernels)

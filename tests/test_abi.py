@@ -27,7 +27,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_struct_sizes_match_the_header():
     # the ctypes mirrors must have the C layout: spot-check through sizes computed by hand from the header
-    assert ctypes.sizeof(_lib.GemmArgs) == 8 + 3 * 8 * 6 + 2 * 8 + 4 * 8 + 2 * 8 + 2 * 8 + 8 + 16
+    assert ctypes.sizeof(_lib.GemmArgs) == 8 + 3 * 8 * 6 + 2 * 8 + 4 * 8 + 2 * 8 + 2 * 8 + 8 + 16 + 3 * 8
     assert ctypes.sizeof(_lib.LoraJob) == 8 * 2 + 4 * 7 + 4 + 8 * 4
     assert ctypes.sizeof(_lib.ConvArgs) == 2 * 8 + 5 * 8 + 8 + 5 * 8 + 16 + 4 * 8 + 8        # + w_tiled (int32, padded)
     assert ctypes.sizeof(_lib.LoraMergeJob) == 8 + 4 * 8 * 2 + 4 * 4 * 2 + 6 * 4 + 2 * 4 + 2 * 8
