@@ -856,6 +856,110 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
         };
         float lse_nx = (i0 * 128 + row < p.Lq) ? p.lse[stat_base + i0 * 128 + row] : 0.f;   // software-prefetched one q tile ahead
         float dlt_nx = (i0 * 128 + row < p.Lq) ? p.delta[stat_base + i0 * 128 + row] : 0.f;
+        // ---- lean loop: full kv tiles without a key bias on the register-resident schedule (every self-attention of the UNet).
+        // The general loop below carries the masking / bias code inside its unrolled bodies and recomputes the swizzled store
+        // addresses and the accumulator pointers per tile: ~700 instructions per thread and q tile for 32 score elements, which
+        // made the 16 softmax warps -- not the tensor pipe or the MUFU -- the limit (2 800 issue cycles per tile against 960 of
+        // tcgen05 work and 1 024 of ex2).  Here everything that does not depend on the tile is hoisted: shared-space store
+        // addresses, TMEM addresses, the fp32 dQ accumulator pointers of this thread's 16-column chunks.
+        const bool lean = p.early_sdp && !special && p.dq_direct == nullptr;
+        if (lean) {
+            const int c = part;
+            const uint32_t sp_a = smem_u32(sP) + (c >> 1) * TILE_BYTES, sds_a = smem_u32(sdS) + (c >> 1) * TILE_BYTES;
+            uint32_t soff[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) soff[g] = sw128_offset(row, (c & 1) * 4 + g);
+            const float sl2 = p.scale_log2, sc = p.scale;
+            const uint32_t ts_c = tS + lb + c * 32, tdp_c = tdP + lb + c * 32;
+            const int nch = p.ncols_out / 16;
+            const int64_t lq4 = (int64_t)p.Lq * 4;
+            // fp32 dQ accumulator [B, H, d/4, Lq, 4]: slot of (first 4-column group of the launch, this thread's row of tile 0)
+            float* dq_row = p.dq_acc + ((((int64_t)b * p.H + h) * (p.dq_ld / 4) + p.col0 / 4) * p.Lq + (i0 * 128 + row)) * 4;
+            const int dvalid = p.d - p.col0;                  // valid output columns of this launch
+            auto drain = [&](float* dst, bool ok) {
+                for (int cc = part; cc < nch; cc += kBwdParts) {
+                    uint32_t o[16];
+                    tmem_ld16(tdQ + lb + cc * 16, o);
+                    tmem_wait_ld();
+                    if (ok) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            if (cc * 16 + g * 4 < dvalid)
+                                red_add_v4(dst + (int64_t)(cc * 4 + g) * lq4, __uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]),
+                                           __uint_as_float(o[g * 4 + 2]), __uint_as_float(o[g * 4 + 3]));
+                    }
+                }
+            };
+            for (int i = 0; i < nq; ++i) {
+                const int qrow = (i0 + i) * 128 + row;
+                const bool qok = qrow < p.Lq;
+                // rows past Lq: Q / dO rows are TMA zero fill, so S = dP = 0 there and a -inf offset makes every P (and dS) exactly 0
+                const float neg_lse2 = qok ? -lse_nx * kLog2e : -INFINITY;
+                const float neg_dlt_s = -dlt_nx * sc;
+                if (i + 1 < nq) {
+                    const int qn = qrow + 128;
+                    lse_nx = (qn < p.Lq) ? p.lse[stat_base + qn] : 0.f;
+                    dlt_nx = (qn < p.Lq) ? p.delta[stat_base + qn] : 0.f;
+                }
+                mbar_wait(sdp_full, i & 1);
+                tc_fence_after();
+                uint32_t pk[16];
+                {
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(ts_c, v0);
+                    tmem_ld16(ts_c + 16, v1);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(sdp_free);                      // S columns free for Q K^T of the next tile
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        pk[e >> 1] = pack_bf16x2(fast_exp2(fmaf(__uint_as_float(v0[e]), sl2, neg_lse2)),
+                                                 fast_exp2(fmaf(__uint_as_float(v0[e + 1]), sl2, neg_lse2)));
+                        pk[8 + (e >> 1)] = pack_bf16x2(fast_exp2(fmaf(__uint_as_float(v1[e]), sl2, neg_lse2)),
+                                                       fast_exp2(fmaf(__uint_as_float(v1[e + 1]), sl2, neg_lse2)));
+                    }
+                }
+                if (i > 0) {
+                    mbar_wait(dq_full, (i - 1) & 1);            // dK/dQ of the previous tile have finished reading sP / sdS
+                    tc_fence_after();
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) sts128(sp_a + soff[g], make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
+                fence_proxy_async_smem();
+                mbar_arrive(p_ready);
+                {
+                    uint32_t w0[16], w1[16];
+                    tmem_ld16(tdp_c, w0);
+                    tmem_ld16(tdp_c + 16, w1);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(dp_free);
+                    // dS = P (dP - delta) scale as a packed bf16x2 product with the bf16-rounded P the tensor pipe sees in dV
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        pk[e >> 1] = mul_bf16x2(pk[e >> 1], pack_bf16x2(fmaf(__uint_as_float(w0[e]), sc, neg_dlt_s),
+                                                                        fmaf(__uint_as_float(w0[e + 1]), sc, neg_dlt_s)));
+                        pk[8 + (e >> 1)] = mul_bf16x2(pk[8 + (e >> 1)], pack_bf16x2(fmaf(__uint_as_float(w1[e]), sc, neg_dlt_s),
+                                                                                    fmaf(__uint_as_float(w1[e + 1]), sc, neg_dlt_s)));
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) sts128(sds_a + soff[g], make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(ds_ready);
+                if (i > 0) {
+                    // dQ of the PREVIOUS tile: its MMAs retired long ago (waited above), so this never blocks, and the tensor pipe is
+                    // meanwhile busy with dV_i, S/dP_{i+1}, dK_i
+                    drain(dq_row + (int64_t)(i - 1) * 512, qrow - 128 < p.Lq);
+                    tc_fence_before();
+                    mbar_arrive(dq_read);
+                }
+            }
+            mbar_wait(dq_full, (nq - 1) & 1);
+            tc_fence_after();
+            drain(dq_row + (int64_t)(nq - 1) * 512, (i0 + nq - 1) * 128 + row < p.Lq);
+        } else {
         for (int i = 0; i < nq; ++i) {
             const int qrow = (i0 + i) * 128 + row;
             const bool qok = qrow < p.Lq;
@@ -1018,6 +1122,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
             tc_fence_after();
             drain_dq((i0 + nq - 1) * 128 + row);
         }
+        }   // !lean
         // ---- dK, dV of this kv tile: thread == kv row
         mbar_wait(acc_full, 0);
         tc_fence_after();
