@@ -138,6 +138,17 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* m, ui
         : "memory");
 }
 
+// TMA store (tile mode, shared::cta -> global), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src_u32_holder, uint32_t smem_addr, int c0, int c1) {
+    (void)smem_src_u32_holder;
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_addr), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory sources (the buffers may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation
 // ---------------------------------------------------------------------------------------------

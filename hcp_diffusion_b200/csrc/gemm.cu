@@ -41,6 +41,7 @@ struct TapEntry {
 struct alignas(64) GemmKParams {
     CUtensorMap tmA[HCP_GEMM_MAX_SEG];
     CUtensorMap tmB[HCP_GEMM_MAX_SEG];
+    CUtensorMap tmOut, tmOut2;         // [M, n_main] / [M, N - n_main] bf16 outputs, box 16 columns x 128 rows, no swizzle (tma_store)
     int32_t nkb[HCP_GEMM_MAX_SEG];     // 64-wide k-blocks per segment (conv: per tap)
     int32_t klast[HCP_GEMM_MAX_SEG];   // 16-wide k-steps issued in the last k-block of the segment (1..4)
     int32_t nseg;
@@ -69,6 +70,7 @@ struct alignas(64) GemmKParams {
     __nv_bfloat16* out2;
     int64_t ldo2;
     int32_t n_main;
+    int32_t tma_store;                 // 1: the rows of every tile are consecutive rows of `out`: parts leave through TMA stores
     // split-K: CTA (x, y) reduces the k-blocks [y*kb_per_split, (y+1)*kb_per_split) and stores raw fp32 partials
     int32_t splits, kb_per_split;
     int32_t epi_batch;                 // epilogue schedule (see the epilogue)
@@ -248,6 +250,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             tma_prefetch_desc(&p.tmA[s]);
             tma_prefetch_desc(&p.tmB[s]);
         }
+        if (p.tma_store) {
+            tma_prefetch_desc(&p.tmOut);
+            if (p.out2) tma_prefetch_desc(&p.tmOut2);
+        }
     }
     if constexpr (PAIR) {            // the peer's barriers must be initialised before anything signals them
         cluster_arrive();
@@ -275,6 +281,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     __nv_bfloat16* const pout2 = p.out2;
     const int64_t pldo2 = p.ldo2;
     const int n_main = p.n_main;
+    const bool tstore = staged && p.tma_store != 0;
     float* const pws = p.ws;
     long long* const ptrace = p.trace;
     pdl_trigger();
@@ -432,6 +439,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         const bool has_bias = staged && pbias != nullptr, has_res = staged && pres != nullptr;
         const float* const rowbias = staged ? prowbias : nullptr;
         const int64_t rowbias_ld = prowbias_ld;
+        // TMA-store layout of the staging buffer: one dense [128 rows x 32 B] box per 16-column chunk (the padded row layout is
+        // kept for the manual store loop).  `pending`: a TMA store of the previous part may still be reading the buffer.
+        auto unit_addr = [&](int rr, int cu) -> uint32_t {
+            return tstore ? stg + (cu >> 1) * 4096 + rr * 32 + (cu & 1) * 16 : stg + rr * Cfg::STG_PITCH + cu * 16;
+        };
+        bool pending = false;
+        auto staging_acquire = [&]() {
+            if (pending) {
+                if (lane == 0) bulk_wait_read0();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                pending = false;
+            }
+        };
         int item = 0;
         for (int w = worker; w < total_work; w += nworkers, ++item) {
             const int split = w / tiles_mn, mn = w % tiles_mn;
@@ -477,10 +497,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                             if (g >= 0 && col < n_main) rbuf[it] = *reinterpret_cast<const uint4*>(pres + g * pldr + col);
                         }
                     }
+                    staging_acquire();
 #pragma unroll
                     for (int it = 0; it < NRES; ++it) {
                         const int u = et + it * kGemmEpiThreads;
-                        if (u < BLOCK_M * UNITS) sts128(stg + (u / UNITS) * Cfg::STG_PITCH + (u % UNITS) * 16, rbuf[it]);
+                        if (u < BLOCK_M * UNITS) sts128(unit_addr(u / UNITS, u % UNITS), rbuf[it]);
                     }
                 }
                 if (has_res || has_bias || nc0 == 0) asm volatile("bar.sync 1, 256;" ::: "memory");      // residual / bias / row table staged
@@ -512,6 +533,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                     }
                 }
                 if (staged) {
+                    staging_acquire();
                     // bias + per-image row bias + residual -> bf16 -> this thread's row of the staging buffer; no branches: columns >= N
                     // carry zeros (TMA zero fill, zeroed bias / residual slots) and are masked by the store loop
                     const float* rb = (rowbias && row_ok) ? rowbias + (int64_t)group * rowbias_ld + n0 + nc0 : nullptr;
@@ -535,7 +557,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                                     f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                                     f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                                 }
-                                const uint32_t slot = my_stg + (c * 2 + g) * 16;
+                                const uint32_t slot = unit_addr(r, c * 2 + g);
                                 if (has_res) {
                                     const uint4 rv = lds128(slot);
                                     float2 t;
@@ -549,6 +571,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                         }
                     }
                     if (dbg) trc[13] = clock64();
+                    if (tstore) {
+                        // the part leaves through the TMA unit: one box store per 16-column chunk (rows / columns beyond the tensor are
+                        // clipped by the map), issued by one thread; the buffer is re-acquired lazily (staging_acquire)
+                        fence_proxy_async_smem();
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (dbg) trc[14] = clock64();
+                        if (lane == 0) {                                            // one issuing lane per epilogue warp: 8 short streams
+                            const int row0 = (int)lds_b64(srow);                    // row of `out` behind tile row 0
+#pragma unroll 1
+                            for (int c = warp - 2; c < CH16; c += kGemmEpiThreads / 32) {
+                                const int col = n0 + nc0 + c * 16;
+                                if (col >= N) break;
+                                if (col < n_main) tma_store_2d(&p.tmOut, nullptr, stg + c * 4096, col, row0);
+                                else tma_store_2d(&p.tmOut2, nullptr, stg + c * 4096, col - n_main, row0);
+                            }
+                            bulk_commit_group();
+                        }
+                        pending = true;
+                        if (dbg) trc[15] = clock64();
+                        continue;
+                    }
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     if (dbg) trc[14] = clock64();
                     if (n0 + nc0 + EBN <= n_main) {                                   // (uniform) the usual case: one output
@@ -601,6 +644,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                 }
             }   // part
         }
+        if (pending && lane == 0) bulk_wait_read0();    // the last stores have left shared memory before the CTA may exit
     }
 
     if (trc && threadIdx.x == 64) trc[6] = clock64();
@@ -730,9 +774,18 @@ __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __gri
     // flat grid over (problem, column chunk, row split)
     int bid = blockIdx.x, z = 0;
     if (p.nprob == 2 && bid >= p.prob[0].col_chunks * p.prob[0].splits) { bid -= p.prob[0].col_chunks * p.prob[0].splits; z = 1; }
-    const LGProblem& q = p.prob[z];
-    const CUtensorMap* tmX = &p.tmX[z];
-    const CUtensorMap* tmS = &p.tmS[z];
+    // This CTA's problem descriptor goes to shared memory once: `p.prob[z].blk[b]` with run-time z and b is a chain of dynamically
+    // indexed constant-bank loads (~200 cycles each, 119 of them in the r01 SASS of the reduction epilogue).
+    __shared__ LGProblem sq;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(z ? &p.prob[1] : &p.prob[0]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sq);
+        for (int i = threadIdx.x; i < (int)(sizeof(LGProblem) / 4); i += kLgThreads) dst[i] = z ? reinterpret_cast<const uint32_t*>(&p.prob[1])[i] : src[i];
+    }
+    __syncthreads();
+    const LGProblem& q = sq;
+    const CUtensorMap* tmX = z ? &p.tmX[1] : &p.tmX[0];
+    const CUtensorMap* tmS = z ? &p.tmS[1] : &p.tmS[0];
     const int ncol0 = q.n_begin + (bid % q.col_chunks) * 128;
     const int total_tiles = (p.M + 127) / 128;
     const int t0 = (bid / q.col_chunks) * q.tiles_per_cta;
@@ -940,6 +993,26 @@ static int dispatch_gemm(int bn, bool cta_pair, GemmKParams& kp, int m_tiles, cu
     }
 }
 
+// Output tensor maps of the TMA-store epilogue: [rows, cols] bf16 with row pitch ld, box 16 columns x 128 rows, no swizzle.
+static int make_out_maps(GemmKParams& kp) {
+    static const bool off = [] { const char* e = getenv("HCP_GEMM_TMA_STORE"); return e && atoi(e) == 0; }();
+    kp.tma_store = 0;
+    if (off || (kp.n_main % 16) != 0 || (kp.ldo % 8) != 0 || (kp.out2 && (kp.ldo2 % 8) != 0)) return HCP_OK;
+    uint64_t dims[2] = {(uint64_t)kp.n_main, (uint64_t)kp.M};
+    uint64_t strides[1] = {(uint64_t)kp.ldo * 2};
+    uint32_t box[2] = {16, BLOCK_M};
+    int rc = make_tmap_nd(&kp.tmOut, kp.out, 2, dims, strides, box, false);
+    if (rc) return rc;
+    if (kp.out2) {
+        uint64_t dims2[2] = {(uint64_t)(kp.N - kp.n_main), (uint64_t)kp.M};
+        uint64_t strides2[1] = {(uint64_t)kp.ldo2 * 2};
+        rc = make_tmap_nd(&kp.tmOut2, kp.out2, 2, dims2, strides2, box, false);
+        if (rc) return rc;
+    }
+    kp.tma_store = 1;
+    return HCP_OK;
+}
+
 // plain or split-K launch (+ finalize).  `ws` may be NULL / too small: then the launch is not split.
 static int run_gemm(int bn, bool cta_pair, int pair_splits, GemmKParams& kp, int m_tiles, int64_t total_kb, float* ws, size_t ws_bytes,
                     bool allow_split, cudaStream_t stream) {
@@ -993,6 +1066,7 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     if (a->residual && (a->ldr % 8) != 0) return set_error(HCP_ERR_INVALID, "gemm: ldr");
     GemmKParams kp;
     memset(&kp, 0, sizeof(kp));
+    int rc0 = HCP_OK;
     int64_t kb_all = 0;
     for (int s = 0; s < a->nseg; ++s) kb_all += (a->k[s] + BLOCK_K - 1) / BLOCK_K;
     const PairPlan pp = plan_pair(a->N, (a->M + BLOCK_M - 1) / BLOCK_M, kb_all, a->workspace != nullptr);
@@ -1041,6 +1115,7 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
         kp.ldo2 = a->ldo2;
         kp.n_main = (int)a->n_main;
     }
+    if ((rc0 = make_out_maps(kp))) return rc0;
     const int m_tiles = (int)((a->M + BLOCK_M - 1) / BLOCK_M);
     int64_t total_kb = 0;
     for (int s = 0; s < a->nseg; ++s) total_kb += kp.nkb[s];
@@ -1124,6 +1199,9 @@ extern "C" int hcp_conv3x3_bf16(const hcp_conv3x3_args* a, hcp_stream_t stream_)
     }
     const int b_box_rows = pair_bn ? (pair_bn > 256 ? pair_bn / 4 : pair_bn / 2) : bn;
     int rc;
+    // the 128 pixels of a forward-mode tile are consecutive rows of `out` (full-width rows of one or several images, or 128 pixels of
+    // one row): its parts can leave through TMA stores; the strided phase launches of the stride-2 dgrad (mode 1) store by hand
+    if (a->mode == 0 && (rc = make_out_maps(kp))) return rc;
     if (a->w_tiled) {          // k-block-major weights [9*Cin/64][Cout][64]
         uint64_t dims[3] = {BLOCK_K, (uint64_t)a->Cout, (uint64_t)(9 * Cin / BLOCK_K)};
         uint64_t strides[2] = {BLOCK_K * 2, (uint64_t)a->Cout * BLOCK_K * 2};
