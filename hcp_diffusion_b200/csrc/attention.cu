@@ -601,6 +601,7 @@ struct alignas(64) AttnBwdParams {
     float* dkv_acc;          // [B,H,Lkv,2,dq_ld] fp32 partial dK/dV when qsplit > 1, else nullptr
     __nv_bfloat16 *dK, *dV;
     int64_t lddk, lddv;
+    long long* trace;        // bring-up only (hcp_debug_attn_trace): cycle sums of the lean loop's phases, CTA 0 only
 };
 
 __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
@@ -890,6 +891,10 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                     }
                 }
             };
+            const bool trc = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+            long long t_wait_sdp = 0, t_exp = 0, t_wait_dq = 0, t_pstore = 0, t_ds = 0, t_dsstore = 0, t_drain = 0, tk = trc ? clock64() : 0;
+            const long long t_begin = tk;
+#define HCP_LAP(acc) do { if (trc) { const long long tn_ = clock64(); acc += tn_ - tk; tk = tn_; } } while (0)
             for (int i = 0; i < nq; ++i) {
                 const int qrow = (i0 + i) * 128 + row;
                 const bool qok = qrow < p.Lq;
@@ -903,6 +908,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                 }
                 mbar_wait(sdp_full, i & 1);
                 tc_fence_after();
+                HCP_LAP(t_wait_sdp);
                 uint32_t pk[16];
                 {
                     uint32_t v0[16], v1[16];
@@ -919,14 +925,17 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                                                        fast_exp2(fmaf(__uint_as_float(v1[e + 1]), sl2, neg_lse2)));
                     }
                 }
+                HCP_LAP(t_exp);
                 if (i > 0) {
                     mbar_wait(dq_full, (i - 1) & 1);            // dK/dQ of the previous tile have finished reading sP / sdS
                     tc_fence_after();
                 }
+                HCP_LAP(t_wait_dq);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) sts128(sp_a + soff[g], make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
                 fence_proxy_async_smem();
                 mbar_arrive(p_ready);
+                HCP_LAP(t_pstore);
                 {
                     uint32_t w0[16], w1[16];
                     tmem_ld16(tdp_c, w0);
@@ -943,11 +952,13 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                                                                                     fmaf(__uint_as_float(w1[e + 1]), sc, neg_dlt_s)));
                     }
                 }
+                HCP_LAP(t_ds);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) sts128(sds_a + soff[g], make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
                 tc_fence_before();
                 fence_proxy_async_smem();
                 mbar_arrive(ds_ready);
+                HCP_LAP(t_dsstore);
                 if (i > 0) {
                     // dQ of the PREVIOUS tile: its MMAs retired long ago (waited above), so this never blocks, and the tensor pipe is
                     // meanwhile busy with dV_i, S/dP_{i+1}, dK_i
@@ -955,6 +966,13 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                     tc_fence_before();
                     mbar_arrive(dq_read);
                 }
+                HCP_LAP(t_drain);
+            }
+#undef HCP_LAP
+            if (trc) {
+                long long* o = p.trace;
+                o[0] = clock64() - t_begin; o[1] = nq; o[2] = t_wait_sdp; o[3] = t_exp; o[4] = t_wait_dq; o[5] = t_pstore; o[6] = t_ds;
+                o[7] = t_dsstore; o[8] = t_drain;
             }
             mbar_wait(dq_full, (nq - 1) & 1);
             tc_fence_after();
@@ -1342,6 +1360,11 @@ static int plan_qsplit(int64_t B, int64_t H, int64_t Lq, int64_t Lkv) {
     return (int)((nq + per - 1) / per);                 // every split owns at least one query tile
 }
 
+static long long* g_attn_trace = nullptr;
+// bring-up hook (not in include/hcp_b200.h): the lean loop of CTA (0,0,0) of every later backward launch writes 9 int64 (total cycles,
+// q tiles, then the cycle sums of: wait S/dP, exp, wait dK/dQ of the previous tile, P store, dS arithmetic, dS store, dQ drain)
+extern "C" int hcp_debug_attn_trace(long long* buf) { g_attn_trace = buf; return HCP_OK; }
+
 extern "C" size_t hcp_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq, int64_t Lkv, int64_t d) {
     const int64_t dq_ld = (d + 3) / 4 * 4;
     size_t n = (size_t)((B * H * Lq + 3) / 4 * 4) + (size_t)(B * H * Lq * dq_ld);   // delta (padded to 16 bytes) + dQ accumulator
@@ -1396,6 +1419,7 @@ extern "C" int hcp_attn_bwd_bf16(const hcp_attn_bwd_args* a, hcp_stream_t stream
     p.dkv_acc = dkv_acc;
     p.dK = (__nv_bfloat16*)a->dk; p.lddk = a->lddk;
     p.dV = (__nv_bfloat16*)a->dv; p.lddv = a->lddv;
+    p.trace = g_attn_trace;
     p.q_stages = (p.nbox == 1) ? 2 : 1;
     p.share_pds = (p.nbox >= 3) ? 1 : 0;
     p.early_sdp = (p.q_stages == 2 && 256 + 3 * p.dn <= 512 && getenv("HCP_ATTN_BWD_NO_EARLY") == nullptr) ? 1 : 0;
