@@ -182,11 +182,15 @@ def time_kernel(fn, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
-def ncu_dram_traffic(summary="profiles/r01_ncu_attn_bwd_v23.summary.csv"):
+def ncu_dram_traffic(summary=None):
     """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed `ncu --set full` summary of the same
     kernel at the same shape (attention backward, B=4 H=8 L=4096 d=40).  None when the file is absent."""
     import csv
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), summary)
+    here = os.path.dirname(os.path.abspath(__file__))
+    if summary is None:          # the newest committed capture of the kernel
+        summary = next((n for n in ("profiles/r02_ncu_attn_bwd.summary.csv", "profiles/r01_ncu_attn_bwd_v23.summary.csv")
+                        if os.path.exists(os.path.join(here, n))), "profiles/r01_ncu_attn_bwd_v23.summary.csv")
+    path = os.path.join(here, summary)
     try:
         rows = list(csv.reader(open(path)))
         hdr, unit, val = rows[0], rows[1], rows[2]
