@@ -277,7 +277,9 @@ def run_product_arm(args, rank, world, local_rank):
         # BASELINE configs[2]: DreamBooth full fine-tune, no LoRA, bs 16 / GPU (reference cfgs/train/examples/DreamBooth.yaml:6-10)
         groups, lora = make_hcpdiff(unet, [{"lr": 1e-6, "layers": [""]}], None)
         B, f_step, metric = 16, 3 * F_FWD, "full fine-tune images/sec SD1.5 512px"
-        use_graph = world == 1            # N > 1: eager launches so that the 3.4 GB gradient all-reduce is bucketed under the backward pass
+        # N > 1: eager launches so that the 3.4 GB gradient all-reduce is bucketed under the backward pass (HCP_BENCH_EAGER=1 forces the
+        # same mode on one GPU: the baseline the exposed all-reduce time of N > 1 is read against)
+        use_graph = world == 1 and os.environ.get("HCP_BENCH_EAGER", "0") != "1"
         what = "SD1.5 UNet full fine-tune (every parameter, %d params), bs=16/GPU"
     else:
         groups, lora = make_hcpdiff(unet, None, [{"lr": 1e-4, "rank": LORA_RANK, "alpha": 1.0, "dropout": 0.0, "layers": [r"re:.*\.attn.?$"]}])

@@ -774,16 +774,11 @@ __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __gri
     // flat grid over (problem, column chunk, row split)
     int bid = blockIdx.x, z = 0;
     if (p.nprob == 2 && bid >= p.prob[0].col_chunks * p.prob[0].splits) { bid -= p.prob[0].col_chunks * p.prob[0].splits; z = 1; }
-    // This CTA's problem descriptor goes to shared memory once: `p.prob[z].blk[b]` with run-time z and b is a chain of dynamically
-    // indexed constant-bank loads (~200 cycles each, 119 of them in the r01 SASS of the reduction epilogue).
+    // The reduction epilogue walks `p.prob[z].blk[b]` with run-time z and b -- chains of dynamically indexed constant-bank loads
+    // (~200 cycles each, 119 of them in the r01 SASS).  The epilogue warps copy the descriptor to shared memory while the main
+    // loop runs (below); the producer / MMA threads only need the three scalars read here.
     __shared__ LGProblem sq;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(z ? &p.prob[1] : &p.prob[0]);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&sq);
-        for (int i = threadIdx.x; i < (int)(sizeof(LGProblem) / 4); i += kLgThreads) dst[i] = z ? reinterpret_cast<const uint32_t*>(&p.prob[1])[i] : src[i];
-    }
-    __syncthreads();
-    const LGProblem& q = sq;
+    const LGProblem& q = z ? p.prob[1] : p.prob[0];
     const CUtensorMap* tmX = z ? &p.tmX[1] : &p.tmX[0];
     const CUtensorMap* tmS = z ? &p.tmS[1] : &p.tmS[0];
     const int ncol0 = q.n_begin + (bid % q.col_chunks) * 128;
@@ -855,6 +850,13 @@ __global__ void __launch_bounds__(kLgThreads, 1) lora_grad_tc_kernel(const __gri
             umma_commit(tmem_full_bar);
         }
     } else {
+        {   // descriptor -> shared memory by the 128 epilogue threads, hidden behind the main loop
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&q);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(&sq);
+            for (int i = threadIdx.x - 64; i < (int)(sizeof(LGProblem) / 4); i += 128) dst[i] = src[i];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        const LGProblem& q = sq;                                         // (shadows the constant-bank reference)
         const int quarter = warp & 3;
         const int n = ncol0 + quarter * 32 + lane;                       // this thread's column of X
         mbar_wait(tmem_full_bar, 0);

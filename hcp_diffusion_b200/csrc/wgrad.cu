@@ -172,33 +172,47 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 // out[g, c] += scale * sum_{r in group g} x[r, c]      x bf16 [M, ld], groups of rows_per_group rows (bias gradient: one group;
 // time-embedding gradient of a resnet: one group per image)
 // ---------------------------------------------------------------------------------------------
-__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int64_t M, int N, int64_t rows_per_group, int chunk,
-                                   float scale, float* __restrict__ out, int64_t ldo) {
+// block = 8 column vectors (8 bf16 = 16 bytes each: a 64-column slab) x 32 row lanes; four rows in flight per thread
+__device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
+    float2 t;
+    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int64_t M, int N, int64_t rows_per_group,
+                                                          int chunk, float scale, float* __restrict__ out, int64_t ldo) {
     pdl_trigger();
     pdl_wait();
-    // block = 32 column pairs x 8 row lanes; grid.x over 64-column slabs, grid.y over row chunks
-    const int cp = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 64 + cp * 2;
+    const int vx = threadIdx.x & 7, ry = threadIdx.x >> 3;
+    const int c = blockIdx.x * 64 + vx * 8;
     const int64_t r0 = (int64_t)blockIdx.y * chunk;
     const int64_t r1 = min(M, r0 + chunk);
-    __shared__ float2 part[8][32];
+    __shared__ float part[32][65];
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (c < N) {
         // a chunk never straddles a group boundary (host picks chunk | rows_per_group)
-        float2 acc = make_float2(0.f, 0.f);
-        for (int64_t r = r0 + rl; r < r1; r += 8) {
-            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + r * ld + c));
-            acc.x += v.x; acc.y += v.y;
-        }
-        part[rl][cp] = acc;
-    }
-    __syncthreads();
-    if (rl == 0 && c < N) {
-        float2 s = part[0][cp];
+        for (int64_t r = r0 + ry; r < r1; r += 128) {
+            uint4 u[4];
 #pragma unroll
-        for (int i = 1; i < 8; ++i) { s.x += part[i][cp].x; s.y += part[i][cp].y; }
-        float* dst = out + (r0 / rows_per_group) * ldo + c;
-        atomicAdd(dst, s.x * scale);
-        atomicAdd(dst + 1, s.y * scale);
+            for (int j = 0; j < 4; ++j) u[j] = (r + 32 * j < r1) ? *reinterpret_cast<const uint4*>(x + (r + 32 * j) * ld + c) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float f[8];
+                unpack8f(u[j], f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] += f[e];
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part[ry][vx * 8 + e] = acc[e];
+    __syncthreads();
+    if (threadIdx.x < 64 && blockIdx.x * 64 + (int)threadIdx.x < N) {
+        float sum = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) sum += part[i][threadIdx.x];
+        atomicAdd(out + (r0 / rows_per_group) * ldo + blockIdx.x * 64 + threadIdx.x, sum * scale);
     }
 }
 
@@ -206,51 +220,82 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t 
 // GroupNorm / LayerNorm affine gradients:  dgamma[c] += sum dz * xhat,  dbeta[c] += sum dz,
 //   xhat = (x - mean) * rstd,  dz = dy (no activation)  or  dy * silu'(gamma xhat + beta)
 // x = [x1 | x2] concatenated along channels (GroupNorm of the up blocks); stats fp32 [rows_or_groups, 2] = (mean, rstd)
+// Same block shape as the column sums: 8 vectors of 8 channels x 32 row lanes, two rows in flight per thread.  A GroupNorm chunk lies
+// inside one image (host: chunk | rows_per_image), so the statistics of a thread's eight channels are loop constants.
 // ---------------------------------------------------------------------------------------------
-__global__ void norm_affine_grad_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int C1, int C2,
-                                        const __nv_bfloat16* __restrict__ dy, const float* __restrict__ stats, const float* __restrict__ gamma,
-                                        const float* __restrict__ beta, int64_t rows, int64_t rows_per_image, int ch_per_group, int groups,
-                                        int silu, int chunk, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+__global__ void __launch_bounds__(256) norm_affine_grad_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int C1, int C2,
+                                                               const __nv_bfloat16* __restrict__ dy, const float* __restrict__ stats,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows,
+                                                               int64_t rows_per_image, int ch_per_group, int groups, int silu, int chunk,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
     pdl_trigger();
     pdl_wait();
     const int C = C1 + C2;
-    const int cp = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 64 + cp * 2;
+    const int vx = threadIdx.x & 7, ry = threadIdx.x >> 3;
+    const int c = blockIdx.x * 64 + vx * 8;
     const int64_t r0 = (int64_t)blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
-    __shared__ float4 part[8][32];
+    __shared__ float part[32][2 * 64 + 1];
+    float ag[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ab[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (c < C) {
-        const float g0 = gamma[c], g1 = gamma[c + 1], b0 = beta[c], b1 = beta[c + 1];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);      // dgamma0, dgamma1, dbeta0, dbeta1
-        for (int64_t r = r0 + rl; r < r1; r += 8) {
-            const __nv_bfloat16* xp = (c < C1) ? x1 + r * C1 + c : x2 + r * C2 + (c - C1);
-            const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xp));
-            const float2 dv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + r * C + c));
-            float m0, rs0, m1, rs1;
-            if (groups > 0) {          // GroupNorm: statistics per (image, group); the two channels of a pair share a group (ch_per_group even)
-                const int64_t si = ((r / rows_per_image) * groups + c / ch_per_group) * 2;
-                m0 = m1 = stats[si]; rs0 = rs1 = stats[si + 1];
-            } else {                   // LayerNorm: statistics per row
-                m0 = m1 = stats[r * 2]; rs0 = rs1 = stats[r * 2 + 1];
-            }
-            const float h0 = (xv.x - m0) * rs0, h1 = (xv.y - m1) * rs1;
-            float d0 = dv.x, d1 = dv.y;
-            if (silu) {
-                const float z0 = g0 * h0 + b0, z1 = g1 * h1 + b1;
-                const float s0 = 1.f / (1.f + __expf(-z0)), s1 = 1.f / (1.f + __expf(-z1));
-                d0 *= s0 * (1.f + z0 * (1.f - s0));
-                d1 *= s1 * (1.f + z1 * (1.f - s1));
-            }
-            acc.x += d0 * h0; acc.y += d1 * h1; acc.z += d0; acc.w += d1;
-        }
-        part[rl][cp] = acc;
-    }
-    __syncthreads();
-    if (rl == 0 && c < C) {
-        float4 s = part[0][cp];
+        float g[8], bt[8], mean[8], rstd[8];
 #pragma unroll
-        for (int i = 1; i < 8; ++i) { s.x += part[i][cp].x; s.y += part[i][cp].y; s.z += part[i][cp].z; s.w += part[i][cp].w; }
-        atomicAdd(dgamma + c, s.x); atomicAdd(dgamma + c + 1, s.y);
-        atomicAdd(dbeta + c, s.z); atomicAdd(dbeta + c + 1, s.w);
+        for (int e = 0; e < 8; ++e) {
+            const int ce = min(c + e, C - 1);
+            g[e] = gamma[ce]; bt[e] = beta[ce];
+            mean[e] = 0.f; rstd[e] = 0.f;
+            if (groups > 0) {
+                const int64_t si = ((r0 / rows_per_image) * groups + ce / ch_per_group) * 2;
+                mean[e] = stats[si]; rstd[e] = stats[si + 1];
+            }
+        }
+        const bool first = c < C1;
+        const __nv_bfloat16* xb = first ? x1 + c : x2 + (c - C1);
+        const int64_t xld = first ? C1 : C2;
+        for (int64_t r = r0 + ry; r < r1; r += 64) {
+            uint4 ux[2], ud[2];
+            float lm[2] = {0.f, 0.f}, lr[2] = {0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int64_t rr = r + 32 * j;
+                ux[j] = ud[j] = make_uint4(0u, 0u, 0u, 0u);
+                if (rr < r1) {
+                    ux[j] = *reinterpret_cast<const uint4*>(xb + rr * xld);
+                    ud[j] = *reinterpret_cast<const uint4*>(dy + rr * C + c);
+                    if (groups == 0) { lm[j] = stats[rr * 2]; lr[j] = stats[rr * 2 + 1]; }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float xv[8], dv[8];
+                unpack8f(ux[j], xv);
+                unpack8f(ud[j], dv);             // rows past the chunk: dv = 0 -> no contribution
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float h = (groups > 0) ? (xv[e] - mean[e]) * rstd[e] : (xv[e] - lm[j]) * lr[j];
+                    float d = dv[e];
+                    if (silu) {
+                        const float z = g[e] * h + bt[e];
+                        const float sg = 1.f / (1.f + __expf(-z));
+                        d *= sg * (1.f + z * (1.f - sg));
+                    }
+                    ag[e] += d * h;
+                    ab[e] += d;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { part[ry][vx * 8 + e] = ag[e]; part[ry][64 + vx * 8 + e] = ab[e]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int which = threadIdx.x >> 6, cl = threadIdx.x & 63;
+        const int cc = blockIdx.x * 64 + cl;
+        if (cc < C) {
+            float sum = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) sum += part[i][which * 64 + cl];
+            atomicAdd((which ? dbeta : dgamma) + cc, sum);
+        }
     }
 }
 
@@ -260,16 +305,39 @@ __global__ void norm_affine_grad_kernel(const __nv_bfloat16* __restrict__ x1, co
 //   dW[n, k] += sum_m dy[m, n] x[m, k],  db[n] += sum_m dy[m, n]      (fp32 master gradients)
 // and SiLU forward / backward on fp32 vectors.
 // ---------------------------------------------------------------------------------------------
-__global__ void small_linear_dx_kernel(const float* __restrict__ dy, int64_t ldy, const __nv_bfloat16* __restrict__ w, int M, int N, int K,
-                                       float* __restrict__ dx) {
+// dx: every thread owns one k and a slice of the n range for up to 16 rows at a time: the weight is streamed ONCE (the first version
+// re-read all of W per row: 840 MB for the 22 stacked time_emb_proj layers at batch 16), partial sums leave through atomics
+constexpr int SLDX_ROWS = 16;
+__global__ void __launch_bounds__(128) small_linear_dx_kernel(const float* __restrict__ dy, int64_t ldy, const __nv_bfloat16* __restrict__ w, int M, int N,
+                                                              int K, int n_chunk, float* __restrict__ dx) {
     pdl_trigger();
     pdl_wait();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int m = blockIdx.y;
-    if (k >= K) return;
-    float acc = 0.f;
-    for (int n = 0; n < N; ++n) acc += dy[(int64_t)m * ldy + n] * __bfloat162float(w[(int64_t)n * K + k]);     // coalesced over k
-    dx[(int64_t)m * K + k] = acc;
+    const int n0 = blockIdx.y * n_chunk, n1 = min(N, n0 + n_chunk);
+    const int m0 = blockIdx.z * SLDX_ROWS;
+    const int rows = min(SLDX_ROWS, M - m0);
+    __shared__ float sdy[SLDX_ROWS][128];
+    float acc[SLDX_ROWS];
+#pragma unroll
+    for (int r = 0; r < SLDX_ROWS; ++r) acc[r] = 0.f;
+    for (int nb = n0; nb < n1; nb += 128) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SLDX_ROWS * 128; i += blockDim.x) {
+            const int r = i >> 7, n = nb + (i & 127);
+            sdy[r][i & 127] = (r < rows && n < n1) ? dy[(int64_t)(m0 + r) * ldy + n] : 0.f;
+        }
+        __syncthreads();
+        if (k < K) {
+            const int lim = min(128, n1 - nb);
+            for (int j = 0; j < lim; ++j) {
+                const float wv = __bfloat162float(w[(int64_t)(nb + j) * K + k]);     // coalesced over k
+#pragma unroll
+                for (int r = 0; r < SLDX_ROWS; ++r) acc[r] = fmaf(sdy[r][j], wv, acc[r]);
+            }
+        }
+    }
+    if (k < K)
+        for (int r = 0; r < rows; ++r) atomicAdd(dx + (int64_t)(m0 + r) * K + k, acc[r]);
 }
 __global__ void small_linear_dw_kernel(const float* __restrict__ dy, int64_t ldy, const float* __restrict__ x, int M, int N, int K,
                                        float* __restrict__ dw, float* __restrict__ db) {
@@ -302,38 +370,57 @@ __global__ void silu_f32_kernel(const float* __restrict__ x, const float* __rest
 //   conv_out: dW[co, ci, kh, kw] += sum_{b,y,x} dy[b, co, y, x] * act[b, y+kh-1, x+kw-1, ci]     dy fp32 NCHW, act bf16 NHWC
 // block = one (small-channel index, tap) pair and a chunk of pixels; threads = the wide channel (coalesced bf16 rows)
 // ---------------------------------------------------------------------------------------------
-__global__ void conv_edge_wgrad_kernel(const __nv_bfloat16* __restrict__ wide, const float* __restrict__ narrow, int B, int H, int W,
-                                       int Cw, int Cn, int wide_is_out, int chunk, float* __restrict__ dw, float* __restrict__ db_wide) {
+// One block owns a chunk of WIDE pixels (rows of the bf16 NHWC tensor) and ALL Cn x 9 (narrow channel, tap) pairs: the 36 fp32
+// narrow values that meet each wide pixel are gathered into shared memory once (zero outside the image), then every thread (= wide
+// channel) reads its bf16 value of a pixel once and feeds 36 accumulators.  (The first version gave every (channel, tap) pair its own
+// blocks and re-read the wide tensor 36 times with a division chain per pixel: 3.6 ms per launch at batch 16.)
+//   conv_in  (wide_is_out = 1): wide = dh (output gradient), narrow = latent; input pixel = output pixel + (kh-1, kw-1)
+//   conv_out (wide_is_out = 0): wide = activation (input),  narrow = dy;     output pixel = input pixel - (kh-1, kw-1)
+constexpr int CEW_PX = 128;          // wide pixels per block
+constexpr int CEW_MAX_PAIRS = 36;    // Cn <= 4
+__global__ void __launch_bounds__(320) conv_edge_wgrad_kernel(const __nv_bfloat16* __restrict__ wide, const float* __restrict__ narrow, int B, int H, int W,
+                                                              int Cw, int Cn, int wide_is_out, int chunk, float* __restrict__ dw,
+                                                              float* __restrict__ db_wide) {
     pdl_trigger();
     pdl_wait();
-    // wide: bf16 NHWC [B, H, W, Cw] (conv_in: the output gradient; conv_out: the input activation)
-    // narrow: fp32 NCHW [B, Cn, H, W] (conv_in: the latent; conv_out: the output gradient)
-    // the tap shifts the INPUT side: conv_in -> narrow is the input (shift narrow); conv_out -> wide is the input (shift wide)
-    const int cn = blockIdx.x / 9, tap = blockIdx.x % 9;
-    const int kh = tap / 3, kw = tap % 3;
+    (void)chunk;
+    __shared__ float tbl[CEW_PX][CEW_MAX_PAIRS + 1];
+    const int npairs = Cn * 9;
     const int64_t npx = (int64_t)B * H * W;
-    const int64_t p0 = (int64_t)blockIdx.y * chunk, p1 = min(npx, p0 + chunk);
-    for (int cw = threadIdx.x; cw < Cw; cw += blockDim.x) {
-        float acc = 0.f, bsum = 0.f;
-        for (int64_t px = p0; px < p1; ++px) {
+    const int64_t p0 = (int64_t)blockIdx.x * CEW_PX;
+    const int np = (int)min((int64_t)CEW_PX, npx - p0);
+    const int sgn = wide_is_out ? 1 : -1;
+    for (int i = threadIdx.x; i < CEW_PX * npairs; i += blockDim.x) {
+        const int pl = i / npairs, pr = i % npairs;
+        float v = 0.f;
+        if (pl < np) {
+            const int64_t px = p0 + pl;
             const int xw = (int)(px % W), yh = (int)((px / W) % H), b = (int)(px / ((int64_t)H * W));
-            float wv, nv;
-            if (wide_is_out) {                         // conv_in: out pixel (yh, xw), input pixel shifted
-                const int ih = yh + kh - 1, iw = xw + kw - 1;
-                wv = __bfloat162float(wide[px * Cw + cw]);
-                nv = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? narrow[(((int64_t)b * Cn + cn) * H + ih) * W + iw] : 0.f;
-                if (cn == 0 && tap == 4) bsum += wv;
-            } else {                                   // conv_out: out pixel (yh, xw) of narrow, input pixel of wide shifted
-                const int ih = yh + kh - 1, iw = xw + kw - 1;
-                nv = narrow[(((int64_t)b * Cn + cn) * H + yh) * W + xw];
-                wv = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __bfloat162float(wide[(((int64_t)b * H + ih) * W + iw) * Cw + cw]) : 0.f;
-            }
-            acc += wv * nv;
+            const int cn = pr / 9, tap = pr % 9;
+            const int ih = yh + sgn * (tap / 3 - 1), iw = xw + sgn * (tap % 3 - 1);
+            if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = narrow[(((int64_t)b * Cn + cn) * H + ih) * W + iw];
         }
-        // nn.Conv2d layout [Cout, Cin, 3, 3]
-        float* dst = wide_is_out ? dw + ((int64_t)cw * Cn + cn) * 9 + tap : dw + ((int64_t)cn * Cw + cw) * 9 + tap;
-        atomicAdd(dst, acc);
-        if (wide_is_out && db_wide && cn == 0 && tap == 4) atomicAdd(db_wide + cw, bsum);
+        tbl[pl][pr] = v;
+    }
+    __syncthreads();
+    for (int cw = threadIdx.x; cw < Cw; cw += blockDim.x) {
+        float acc[CEW_MAX_PAIRS];
+#pragma unroll
+        for (int j = 0; j < CEW_MAX_PAIRS; ++j) acc[j] = 0.f;
+        float bsum = 0.f;
+        for (int pl = 0; pl < np; ++pl) {
+            const float wv = __bfloat162float(wide[(p0 + pl) * Cw + cw]);        // coalesced over cw
+            bsum += wv;
+#pragma unroll
+            for (int j = 0; j < CEW_MAX_PAIRS; ++j) acc[j] = fmaf(wv, tbl[pl][j], acc[j]);   // pairs >= npairs: table column unused, acc ignored
+        }
+        for (int j = 0; j < npairs; ++j) {
+            const int cn = j / 9, tap = j % 9;
+            // nn.Conv2d layout [Cout, Cin, 3, 3]
+            float* dst = wide_is_out ? dw + ((int64_t)cw * Cn + cn) * 9 + tap : dw + ((int64_t)cn * Cw + cw) * 9 + tap;
+            atomicAdd(dst, acc[j]);
+        }
+        if (wide_is_out && db_wide) atomicAdd(db_wide + cw, bsum);
     }
 }
 // db[c] += sum over (b, y, x) of a fp32 NCHW tensor (conv_out bias gradient)
@@ -368,32 +455,102 @@ struct RepackJob {
     void* dst1;
     int32_t kind, rows, K, o0, n_tot, flip;
 };
-__global__ void repack_kernel(const RepackJob* __restrict__ jobs) {
+// Tiled: a block walks tiles of its job (blockIdx.y); both destinations are written in runs of consecutive elements.
+//   kind 0 / 3: 64 x 64 tiles of W [rows, K]: rows of dst0 directly, the transposed tile through shared memory
+//   kind 1: 16 output channels x 64 input channels x 9 taps of a 3x3 weight [Cout, Cin, 3, 3]: the 16 x 576 fp32 source rows are read
+//           contiguously; dst0 [co][tap][ci] leaves in 64-element rows, dst1 [ci][tap'][co] in 16-element runs
+// (The element-wise first version scattered 2-byte writes at a stride of n_tot: 11.6 ms for the 859 M parameters of the full UNet.)
+__global__ void __launch_bounds__(256) repack_kernel(const RepackJob* __restrict__ jobs) {
     pdl_trigger();
     pdl_wait();
     const RepackJob jb = jobs[blockIdx.y];
-    const int64_t total = (int64_t)jb.rows * jb.K * (jb.kind == 1 ? 9 : 1);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-        if (jb.kind == 0) {
-            const int r = (int)(i / jb.K), k = (int)(i % jb.K);
-            const __nv_bfloat16 v = __float2bfloat16(jb.src[i]);
-            reinterpret_cast<__nv_bfloat16*>(jb.dst0)[(int64_t)(jb.o0 + r) * jb.K + k] = v;
-            reinterpret_cast<__nv_bfloat16*>(jb.dst1)[(int64_t)k * jb.n_tot + jb.o0 + r] = v;
-        } else if (jb.kind == 1) {
-            // src index = ((co * Cin + ci) * 9 + tap); rows = Cout, K = Cin
-            const int tap = (int)(i % 9);
-            const int ci = (int)((i / 9) % jb.K), co = (int)(i / (9 * (int64_t)jb.K));
-            const __nv_bfloat16 v = __float2bfloat16(jb.src[i]);
-            reinterpret_cast<__nv_bfloat16*>(jb.dst0)[((int64_t)co * 9 + tap) * jb.K + ci] = v;
-            const int tap_d = jb.flip ? 8 - tap : tap;
-            reinterpret_cast<__nv_bfloat16*>(jb.dst1)[((int64_t)ci * 9 + tap_d) * jb.rows + co] = v;
-        } else if (jb.kind == 2) {
+    __shared__ __align__(16) uint8_t sraw[16 * 576 * 4 + 64];
+    if (jb.kind == 2) {
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < jb.rows; i += (int64_t)gridDim.x * blockDim.x)
             reinterpret_cast<float*>(jb.dst0)[jb.o0 + i] = jb.src[i];
-        } else {
-            const int r = (int)(i / jb.K), k = (int)(i % jb.K);
-            reinterpret_cast<__nv_bfloat16*>(jb.dst0)[(int64_t)(jb.o0 + r) * jb.K + k] = __float2bfloat16(jb.src[i]);
+        return;
+    }
+    const int tid = threadIdx.x;
+    if (jb.kind == 0 || jb.kind == 3) {
+        __nv_bfloat16 (*st)[72] = reinterpret_cast<__nv_bfloat16 (*)[72]>(sraw);          // [64 k][64 rows + pad]
+        const int K = jb.K, rows = jb.rows;
+        const int tiles_k = (K + 63) / 64, ntiles = ((rows + 63) / 64) * tiles_k;
+        __nv_bfloat16* d0 = reinterpret_cast<__nv_bfloat16*>(jb.dst0);
+        __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(jb.dst1);
+        const int tx = tid & 15, ty = tid >> 4;                                            // 4 consecutive k, rows ty + 16 i
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int r_base = (t / tiles_k) * 64, k_base = (t % tiles_k) * 64;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rl = ty + 16 * i, r = r_base + rl, k = k_base + tx * 4;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (r < rows) {
+                    if (k + 4 <= K && (K & 3) == 0) {
+                        const float4 f = *reinterpret_cast<const float4*>(jb.src + (int64_t)r * K + k);
+                        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                    } else {
+                        for (int e = 0; e < 4; ++e) if (k + e < K) v[e] = jb.src[(int64_t)r * K + k + e];
+                    }
+                    if (k + 4 <= K && (K & 3) == 0) {
+                        uint2 pk;
+                        pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+                        *reinterpret_cast<uint2*>(d0 + (int64_t)(jb.o0 + r) * K + k) = pk;
+                    } else {
+                        for (int e = 0; e < 4; ++e)
+                            if (k + e < K) d0[(int64_t)(jb.o0 + r) * K + k + e] = __float2bfloat16(v[e]);
+                    }
+                }
+                if (d1) for (int e = 0; e < 4; ++e) st[tx * 4 + e][rl] = __float2bfloat16(v[e]);
+            }
+            if (d1) {
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int kl = ty + 16 * i, k = k_base + kl;
+                    if (k < K) {
+                        const int r4 = r_base + tx * 4;
+                        if (r4 + 4 <= rows && ((jb.n_tot | jb.o0) & 3) == 0) {
+                            *reinterpret_cast<uint2*>(d1 + (int64_t)k * jb.n_tot + jb.o0 + r4) = *reinterpret_cast<const uint2*>(&st[kl][tx * 4]);
+                        } else {
+                            for (int e = 0; e < 4; ++e)
+                                if (r4 + e < rows) d1[(int64_t)k * jb.n_tot + jb.o0 + r4 + e] = st[kl][tx * 4 + e];
+                        }
+                    }
+                }
+                __syncthreads();
+            }
         }
+        return;
+    }
+    // kind 1: rows = Cout, K = Cin; src index = ((co * Cin + ci) * 9 + tap)
+    float (*sf)[577] = reinterpret_cast<float (*)[577]>(sraw);                              // [16 co][64 ci * 9 taps] (+1: bank spread)
+    static_assert(sizeof(sraw) >= 16 * 577 * 4, "kind-1 tile");
+    const int Cin = jb.K, Cout = jb.rows;
+    const int tiles_ci = (Cin + 63) / 64, ntiles = ((Cout + 15) / 16) * tiles_ci;
+    __nv_bfloat16* d0 = reinterpret_cast<__nv_bfloat16*>(jb.dst0);
+    __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(jb.dst1);
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int co_base = (t / tiles_ci) * 16, ci_base = (t % tiles_ci) * 64;
+        const int nci = min(64, Cin - ci_base), nco = min(16, Cout - co_base);
+        for (int i = tid; i < 16 * 576; i += 256) {
+            const int col = i / 576, e = i % 576;                                          // e = ci_local * 9 + tap
+            sf[col][e] = (col < nco && e < nci * 9) ? jb.src[((int64_t)(co_base + col) * Cin + ci_base) * 9 + e] : 0.f;
+        }
+        __syncthreads();
+        // dst0 [co][tap][ci]: consecutive threads -> consecutive ci
+        for (int i = tid; i < 16 * 9 * 64; i += 256) {
+            const int cil = i & 63, tap = (i >> 6) % 9, col = i / 576;
+            if (col < nco && cil < nci) d0[((int64_t)(co_base + col) * 9 + tap) * Cin + ci_base + cil] = __float2bfloat16(sf[col][cil * 9 + tap]);
+        }
+        // dst1 [ci][tap'][co]: consecutive threads -> consecutive co (16-element runs)
+        for (int i = tid; i < 64 * 9 * 16; i += 256) {
+            const int col = i & 15, tap = (i >> 4) % 9, cil = i / 144;
+            if (col < nco && cil < nci) {
+                const int tap_d = jb.flip ? 8 - tap : tap;
+                d1[((int64_t)(ci_base + cil) * 9 + tap_d) * Cout + co_base + col] = __float2bfloat16(sf[col][cil * 9 + tap]);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -505,7 +662,8 @@ extern "C" int hcp_wgrad_conv3x3_bf16(const void* dy, int64_t Cout, const void* 
 
 extern "C" int hcp_colsum_bf16(const void* x, int64_t ld, int64_t M, int64_t N, int64_t rows_per_group, float scale, float* out,
                                int64_t ldo, hcp_stream_t st) {
-    if (!x || !out || M <= 0 || N <= 0 || (N & 1) || (ld & 1)) return set_error(HCP_ERR_INVALID, "colsum: arguments (even N / ld)");
+    if (!x || !out || M <= 0 || N <= 0 || (N % 8) || (ld % 8) || ((uintptr_t)x & 15))
+        return set_error(HCP_ERR_INVALID, "colsum: arguments (N, ld multiples of 8; 16-byte aligned x)");
     if (rows_per_group <= 0) rows_per_group = M;
     if (M % rows_per_group) return set_error(HCP_ERR_INVALID, "colsum: M must be a multiple of rows_per_group");
     int64_t chunk = rows_per_group;
@@ -520,14 +678,19 @@ extern "C" int hcp_norm_affine_grad_bf16(const void* x1, const void* x2, int64_t
                                          const float* gamma, const float* beta, int64_t rows, int64_t rows_per_image, int64_t groups,
                                          int32_t silu, float* dgamma, float* dbeta, hcp_stream_t st) {
     const int64_t C = C1 + C2;
-    if (!x1 || !dy || !stats || !gamma || !beta || !dgamma || !dbeta || rows <= 0 || C <= 0 || (C1 & 1) || (C2 & 1) || (C2 && !x2))
-        return set_error(HCP_ERR_INVALID, "norm_affine_grad: arguments");
+    if (!x1 || !dy || !stats || !gamma || !beta || !dgamma || !dbeta || rows <= 0 || C <= 0 || (C1 % 8) || (C2 % 8) || (C2 && !x2))
+        return set_error(HCP_ERR_INVALID, "norm_affine_grad: arguments (channel counts must be multiples of 8)");
     int cpg = 0;
     if (groups > 0) {
         if (C % groups || ((C / groups) & 1) || rows_per_image <= 0) return set_error(HCP_ERR_INVALID, "norm_affine_grad: groups");
         cpg = (int)(C / groups);
     }
     int64_t chunk = 1024;
+    if (groups > 0) {                       // a block stays inside one image: its statistics are loop constants
+        if (rows % rows_per_image) return set_error(HCP_ERR_INVALID, "norm_affine_grad: rows must be a multiple of rows_per_image");
+        chunk = rows_per_image;
+        while (chunk > 1024 && (chunk % 2) == 0) chunk /= 2;
+    }
     dim3 grid((unsigned)((C + 63) / 64), (unsigned)((rows + chunk - 1) / chunk));
     launch_k(norm_affine_grad_kernel, grid, dim3(256), 0, (cudaStream_t)st, (const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2, (int)C1, (int)C2,
              (const __nv_bfloat16*)dy, stats, gamma, beta, rows, rows_per_image, cpg, (int)groups, (int)silu, (int)chunk, dgamma, dbeta);
@@ -540,8 +703,13 @@ extern "C" int hcp_small_linear_bwd_f32(const float* dy, int64_t ldy, const floa
     if (!dy || M <= 0 || N <= 0 || K <= 0 || M > 4096 || ldy < N) return set_error(HCP_ERR_INVALID, "small_linear_bwd: arguments");
     if (dx) {
         if (!w_bf16) return set_error(HCP_ERR_INVALID, "small_linear_bwd: dx needs the weight");
-        launch_k(small_linear_dx_kernel, dim3((unsigned)((K + 127) / 128), (unsigned)M), dim3(128), 0, (cudaStream_t)st, dy, ldy, (const __nv_bfloat16*)w_bf16,
-                 (int)M, (int)N, (int)K, dx);
+        cudaError_t ez = cudaMemsetAsync(dx, 0, (size_t)M * K * sizeof(float), (cudaStream_t)st);      // the kernel accumulates n slices
+        if (ez != cudaSuccess) return set_cuda_error(ez, "small_linear dx memset");
+        const int kb = (int)((K + 127) / 128);
+        int n_chunk = 512;
+        while (n_chunk < N && (int64_t)kb * ((N + n_chunk - 1) / n_chunk) > 592) n_chunk *= 2;
+        launch_k(small_linear_dx_kernel, dim3((unsigned)kb, (unsigned)((N + n_chunk - 1) / n_chunk), (unsigned)((M + SLDX_ROWS - 1) / SLDX_ROWS)), dim3(128), 0,
+                 (cudaStream_t)st, dy, ldy, (const __nv_bfloat16*)w_bf16, (int)M, (int)N, (int)K, n_chunk, dx);
         LAUNCH_CHECK("small_linear dx launch");
     }
     if (dw) {
@@ -563,8 +731,9 @@ extern "C" int hcp_conv_in_wgrad_f32(const void* dh_nhwc_bf16, const float* x_nc
                                      float* dw, float* db, hcp_stream_t st) {
     if (!dh_nhwc_bf16 || !x_nchw || !dw) return set_error(HCP_ERR_INVALID, "conv_in_wgrad: null pointer");
     const int64_t npx = B * H * W;
-    const int chunk = 512;
-    dim3 grid((unsigned)(Cin * 9), (unsigned)((npx + chunk - 1) / chunk));
+    if (Cin > 4) return set_error(HCP_ERR_INVALID, "conv_in_wgrad: at most 4 input channels");
+    const int chunk = CEW_PX;
+    dim3 grid((unsigned)((npx + chunk - 1) / chunk));
     launch_k(conv_edge_wgrad_kernel, grid, dim3(320), 0, (cudaStream_t)st, (const __nv_bfloat16*)dh_nhwc_bf16, x_nchw, (int)B, (int)H, (int)W, (int)Cout,
              (int)Cin, 1, chunk, dw, db);
     LAUNCH_CHECK("conv_in_wgrad launch");
@@ -575,8 +744,9 @@ extern "C" int hcp_conv_out_wgrad_f32(const float* dy_nchw, const void* x_nhwc_b
                                       float* dw, float* db, hcp_stream_t st) {
     if (!dy_nchw || !x_nhwc_bf16 || !dw) return set_error(HCP_ERR_INVALID, "conv_out_wgrad: null pointer");
     const int64_t npx = B * H * W;
-    const int chunk = 512;
-    dim3 grid((unsigned)(Cout * 9), (unsigned)((npx + chunk - 1) / chunk));
+    if (Cout > 4) return set_error(HCP_ERR_INVALID, "conv_out_wgrad: at most 4 output channels");
+    const int chunk = CEW_PX;
+    dim3 grid((unsigned)((npx + chunk - 1) / chunk));
     launch_k(conv_edge_wgrad_kernel, grid, dim3(320), 0, (cudaStream_t)st, (const __nv_bfloat16*)x_nhwc_bf16, dy_nchw, (int)B, (int)H, (int)W, (int)Cin,
              (int)Cout, 0, chunk, dw, (float*)nullptr);
     LAUNCH_CHECK("conv_out_wgrad launch");

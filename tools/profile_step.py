@@ -18,7 +18,10 @@ from hcp_diffusion_b200.utils.cfg_net_tools import make_hcpdiff  # noqa: E402
 B = int(os.environ.get("HCP_BATCH", "4"))
 torch.manual_seed(0)
 unet = UNet2DConditionModel().cuda().requires_grad_(False).eval()      # random init: timing only
-groups, lora = make_hcpdiff(unet, None, [{"rank": 8, "dropout": 0.0, "layers": [r"re:.*\.attn.?$"]}])
+if os.environ.get("HCP_PROFILE_CONFIG", "2") == "3":      # BASELINE config 3: full fine-tune (run with HCP_BATCH=16)
+    groups, lora = make_hcpdiff(unet, [{"lr": 1e-6, "layers": [""]}], None)
+else:
+    groups, lora = make_hcpdiff(unet, None, [{"rank": 8, "dropout": 0.0, "layers": [r"re:.*\.attn.?$"]}])
 step = LoraTrainStep(unet, [p for g in groups for p in g["params"]], use_cuda_graph=False)
 lat, noise = torch.randn(B, 4, 64, 64), torch.randn(B, 4, 64, 64)
 t, ehs = torch.randint(0, 1000, (B,)), torch.randn(B, 77, 768)
