@@ -197,7 +197,7 @@ def lib() -> C.CDLL:
             l.hcp_sinusoid_f32.argtypes = [vp, i64, i64, i64, vp, i64, vp]
             l.hcp_lora_pack.argtypes = [vp, i64, vp]
             l.hcp_lora_pack_conv.argtypes = [vp, i64, vp]
-            l.hcp_lora_merge.argtypes = [vp, i64, i64, vp, vp]
+            l.hcp_lora_merge.argtypes = [vp, i64, i64, vp, C.c_int32, vp]
             l.hcp_lora_grad_conv3x3.argtypes = [vp, i64, vp, i64, i64, i64, i64, C.c_int32, C.POINTER(LoraGradBlock), C.c_int32, vp]
             l.hcp_lora_grad.argtypes = [vp, i64, vp, i64, i64, i64, i64, C.POINTER(LoraGradBlock), C.c_int32, vp]
             l.hcp_lora_grad_pair.argtypes = [vp, vp, i64, i64, C.POINTER(LoraGradBlock), vp, vp, i64, i64, C.POINTER(LoraGradBlock),

@@ -270,10 +270,17 @@ __global__ void lora_pack_conv_kernel(const hcp_lora_conv_job* __restrict__ jobs
 // ---------------------------------------------------------------------------------------------
 constexpr int MG_T = 64;          // tile edge
 constexpr int MG_RMAX = 64;       // sum of the ranks stacked on one host
-__global__ void __launch_bounds__(256) lora_merge_kernel(const hcp_lora_merge_job* __restrict__ jobs, int njobs, const int32_t* __restrict__ tile_job) {
-    __shared__ float s_dn[MG_RMAX][MG_T + 4];          // W_down rows (all stacked blocks) over the tile's k range
-    __shared__ float s_up[MG_T][MG_RMAX + 1];          // alpha * W_up rows of the tile's o range
-    __shared__ __align__(16) __nv_bfloat16 s_t[MG_T][MG_T + 8];      // the merged tile, for the transposed store
+// Shared memory is sized by the launch for `rcap` = the largest rank sum of any job rounded up to 8 (9 KB + rcap * 528 B: 13 KB for
+// rank 8 instead of the 43 KB a rank-64 layout needs), so that 16 instead of 5 blocks share an SM and their load / compute / store
+// phases overlap.
+__global__ void __launch_bounds__(256) lora_merge_kernel(const hcp_lora_merge_job* __restrict__ jobs, int njobs, const int32_t* __restrict__ tile_job,
+                                                         int rcap) {
+    extern __shared__ __align__(16) uint8_t mg_smem[];
+    __nv_bfloat16 (*s_t)[MG_T + 8] = reinterpret_cast<__nv_bfloat16 (*)[MG_T + 8]>(mg_smem);                  // the merged tile (transposed store)
+    float (*s_dn)[MG_T + 4] = reinterpret_cast<float (*)[MG_T + 4]>(mg_smem + MG_T * (MG_T + 8) * 2);          // [rcap] W_down rows over the tile's k range
+    float* s_up_base = reinterpret_cast<float*>(mg_smem + MG_T * (MG_T + 8) * 2 + rcap * (MG_T + 4) * 4);      // [64][rcap + 1] alpha * W_up rows
+    const int up_ld = rcap + 1;
+#define s_up(o, r) s_up_base[(o) * up_ld + (r)]
     pdl_trigger();
     pdl_wait();
     // job of this tile: one load from the caller's tile -> job table, or (no table) the last job with tile0 <= blockIdx.x by a
@@ -318,7 +325,7 @@ __global__ void __launch_bounds__(256) lora_merge_kernel(const hcp_lora_merge_jo
         }
         for (int i = tid; i < MG_T * r; i += 256) {
             const int o = o_base + i / r, rr = i % r;
-            s_up[i / r][rtot + rr] = (o < out) ? alpha * up[(int64_t)o * r + rr] : 0.f;
+            s_up(i / r, rtot + rr) = (o < out) ? alpha * up[(int64_t)o * r + rr] : 0.f;
         }
         rtot += r;
     }
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(256) lora_merge_kernel(const hcp_lora_merge_jo
         const int ol = ty + 32 * i, o = o_base + ol, k = k_base + tx * 8;
         float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int r = 0; r < rtot; ++r) {
-            const float u = s_up[ol][r];
+            const float u = s_up(ol, r);
             const float4 d0 = *reinterpret_cast<const float4*>(&s_dn[r][tx * 8]), d1 = *reinterpret_cast<const float4*>(&s_dn[r][tx * 8 + 4]);
             d[0] = fmaf(u, d0.x, d[0]); d[1] = fmaf(u, d0.y, d[1]); d[2] = fmaf(u, d0.z, d[2]); d[3] = fmaf(u, d0.w, d[3]);
             d[4] = fmaf(u, d1.x, d[4]); d[5] = fmaf(u, d1.y, d[5]); d[6] = fmaf(u, d1.z, d[6]); d[7] = fmaf(u, d1.w, d[7]);
@@ -365,6 +372,8 @@ __global__ void __launch_bounds__(256) lora_merge_kernel(const hcp_lora_merge_jo
         }
     }
 }
+
+#undef s_up
 
 // ---------------------------------------------------------------------------------------------
 // loss = mean((pred - target)^2) (fp32, reference train_ac.py:506-515 with loss.type == 'eps'), dpred = 2(pred-target)/n
@@ -567,9 +576,12 @@ extern "C" int hcp_lora_pack(const hcp_lora_job* jobs_device, int64_t njobs, hcp
 }
 
 extern "C" int hcp_lora_merge(const hcp_lora_merge_job* jobs_device, int64_t njobs, int64_t total_tiles, const int32_t* tile_job_device,
-                              hcp_stream_t st) {
+                              int32_t max_rank_sum, hcp_stream_t st) {
     if (!jobs_device || njobs <= 0 || total_tiles <= 0) return set_error(HCP_ERR_INVALID, "lora_merge: jobs");
-    launch_k(lora_merge_kernel, dim3((unsigned)total_tiles), dim3(256), 0, (cudaStream_t)st, jobs_device, (int)njobs, tile_job_device);
+    if (max_rank_sum <= 0 || max_rank_sum > MG_RMAX) max_rank_sum = MG_RMAX;
+    const int rcap = (max_rank_sum + 7) / 8 * 8;
+    const size_t smem = (size_t)MG_T * (MG_T + 8) * 2 + (size_t)rcap * (MG_T + 4) * 4 + (size_t)MG_T * (rcap + 1) * 4;
+    launch_k(lora_merge_kernel, dim3((unsigned)total_tiles), dim3(256), smem, (cudaStream_t)st, jobs_device, (int)njobs, tile_job_device, rcap);
     LAUNCH_CHECK("lora_merge launch");
     return HCP_OK;
 }

@@ -153,6 +153,7 @@ class _JobTable:
     def __init__(self):
         self.key = None
         self.dev = self.cdev = self.mdev = self.mmap = None
+        self.mrank = 0
         self.n = self.cn = self.mn = self.mtiles = 0
 
 
@@ -185,6 +186,7 @@ def pack_lora(groups: Sequence, table: Optional[_JobTable] = None) -> None:
                 tmap += [i] * n
                 tiles += n
             table.mmap = torch.tensor(tmap, dtype=torch.int32).cuda()
+            table.mrank = max(sum(j.rank[i] for i in range(j.nblocks)) for j in mjobs)
             marr = (_lib.LoraMergeJob * len(mjobs))(*mjobs)
             table.mdev = torch.frombuffer(bytearray(bytes(marr)), dtype=torch.uint8).cuda()
             table.mn, table.mtiles = len(mjobs), tiles
@@ -197,7 +199,7 @@ def pack_lora(groups: Sequence, table: Optional[_JobTable] = None) -> None:
         table.key, table.n, table.cn = key, len(jobs), len(cjobs)
     _lib.call("hcp_lora_pack", table.dev.data_ptr(), table.n, _lib.stream_ptr())
     if table.mdev is not None:
-        _lib.call("hcp_lora_merge", table.mdev.data_ptr(), table.mn, table.mtiles, table.mmap.data_ptr(), _lib.stream_ptr())
+        _lib.call("hcp_lora_merge", table.mdev.data_ptr(), table.mn, table.mtiles, table.mmap.data_ptr(), table.mrank, _lib.stream_ptr())
     if table.cdev is not None:
         _lib.call("hcp_lora_pack_conv", table.cdev.data_ptr(), table.cn, _lib.stream_ptr())
 

@@ -275,9 +275,10 @@ typedef struct hcp_lora_merge_job {
     void* W;
     void* WT;
 } hcp_lora_merge_job;
-/* tile_job_device: optional int32 [total_tiles] table, tile index -> job index (NULL: the kernel searches the job table itself). */
+/* tile_job_device: optional int32 [total_tiles] table, tile index -> job index (NULL: the kernel searches the job table itself);
+ * max_rank_sum: the largest sum of stacked ranks of any job (sizes the kernel's shared memory; <= 0: assume 64). */
 int hcp_lora_merge(const hcp_lora_merge_job* jobs_device, int64_t njobs, int64_t total_tiles, const int32_t* tile_job_device,
-                   hcp_stream_t stream);
+                   int32_t max_rank_sum, hcp_stream_t stream);
 /* Conv2d LoRA down-projection W_down fp32 [rank, Cin, 3, 3] -> the two bf16 operands the 3x3 kernels take:
  *   wt [R, 3, 3, Cin]  forward weights of T = conv3x3(x, W_down) (rows c0 .. c0+rank of the group's R-row matrix)
  *   wd [Cin, 3, 3, R]  dgrad arrangement of the same taps (flipped for stride 1, as-is for the stride-2 phase kernels)
