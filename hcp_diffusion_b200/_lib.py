@@ -35,7 +35,7 @@ def build(verbose: bool = False) -> str:
                                                       os.path.join(_HERE, "..", "include", "hcp_b200.h")])
     if os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
         return LIB_PATH
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH, *srcs, "-lcudart"]
+    cmd = ["nvcc", *NVCC_FLAGS, *os.environ.get("HCP_EXTRA_NVCC_FLAGS", "").split(), "-o", LIB_PATH, *srcs, "-lcudart"]   # e.g. -DHCP_ATTN_TRACE
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

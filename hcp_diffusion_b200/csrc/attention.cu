@@ -891,10 +891,16 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                     }
                 }
             };
+            // phase trace of the loop (tools/probe_attn_trace.py): compiled in only with -DHCP_ATTN_TRACE (HCP_EXTRA_NVCC_FLAGS), the
+            // seven 64-bit accumulators would otherwise sit in every softmax thread's registers
+#ifdef HCP_ATTN_TRACE
             const bool trc = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
             long long t_wait_sdp = 0, t_exp = 0, t_wait_dq = 0, t_pstore = 0, t_ds = 0, t_dsstore = 0, t_drain = 0, tk = trc ? clock64() : 0;
             const long long t_begin = tk;
 #define HCP_LAP(acc) do { if (trc) { const long long tn_ = clock64(); acc += tn_ - tk; tk = tn_; } } while (0)
+#else
+#define HCP_LAP(acc) do { } while (0)
+#endif
             for (int i = 0; i < nq; ++i) {
                 const int qrow = (i0 + i) * 128 + row;
                 const bool qok = qrow < p.Lq;
@@ -969,11 +975,13 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __gr
                 HCP_LAP(t_drain);
             }
 #undef HCP_LAP
+#ifdef HCP_ATTN_TRACE
             if (trc) {
                 long long* o = p.trace;
                 o[0] = clock64() - t_begin; o[1] = nq; o[2] = t_wait_sdp; o[3] = t_exp; o[4] = t_wait_dq; o[5] = t_pstore; o[6] = t_ds;
                 o[7] = t_dsstore; o[8] = t_drain;
             }
+#endif
             mbar_wait(dq_full, (nq - 1) & 1);
             tc_fence_after();
             drain(dq_row + (int64_t)(nq - 1) * 512, (i0 + nq - 1) * 128 + row < p.Lq);

@@ -1,5 +1,7 @@
 """Where does a q tile of the attention backward go?  (hcp_debug_attn_trace: cycle sums per phase of the lean softmax loop,
-thread 0 of CTA 0.)   python tools/probe_attn_trace.py [B H L d]"""
+thread 0 of CTA 0.)  Needs a library built with the trace compiled in:
+    HCP_EXTRA_NVCC_FLAGS=-DHCP_ATTN_TRACE python -c "import hcp_diffusion_b200 as p, os; os.remove(p._lib.LIB_PATH) if os.path.exists(p._lib.LIB_PATH) else None; p.build()"
+    python tools/probe_attn_trace.py [B H L d]"""
 import ctypes as C
 import os
 import sys
