@@ -234,6 +234,43 @@ def dominant_kernel_roofline(peak_tflops):
     return out
 
 
+def count_step_flops(step, host):
+    """Algorithmic FLOP of ONE training step, summed over the C-ABI GEMM / convolution / attention calls it makes (2 M N K per GEMM
+    segment, 2 M Cout 9 Cin per convolution, 4 / 10 B H Lq Lkv d per attention forward / backward).  Used for workloads without a
+    published per-image figure (config 4); the LoRA-gradient kernels are not counted.  The calls are logged while the step's CUDA graph
+    is captured, nothing is timed here."""
+    import hcp_diffusion_b200.engine as _eng
+    import hcp_diffusion_b200.ops as _ops
+    from hcp_diffusion_b200 import _lib
+    total = [0.0]
+    orig = _lib.call
+
+    def logged(name, *a):
+        try:
+            o = a[0]._obj if a and hasattr(a[0], "_obj") else None
+            if name == "hcp_gemm_bf16":
+                total[0] += 2.0 * o.M * o.N * sum(o.k[i] for i in range(o.nseg))
+            elif name == "hcp_conv3x3_bf16":
+                s_ = o.stride
+                mo = o.B * (o.Hin // s_) * (o.Win // s_) if o.mode == 0 else o.B * o.Hin * o.Win     # mode 1: dY pixels of the stride-2 dgrad
+                total[0] += 2.0 * mo * o.Cout * 9 * o.Cin
+            elif name == "hcp_attn_fwd_bf16":
+                total[0] += 4.0 * o.B * o.H * o.Lq * o.Lkv * o.d
+            elif name == "hcp_attn_bwd_bf16":
+                total[0] += 10.0 * o.B * o.H * o.Lq * o.Lkv * o.d
+        except Exception:      # noqa: BLE001  (a logging helper must never break the run)
+            pass
+        return orig(name, *a)
+
+    _lib.call = _ops.call = _eng.call = logged
+    try:
+        step.step(*host)                               # first call: warm-up + CUDA-graph capture; every launch goes through `call` once per pass
+    finally:
+        _lib.call = _ops.call = _eng.call = orig
+    # the capture path runs the step three times (two warm-up passes + the capture): FLOP of one pass
+    return total[0] / 3.0
+
+
 def attn_tensor_pipe_pct():
     """BASELINE.json's second metric, "attn tensor-pipe % of peak": sm__pipe_tensor... pct of peak of the attention kernels at the
     benchmark shape (B=4, H=8, L=4096, d=40), read from the committed `ncu --set full` summaries (a number taken under a profiler is
@@ -270,10 +307,38 @@ def run_product_arm(args, rank, world, local_rank):
     sustained, burst, hbm, peak_src = measured_peaks()
 
     spec = U.SD15
-    unet = UNet2DConditionModel()
-    unet.load_state_dict(U.init_params(spec, seed=0))
-    unet = unet.to(dev).requires_grad_(False).eval()
-    if args.config == 3:
+    added = None
+    if args.config == 4:
+        # BASELINE configs[3]: SDXL-base UNet, LoRA rank 16 on attn + ff Linears and the resnet / sampler convolutions (locon), bs 2 / GPU,
+        # 1024x1024 (128x128 latent), 77 x 2048 text tokens + text_time conditioning (reference cfgs/train/examples/locon.yaml shapes)
+        with torch.device("meta"):
+            unet = UNet2DConditionModel(sample_size=128, block_out_channels=(320, 640, 1280), attention_head_dim=(5, 10, 20), cross_attention_dim=2048,
+                                        down_block_types=("DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"),
+                                        up_block_types=("CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"),
+                                        transformer_layers_per_block=(1, 2, 10), use_linear_projection=True, addition_embed_type="text_time",
+                                        addition_time_embed_dim=256, projection_class_embeddings_input_dim=2816)
+        unet = unet.to_empty(device=dev)
+        gen = torch.Generator(device=dev).manual_seed(0)
+        with torch.no_grad():
+            for name, p_ in unet.named_parameters():           # random init (no checkpoints offline): fan-in scaled weights, unit norm scales
+                if p_.dim() > 1:
+                    p_.normal_(0, p_[0].numel() ** -0.5, generator=gen)
+                elif "norm" in name and name.endswith("weight"):
+                    p_.fill_(1.0)
+                else:
+                    p_.zero_()
+        unet = unet.requires_grad_(False).eval()
+    else:
+        unet = UNet2DConditionModel()
+        unet.load_state_dict(U.init_params(spec, seed=0))
+        unet = unet.to(dev).requires_grad_(False).eval()
+    if args.config == 4:
+        layers = [r"re:.*\.attn.?$", r"re:.*\.ff$", r"re:.*\.resnets\.\d+\.conv[12]$", r"re:.*\.conv_shortcut$", r"re:.*samplers\.0\.conv$"]
+        groups, lora = make_hcpdiff(unet, None, [{"lr": 1e-4, "rank": 16, "alpha": 1.0, "dropout": 0.0, "layers": layers}])
+        B, f_step, metric = 2, None, "LoRA-train images/sec SDXL 1024px"
+        use_graph = True
+        what = "SDXL-base UNet LoRA r=16 on attn + ff Linear and resnet / sampler Conv2d (locon, %d params), bs=2/GPU"
+    elif args.config == 3:
         # BASELINE configs[2]: DreamBooth full fine-tune, no LoRA, bs 16 / GPU (reference cfgs/train/examples/DreamBooth.yaml:6-10)
         groups, lora = make_hcpdiff(unet, [{"lr": 1e-6, "layers": [""]}], None)
         B, f_step, metric = 16, 3 * F_FWD, "full fine-tune images/sec SD1.5 512px"
@@ -290,9 +355,20 @@ def run_product_arm(args, rank, world, local_rank):
     step = LoraTrainStep(unet, groups, weight_decay=1e-2, max_grad_norm=1.0, use_cuda_graph=use_graph)
     step.sync_params(0)
 
-    lat, noise, t, ehs = U.synthetic_batch(B, spec, seed=1234 + rank)
+    if args.config == 4:
+        g = torch.Generator().manual_seed(1234 + rank)
+        lat, noise = torch.randn(B, 4, 128, 128, generator=g), torch.randn(B, 4, 128, 128, generator=g)
+        t, ehs = torch.randint(0, 1000, (B,), generator=g), torch.randn(B, 77, 2048, generator=g)
+        added = {"text_embeds": torch.randn(B, 1280, generator=g).pin_memory(),
+                 "time_ids": torch.tensor([[1024.0, 1024.0, 0.0, 0.0, 1024.0, 1024.0]]).repeat(B, 1).pin_memory()}
+    else:
+        lat, noise, t, ehs = U.synthetic_batch(B, spec, seed=1234 + rank)
     host = [x.pin_memory() for x in (lat, noise, t, ehs)]
-    h2d = sum(x.numel() * x.element_size() for x in host)
+    h2d = sum(x.numel() * x.element_size() for x in host) + (sum(v.numel() * v.element_size() for v in added.values()) if added else 0)
+    if added is not None:
+        host.append(added)
+    if f_step is None:
+        f_step = count_step_flops(step, host) / B          # algorithmic FLOP of the GEMM / conv / attention calls of one step, per image
 
     def barrier():
         if world > 1:
@@ -318,7 +394,7 @@ def run_product_arm(args, rank, world, local_rank):
         loss = step.step(*host)
         losses.append(float(loss.cpu()))          # the per-step D2H read of the result (reference: loss.item(), train_ac.py:504)
 
-    dev_in = [x.to(dev) for x in host]
+    dev_in = [({k: v.to(dev) for k, v in x.items()} if isinstance(x, dict) else x.to(dev)) for x in host]
 
     def resident_step():
         if use_graph:
@@ -357,13 +433,13 @@ def run_product_arm(args, rank, world, local_rank):
     boosted = bool(clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.9 * clocks["sm_max_mhz"])
     peak = burst if boosted else sustained
     kern = dominant_kernel_roofline(burst) if (world == 1 and args.config == 2) else None
+    res_txt = "1024x1024 (128x128 latent), 77 x 2048 tokens + text_time conditioning" if args.config == 4 else "512x512 (64x64 latent), 77 tokens"
     line = {
         "metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": (what % n_train) + ", 512x512 (64x64 latent), 77 tokens; step = add_noise + UNet fwd + MSE + bwd + grad "
-                               "all-reduce + clip + AdamW",
-                   "baseline_config": args.config, "global_batch": world * B, "per_gpu_batch": B, "lora_rank": LORA_RANK if args.config == 2 else 0,
+        "config": {"workload": (what % n_train) + ", " + res_txt + "; step = add_noise + UNet fwd + MSE + bwd + grad all-reduce + clip + AdamW",
+                   "baseline_config": args.config, "global_batch": world * B, "per_gpu_batch": B, "lora_rank": {2: LORA_RANK, 3: 0, 4: 16}[args.config],
                    "parallelism": f"dp{world}",
                    "l2": "working set (1.7 GB bf16 weights + activations) is far larger than the 126 MB L2; no explicit flush",
                    "cuda_graph": use_graph, "grad_checkpointing": False,
@@ -396,8 +472,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="hcpb200", choices=["hcpb200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
-                    help="BASELINE.json config: 2 = SD1.5 LoRA r8 bs 4/GPU (the headline, default); 3 = SD1.5 full fine-tune bs 16/GPU")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json config: 2 = SD1.5 LoRA r8 bs 4/GPU (the headline, default); 3 = SD1.5 full fine-tune bs 16/GPU; "
+                         "4 = SDXL-base LoRA r16 attn + Conv2d bs 2/GPU, 1024x1024")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
