@@ -3,15 +3,17 @@
 //
 //   out[M,N] = sum_s A_s[M,K_s] . B_s[N,K_s]^T + bias[N] + rowbias[row/rows_per_group, N] + residual[M,N]
 //
-// One CTA computes one 128 x BN output tile.  Warp roles (192 threads):
-//   warp 0   : TMA producer  (one elected lane; A and B tiles of 64 K-elements per stage, SWIZZLE_128B)
-//   warp 1   : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma, fp32 accumulator in TMEM)
-//   warps 2-5: epilogue (tcgen05.ld the accumulator, fused bias / per-image bias / residual, bf16 store)
-// smem stages are sized so that two CTAs fit on one SM: one CTA's epilogue overlaps the other's main loop.
+// Persistent kernel, one CTA (or CTA pair, tcgen05 cta_group::2) per SM walking 128 x BN (256 x BN) work items.  Warp roles
+// (320 threads):
+//   warp 0    : TMA producer  (one elected lane; A and B tiles of 64 K-elements per stage, SWIZZLE_128B)
+//   warp 1    : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma, fp32 accumulators in TMEM)
+//   warps 2-9 : epilogue (tcgen05.ld the accumulator, fused bias / per-image bias / residual, bf16, TMA or coalesced stores);
+//               two TMEM accumulators let the epilogue of item i run under the main loop of item i+1
 //
-// The LoRA delta of hcpdiff (reference: hcpdiff/models/lora_layers_patch.py:44-57) enters as an extra
-// K-segment: A_1 = (x . W_down^T) [M, 64-padded], B_1 = alpha * W_up [N, 64-padded]; only ceil(r/16)
-// k-steps of that block are issued.
+// hcpdiff's LoRA (reference: hcpdiff/models/lora_layers_patch.py:44-57) reaches this kernel in two forms: adapters that apply to all
+// rows are merged into the weight operand once per step (misc.cu: lora_merge_kernel) and their rank products T / U leave as a second
+// output (`out2`: extra rows of the operand); DreamArtist++ adapters enter as an extra K-segment A_1 = (x . W_down^T) [M, 64-padded],
+// B_1 = alpha * W_up [N, 64-padded], of which only ceil(r/16) k-steps are issued.
 //
 // The 3x3 convolution uses the same pipeline: the A tile of tap (kh,kw) and channel block c is a 4D (or 5D
 // for stride 2) TMA box over the NHWC activation at a shifted coordinate; coordinates outside the image are
@@ -73,7 +75,6 @@ struct alignas(64) GemmKParams {
     int32_t tma_store;                 // 1: the rows of every tile are consecutive rows of `out`: parts leave through TMA stores
     // split-K: CTA (x, y) reduces the k-blocks [y*kb_per_split, (y+1)*kb_per_split) and stores raw fp32 partials
     int32_t splits, kb_per_split;
-    int32_t epi_batch;                 // epilogue schedule (see the epilogue)
     float* ws;                         // [splits, M, N] fp32
     long long* trace;                  // bring-up only (hcp_gemm_set_trace): 16 int64 slots per CTA (clock64 stamps / wait sums), NULL in production
 };
@@ -964,15 +965,11 @@ static PairPlan plan_pair(int64_t N, int64_t m_tiles, int64_t total_kb, bool all
     return none;
 }
 
-static int pick_bn_gemm(int64_t N, int64_t, int64_t) { return pick_bn(N); }      // (the 128x80 tiling for half-filled grids measured neutral in r01 and is gone)
-
 static long long* g_gemm_trace = nullptr;
 
 static int dispatch_gemm(int bn, bool cta_pair, GemmKParams& kp, int m_tiles, cudaStream_t stream) {
     kp.tiles_m = m_tiles;
     kp.trace = g_gemm_trace;
-    static const int epi_batch = [] { const char* e = getenv("HCP_GEMM_EPI_BATCH"); return e ? atoi(e) : 1; }();
-    kp.epi_batch = epi_batch;
     if (cta_pair) {
         if (bn == 320) return launch_gemm<320, 1, true>(kp, stream);
         if (bn == 256) return launch_gemm<256, 1, true>(kp, stream);
@@ -1073,7 +1070,7 @@ extern "C" int hcp_gemm_bf16(const hcp_gemm_args* a, hcp_stream_t stream_) {
     for (int s = 0; s < a->nseg; ++s) kb_all += (a->k[s] + BLOCK_K - 1) / BLOCK_K;
     const PairPlan pp = plan_pair(a->N, (a->M + BLOCK_M - 1) / BLOCK_M, kb_all, a->workspace != nullptr);
     const int pair_bn = pp.bn;
-    const int bn = pair_bn ? pair_bn : pick_bn_gemm(a->N, (a->M + BLOCK_M - 1) / BLOCK_M, kb_all);
+    const int bn = pair_bn ? pair_bn : pick_bn(a->N);
     const int b_box_rows = pair_bn ? (pair_bn > 256 ? pair_bn / 4 : pair_bn / 2) : bn;       // rows of one TMA box of B (see GemmCfg::B_BOX_ROWS)
     for (int s = 0; s < a->nseg; ++s) {
         if (a->k[s] <= 0) return set_error(HCP_ERR_INVALID, "gemm: k must be positive");

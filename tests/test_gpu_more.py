@@ -314,3 +314,65 @@ def test_tiny_unet_shipped_locon_yaml_items_match_oracle():
                 tnum, tden = tnum + e, tden + n
     assert math.sqrt(num / den) < 5e-2
     assert math.sqrt(tnum / tden) < 5e-2          # the time-embedding adapters on their own
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# round-2 C-ABI additions, called directly: the second GEMM output and the LoRA weight merge
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,K,N,rp", [(300, 320, 320, 8), (1024, 640, 640, 24), (16384, 320, 960, 24), (77, 768, 1280, 16)])
+def test_gemm_second_output_matches_torch(M, K, N, rp):
+    """hcp_gemm_args.out2 / n_main: columns [N, N + rp) of x . W_ext^T leave raw in a second buffer, the first N get bias + residual
+    (M tails, the partly filled last 176-column tile; the main part goes through the TMA-store epilogue)."""
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(M, K, generator=g).to(DEV).to(BF)
+    w_ext = (torch.randn(N + rp, K, generator=g) / math.sqrt(K)).to(DEV).to(BF)
+    bias = (torch.randn(N, generator=g) * 0.1).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV).to(BF)
+    out = torch.empty((M, N), dtype=BF, device=DEV)
+    t2 = torch.zeros((M, 64), dtype=BF, device=DEV)
+    ops.gemm_raw([(x, K, K)], [(w_ext, K, N + rp, 0)], M, N + rp, out, N, bias=bias, residual=res, ldr=N, out2=t2, ldo2=64, n_main=N)
+    ref = x.float() @ w_ext.float().t()
+    assert rel_l2(out, ref[:, :N] + bias + res.float()) < 1e-2
+    assert rel_l2(t2[:, :rp], ref[:, N:]) < 1e-2
+    assert float(t2[:, rp:].float().abs().sum()) == 0.0           # nothing beyond the rank columns is written
+
+
+def test_lora_merge_kernel_matches_fp32_sum_and_carries_rank_rows():
+    """hcp_lora_merge through LinearPack.enable_merge + runtime.pack_lora: W = bf16(W_host + sum alpha W_up W_down) (fp32 sum, one
+    rounding), W^T its exact transpose, the extra operand rows = the factors the rank products need."""
+    from hcp_diffusion_b200.ops import LinearPack, LoraBlockRef
+    from hcp_diffusion_b200.runtime import pack_lora
+    g = torch.Generator().manual_seed(11)
+    K, n_per = 640, 320
+    hosts = [(torch.randn(n_per, K, generator=g) / math.sqrt(K)).to(DEV) for _ in range(2)]        # a fused group of two hosts
+    pack = LinearPack(torch.cat(hosts, 0), None)
+    refs, per_host = [], []
+    for i, (ranks, alpha) in enumerate((((8, 4), 0.125), ((16,), 0.5))):                             # host 0 carries two stacked blocks
+        mine = []
+        for r in ranks:
+            down = (torch.randn(r, K, generator=g) / math.sqrt(K)).to(DEV)
+            up = (torch.randn(n_per, r, generator=g) * 0.3).to(DEV)
+            ref = LoraBlockRef(down, up, alpha, i * n_per)
+            refs.append(ref)
+            mine.append(ref)
+        per_host.append((hosts[i], i * n_per, n_per, mine))
+    pack.attach_lora(refs)
+    assert pack.enable_merge(per_host) and pack.ext_rp == 32
+
+    class G:
+        pass
+    grp = G()
+    grp.pack = pack
+    pack_lora([grp])
+    torch.cuda.synchronize()
+    N = 2 * n_per
+    want = torch.cat([h + sum(b.alpha * (b.w_up @ b.w_down) for b in blocks) for h, _, _, blocks in per_host], 0)
+    got = pack.W[:N].float()
+    assert rel_l2(got, want) < 3e-3                                   # bf16 rounding of the fp32 sum
+    assert float((got - want.to(BF).float()).abs().max()) <= float(want.abs().max()) * 2 ** -7      # at most one bf16 ulp apart
+    assert torch.equal(pack.WT[:K], pack.W[:N].t())
+    c0 = 0
+    for b in refs:
+        assert torch.equal(pack.W[N + c0:N + c0 + b.rank], b.w_down.to(BF))
+        assert torch.equal(pack.WT[K + c0:K + c0 + b.rank, b.o0:b.o0 + n_per], (b.alpha * b.w_up).to(BF).t())
+        c0 += b.rank
