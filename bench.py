@@ -284,9 +284,12 @@ def attn_tensor_pipe_pct():
             try:
                 rows = list(csv.reader(open(path)))
                 hdr, val = rows[0], rows[2]
-                cols = [i for i, h in enumerate(hdr) if h.startswith("sm__pipe_tensor") and "pct_of_peak" in h]
+                # the SM-average over the kernel's whole duration (not the busiest SM, not "while active")
+                pref = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"
+                cols = [i for i, h in enumerate(hdr) if h == pref] or \
+                       [i for i, h in enumerate(hdr) if h.startswith("sm__pipe_tensor") and "avg.pct_of_peak_sustained_elapsed" in h]
                 if cols:
-                    out[key] = {"pct": max(float(val[i]) for i in cols), "source": name}
+                    out[key] = {"pct": float(val[cols[0]]), "metric": hdr[cols[0]], "source": name}
                     break
             except (OSError, ValueError, IndexError):
                 continue
